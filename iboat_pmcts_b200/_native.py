@@ -1,0 +1,87 @@
+"""ctypes binding of libpmcts_b200.so (include/pmcts_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+Python / CPU fallback: if the library is missing, or no CUDA device is visible when an engine is
+created, this module raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpmcts_b200.so")
+
+# mirrors of the header constants
+ST_OK, ST_ARRIVED, ST_HORIZON, ST_OUT_OF_BOX, ST_OUT_OF_GRID, ST_DEGENERATE, ST_PAST_HORIZON = range(7)
+STEP_STOP_BEFORE_TERMINAL = 0x1
+ROLL_REPLAY_FULL_PREFIX = 0x2
+ROLL_PLAN_EVAL = 0x4
+MEM_HOST = 0x100
+PREC_F64, PREC_FAST = 0, 1
+NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
+ERR_NO_DEVICE = -3
+
+EXPORTS = [
+    "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
+    "pmcts_synchronize", "pmcts_set_precision", "pmcts_launch_count", "pmcts_enable_timing",
+    "pmcts_kernel_ms_total", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
+    "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_backup", "pmcts_hist_stats",
+]
+
+
+class Noise(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("z", C.c_void_p),
+                ("seed", C.c_uint64), ("stream", C.c_uint64), ("id0", C.c_uint64)]
+
+
+class PmctsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pmcts_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA extension; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "pmcts_b200: CUDA extension %s is missing -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.pmcts_create.argtypes = [i32, C.POINTER(vp)]
+    L.pmcts_destroy.argtypes = [vp]
+    L.pmcts_destroy.restype = None
+    L.pmcts_last_error.restype = C.c_char_p
+    L.pmcts_version.restype = C.c_char_p
+    L.pmcts_set_stream.argtypes = [vp, vp]
+    L.pmcts_reset_stream.argtypes = [vp]
+    L.pmcts_synchronize.argtypes = [vp]
+    L.pmcts_set_precision.argtypes = [vp, i32]
+    L.pmcts_launch_count.argtypes = [vp]
+    L.pmcts_launch_count.restype = i64
+    L.pmcts_enable_timing.argtypes = [vp, i32]
+    L.pmcts_kernel_ms_total.argtypes = [vp, i32]
+    L.pmcts_kernel_ms_total.restype = dbl
+    L.pmcts_set_params.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl, dbl]
+    L.pmcts_scenario_upload.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp]
+    L.pmcts_scenario_free.argtypes = [vp, i32]
+    L.pmcts_get_wind.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32]
+    L.pmcts_step_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Noise),
+                                   vp, vp, vp, i32]
+    L.pmcts_rollout_batch.argtypes = [vp, i32, i64, i32, vp, vp, dbl, vp, vp, i32, C.POINTER(Noise),
+                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32]
+    L.pmcts_backup.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i32]
+    L.pmcts_hist_stats.argtypes = [vp, vp, i64, vp, vp, i32]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise PmctsError(rc, lib().pmcts_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,906 @@
+// pmcts_b200 -- kernels and C ABI (include/pmcts_b200.h) of the B200-native rollout engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//        (see __graft_entry__.build()).  Depends on the CUDA runtime only.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pmcts_device.cuh"
+
+namespace pmcts {
+
+// ================================================================================================
+// Kernels
+// ================================================================================================
+
+constexpr int kBlock = 128;
+
+// Scenario upload: blends the weather grid in time once per simulator instant.
+//   slab[k][a][o] = (1 - wt[k]) * W[it[k]][a][o] + wt[k] * W[it[k] + 1][a][o]
+// SciPy applies the time weight inside the 8-corner sum (_rgi.py:520-549); blending first is the
+// same polynomial and differs only in rounding (~1e-16 relative).
+template <typename T>
+__global__ void blend_time_slabs_kernel(const T *__restrict__ u, const T *__restrict__ v,
+                                        const int *__restrict__ it, const double *__restrict__ wt,
+                                        int nT, int plane, double2 *__restrict__ slab64,
+                                        float2 *__restrict__ slab32) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)nT * plane) return;
+    const int k = (int)(idx / plane), p = (int)(idx % plane);
+    const size_t lo = (size_t)it[k] * plane + p, hi = lo + plane;
+    const double w = wt[k];
+    const double uu = (double)u[lo] * (1.0 - w) + (double)u[hi] * w;
+    const double vv = (double)v[lo] * (1.0 - w) + (double)v[hi] * w;
+    slab64[idx] = make_double2(uu, vv);
+    slab32[idx] = make_float2((float)uu, (float)vv);
+}
+
+__global__ void get_wind_kernel(ScenarioView sc, int64_t n, const int32_t *__restrict__ k,
+                                const double *__restrict__ lat, const double *__restrict__ lon,
+                                double *__restrict__ u, double *__restrict__ v,
+                                uint8_t *__restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double uu = NAN, vv = NAN;
+    const int kk = k[i];
+    const bool ok = kk >= 0 && kk < sc.nT && wind_f64(sc, kk, lat[i], lon[i], uu, vv);
+    u[i] = uu;
+    v[i] = vv;
+    if (status) status[i] = ok ? PMCTS_ST_OK : PMCTS_ST_OUT_OF_GRID;
+}
+
+// K1 -- Simulator.doStep for n boats, nsteps transitions fused in one launch.
+// One thread per boat; state lives in registers across the steps; headings are re-read once per
+// segment (coalesced, [segment][boat]).
+template <int kMode>
+__global__ void __launch_bounds__(kBlock)
+step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
+                  double *__restrict__ lat_io, double *__restrict__ lon_io,
+                  double *__restrict__ prev_lat, double *__restrict__ prev_lon,
+                  const double *__restrict__ heading, int seg_len, NoiseView nz,
+                  uint8_t *__restrict__ status_io, double *__restrict__ traj_lat,
+                  double *__restrict__ traj_lon, int flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = k_io[i];
+    double lat = lat_io[i], lon = lon_io[i];
+    double pla = prev_lat ? prev_lat[i] : lat, plo = prev_lon ? prev_lon[i] : lon;
+    int st = status_io ? status_io[i] : PMCTS_ST_OK;
+    NoiseStream ns;
+    double h = 0.0;
+    for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) {
+        if (j % seg_len == 0) h = heading[(size_t)(j / seg_len) * n + i];
+        if (flags & PMCTS_STEP_STOP_BEFORE_TERMINAL) {  // forest.py:239
+            if (k + 1 >= sc.nT) { st = PMCTS_ST_PAST_HORIZON; break; }
+            if (is_terminal(sc, k + 1, lat, lon)) {
+                st = (k + 1 >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
+                break;
+            }
+        }
+        const double z = ns.draw<kMode == PMCTS_PREC_FAST>(nz, n, i, j);
+        const double la0 = lat, lo0 = lon;
+        st = do_step_literal(sc, bp, k, lat, lon, h, z);
+        if (st == PMCTS_ST_OK) {
+            pla = la0;
+            plo = lo0;
+            if (traj_lat) traj_lat[(size_t)j * n + i] = lat;
+            if (traj_lon) traj_lon[(size_t)j * n + i] = lon;
+        }
+    }
+    k_io[i] = k;
+    lat_io[i] = lat;
+    lon_io[i] = lon;
+    if (prev_lat) prev_lat[i] = pla;
+    if (prev_lon) prev_lon[i] = plo;
+    if (status_io) status_io[i] = (uint8_t)st;
+}
+
+struct RolloutArgs {
+    int64_t n_leaf;
+    int replicas;
+    double root_k, root_lat, root_lon, dest_lat, dest_lon, tmin;
+    const double *prefix;
+    const int32_t *prefix_len;
+    int prefix_stride;
+    double *reward, *t_arr;
+    int32_t *steps;
+    uint8_t *status;
+    int32_t *bin;
+    double *frac, *final_lat, *final_lon, *traj_lat, *traj_lon;
+    int traj_stride;
+    uint32_t *leaf_bins;
+    double *stats;
+    int flags;
+};
+
+// K2 / K4 / K5 -- one default-policy rollout per thread (worker.py:255-300), reward binned and
+// reduced per leaf with warp votes, optional (count, sum t, sum t^2, arrived) reduction for plan
+// evaluation (isochrones.py:537-550).
+template <int kMode>
+__global__ void __launch_bounds__(kBlock)
+rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a) {
+    const int64_t n = a.n_leaf * a.replicas;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < n;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
+    int bin = 0, st = PMCTS_ST_OK;
+    int64_t leaf = 0;
+    double ta = NAN, rw = 0.0;
+    if (live) {
+        leaf = r / a.replicas;
+        int k = (int)a.root_k;
+        double alat = a.root_lat, alon = a.root_lon, blat = a.root_lat, blon = a.root_lon;
+        double xd, yd, zd;
+        geo_to_cart(a.dest_lat, a.dest_lon, xd, yd, zd);
+        int nstep = 0, at = 0;
+        double frac = 0.0, brg = 0.0;
+        NoiseStream ns;
+        const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
+        const int plen = a.prefix_len ? a.prefix_len[leaf] : 0;
+
+        auto step = [&](double action) {
+            const double z = ns.draw<kMode == PMCTS_PREC_FAST>(nz, n, r, nstep);
+            const double la0 = blat, lo0 = blon;
+            st = do_step_literal(sc, bp, k, blat, blon, action, z);
+            if (st == PMCTS_ST_OK) {
+                alat = la0;
+                alon = lo0;
+                if (a.traj_lat && nstep < a.traj_stride) a.traj_lat[(size_t)nstep * n + r] = blat;
+                if (a.traj_lon && nstep < a.traj_stride) a.traj_lon[(size_t)nstep * n + r] = blon;
+                ++nstep;
+            }
+        };
+        auto at_dest = [&]() {
+            double xa, ya, za, xb, yb, zb;
+            geo_to_cart(alat, alon, xa, ya, za);
+            geo_to_cart(blat, blon, xb, yb, zb);
+            const int res = at_dest_cart(bp, xa, ya, za, xb, yb, zb, xd, yd, zd, frac);
+            if (res < 0) st = PMCTS_ST_DEGENERATE; else at = res;
+        };
+
+        if (!(a.flags & PMCTS_ROLL_PLAN_EVAL)) {
+            // Tree.get_sim_to_estimate_state (worker.py:283-300): the first action always; the rest
+            // only when asked to (the reference's guard never lets its loop run -- quirk Q1).
+            if (plen > 0) step(pre[0]);
+            if (a.flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) {
+                for (int j = 1; j < plen && st == PMCTS_ST_OK; ++j) {
+                    if (is_terminal(sc, k, blat, blon)) break;
+                    at_dest();
+                    if (st != PMCTS_ST_OK || at) break;
+                    step(pre[j]);
+                }
+            }
+        } else {
+            // estimate_perfomance_plan (isochrones.py:498-511): whole plan, unchecked.
+            for (int j = 0; j < plen && st == PMCTS_ST_OK; ++j) step(pre[j]);
+            if (plen == 0) step(bearing_to(blat, blon, a.dest_lat, a.dest_lon));
+        }
+        // Tree.default_policy (worker.py:264-271)
+        if (st == PMCTS_ST_OK) {
+            brg = bearing_to(blat, blon, a.dest_lat, a.dest_lon);
+            at_dest();
+            while (st == PMCTS_ST_OK && !at && !is_terminal(sc, k, blat, blon)) {
+                step(brg);
+                if (st != PMCTS_ST_OK) break;
+                brg = bearing_to(blat, blon, a.dest_lat, a.dest_lon);
+                at_dest();
+            }
+        }
+        if (st == PMCTS_ST_OK) {
+            if (at) {
+                const double tk = sc.times[k];
+                ta = tk - (1.0 - frac) * (tk - sc.times[k - 1]);  // worker.py:274-275
+                rw = reward_of(sc.tmax, a.tmin, ta);
+                st = PMCTS_ST_ARRIVED;
+            } else {
+                st = (k >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
+                if (a.flags & PMCTS_ROLL_PLAN_EVAL) ta = sc.tmax;  // isochrones.py:527-530
+            }
+        }
+        bin = hist_bin(rw);
+        if (a.reward) a.reward[r] = rw;
+        if (a.t_arr) a.t_arr[r] = ta;
+        if (a.steps) a.steps[r] = nstep;
+        if (a.status) a.status[r] = (uint8_t)st;
+        if (a.bin) a.bin[r] = bin;
+        if (a.frac) a.frac[r] = (st == PMCTS_ST_ARRIVED) ? frac : NAN;
+        if (a.final_lat) a.final_lat[r] = blat;
+        if (a.final_lon) a.final_lon[r] = blon;
+    }
+    // ---- per-leaf reduction of the reward bins: lanes of the same leaf vote, one lane adds -------
+    if (a.leaf_bins && warp_mask) {
+        if (live) {
+            const unsigned peers = __match_any_sync(warp_mask, leaf);
+            const int leader = __ffs(peers) - 1;
+            const int lane = threadIdx.x & 31;
+#pragma unroll
+            for (int b = 0; b < 12; ++b) {
+                const unsigned votes = __ballot_sync(warp_mask, bin == b) & peers;
+                if (lane == leader && votes) atomicAdd(&a.leaf_bins[leaf * 12 + b], (uint32_t)__popc(votes));
+            }
+        }
+    }
+    if (a.stats && warp_mask) {
+        if (live) {
+            const bool has_t = !isnan(ta);
+            double c = has_t ? 1.0 : 0.0, s1 = has_t ? ta : 0.0, s2 = has_t ? ta * ta : 0.0;
+            double arrived = (st == PMCTS_ST_ARRIVED) ? 1.0 : 0.0;
+            for (int off = 16; off > 0; off >>= 1) {
+                c += __shfl_xor_sync(warp_mask, c, off);
+                s1 += __shfl_xor_sync(warp_mask, s1, off);
+                s2 += __shfl_xor_sync(warp_mask, s2, off);
+                arrived += __shfl_xor_sync(warp_mask, arrived, off);
+            }
+            if ((threadIdx.x & 31) == (__ffs(warp_mask) - 1)) {
+                atomicAdd(&a.stats[0], c);
+                atomicAdd(&a.stats[1], s1);
+                atomicAdd(&a.stats[2], s2);
+                atomicAdd(&a.stats[3], arrived);
+            }
+        }
+    }
+}
+
+// K3 -- Node.back_up (worker.py:55-70): one thread per (leaf, bin).
+__global__ void backup_kernel(uint32_t *__restrict__ table, const int32_t *__restrict__ parent,
+                              const int8_t *__restrict__ arm, int64_t n_leaf,
+                              const int32_t *__restrict__ leaf_node,
+                              const int8_t *__restrict__ leaf_slot,
+                              const uint32_t *__restrict__ leaf_bins) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_leaf * 12) return;
+    const int64_t l = t / 12;
+    const int b = (int)(t % 12);
+    const uint32_t c = leaf_bins[t];
+    if (c == 0) return;
+    int node = leaf_node[l];
+    atomicAdd(&table[((size_t)node * 8 + leaf_slot[l]) * 12 + b], c);
+    for (int p = parent[node]; p >= 0; p = parent[node]) {
+        atomicAdd(&table[((size_t)p * 8 + arm[node]) * 12 + b], c);
+        node = p;
+    }
+}
+
+// Hist.get_mean per (node, action) + visit total per node (utils.py:49-59, worker.py:91-95).
+// Bin centres (b + 0.5) / 8 and counts are exact in fp64, so the dot product is exact in any order.
+__global__ void hist_stats_kernel(const uint32_t *__restrict__ table, int64_t n_nodes,
+                                  double *__restrict__ mean, uint32_t *__restrict__ visits) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (node, action)
+    const bool live = t < n_nodes * 8;
+    uint32_t tot = 0;
+    if (live) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(table + t * 12);
+        const uint4 q0 = __ldg(row), q1 = __ldg(row + 1), q2 = __ldg(row + 2);
+        const uint32_t h[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        double dot = 0.0;
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+            tot += h[b];
+            dot += (double)h[b] * ((b + 0.5) * 0.125);
+        }
+        if (mean) mean[t] = tot ? dot / (double)tot : 0.0;
+    }
+    if (visits) {
+        // 8 consecutive lanes hold the 8 actions of one node
+        uint32_t s = tot;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (live && (t & 7) == 0) visits[t >> 3] = s;
+    }
+}
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(PMCTS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+struct Scenario {
+    ScenarioView view{};
+    void *blob = nullptr;  // one allocation holding slabs + axes
+};
+
+}  // namespace pmcts
+
+using namespace pmcts;
+
+struct pmcts_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int precision = PMCTS_PREC_F64;
+    BoatParams params{};
+    std::map<int, Scenario> scenarios;
+    // grow-only device scratch for PMCTS_MEM_HOST calls
+    char *scratch = nullptr;
+    size_t scratch_cap = 0, scratch_used = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+    double timed_ms = 0.0;
+    std::mutex mu;
+};
+
+namespace {
+
+const double kFitVelocity[36] = {
+    -0.0310198207067136, -0.0600881995286002, 0.0286695485969272, -0.00684406929296715, 0.000379636836557256, -6.77704610076153e-06,
+    0.0106968590293653, 0.00665508747173206, -4.03686836415123e-05, 2.38962919033178e-05, -6.16724919464073e-07, 0,
+    -0.000370260554113750, -7.68003222256045e-05, -2.44425618051996e-06, -2.16961875441841e-08, 0, 0,
+    4.94175336099537e-06, 5.68757177397705e-07, 1.17646387245609e-08, 0, 0, 0,
+    -2.91900968067076e-08, -1.67287818401469e-09, 0, 0, 0, 0,
+    6.34463723894578e-11, 0, 0, 0, 0, 0};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// Bump allocator over the ctx scratch buffer (PMCTS_MEM_HOST staging).
+struct Stager {
+    pmcts_ctx *ctx;
+    bool host;
+    struct Out { void *host_ptr; void *dev_ptr; size_t bytes; };
+    std::vector<Out> outs;
+
+    Stager(pmcts_ctx *c, bool h) : ctx(c), host(h) {}
+
+    static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+    int reserve(size_t total) {
+        if (!host) return PMCTS_OK;
+        total += 4096;
+        if (total > ctx->scratch_cap) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (ctx->scratch) CUDA_TRY(cudaFree(ctx->scratch));
+            ctx->scratch = nullptr;
+            ctx->scratch_cap = 0;
+            size_t cap = total + total / 4;
+            CUDA_TRY(cudaMalloc((void **)&ctx->scratch, cap));
+            ctx->scratch_cap = cap;
+        }
+        ctx->scratch_used = 0;
+        return PMCTS_OK;
+    }
+
+    void *carve(size_t bytes) {
+        void *p = ctx->scratch + ctx->scratch_used;
+        ctx->scratch_used += align(bytes);
+        return p;
+    }
+
+    // input (and optionally output) array
+    template <typename T>
+    int in(T *&ptr, size_t count, bool also_out = false) {
+        if (!host || ptr == nullptr) return PMCTS_OK;
+        const size_t bytes = count * sizeof(T);
+        void *d = carve(bytes);
+        CUDA_TRY(cudaMemcpyAsync(d, (const void *)ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (also_out) outs.push_back({(void *)ptr, d, bytes});
+        ptr = (T *)d;
+        return PMCTS_OK;
+    }
+    // fill: -1 leave as is, 0 zero, 0xFF all-ones (a quiet NaN for fp64)
+    template <typename T>
+    int out(T *&ptr, size_t count, int fill = -1) {
+        if (ptr == nullptr) return PMCTS_OK;
+        const size_t bytes = count * sizeof(T);
+        if (host) {
+            void *d = carve(bytes);
+            outs.push_back({(void *)ptr, d, bytes});
+            ptr = (T *)d;
+        }
+        if (fill >= 0) CUDA_TRY(cudaMemsetAsync(ptr, fill, bytes, ctx->stream));
+        return PMCTS_OK;
+    }
+    int finish() {
+        if (!host) return PMCTS_OK;
+        for (auto &o : outs)
+            CUDA_TRY(cudaMemcpyAsync(o.host_ptr, o.dev_ptr, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PMCTS_OK;
+    }
+};
+
+size_t al(size_t bytes) { return Stager::align(bytes); }
+
+struct LaunchTimer {
+    pmcts_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit LaunchTimer(pmcts_ctx *c) : ctx(c) {
+        ctx->launches++;
+        if (!ctx->timing) return;
+        if (!ctx->event_pool.empty()) {
+            a = ctx->event_pool.back().first;
+            b = ctx->event_pool.back().second;
+            ctx->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+        }
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~LaunchTimer() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->timed.push_back({a, b});
+    }
+};
+
+int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+int find_scenario(pmcts_ctx *ctx, int scen, Scenario **out) {
+    auto it = ctx->scenarios.find(scen);
+    if (it == ctx->scenarios.end()) return fail(PMCTS_ERR_SCENARIO, "scenario slot %d not uploaded", scen);
+    *out = &it->second;
+    return PMCTS_OK;
+}
+
+NoiseView noise_view(const pmcts_noise *nz) {
+    NoiseView v{};
+    if (!nz) {
+        v.mode = PMCTS_NOISE_NONE;
+        return v;
+    }
+    v.mode = nz->mode;
+    v.z = nz->z;
+    v.seed = nz->seed;
+    v.stream = nz->stream;
+    v.id0 = nz->id0;
+    return v;
+}
+
+bool uniform_axis(const double *g, int n, double *inv_step) {
+    if (n < 2) return false;
+    const double step = (g[n - 1] - g[0]) / (n - 1);
+    if (!(step > 0)) return false;
+    for (int i = 0; i < n; ++i)
+        if (std::fabs(g[i] - (g[0] + i * step)) > 1e-9 * std::fabs(step) + 1e-12 * std::fabs(g[i])) return false;
+    *inv_step = 1.0 / step;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pmcts_last_error(void) { return g_last_error.c_str(); }
+const char *pmcts_version(void) { return "pmcts_b200 0.1 (sm_100a)"; }
+
+int pmcts_create(int device, pmcts_ctx **out) {
+    if (!out) return fail(PMCTS_ERR_ARG, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PMCTS_ERR_NO_DEVICE, "no CUDA device (%s); pmcts_b200 has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(PMCTS_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    DeviceGuard g(device);
+    pmcts_ctx *ctx = new pmcts_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(PMCTS_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    pmcts_set_params(ctx, kFitVelocity, 19.1, 35.0, 160.0, 0.2, 0.005 * kDegToRad, 6371e3);
+    *out = ctx;
+    return PMCTS_OK;
+}
+
+void pmcts_destroy(pmcts_ctx *ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto &p : ctx->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : ctx->event_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return PMCTS_OK;
+}
+
+int pmcts_reset_stream(pmcts_ctx *ctx) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    ctx->stream = ctx->own_stream;
+    return PMCTS_OK;
+}
+
+int pmcts_synchronize(pmcts_ctx *ctx) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PMCTS_OK;
+}
+
+int pmcts_set_precision(pmcts_ctx *ctx, int mode) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    if (mode != PMCTS_PREC_F64 && mode != PMCTS_PREC_FAST) return fail(PMCTS_ERR_ARG, "unknown precision mode %d", mode);
+    ctx->precision = mode;
+    return PMCTS_OK;
+}
+
+int64_t pmcts_launch_count(pmcts_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pmcts_enable_timing(pmcts_ctx *ctx, int on) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    ctx->timing = on != 0;
+    return PMCTS_OK;
+}
+
+double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset) {
+    if (!ctx) return -1.0;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->timed_ms += ms;
+        ctx->event_pool.push_back(p);
+    }
+    ctx->timed.clear();
+    const double r = ctx->timed_ms;
+    if (reset) ctx->timed_ms = 0.0;
+    return r;
+}
+
+int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, double pofsail_min,
+                     double pofsail_max, double sigma_coeff, double dest_angle, double earth_radius) {
+    if (!ctx || !polar) return fail(PMCTS_ERR_ARG, "NULL argument");
+    BoatParams &p = ctx->params;
+    for (int i = 0; i < 36; ++i) {
+        p.polar[i] = polar[i];
+        p.polar_f[i] = (float)polar[i];
+    }
+    p.wind_max = wind_max;
+    p.pofsail_min = pofsail_min;
+    p.pofsail_max = pofsail_max;
+    p.sigma_coeff = sigma_coeff;
+    p.dest_angle = dest_angle;
+    p.earth_radius = earth_radius;
+    p.cos_pmin = std::cos(kPi * pofsail_min / 180.0);
+    p.cos_pmax = std::cos(kPi * pofsail_max / 180.0);
+    return PMCTS_OK;
+}
+
+int pmcts_scenario_free(pmcts_ctx *ctx, int scen) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    auto it = ctx->scenarios.find(scen);
+    if (it == ctx->scenarios.end()) return PMCTS_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaFree(it->second.blob));
+    ctx->scenarios.erase(it);
+    return PMCTS_OK;
+}
+
+int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt, const double *wlat,
+                          int nlat, const double *wlon, int nlon, const void *u, const void *v,
+                          int dtype, const double *sim_times, int nT, const double box[4]) {
+    if (!ctx || !wtime || !wlat || !wlon || !u || !v || !sim_times || !box)
+        return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (nt < 2 || nlat < 2 || nlon < 2 || nT < 1) return fail(PMCTS_ERR_ARG, "axes too short");
+    if (dtype != 0 && dtype != 1) return fail(PMCTS_ERR_ARG, "dtype must be 0 (f64) or 1 (f32)");
+    double inv_dlat, inv_dlon;
+    if (!uniform_axis(wlat, nlat, &inv_dlat) || !uniform_axis(wlon, nlon, &inv_dlon))
+        return fail(PMCTS_ERR_AXIS, "latitude / longitude axes must be ascending and uniformly spaced");
+    for (int i = 1; i < nt; ++i)
+        if (!(wtime[i] > wtime[i - 1])) return fail(PMCTS_ERR_AXIS, "weather time axis must be strictly ascending");
+    DeviceGuard g(ctx->device);
+    int rc = pmcts_scenario_free(ctx, scen);
+    if (rc) return rc;
+
+    // per-instant time cell and weight (SciPy find_indices semantics on the time axis)
+    std::vector<int> it(nT);
+    std::vector<double> wt(nT), dt(nT, 0.0);
+    std::vector<uint8_t> valid(nT);
+    for (int k = 0; k < nT; ++k) {
+        const double t = sim_times[k];
+        valid[k] = (t >= wtime[0] && t <= wtime[nt - 1]) ? 1 : 0;
+        int lo = 0, hi = nt;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (wtime[mid] <= t) lo = mid + 1; else hi = mid;
+        }
+        int i = lo - 1;
+        if (i < 0) i = 0;
+        if (i > nt - 2) i = nt - 2;
+        it[k] = i;
+        wt[k] = valid[k] ? (t - wtime[i]) / (wtime[i + 1] - wtime[i]) : 0.0;
+        if (k + 1 < nT) dt[k] = (sim_times[k + 1] - sim_times[k]) * 86400.0;
+    }
+
+    const size_t plane = (size_t)nlat * nlon, cells = plane * nT;
+    const size_t esz = dtype == 0 ? 8 : 4;
+    const size_t o_slab64 = 0;
+    const size_t o_slab32 = o_slab64 + al(cells * sizeof(double2));
+    const size_t o_times = o_slab32 + al(cells * sizeof(float2));
+    const size_t o_dt = o_times + al(nT * sizeof(double));
+    const size_t o_valid = o_dt + al(nT * sizeof(double));
+    const size_t total = o_valid + al(nT);
+    // temporaries: raw grid + time cells
+    const size_t raw = (size_t)nt * plane * esz;
+    const size_t t_u = 0, t_v = al(raw), t_it = t_v + al(raw), t_wt = t_it + al(nT * sizeof(int));
+    const size_t tmp_total = t_wt + al(nT * sizeof(double));
+
+    Scenario sc;
+    char *tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&sc.blob, total));
+    cudaError_t e = cudaMalloc((void **)&tmp, tmp_total);
+    if (e != cudaSuccess) {
+        cudaFree(sc.blob);
+        return fail(PMCTS_ERR_CUDA, "cudaMalloc(%zu) failed: %s", tmp_total, cudaGetErrorString(e));
+    }
+    char *base = (char *)sc.blob;
+    cudaStream_t s = ctx->stream;
+    auto cleanup = [&]() { cudaFree(tmp); cudaFree(sc.blob); };
+#define UP_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e2_ = (expr);                                                                 \
+        if (e2_ != cudaSuccess) {                                                                 \
+            cleanup();                                                                            \
+            return fail(PMCTS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e2_));         \
+        }                                                                                         \
+    } while (0)
+    UP_TRY(cudaMemcpyAsync(tmp + t_u, u, raw, cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(tmp + t_v, v, raw, cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(tmp + t_it, it.data(), nT * sizeof(int), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(tmp + t_wt, wt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_times, sim_times, nT * sizeof(double), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_dt, dt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_valid, valid.data(), nT, cudaMemcpyHostToDevice, s));
+    {
+        LaunchTimer lt(ctx);
+        const int grid = (int)((cells + 255) / 256);
+        if (dtype == 0)
+            blend_time_slabs_kernel<double><<<grid, 256, 0, s>>>(
+                (const double *)(tmp + t_u), (const double *)(tmp + t_v), (const int *)(tmp + t_it),
+                (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
+                (float2 *)(base + o_slab32));
+        else
+            blend_time_slabs_kernel<float><<<grid, 256, 0, s>>>(
+                (const float *)(tmp + t_u), (const float *)(tmp + t_v), (const int *)(tmp + t_it),
+                (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
+                (float2 *)(base + o_slab32));
+    }
+    UP_TRY(cudaGetLastError());
+    UP_TRY(cudaStreamSynchronize(s));  // host vectors and tmp die here
+#undef UP_TRY
+    cudaFree(tmp);
+
+    ScenarioView &vw = sc.view;
+    vw.slab64 = (const double2 *)(base + o_slab64);
+    vw.slab32 = (const float2 *)(base + o_slab32);
+    vw.times = (const double *)(base + o_times);
+    vw.dt_sec = (const double *)(base + o_dt);
+    vw.k_valid = (const uint8_t *)(base + o_valid);
+    vw.nT = nT;
+    vw.nlat = nlat;
+    vw.nlon = nlon;
+    vw.lat0 = wlat[0];
+    vw.lon0 = wlon[0];
+    vw.inv_dlat = inv_dlat;
+    vw.inv_dlon = inv_dlon;
+    vw.lat_last = wlat[nlat - 1];
+    vw.lon_last = wlon[nlon - 1];
+    vw.box_lat_lo = box[0];
+    vw.box_lat_hi = box[1];
+    vw.box_lon_lo = box[2];
+    vw.box_lon_hi = box[3];
+    vw.tmax = sim_times[nT - 1];
+    ctx->scenarios[scen] = sc;
+    return PMCTS_OK;
+}
+
+int pmcts_get_wind(pmcts_ctx *ctx, int scen, int64_t n, const int32_t *k, const double *lat,
+                   const double *lon, double *u, double *v, uint8_t *status, int flags) {
+    if (!ctx || !k || !lat || !lon || !u || !v) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n <= 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    Scenario *sc;
+    int rc = find_scenario(ctx, scen, &sc);
+    if (rc) return rc;
+    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(n));
+    if (rc) return rc;
+    if ((rc = st.in(k, n)) || (rc = st.in(lat, n)) || (rc = st.in(lon, n)) || (rc = st.out(u, n)) ||
+        (rc = st.out(v, n)) || (rc = st.out(status, n)))
+        return rc;
+    {
+        LaunchTimer lt(ctx);
+        get_wind_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, n, k, lat, lon, u, v, status);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return st.finish();
+}
+
+int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k, double *lat,
+                     double *lon, double *prev_lat, double *prev_lon, const double *heading,
+                     int seg_len, const pmcts_noise *noise, uint8_t *status, double *traj_lat,
+                     double *traj_lon, int flags) {
+    if (!ctx || !k || !lat || !lon || !heading) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n < 0 || nsteps < 0 || seg_len < 1) return fail(PMCTS_ERR_ARG, "bad sizes");
+    if (n == 0 || nsteps == 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    Scenario *sc;
+    int rc = find_scenario(ctx, scen, &sc);
+    if (rc) return rc;
+    NoiseView nz = noise_view(noise);
+    if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
+    const size_t nseg = ((size_t)nsteps + seg_len - 1) / seg_len;
+    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(nseg * n * 8) + al(n) +
+                    (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)nsteps * n * 8) : 0) +
+                    (traj_lat ? al((size_t)nsteps * n * 8) : 0) + (traj_lon ? al((size_t)nsteps * n * 8) : 0));
+    if (rc) return rc;
+    if ((rc = st.in(k, n, true)) || (rc = st.in(lat, n, true)) || (rc = st.in(lon, n, true)) ||
+        (rc = st.in(prev_lat, n, true)) || (rc = st.in(prev_lon, n, true)) ||
+        (rc = st.in(heading, nseg * n)) || (rc = st.in(status, n, true)) ||
+        (rc = st.out(traj_lat, (size_t)nsteps * n, 0xFF)) || (rc = st.out(traj_lon, (size_t)nsteps * n, 0xFF)))
+        return rc;
+    if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)nsteps * n))) return rc;
+    {
+        LaunchTimer lt(ctx);
+        if (ctx->precision == PMCTS_PREC_FAST)
+            step_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
+                status, traj_lat, traj_lon, flags);
+        else
+            step_batch_kernel<PMCTS_PREC_F64><<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
+                status, traj_lat, traj_lon, flags);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return st.finish();
+}
+
+int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],
+                        const double dest[2], double tmin, const double *prefix,
+                        const int32_t *prefix_len, int prefix_stride, const pmcts_noise *noise,
+                        double *reward, double *t_arr, int32_t *steps, uint8_t *status, int32_t *bin,
+                        double *frac, double *final_lat, double *final_lon, double *traj_lat,
+                        double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
+                        int flags) {
+    if (!ctx || !root || !dest) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n_leaf < 0 || replicas < 1 || prefix_stride < 0 || traj_stride < 0) return fail(PMCTS_ERR_ARG, "bad sizes");
+    if ((prefix == nullptr) != (prefix_len == nullptr)) return fail(PMCTS_ERR_ARG, "prefix and prefix_len go together");
+    if (n_leaf == 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    Scenario *sc;
+    int rc = find_scenario(ctx, scen, &sc);
+    if (rc) return rc;
+    const int64_t n = n_leaf * replicas;
+    NoiseView nz = noise_view(noise);
+    const int max_steps = sc->view.nT;
+    if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
+    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    const size_t traj_bytes = al((size_t)traj_stride * n * 8);
+    rc = st.reserve(al((size_t)n_leaf * prefix_stride * 8) + al(n_leaf * 4) + 6 * al(n * 8) + 2 * al(n * 4) + al(n) +
+                    (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(n_leaf * 48) + al(32) +
+                    (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)max_steps * n * 8) : 0));
+    if (rc) return rc;
+    if ((rc = st.in(prefix, (size_t)n_leaf * prefix_stride)) || (rc = st.in(prefix_len, n_leaf)) ||
+        (rc = st.out(reward, n)) || (rc = st.out(t_arr, n)) || (rc = st.out(steps, n)) ||
+        (rc = st.out(status, n)) || (rc = st.out(bin, n)) || (rc = st.out(frac, n)) ||
+        (rc = st.out(final_lat, n)) || (rc = st.out(final_lon, n)) ||
+        (rc = st.out(traj_lat, (size_t)traj_stride * n, 0xFF)) ||
+        (rc = st.out(traj_lon, (size_t)traj_stride * n, 0xFF)) ||
+        (rc = st.out(leaf_bins, (size_t)n_leaf * 12, 0)) || (rc = st.out(stats, 4, 0)))
+        return rc;
+    if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)max_steps * n))) return rc;
+    RolloutArgs a{};
+    a.n_leaf = n_leaf;
+    a.replicas = replicas;
+    a.root_k = root[0];
+    a.root_lat = root[1];
+    a.root_lon = root[2];
+    a.dest_lat = dest[0];
+    a.dest_lon = dest[1];
+    a.tmin = tmin;
+    a.prefix = prefix;
+    a.prefix_len = prefix_len;
+    a.prefix_stride = prefix_stride;
+    a.reward = reward;
+    a.t_arr = t_arr;
+    a.steps = steps;
+    a.status = status;
+    a.bin = bin;
+    a.frac = frac;
+    a.final_lat = final_lat;
+    a.final_lon = final_lon;
+    a.traj_lat = traj_lat;
+    a.traj_lon = traj_lon;
+    a.traj_stride = traj_stride;
+    a.leaf_bins = leaf_bins;
+    a.stats = stats;
+    a.flags = flags;
+    {
+        LaunchTimer lt(ctx);
+        if (ctx->precision == PMCTS_PREC_FAST)
+            rollout_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, ctx->params, nz, a);
+        else
+            rollout_batch_kernel<PMCTS_PREC_F64><<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, ctx->params, nz, a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return st.finish();
+}
+
+int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, const int32_t *parent, const int8_t *arm,
+                 int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
+                 const uint32_t *leaf_bins, int flags) {
+    if (!ctx || !table || !parent || !arm || !leaf_node || !leaf_slot || !leaf_bins)
+        return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (flags & PMCTS_MEM_HOST) return fail(PMCTS_ERR_ARG, "pmcts_backup works on a device-resident table");
+    if (n_leaf <= 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    {
+        LaunchTimer lt(ctx);
+        backup_kernel<<<grid_for(n_leaf * 12), kBlock, 0, ctx->stream>>>(table, parent, arm, n_leaf, leaf_node,
+                                                                        leaf_slot, leaf_bins);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PMCTS_OK;
+}
+
+int pmcts_hist_stats(pmcts_ctx *ctx, const uint32_t *table, int64_t n_nodes, double *mean,
+                     uint32_t *visits, int flags) {
+    if (!ctx || !table) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n_nodes <= 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    int rc = st.reserve(al(n_nodes * 96 * 4) + al(n_nodes * 8 * 8) + al(n_nodes * 4));
+    if (rc) return rc;
+    if ((rc = st.in(table, (size_t)n_nodes * 96)) || (rc = st.out(mean, (size_t)n_nodes * 8)) ||
+        (rc = st.out(visits, n_nodes)))
+        return rc;
+    {
+        LaunchTimer lt(ctx);
+        hist_stats_kernel<<<grid_for(n_nodes * 8), kBlock, 0, ctx->stream>>>(table, n_nodes, mean, visits);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return st.finish();
+}
+
+}  // extern "C"

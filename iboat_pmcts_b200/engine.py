@@ -1,0 +1,258 @@
+"""Engine: one GPU context of the rollout engine (thin object layer over include/pmcts_b200.h).
+
+Array arguments are either NumPy arrays (host memory: the library copies them to the device and
+the results back inside the call -- ``PMCTS_MEM_HOST``) or CUDA ``torch.Tensor``s (device memory:
+the call is asynchronous on the ctx stream).  A call must not mix the two kinds.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+try:  # torch is plumbing only (device buffers / streams); the host path needs NumPy alone
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_NP = {"f64": np.float64, "i32": np.int32, "u8": np.uint8, "u32": np.uint32, "i8": np.int8}
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class _Args:
+    """Collects array arguments, checks host/device consistency, keeps them alive for the call."""
+
+    def __init__(self):
+        self.kind = None
+        self.keep = []
+
+    def _set_kind(self, kind):
+        if self.kind is None:
+            self.kind = kind
+        elif self.kind != kind:
+            raise TypeError("pmcts_b200: a call takes either NumPy (host) or CUDA tensor (device) arrays, not both")
+
+    def ptr(self, x, dtype, size=None, writable=False):
+        if x is None:
+            return None
+        if _is_tensor(x):
+            if not x.is_cuda:
+                raise TypeError("pmcts_b200: torch tensors must live on a CUDA device")
+            want = {"f64": torch.float64, "i32": torch.int32, "u8": torch.uint8, "u32": torch.int32,
+                    "i8": torch.int8}[dtype]
+            if x.dtype != want or not x.is_contiguous():
+                raise TypeError("pmcts_b200: expected contiguous %s tensor, got %s" % (want, x.dtype))
+            if size is not None and x.numel() < size:
+                raise ValueError("pmcts_b200: tensor too small (%d < %d)" % (x.numel(), size))
+            self._set_kind("device")
+            self.keep.append(x)
+            return x.data_ptr()
+        if not isinstance(x, np.ndarray) or x.dtype != _NP[dtype] or not x.flags.c_contiguous:
+            if writable:
+                raise TypeError("pmcts_b200: output arrays must be C-contiguous %s ndarrays" % dtype)
+            x = np.ascontiguousarray(x, dtype=_NP[dtype])
+        if size is not None and x.size < size:
+            raise ValueError("pmcts_b200: array too small (%d < %d)" % (x.size, size))
+        self._set_kind("host")
+        self.keep.append(x)
+        return x.ctypes.data
+
+    @property
+    def mem_flag(self):
+        return N.MEM_HOST if self.kind != "device" else 0
+
+
+def make_noise(args, z=None, seed=None, stream=0, id0=0, size=None):
+    nz = N.Noise()
+    if z is not None:
+        nz.mode = N.NOISE_INJECTED
+        nz.z = args.ptr(z, "f64", size)
+    elif seed is not None:
+        nz.mode = N.NOISE_PHILOX
+        nz.seed, nz.stream, nz.id0 = int(seed), int(stream), int(id0)
+    else:
+        nz.mode = N.NOISE_NONE
+    return nz
+
+
+class Engine:
+    """One ``pmcts_ctx``: owns the uploaded scenarios of one GPU."""
+
+    def __init__(self, device=0, precision=N.PREC_F64):
+        self._lib = N.lib()
+        h = C.c_void_p()
+        N.check(self._lib.pmcts_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.set_precision(precision)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pmcts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- context ----------------------------------------------------------------------------
+    def set_precision(self, mode):
+        N.check(self._lib.pmcts_set_precision(self._h, int(mode)))
+        self.precision = int(mode)
+
+    def use_torch_stream(self):
+        """Orders the engine's work on torch's current stream of this device."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self._lib.pmcts_set_stream(self._h, C.c_void_p(s)))
+
+    def use_own_stream(self):
+        N.check(self._lib.pmcts_reset_stream(self._h))
+
+    def synchronize(self):
+        N.check(self._lib.pmcts_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.pmcts_launch_count(self._h))
+
+    def enable_timing(self, on=True):
+        N.check(self._lib.pmcts_enable_timing(self._h, int(bool(on))))
+
+    def kernel_ms(self, reset=True):
+        return float(self._lib.pmcts_kernel_ms_total(self._h, int(bool(reset))))
+
+    def set_params(self, polar, wind_max, pofsail_min, pofsail_max, sigma_coeff, dest_angle, earth_radius):
+        pol = np.ascontiguousarray(polar, dtype=np.float64).reshape(36)
+        N.check(self._lib.pmcts_set_params(self._h, pol.ctypes.data, float(wind_max), float(pofsail_min),
+                                           float(pofsail_max), float(sigma_coeff), float(dest_angle),
+                                           float(earth_radius)))
+
+    # ---- scenarios ----------------------------------------------------------------------------
+    def upload_scenario(self, scen, wtime, wlat, wlon, u, v, sim_times, box):
+        wtime = np.ascontiguousarray(wtime, np.float64)
+        wlat = np.ascontiguousarray(wlat, np.float64)
+        wlon = np.ascontiguousarray(wlon, np.float64)
+        u = np.asarray(u)
+        v = np.asarray(v)
+        dt = np.float32 if (u.dtype == np.float32 and v.dtype == np.float32) else np.float64
+        u = np.ascontiguousarray(u, dt)
+        v = np.ascontiguousarray(v, dt)
+        if u.shape != (wtime.size, wlat.size, wlon.size) or v.shape != u.shape:
+            raise ValueError("u, v must have shape (ntime, nlat, nlon)")
+        sim_times = np.ascontiguousarray(sim_times, np.float64)
+        box = np.ascontiguousarray(box, np.float64).reshape(4)
+        N.check(self._lib.pmcts_scenario_upload(
+            self._h, int(scen), wtime.ctypes.data, wtime.size, wlat.ctypes.data, wlat.size,
+            wlon.ctypes.data, wlon.size, u.ctypes.data, v.ctypes.data, 1 if dt == np.float32 else 0,
+            sim_times.ctypes.data, sim_times.size, box.ctypes.data))
+
+    def free_scenario(self, scen):
+        N.check(self._lib.pmcts_scenario_free(self._h, int(scen)))
+
+    def get_wind(self, scen, k, lat, lon):
+        """Simulator.getWind for arrays of query points (host arrays in, host arrays out)."""
+        lat = np.ascontiguousarray(lat, np.float64).ravel()
+        lon = np.ascontiguousarray(lon, np.float64).ravel()
+        n = lat.size
+        k = np.ascontiguousarray(np.broadcast_to(np.asarray(k, np.int32), (n,)))
+        u, v, st = np.empty(n), np.empty(n), np.empty(n, np.uint8)
+        N.check(self._lib.pmcts_get_wind(self._h, int(scen), n, k.ctypes.data, lat.ctypes.data, lon.ctypes.data,
+                                         u.ctypes.data, v.ctypes.data, st.ctypes.data, N.MEM_HOST))
+        return u, v, st
+
+    # ---- K1 ---------------------------------------------------------------------------------------
+    def step_batch(self, scen, k, lat, lon, heading, nsteps=1, seg_len=1, prev_lat=None, prev_lon=None,
+                   status=None, z=None, seed=None, stream=0, id0=0, traj_lat=None, traj_lon=None, flags=0):
+        """In-place batched Simulator.doStep.  k/lat/lon/(prev_*)/(status) are updated in place."""
+        a = _Args()
+        n = lat.numel() if _is_tensor(lat) else lat.size
+        nseg = (nsteps + seg_len - 1) // seg_len
+        pk = a.ptr(k, "i32", n, True)
+        plat, plon = a.ptr(lat, "f64", n, True), a.ptr(lon, "f64", n, True)
+        ppl, ppo = a.ptr(prev_lat, "f64", n, True), a.ptr(prev_lon, "f64", n, True)
+        ph = a.ptr(heading, "f64", nseg * n)
+        pst = a.ptr(status, "u8", n, True)
+        ptl, pto = a.ptr(traj_lat, "f64", nsteps * n, True), a.ptr(traj_lon, "f64", nsteps * n, True)
+        nz = make_noise(a, z, seed, stream, id0, nsteps * n)
+        N.check(self._lib.pmcts_step_batch(self._h, int(scen), n, int(nsteps), pk, plat, plon, ppl, ppo, ph,
+                                           int(seg_len), C.byref(nz), pst, ptl, pto, int(flags) | a.mem_flag))
+
+    # ---- K2 / K4 / K5 -----------------------------------------------------------------------------
+    def rollout_batch(self, scen, n_leaf, replicas, root, dest, tmin, prefix=None, prefix_len=None,
+                      prefix_stride=0, z=None, seed=None, stream=0, id0=0, out=None, traj_stride=0, flags=0):
+        """Batched default-policy rollouts.  ``out`` maps output names (reward, t_arr, steps, status,
+        bin, frac, final_lat, final_lon, traj_lat, traj_lon, leaf_bins, stats) to preallocated arrays."""
+        out = out or {}
+        a = _Args()
+        n = int(n_leaf) * int(replicas)
+        root = np.ascontiguousarray(root, np.float64).reshape(3)
+        dest = np.ascontiguousarray(dest, np.float64).reshape(2)
+        ppre = a.ptr(prefix, "f64", n_leaf * prefix_stride) if prefix is not None else None
+        plen = a.ptr(prefix_len, "i32", n_leaf) if prefix_len is not None else None
+        g = lambda name, dt, size: a.ptr(out.get(name), dt, size, True)  # noqa: E731
+        ptrs = [g("reward", "f64", n), g("t_arr", "f64", n), g("steps", "i32", n), g("status", "u8", n),
+                g("bin", "i32", n), g("frac", "f64", n), g("final_lat", "f64", n), g("final_lon", "f64", n),
+                g("traj_lat", "f64", traj_stride * n), g("traj_lon", "f64", traj_stride * n)]
+        plb = g("leaf_bins", "u32", n_leaf * 12)
+        pstats = g("stats", "f64", 4)
+        nz = make_noise(a, z, seed, stream, id0)
+        N.check(self._lib.pmcts_rollout_batch(self._h, int(scen), int(n_leaf), int(replicas), root.ctypes.data,
+                                              dest.ctypes.data, float(tmin), ppre, plen, int(prefix_stride),
+                                              C.byref(nz), *ptrs, int(traj_stride), plb, pstats,
+                                              int(flags) | a.mem_flag))
+
+    def rollout_batch_host(self, scen, n_leaf, replicas, root, dest, tmin, prefix=None, prefix_len=None,
+                           z=None, seed=None, stream=0, id0=0, traj_steps=0, flags=0, want=None):
+        """Convenience wrapper: allocates NumPy outputs and returns them as a dict."""
+        n = int(n_leaf) * int(replicas)
+        names = want or ("reward", "t_arr", "steps", "status", "bin", "frac", "final_lat", "final_lon",
+                         "leaf_bins", "stats")
+        spec = dict(reward=(np.float64, n), t_arr=(np.float64, n), steps=(np.int32, n), status=(np.uint8, n),
+                    bin=(np.int32, n), frac=(np.float64, n), final_lat=(np.float64, n),
+                    final_lon=(np.float64, n), leaf_bins=(np.uint32, n_leaf * 12), stats=(np.float64, 4))
+        out = {nm: np.empty(spec[nm][1], spec[nm][0]) for nm in names}
+        if traj_steps:
+            out["traj_lat"] = np.full((traj_steps, n), np.nan)
+            out["traj_lon"] = np.full((traj_steps, n), np.nan)
+        stride = 0
+        if prefix is not None:
+            prefix = np.ascontiguousarray(prefix, np.float64).reshape(n_leaf, -1)
+            stride = prefix.shape[1]
+            if prefix_len is None:
+                prefix_len = np.full(n_leaf, stride, np.int32)
+            prefix_len = np.ascontiguousarray(prefix_len, np.int32)
+        if z is not None:
+            z = np.ascontiguousarray(z, np.float64)
+        self.rollout_batch(scen, n_leaf, replicas, root, dest, tmin, prefix, prefix_len, stride, z, seed,
+                           stream, id0, out, traj_steps, flags)
+        if "leaf_bins" in out:
+            out["leaf_bins"] = out["leaf_bins"].reshape(n_leaf, 12)
+        return out
+
+    # ---- K3 / statistics --------------------------------------------------------------------------
+    def backup(self, table, parent, arm, leaf_node, leaf_slot, leaf_bins):
+        a = _Args()
+        n_leaf = leaf_node.numel()
+        N.check(self._lib.pmcts_backup(self._h, a.ptr(table, "u32"), a.ptr(parent, "i32"), a.ptr(arm, "i8"),
+                                       n_leaf, a.ptr(leaf_node, "i32", n_leaf), a.ptr(leaf_slot, "i8", n_leaf),
+                                       a.ptr(leaf_bins, "u32", n_leaf * 12), a.mem_flag))
+
+    def hist_stats(self, table, n_nodes, mean=None, visits=None):
+        a = _Args()
+        N.check(self._lib.pmcts_hist_stats(self._h, a.ptr(table, "u32", n_nodes * 96), int(n_nodes),
+                                           a.ptr(mean, "f64", n_nodes * 8, True),
+                                           a.ptr(visits, "u32", n_nodes, True), a.mem_flag))
+
+
+_default = {}
+
+
+def default_engine(device=0):
+    """Process-wide engine per device, created on first use."""
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

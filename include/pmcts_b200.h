@@ -1,0 +1,152 @@
+/* pmcts_b200 -- C ABI of the B200-native rollout engine for IBoat-PMCTS.
+ *
+ * The reference (PBarde/IBoat-PMCTS) is pure Python and has no FFI; the boundary it exposes for
+ * this path is its Python object API.  Each entry point below names the reference interface it
+ * replaces (file:line in the reference checkout).  The Python mirror of that API
+ * (iboat_pmcts_b200/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every call returns 0 on success or a negative PMCTS_ERR_* code; pmcts_last_error() returns the
+ *    message of the last failure on the calling thread;
+ *  - one pmcts_ctx per GPU; calls on a ctx are ordered on its CUDA stream (pmcts_set_stream);
+ *  - array arguments are DEVICE pointers and the call returns without synchronising, unless
+ *    PMCTS_MEM_HOST is set in `flags`: then every array argument is HOST memory (pinned or
+ *    pageable), the library stages it through device scratch and the call returns after the
+ *    results are back in the caller's arrays;
+ *  - optional outputs may be NULL;
+ *  - there is no CPU fallback: without a CUDA device pmcts_create fails.
+ */
+#ifndef PMCTS_B200_H
+#define PMCTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmcts_ctx pmcts_ctx;
+
+/* error codes */
+#define PMCTS_OK 0
+#define PMCTS_ERR_CUDA (-1)       /* a CUDA runtime call failed (message has the CUDA error string) */
+#define PMCTS_ERR_ARG (-2)        /* invalid argument */
+#define PMCTS_ERR_NO_DEVICE (-3)  /* no usable CUDA device: the engine has no CPU path */
+#define PMCTS_ERR_AXIS (-4)       /* weather axes not ascending / not uniformly spaced */
+#define PMCTS_ERR_SCENARIO (-5)   /* unknown scenario slot */
+
+/* per-boat / per-rollout status byte (what the Python layer turns into the reference's exceptions) */
+#define PMCTS_ST_OK 0            /* still sailing */
+#define PMCTS_ST_ARRIVED 1       /* Tree.is_state_at_dest true (worker.py:380-415) */
+#define PMCTS_ST_HORIZON 2       /* times[k] == times[-1] (worker.py:427) */
+#define PMCTS_ST_OUT_OF_BOX 3    /* outside [lats[0],lats[-1]] x [lons[0],lons[-1]] (worker.py:430-434) */
+#define PMCTS_ST_OUT_OF_GRID 4   /* SciPy bounds_error -> ValueError (weatherTLKT.py:377-378) */
+#define PMCTS_ST_DEGENERATE 5    /* ZeroDivisionError inside is_state_at_dest (worker.py:396-397) */
+#define PMCTS_ST_PAST_HORIZON 6  /* IndexError: times[k+1] past the axis (simulatorTLKT.py:208) */
+
+/* flags */
+#define PMCTS_STEP_STOP_BEFORE_TERMINAL 0x1 /* step_batch: fixed-heading sweep of initialize_simulators (forest.py:239) */
+#define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
+#define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
+#define PMCTS_MEM_HOST 0x100                /* array arguments are host memory */
+
+/* arithmetic mode */
+#define PMCTS_PREC_F64 0   /* literal fp64 transcription of the reference formulas */
+#define PMCTS_PREC_FAST 1  /* fp32 wind / polar / noise, re-derived fp64 geodesy; same results within 1e-6 relative */
+
+/* noise source for Boat.addUncertainty (simulatorTLKT.py:504-517): speed + z * (speed * sigma) */
+#define PMCTS_NOISE_INJECTED 0 /* z[step * n + i], fp64 (parity tests) */
+#define PMCTS_NOISE_PHILOX 1   /* Philox4x32-10, counter (id0 + i, step / 4, stream), key seed */
+#define PMCTS_NOISE_NONE 2     /* z = 0 (UNCERTAINTY_COEFF = 0, Tutorial.py:81) */
+typedef struct {
+    int32_t mode;
+    int32_t reserved;
+    const double *z;
+    uint64_t seed, stream, id0;
+} pmcts_noise;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pmcts_create(int device, pmcts_ctx **out);
+void pmcts_destroy(pmcts_ctx *ctx);
+const char *pmcts_last_error(void);
+const char *pmcts_version(void);
+/* cudaStream_t to run on (NULL = the CUDA default stream); a new ctx runs on its own non-blocking
+ * stream, which pmcts_reset_stream restores. */
+int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream);
+int pmcts_reset_stream(pmcts_ctx *ctx);
+int pmcts_synchronize(pmcts_ctx *ctx);
+int pmcts_set_precision(pmcts_ctx *ctx, int mode);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+int64_t pmcts_launch_count(pmcts_ctx *ctx);
+/* milliseconds the last timed kernel took on the ctx stream (cudaEvent pair recorded around every
+ * launch while timing is enabled); returns <0 if nothing was timed. */
+int pmcts_enable_timing(pmcts_ctx *ctx, int on);
+double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset);
+
+/* Module globals the reference reads at call time -- Boat.FIT_VELOCITY / POLAR_* /
+ * UNCERTAINTY_COEFF (simulatorTLKT.py:454-471), DESTINATION_ANGLE (:43), EARTH_RADIUS (:40). */
+int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, double pofsail_min,
+                     double pofsail_max, double sigma_coeff, double dest_angle, double earth_radius);
+
+/* ---- scenarios ------------------------------------------------------------------------------
+ * Replaces Weather.__init__ + Weather.Interpolators (weatherTLKT.py:40-49, 369-378) and
+ * Simulator.__init__ (simulatorTLKT.py:75-88) for scenario slot `scen`.
+ * Weather axes ascending and uniformly spaced; u, v are [nt][nlat][nlon] host arrays, fp64
+ * (dtype 0) or fp32 (dtype 1).  sim_times[nT] is the simulator axis in days; box = {lats[0],
+ * lats[-1], lons[0], lons[-1]} of the Simulator (the terminal box of worker.py:430-434).
+ * On the device the scenario is stored as one time-blended (u, v) slab per simulator instant. */
+int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt, const double *wlat,
+                          int nlat, const double *wlon, int nlon, const void *u, const void *v,
+                          int dtype, const double *sim_times, int nT, const double box[4]);
+int pmcts_scenario_free(pmcts_ctx *ctx, int scen);
+/* Simulator.getWind (simulatorTLKT.py:168-179) for n query points at time index k[i]. */
+int pmcts_get_wind(pmcts_ctx *ctx, int scen, int64_t n, const int32_t *k, const double *lat,
+                   const double *lon, double *u, double *v, uint8_t *status, int flags);
+
+/* ---- K1: Simulator.doStep (simulatorTLKT.py:181-216) for n boats, nsteps fused ---------------
+ * State is structure-of-arrays: k[n] time index, lat[n], lon[n] degrees, prev_lat/prev_lon[n]
+ * (Simulator.prevState), updated in place.  heading[(j / seg_len) * n + i] is the heading in degrees
+ * of boat i at step j.  A boat whose status is or becomes non-zero is frozen.  traj_lat / traj_lon
+ * (optional) receive the position after every step, [nsteps][n] (NaN where a boat was frozen). */
+int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k, double *lat,
+                     double *lon, double *prev_lat, double *prev_lon, const double *heading,
+                     int seg_len, const pmcts_noise *noise, uint8_t *status, double *traj_lat,
+                     double *traj_lon, int flags);
+
+/* ---- K2 / K4 / K5: Tree.get_sim_to_estimate_state + Tree.default_policy (worker.py:255-300),
+ * estimate_perfomance_plan (isochrones.py:491-530), initialize_simulators phase 2 (forest.py:261-299)
+ * n_leaf * replicas rollouts, rollout r = leaf * replicas + rep, all starting at root = {k, lat, lon}.
+ * prefix[leaf * prefix_stride + a] (degrees), prefix_len[leaf] actions (NULL: 0 everywhere).
+ * Outputs per rollout (all optional): reward, t_arr (days; NaN if not arrived, times[-1] in plan
+ * mode), steps, status, bin (Hist bin of the reward, utils.py:34-47), frac, final_lat, final_lon;
+ * traj_lat/traj_lon [traj_stride][n] positions after each transition (NaN where not reached).
+ * leaf_bins (optional) [n_leaf][12] uint32: per-leaf histogram of the replicas' reward bins.
+ * stats (optional) [4] doubles: {count, sum t_arr, sum t_arr^2, arrived} over all rollouts. */
+int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],
+                        const double dest[2], double tmin, const double *prefix,
+                        const int32_t *prefix_len, int prefix_stride, const pmcts_noise *noise,
+                        double *reward, double *t_arr, int32_t *steps, uint8_t *status, int32_t *bin,
+                        double *frac, double *final_lat, double *final_lon, double *traj_lat,
+                        double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
+                        int flags);
+
+/* ---- K3: Node.back_up (worker.py:55-70) / MasterNode.add_reward* (master_node.py:34-54) --------
+ * table[node][8][12] uint32 visit counts.  For every leaf l: table[leaf_node[l]][leaf_slot[l]] +=
+ * leaf_bins[l], then for every ancestor chain node x -> parent[x]: table[parent[x]][arm[x]] +=
+ * leaf_bins[l] (arm[x] = index in ACTIONS of the action that expanded x). */
+int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, const int32_t *parent, const int8_t *arm,
+                 int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
+                 const uint32_t *leaf_bins, int flags);
+
+/* Per-(node, action) binned means and visit totals of a histogram table (Hist.get_mean,
+ * utils.py:49-59; Node.get_uct's exploitation term, worker.py:91-104):
+ * mean[node][8] = sum(h * centre) / sum(h) (0 if empty), visits[node] = sum over 8x12. */
+int pmcts_hist_stats(pmcts_ctx *ctx, const uint32_t *table, int64_t n_nodes, double *mean,
+                     uint32_t *visits, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,306 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU restatement (oracle/) on the
+same seeded inputs, and against the golden fixtures generated from the reference itself.
+
+Tolerances (BASELINE.json north_star): per-step lat / lon within 1e-6 relative, arrival to the step,
+frac / arrival time within 1e-6; integer outputs (steps, status, bins, histograms) bit-exact.
+The literal fp64 mode is additionally held to 1e-11 (it differs from the reference only by libm ulps).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import pmcts_helpers as H
+from iboat_pmcts_b200 import _native as N
+from iboat_pmcts_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+MODES = [N.PREC_F64, N.PREC_FAST]
+
+
+def rtol_for(mode):
+    return 1e-11 if mode == N.PREC_F64 else RTOL
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from iboat_pmcts_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def upload(eng, slot, scenario, times=None):
+    t, la, lo, u, v = synth.wind_fields(scenario)
+    if times is None:
+        times, lats, lons = H.sim_axes(la, lo)
+    else:
+        lats, lons = la, lo
+    eng.upload_scenario(slot, t, la, lo, u, v, times, [lats[0], lats[-1], lons[0], lons[-1]])
+    return times
+
+
+def relerr(a, b):
+    return np.nanmax(np.abs(a - b) / np.abs(b))
+
+
+def test_get_wind_matches_reference(eng, golden_dir):
+    with open(os.path.join(golden_dir, "kat.json")) as f:
+        kat = json.load(f)
+    t, la, lo, u, v = synth.wind_fields(0)
+    pts = np.array(kat["getWind_scenario0"])
+    # one simulator instant per query time, so the time-blended slabs are exercised at arbitrary times
+    order = np.argsort(pts[:, 0])
+    pts = pts[order]
+    eng.upload_scenario(7, t, la, lo, u, v, pts[:, 0], [40, 50, 345, 360])
+    uu, vv, st = eng.get_wind(7, np.arange(len(pts)), pts[:, 1], pts[:, 2])
+    assert (st == 0).all()
+    assert np.allclose(uu, pts[:, 3], rtol=1e-12, atol=1e-13)
+    assert np.allclose(vv, pts[:, 4], rtol=1e-12, atol=1e-13)
+    _, _, st = eng.get_wind(7, [0, 0], [39.99, 45.0], [350.0, 360.01])
+    assert (st == N.ST_OUT_OF_GRID).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_raw_steps_config3_golden(eng, golden_dir, mode):
+    """BASELINE config 3 shape against trajectories recorded from the reference (24 boats x 500 steps)."""
+    g = np.load(os.path.join(golden_dir, "raw_steps_c3.npz"))
+    eng.set_precision(mode)
+    upload(eng, 3, 0, times=g["times"])
+    nsteps, n = g["traj_lat"].shape
+    head = synth.octagon_headings(g["h0"], nsteps)
+    k = np.zeros(n, np.int32)
+    lat, lon = g["lat0"].copy(), g["lon0"].copy()
+    pl, po = lat.copy(), lon.copy()
+    st = np.zeros(n, np.uint8)
+    tl, to = np.empty((nsteps, n)), np.empty((nsteps, n))
+    eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=25, prev_lat=pl, prev_lon=po, status=st,
+                   z=np.ascontiguousarray(g["z"]), traj_lat=tl, traj_lon=to)
+    assert (st == 0).all() and (k == nsteps).all()
+    assert relerr(tl, g["traj_lat"]) < rtol_for(mode)
+    assert relerr(to, g["traj_lon"]) < rtol_for(mode)
+    assert np.array_equal(lat, tl[-1]) and np.array_equal(pl, tl[-2])
+    # stepping at the last time index is the reference's IndexError (simulatorTLKT.py:208)
+    eng.step_batch(3, k, lat, lon, head[:1], nsteps=1, status=st, z=np.zeros((1, n)))
+    assert (st == N.ST_PAST_HORIZON).all() and (k == nsteps).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_raw_steps_vs_oracle_seeded(eng, mode):
+    """Larger seeded sweep against the oracle, one launch per step and fused, Philox and injected noise."""
+    eng.set_precision(mode)
+    nsteps, n = 200, 4096
+    times = np.linspace(0, 5, 501)
+    upload(eng, 3, 1, times=times)
+    o = H.oracle_sim(1, times=times)
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=9)
+    head = synth.octagon_headings(h0, nsteps)
+    want = o.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=25, seed=42, stream=3, id0=100, nthreads=8)
+    k = np.zeros(n, np.int32)
+    lat, lon = lat0.copy(), lon0.copy()
+    st = np.zeros(n, np.uint8)
+    eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=25, status=st, seed=42, stream=3, id0=100)
+    # in-kernel Philox: integers identical, Box-Muller in fp32 (fast) or fp64 -> looser in fast mode
+    tol = 1e-11 if mode == N.PREC_F64 else 2e-6
+    assert (st == 0).all() and np.array_equal(k, want["k"])
+    assert relerr(lat, want["lat"]) < tol and relerr(lon, want["lon"]) < tol
+    # one launch per step == fused
+    z = np.random.default_rng(3).standard_normal((20, n))
+    k1 = np.zeros(n, np.int32)
+    a1, o1 = lat0.copy(), lon0.copy()
+    eng.step_batch(3, k1, a1, o1, head, nsteps=20, seg_len=25, z=z)
+    k2 = np.zeros(n, np.int32)
+    a2, o2 = lat0.copy(), lon0.copy()
+    for j in range(20):
+        eng.step_batch(3, k2, a2, o2, head[0], nsteps=1, z=z[j:j + 1])
+    assert np.array_equal(a1, a2) and np.array_equal(o1, o2) and np.array_equal(k1, k2)
+    w = o.step_batch(0, lat0, lon0, head, nsteps=20, seg_len=25, z=z, nthreads=8)
+    assert relerr(a1, w["lat"]) < rtol_for(mode) and relerr(o1, w["lon"]) < rtol_for(mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_rollouts_golden(eng, golden_dir, mode):
+    """Default-policy rollouts recorded from the reference's Tree.default_policy (3 scenarios)."""
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    eng.set_precision(mode)
+    dest, tmin = g["destination"].tolist(), float(g["timemin"])
+    S, nT, n = g["traj_lat"].shape
+    for si, scen in enumerate(g["scenarios"]):
+        upload(eng, si, int(scen))
+        z = np.ascontiguousarray(g["zroll"][si].T)
+        r = eng.rollout_batch_host(si, n, 1, H.STATE0, dest, tmin, prefix=g["prefix"], prefix_len=g["prefix_len"],
+                                   z=z, traj_steps=nT)
+        assert np.array_equal(r["steps"], g["steps"][si])
+        assert np.array_equal(r["status"] == N.ST_ARRIVED, g["atdest"][si] == 1)
+        assert relerr(r["traj_lat"], g["traj_lat"][si]) < rtol_for(mode)
+        assert relerr(r["traj_lon"], g["traj_lon"][si]) < rtol_for(mode)
+        assert np.array_equal(np.isnan(r["traj_lat"]), np.isnan(g["traj_lat"][si]))
+        arrived = g["atdest"][si] == 1
+        assert arrived.any()
+        assert np.allclose(r["frac"][arrived], g["frac"][si][arrived], rtol=1e-6, atol=1e-9)
+        assert np.allclose(r["reward"], g["reward"][si], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_rollouts_vs_oracle_and_leaf_reduction(eng, mode):
+    eng.set_precision(mode)
+    upload(eng, 0, 4)
+    o = H.oracle_sim(4)
+    dest, tmin = [46.77751005, 355.0], 2.0223605
+    n_leaf, rep = 37, 48  # ragged: leaves straddle warps
+    n = n_leaf * rep
+    rng = np.random.default_rng(1)
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 4))
+    plen = rng.integers(1, 5, n_leaf).astype(np.int32)
+    z = rng.standard_normal((13, n))
+    for flags, full in ((0, False), (N.ROLL_REPLAY_FULL_PREFIX, True)):
+        got = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen, z=z,
+                                     flags=flags)
+        want = o.rollout_batch(n, H.STATE0, dest, tmin, prefix=np.repeat(prefix, rep, 0),
+                               prefix_len=np.repeat(plen, rep), replay_full=full, z=z, nthreads=8)
+        assert np.array_equal(got["steps"], want["steps"])
+        assert np.array_equal(got["status"], want["status"])
+        assert np.array_equal(got["bin"], want["bin"])
+        assert relerr(got["final_lat"], want["final_lat"]) < rtol_for(mode)
+        assert relerr(got["final_lon"], want["final_lon"]) < rtol_for(mode)
+        assert np.allclose(got["reward"], want["reward"], rtol=1e-6, atol=1e-12)
+        arr = want["status"] == 1
+        assert np.allclose(got["t_arr"][arr], want["t_arr"][arr], rtol=1e-6)
+        assert np.isnan(got["t_arr"][~arr]).all()
+        bins = np.zeros((n_leaf, 12), np.uint32)
+        np.add.at(bins, (np.repeat(np.arange(n_leaf), rep), want["bin"]), 1)
+        assert np.array_equal(got["leaf_bins"], bins)
+        assert got["stats"][0] == arr.sum() and got["stats"][3] == arr.sum()
+        assert np.isclose(got["stats"][1], want["t_arr"][arr].sum(), rtol=1e-9)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_initialisation_and_plan_eval_golden(eng, golden_dir, mode):
+    """initialize_simulators (forest.py:210-299) and estimate_perfomance_plan (isochrones.py:469-580)
+    rebuilt from K1 / K2 launches, against values recorded from the reference."""
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    pe = np.load(os.path.join(golden_dir, "plan_eval_c5.npz"))
+    eng.set_precision(mode)
+    ntra = int(g["ntra"])
+    S = len(g["scenarios"])
+    nT = g["times"].size
+    means = []
+    osim = H.oracle_sim(0)
+    for s, scen in enumerate(g["scenarios"]):
+        upload(eng, s, int(scen))
+        z = np.ascontiguousarray(g["zinit"][s * ntra:(s + 1) * ntra].T)
+        k = np.zeros(ntra, np.int32)
+        lat, lon = np.full(ntra, 44.0), np.full(ntra, 355.0)
+        st = np.zeros(ntra, np.uint8)
+        eng.step_batch(s, k, lat, lon, np.zeros((1, ntra)), nsteps=nT, seg_len=nT, status=st, z=z,
+                       flags=N.STEP_STOP_BEFORE_TERMINAL)
+        assert (st == N.ST_HORIZON).all() and (k == nT - 2).all()
+        means.append(np.mean([osim.dist_bearing(44.0, 355.0, a, b)[0] for a, b in zip(lat, lon)]))
+    dest = osim.get_destination(np.min(means), 0, 44.0, 355.0)
+    assert np.allclose(dest, g["destination"], rtol=1e-6)
+    tmins = []
+    for s in range(S):
+        z = np.ascontiguousarray(g["zinit"][(S + s) * ntra:(S + s + 1) * ntra].T)
+        r = eng.rollout_batch_host(s, ntra, 1, H.STATE0, g["destination"].tolist(), 0.0, z=z, flags=N.ROLL_PLAN_EVAL)
+        tmins.append(r["t_arr"][r["status"] == N.ST_ARRIVED].min())
+    assert np.isclose(min(tmins), float(g["timemin"]), rtol=1e-6)
+    for name in ("plan", "empty"):
+        nt2 = int(pe[name + "_ntra"])
+        plan = pe[name + "_plan"].astype(np.float64)
+        means, all_t = [], []
+        for s in range(S):
+            z = np.ascontiguousarray(pe[name + "_z"][s * nt2:(s + 1) * nt2].T)
+            pre = np.tile(plan, (nt2, 1)) if plan.size else None
+            r = eng.rollout_batch_host(s, nt2, 1, H.STATE0, g["destination"].tolist(), 0.0, prefix=pre, z=z,
+                                       flags=N.ROLL_PLAN_EVAL)
+            means.append(r["t_arr"].mean())
+            all_t.append(r["t_arr"])
+            assert np.isclose(r["stats"][1] / r["stats"][0], means[-1], rtol=1e-12)
+        all_t = np.concatenate(all_t)
+        assert np.allclose([all_t.mean()] + means, pe[name + "_mean"], rtol=1e-6)
+        v = [np.mean((all_t - all_t.mean()) ** 2)] + [np.mean((t - t.mean()) ** 2) for t in np.split(all_t, S)]
+        assert np.allclose(v, pe[name + "_var"], rtol=1e-4, atol=1e-12)
+
+
+def test_edge_cases(eng):
+    eng.set_precision(N.PREC_F64)
+    times = upload(eng, 0, 2)
+    nT = times.size
+    # empty batches are no-ops
+    eng.step_batch(0, np.zeros(0, np.int32), np.zeros(0), np.zeros(0), np.zeros((1, 0)))
+    r = eng.rollout_batch_host(0, 0, 1, H.STATE0, [46.0, 355.0], 2.0)
+    assert r["reward"].size == 0
+    # a boat leaving the weather grid freezes with OUT_OF_GRID (SciPy ValueError) at its last valid state
+    k = np.zeros(2, np.int32)
+    lat, lon = np.array([49.9, 44.0]), np.array([359.9, 355.0])
+    st = np.zeros(2, np.uint8)
+    eng.step_batch(0, k, lat, lon, np.full((1, 2), 45.0), nsteps=nT - 1, seg_len=nT, status=st)
+    assert st[0] == N.ST_OUT_OF_GRID and 0 < k[0] < nT - 1 and (lat[0] > 50.0 or lon[0] > 360.0)
+    assert st[1] in (N.ST_OK, N.ST_OUT_OF_GRID)
+    # unknown scenario slot, mixed host/device arguments
+    with pytest.raises(N.PmctsError):
+        eng.step_batch(99, k, lat, lon, np.zeros((1, 2)))
+    # rollout from a root on the horizon: the first prefix step is the IndexError case
+    r = eng.rollout_batch_host(0, 1, 1, (nT - 1, 44.0, 355.0), [46.0, 355.0], 2.0, prefix=[[0.0]])
+    assert r["status"][0] == N.ST_PAST_HORIZON
+
+
+def test_device_pointer_path_and_backup(eng):
+    """Device-resident arrays (torch tensors): same results as the host-buffer path; K3 back-up and
+    histogram statistics against a NumPy restatement."""
+    import torch
+    eng.set_precision(N.PREC_F64)
+    upload(eng, 0, 5)
+    dev = torch.device("cuda:0")
+    n_leaf, rep = 64, 32
+    n = n_leaf * rep
+    dest, tmin = [46.77751005, 355.0], 2.0223605
+    prefix = 45.0 * (np.arange(n_leaf) % 8).reshape(n_leaf, 1).astype(np.float64)
+    host = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, seed=5, stream=1)
+    eng.use_torch_stream()
+    out = dict(reward=torch.empty(n, dtype=torch.float64, device=dev),
+               status=torch.empty(n, dtype=torch.uint8, device=dev),
+               leaf_bins=torch.zeros(n_leaf * 12, dtype=torch.int32, device=dev))
+    eng.rollout_batch(0, n_leaf, rep, H.STATE0, dest, tmin, torch.tensor(prefix, device=dev).reshape(-1),
+                      torch.ones(n_leaf, dtype=torch.int32, device=dev), 1, seed=5, stream=1, out=out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["reward"].cpu().numpy(), host["reward"])
+    assert np.array_equal(out["status"].cpu().numpy(), host["status"])
+    assert np.array_equal(out["leaf_bins"].cpu().numpy().astype(np.uint32).reshape(n_leaf, 12), host["leaf_bins"])
+    # a small tree: node 0 root, nodes 1..8 children of the root, leaves = children of node 1..8
+    n_nodes = 1 + 8 + n_leaf
+    parent = np.full(n_nodes, -1, np.int32)
+    arm = np.zeros(n_nodes, np.int8)
+    parent[1:9] = 0
+    arm[1:9] = np.arange(8)
+    leaf_node = np.arange(9, 9 + n_leaf, dtype=np.int32)
+    parent[9:] = 1 + (np.arange(n_leaf) % 8)
+    arm[9:] = (np.arange(n_leaf) // 8) % 8
+    slot = np.random.default_rng(0).integers(0, 8, n_leaf).astype(np.int8)
+    table = torch.zeros(n_nodes * 96, dtype=torch.int32, device=dev)
+    t = lambda a: torch.as_tensor(a, device=dev)  # noqa: E731
+    eng.backup(table, t(parent), t(arm), t(leaf_node), t(slot), out["leaf_bins"])
+    want = np.zeros((n_nodes, 8, 12), np.int64)
+    for l in range(n_leaf):
+        node = leaf_node[l]
+        want[node, slot[l]] += host["leaf_bins"][l]
+        while parent[node] >= 0:
+            want[parent[node], arm[node]] += host["leaf_bins"][l]
+            node = parent[node]
+    torch.cuda.synchronize()
+    got = table.cpu().numpy().reshape(n_nodes, 8, 12)
+    assert np.array_equal(got, want)
+    assert got[0].sum() == n
+    mean = torch.empty(n_nodes * 8, dtype=torch.float64, device=dev)
+    visits = torch.empty(n_nodes, dtype=torch.int32, device=dev)
+    eng.hist_stats(table, n_nodes, mean, visits)
+    torch.cuda.synchronize()
+    centres = (np.arange(12) + 0.5) * 0.125
+    tot = want.sum(-1)
+    wmean = np.where(tot > 0, (want * centres).sum(-1) / np.maximum(tot, 1), 0.0)
+    assert np.array_equal(mean.cpu().numpy().reshape(n_nodes, 8), wmean)
+    assert np.array_equal(visits.cpu().numpy(), want.sum((1, 2)))
+    eng.use_own_stream()
