@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the IBoat-PMCTS rollout hot path on B200 (contract: see DESIGN.md).
+
+Default workload ("c4-shard", BASELINE.json configs[3] per GPU): every rank owns 8 synthetic
+GFS-ensemble-shaped weather scenarios; one *step* is 10^6 leaf-batched default-policy rollouts per
+scenario, issued as 8 waves of 4096 leaves x 32 noise replicas, each wave followed by the per-leaf
+reward-bin reduction (in K2), one all-gather of the per-scenario update blocks (N > 1 only) and the
+back-up of every scenario's blocks into the replicated master table (K3).  Scenarios are the unit of
+sharding, so scaling is weak: per-GPU work is fixed as N grows.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident whole-job transitions/s; `e2e` is the same
+metric through the host-buffer C ABI calls (H2D / D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from iboat_pmcts_b200 import synth  # noqa: E402
+
+# ---- workload constants ------------------------------------------------------------
+SCEN_PER_GPU = 8
+N_LEAF = 4096          # a complete depth-4 tree over the 8 headings has 8^4 leaves
+REPLICAS = 32
+WAVES = 8
+STATE0 = (0, 44.0, 355.0)
+DEST = (46.77751005, 355.0)   # initialize_simulators on scenarios 0-2 (tests/golden/rollouts_c1.npz)
+TMIN = 2.022360548788055
+SEED = 42
+F_ALG_ROLLOUT = 480.0  # algorithmic flop per default-policy transition
+F_ALG_RAW = 328.0      # per raw doStep
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, nominal (no measured fp32 entry in MEASURED_PEAKS.json)
+C3_BOATS, C3_STEPS = 1_000_000, 500
+
+
+def sim_axes(wlat, wlon, simtimestep=6, ndaysim=3, d=0.5):
+    times = np.arange(0, ndaysim + simtimestep / 24, simtimestep * (1 / 24))
+    return times, np.arange(wlat[0], wlat[-1], d), np.arange(wlon[0], wlon[-1], d)
+
+
+def depth4_tree():
+    """Complete 8-ary tree of depth 4: parent / arm arrays, the 4096 leaves and their action paths."""
+    parent, arm, paths = [-1], [0], [[]]
+    level = [0]
+    for _ in range(4):
+        nxt = []
+        for p in level:
+            for a in range(8):
+                parent.append(p)
+                arm.append(a)
+                paths.append(paths[p] + [45.0 * a])
+                nxt.append(len(parent) - 1)
+        level = nxt
+    leaves = np.array(level, np.int32)
+    prefix = np.array([paths[i] for i in level], np.float64)
+    return np.array(parent, np.int32), np.array(arm, np.int8), leaves, prefix
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # "under load": the upper half of the samples (idle samples before/after the timed region drop out)
+            sm_sorted = sorted(sm)
+            out["sm_mhz"] = statistics.median(sm_sorted[len(sm_sorted) // 2:])
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ====================================================================================================
+# reference arm: the CPU restatement of the reference's own path on all host threads
+# ====================================================================================================
+def cpu_rollout_sample(n_rollouts, nthreads, scenario=0):
+    """Times the oracle port (oracle/pmcts_oracle.c, bit-exact to the Python reference) on one scenario."""
+    from oracle import cport
+    t, la, lo, u, v = synth.wind_fields(scenario)
+    times, lats, lons = sim_axes(la, lo)
+    o = cport.OracleSim(t, la, lo, u, v, times, lats, lons)
+    _, _, _, prefix = depth4_tree()
+    reps = (n_rollouts + N_LEAF - 1) // N_LEAF
+    pre = np.repeat(prefix, reps, 0)[:n_rollouts]
+    t0 = time.perf_counter()
+    r = o.rollout_batch(n_rollouts, STATE0, DEST, TMIN, prefix=pre, seed=SEED, stream=scenario, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return int(r["steps"].sum()), n_rollouts, dt
+
+
+def cpu_raw_sample(n_boats, nsteps, nthreads):
+    from oracle import cport
+    t, la, lo, u, v = synth.wind_fields(0)
+    times = np.linspace(0, 5, C3_STEPS + 1)
+    o = cport.OracleSim(t, la, lo, u, v, times, la, lo)
+    lat0, lon0, h0 = synth.octagon_fleet(n_boats)
+    head = synth.octagon_headings(h0, nsteps)
+    t0 = time.perf_counter()
+    r = o.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=25, seed=SEED, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return int(r["k"].sum()), n_boats, dt
+
+
+def cpu_baseline(workload, budget_s=12.0):
+    cores = os.cpu_count() or 1
+    if workload == "c3":
+        tr, n, dt = cpu_raw_sample(2048 * cores, 50, cores)            # calibration
+        nb = int(min(C3_BOATS, max(2048 * cores, 2048 * cores * budget_s / max(dt, 1e-3) / 10)))
+        tr, n, dt = cpu_raw_sample(nb, C3_STEPS, cores)
+        sample = "%d boats x %d steps of the c3 sweep, scenario 0" % (nb, C3_STEPS)
+        return dict(value=tr / dt, unit="transitions/s", cores=cores, kind="port", sample=sample,
+                    rollouts_per_s=None, seconds=dt)
+    tr, n, dt = cpu_rollout_sample(4096 * cores, cores)                # calibration
+    nr = int(max(4096 * cores, min(8 * N_LEAF * REPLICAS * WAVES, 4096 * cores * budget_s / max(dt, 1e-3))))
+    tr, n, dt = cpu_rollout_sample(nr, cores)
+    sample = "%d default-policy rollouts of scenario 0 (same leaves, Philox noise)" % nr
+    return dict(value=tr / dt, unit="transitions/s", cores=cores, kind="port", sample=sample,
+                rollouts_per_s=n / dt, seconds=dt)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = 4096 * cores if args.workload != "c3" else 1024 * cores
+    times_, tr_tot, n_tot = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        if args.workload == "c3":
+            tr, n, dt = cpu_raw_sample(per_step, C3_STEPS, cores)
+        else:
+            tr, n, dt = cpu_rollout_sample(per_step, cores, scenario=i % SCEN_PER_GPU)
+        if i >= args.warmup:
+            times_.append(dt)
+            tr_tot += tr
+            n_tot += n
+    total = sum(times_)
+    value = tr_tot / total
+    sample = ("each step = %d %s on all %d host threads (bounded sample of the %s workload)"
+              % (per_step, "boats x 500 steps" if args.workload == "c3" else "rollouts", cores, args.workload))
+    line = dict(metric="sim transitions/s", value=value, unit="transitions/s", impl="reference",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                rollouts_per_s=(n_tot / total) if args.workload != "c3" else None,
+                config=workload_config(args.workload, args.gpus),
+                cpu_baseline=dict(value=value, unit="transitions/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="transitions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="oracle/pmcts_oracle.c: C fp64 restatement, bit-exact to the Python reference (which cannot "
+                     "travel to the GPU box); the Python reference itself measured 3.0e3 transitions/s/core (BASELINE.md)")
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n_gpus):
+    if workload == "c3":
+        return dict(workload="c3 raw Simulator.doStep sweep: 10^6 boats x 500 steps per GPU on one 0.5-deg 3-hourly "
+                             "5-day grid (BASELINE.json configs[2])",
+                    boats_per_gpu=C3_BOATS, steps=C3_STEPS, sharding="boats split across GPUs, grid replicated",
+                    l2="state arrays 28 MB/GPU; L2 flushed between timed steps", noise="philox4x32-10 seed 42")
+    return dict(workload="c4 large-ensemble shard: 8 scenarios per GPU x 10^6 leaf-batched default-policy rollouts per "
+                         "scenario per step (BASELINE.json configs[3]; 64 scenarios at 8 GPUs)",
+                scenarios_per_gpu=SCEN_PER_GPU, scenarios_total=SCEN_PER_GPU * n_gpus, leaves=N_LEAF,
+                replicas=REPLICAS, waves=WAVES, rollouts_per_scenario_per_step=N_LEAF * REPLICAS * WAVES,
+                sim_axis="6-hourly over 3 days (13 instants)", grid="41x21x31 (t, lat, lon), 0.5 deg, 3-hourly",
+                sharding="scenario s on GPU s // 8; master table replicated; one all-gather per wave",
+                l2="L2 flushed (256 MiB write) between timed steps", noise="philox4x32-10 seed 42")
+
+
+# ====================================================================================================
+# B200 arm
+# ====================================================================================================
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c3"])
+    ap.add_argument("--precision", default="default", choices=["default", "f64", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from iboat_pmcts_b200 import _native as N
+    from iboat_pmcts_b200.engine import Engine
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(3, args.warmup)
+    args.warmup = warm
+
+    eng = Engine(local)
+    eng.use_torch_stream()
+    prec = {"default": N.PREC_FAST, "f64": N.PREC_F64, "fast": N.PREC_FAST}[args.precision]
+    eng.set_precision(prec)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "c4":
+        run = setup_c4(eng, torch, dist, dev, rank, world)
+    else:
+        run = setup_c3(eng, torch, dev, rank, world)
+
+    # ---- device-resident timing: W warm-up steps, then K steps, each bracketed by CUDA events ------
+    for i in range(warm):
+        run["device_step"](i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.enable_timing(True)
+    eng.kernel_ms(reset=True)
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    run["reset_counters"]()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2()
+        ev[i][0].record()
+        run["device_step"](warm + i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count() - launches0
+    dom_kernel_ms = eng.kernel_ms(reset=False, kind=run["dominant"]["kind"])
+    kernel_ms = eng.kernel_ms(reset=True)
+    eng.enable_timing(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    counters = run["read_counters"]()  # transitions, rollouts of this rank over the K timed steps
+    stat = torch.tensor([dev_ms, counters[0], counters[1], kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, kernel_ms = float(mx[0]), float(mx[3])
+        transitions, rollouts = float(sm[1]), float(sm[2])
+    else:
+        transitions, rollouts = counters
+    value = transitions / (dev_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI ------------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    run["e2e_step"](0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_tr, h2d, d2h = 0, 0, 0
+    for i in range(e2e_steps):
+        tr, bi, bo = run["e2e_step"](1 + i)
+        e2e_tr += tr
+        h2d, d2h = bi, bo
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_stat = torch.tensor([e2e_s, float(e2e_tr)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = e2e_stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = e2e_stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_tr = float(mx[0]), float(sm[1])
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        per_launch_units = run["dominant"]["units_per_launch"]
+        n_dom = run["dominant"]["launches_per_step"] * args.steps
+        dom_ms = dom_kernel_ms / n_dom
+        f_alg = run["dominant"]["flop_per_unit"]
+        # units per launch are transitions: measured, averaged over the timed launches of this rank
+        units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
+        achieved = units * f_alg / (dom_ms * 1e-3) / 1e12
+        roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=FP32_PEAK_TFLOPS,
+                        unit="TFLOP/s", frac=achieved / FP32_PEAK_TFLOPS, traffic=None,
+                        peak_source="nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has "
+                                    "HBM and bf16-tensor entries only; the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
+                        algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
+                        hbm_bytes_per_launch=run["dominant"]["hbm_bytes_per_launch"],
+                        hbm_gbs=run["dominant"]["hbm_bytes_per_launch"] / (dom_ms * 1e-3) / 1e9)
+        line = dict(metric="sim transitions/s", value=value, unit="transitions/s", n_gpus=world, steps=args.steps,
+                    warmup=warm, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f64" if prec == N.PREC_F64 else "f32+f64", data="synthetic",
+                    rollouts_per_s=rollouts / (dev_ms * 1e-3) if rollouts else None,
+                    config=workload_config(args.workload, world), precision_mode="f64" if prec == N.PREC_F64 else "fast",
+                    e2e=dict(value=e2e_tr / e2e_s, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             steps=e2e_steps, api="pmcts_rollout_batch / pmcts_step_batch with PMCTS_MEM_HOST"),
+                    gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
+                    roofline=roofline)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def setup_c4(eng, torch, dist, dev, rank, world):
+    from iboat_pmcts_b200 import _native as N
+    S_local, S_total = SCEN_PER_GPU, SCEN_PER_GPU * world
+    box = None
+    for j in range(S_local):
+        t, la, lo, u, v = synth.wind_fields(rank * S_local + j)
+        times, lats, lons = sim_axes(la, lo)
+        box = [lats[0], lats[-1], lons[0], lons[-1]]
+        eng.upload_scenario(j, t, la, lo, u.astype(np.float32), v.astype(np.float32), times, box)
+    parent_h, arm_h, leaves_h, prefix_h = depth4_tree()
+    n_nodes = parent_h.size
+    n = N_LEAF * REPLICAS
+    parent = torch.tensor(parent_h, device=dev)
+    arm = torch.tensor(arm_h, device=dev)
+    prefix = torch.tensor(prefix_h, device=dev).reshape(-1)
+    plen = torch.full((N_LEAF,), 4, dtype=torch.int32, device=dev)
+    leaf_node = torch.tensor(np.tile(leaves_h, S_total), device=dev)
+    slots = torch.tensor(np.random.default_rng(3).integers(0, 8, S_total * N_LEAF).astype(np.int8), device=dev)
+    master = torch.zeros(S_total * n_nodes * 96, dtype=torch.int32, device=dev)
+    bins_local = torch.zeros(S_local * N_LEAF * 12, dtype=torch.int32, device=dev)
+    bins_all = torch.zeros(S_total * N_LEAF * 12, dtype=torch.int32, device=dev) if world > 1 else bins_local
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    plen_h = np.full(N_LEAF, 4, np.int32)
+
+    def device_step(i):
+        for w in range(WAVES):
+            bins_local.zero_()
+            for j in range(S_local):
+                g = rank * S_local + j
+                eng.rollout_batch(j, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, seed=SEED, stream=g,
+                                  id0=(i * WAVES + w) * n,
+                                  out=dict(leaf_bins=bins_local[j * N_LEAF * 12:(j + 1) * N_LEAF * 12], stats=stats),
+                                  flags=N.ROLL_ACCUMULATE)
+            if world > 1:
+                dist.all_gather_into_tensor(bins_all, bins_local)
+            eng.backup(master, n_nodes, parent, arm, leaf_node, slots, bins_all, n_scen=S_total)
+
+    def reset_counters():
+        stats.zero_()
+        master.zero_()
+
+    def read_counters():
+        s = stats.cpu().numpy()
+        root_visits = int(master.view(S_total, n_nodes, 96)[:, 0].sum().item())
+        assert root_visits == int(round(s[5])) * world or world > 1, (root_visits, s[5])
+        return float(s[4]), float(s[5])
+
+    def e2e_step(i):
+        tr = 0
+        for w in range(WAVES):
+            for j in range(S_local):
+                g = rank * S_local + j
+                r = eng.rollout_batch_host(j, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix=prefix_h, prefix_len=plen_h,
+                                           seed=SEED, stream=g, id0=(1000 + i * WAVES + w) * n,
+                                           want=("leaf_bins", "stats"))
+                tr += int(r["stats"][4])
+        calls = WAVES * S_local
+        return tr, calls * (prefix_h.nbytes + plen_h.nbytes), calls * (N_LEAF * 12 * 4 + 64)
+
+    return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
+                e2e_step=e2e_step,
+                dominant=dict(kernel="rollout_batch_kernel", launches_per_step=WAVES * S_local, units_per_launch=None,
+                              flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
+                              hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + N_LEAF * 48 + n * 0))
+
+
+def setup_c3(eng, torch, dev, rank, world):
+    t, la, lo, u, v = synth.wind_fields(0)
+    times = np.linspace(0, 5, C3_STEPS + 1)
+    eng.upload_scenario(0, t, la, lo, u.astype(np.float32), v.astype(np.float32), times, [la[0], la[-1], lo[0], lo[-1]])
+    n = C3_BOATS
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=7 + rank)
+    head_h = synth.octagon_headings(h0, C3_STEPS)
+    head = torch.tensor(head_h, device=dev).reshape(-1)
+    lat0_d, lon0_d = torch.tensor(lat0, device=dev), torch.tensor(lon0, device=dev)
+    k = torch.zeros(n, dtype=torch.int32, device=dev)
+    lat, lon = lat0_d.clone(), lon0_d.clone()
+    st = torch.zeros(n, dtype=torch.uint8, device=dev)
+    tr_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def device_step(i):
+        k.zero_()
+        st.zero_()
+        lat.copy_(lat0_d)
+        lon.copy_(lon0_d)
+        eng.step_batch(0, k, lat, lon, head, nsteps=C3_STEPS, seg_len=25, status=st, seed=SEED, stream=rank,
+                       id0=i * n)
+        tr_acc.add_(k.sum())
+
+    def reset_counters():
+        tr_acc.zero_()
+
+    def read_counters():
+        return float(tr_acc.item()), 0.0
+
+    def e2e_step(i):
+        kk = np.zeros(n, np.int32)
+        la_, lo_ = lat0.copy(), lon0.copy()
+        s_ = np.zeros(n, np.uint8)
+        eng.step_batch(0, kk, la_, lo_, head_h, nsteps=C3_STEPS, seg_len=25, status=s_, seed=SEED, stream=rank,
+                       id0=(1000 + i) * n)
+        return int(kk.sum()), n * (4 + 8 + 8 + 1) + head_h.nbytes, n * (4 + 8 + 8 + 1)
+
+    return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
+                e2e_step=e2e_step,
+                dominant=dict(kernel="step_batch_kernel", launches_per_step=1, units_per_launch=None,
+                              flop_per_unit=F_ALG_RAW, kind=0,
+                              hbm_bytes_per_launch=n * (21 + 21) + head_h.nbytes))
+
+
+if __name__ == "__main__":
+    main()

@@ -15,15 +15,17 @@ ST_OK, ST_ARRIVED, ST_HORIZON, ST_OUT_OF_BOX, ST_OUT_OF_GRID, ST_DEGENERATE, ST_
 STEP_STOP_BEFORE_TERMINAL = 0x1
 ROLL_REPLAY_FULL_PREFIX = 0x2
 ROLL_PLAN_EVAL = 0x4
+ROLL_ACCUMULATE = 0x8
 MEM_HOST = 0x100
 PREC_F64, PREC_FAST = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
+KERNEL_STEP, KERNEL_ROLLOUT, KERNEL_BACKUP, KERNEL_OTHER = 0, 1, 2, 3
 ERR_NO_DEVICE = -3
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_synchronize", "pmcts_set_precision", "pmcts_launch_count", "pmcts_enable_timing",
-    "pmcts_kernel_ms_total", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
+    "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_backup", "pmcts_hist_stats",
 ]
 
@@ -68,6 +70,8 @@ def lib():
     L.pmcts_enable_timing.argtypes = [vp, i32]
     L.pmcts_kernel_ms_total.argtypes = [vp, i32]
     L.pmcts_kernel_ms_total.restype = dbl
+    L.pmcts_kernel_ms.argtypes = [vp, i32, i32]
+    L.pmcts_kernel_ms.restype = dbl
     L.pmcts_set_params.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl, dbl]
     L.pmcts_scenario_upload.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp]
     L.pmcts_scenario_free.argtypes = [vp, i32]
@@ -76,7 +80,7 @@ def lib():
                                    vp, vp, vp, i32]
     L.pmcts_rollout_batch.argtypes = [vp, i32, i64, i32, vp, vp, dbl, vp, vp, i32, C.POINTER(Noise),
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32]
-    L.pmcts_backup.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i32]
+    L.pmcts_backup.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp, vp, vp, i32]
     L.pmcts_hist_stats.argtypes = [vp, vp, i64, vp, vp, i32]
     _lib = L
     return L

@@ -131,7 +131,7 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = r < n;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
-    int bin = 0, st = PMCTS_ST_OK;
+    int bin = 0, st = PMCTS_ST_OK, nstep_out = 0;
     int64_t leaf = 0;
     double ta = NAN, rw = 0.0;
     if (live) {
@@ -206,6 +206,7 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
             }
         }
         bin = hist_bin(rw);
+        nstep_out = nstep;
         if (a.reward) a.reward[r] = rw;
         if (a.t_arr) a.t_arr[r] = ta;
         if (a.steps) a.steps[r] = nstep;
@@ -231,40 +232,38 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
     if (a.stats && warp_mask) {
         if (live) {
             const bool has_t = !isnan(ta);
-            double c = has_t ? 1.0 : 0.0, s1 = has_t ? ta : 0.0, s2 = has_t ? ta * ta : 0.0;
-            double arrived = (st == PMCTS_ST_ARRIVED) ? 1.0 : 0.0;
-            for (int off = 16; off > 0; off >>= 1) {
-                c += __shfl_xor_sync(warp_mask, c, off);
-                s1 += __shfl_xor_sync(warp_mask, s1, off);
-                s2 += __shfl_xor_sync(warp_mask, s2, off);
-                arrived += __shfl_xor_sync(warp_mask, arrived, off);
-            }
+            double v[6] = {has_t ? 1.0 : 0.0, has_t ? ta : 0.0, has_t ? ta * ta : 0.0,
+                           (st == PMCTS_ST_ARRIVED) ? 1.0 : 0.0, (double)nstep_out, 1.0};
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+                for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(warp_mask, v[q], off);
             if ((threadIdx.x & 31) == (__ffs(warp_mask) - 1)) {
-                atomicAdd(&a.stats[0], c);
-                atomicAdd(&a.stats[1], s1);
-                atomicAdd(&a.stats[2], s2);
-                atomicAdd(&a.stats[3], arrived);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) atomicAdd(&a.stats[q], v[q]);
             }
         }
     }
 }
 
-// K3 -- Node.back_up (worker.py:55-70): one thread per (leaf, bin).
-__global__ void backup_kernel(uint32_t *__restrict__ table, const int32_t *__restrict__ parent,
-                              const int8_t *__restrict__ arm, int64_t n_leaf,
-                              const int32_t *__restrict__ leaf_node,
+// K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
+// blockIdx.y = scenario.
+__global__ void backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes,
+                              const int32_t *__restrict__ parent, const int8_t *__restrict__ arm,
+                              int64_t n_leaf, const int32_t *__restrict__ leaf_node,
                               const int8_t *__restrict__ leaf_slot,
                               const uint32_t *__restrict__ leaf_bins) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_leaf * 12) return;
+    const int64_t s = blockIdx.y;
     const int64_t l = t / 12;
     const int b = (int)(t % 12);
-    const uint32_t c = leaf_bins[t];
+    const uint32_t c = leaf_bins[s * n_leaf * 12 + t];
     if (c == 0) return;
-    int node = leaf_node[l];
-    atomicAdd(&table[((size_t)node * 8 + leaf_slot[l]) * 12 + b], c);
+    uint32_t *tab = table + (size_t)s * n_nodes * 96;
+    int node = leaf_node[s * n_leaf + l];
+    atomicAdd(&tab[((size_t)node * 8 + leaf_slot[s * n_leaf + l]) * 12 + b], c);
     for (int p = parent[node]; p >= 0; p = parent[node]) {
-        atomicAdd(&table[((size_t)p * 8 + arm[node]) * 12 + b], c);
+        atomicAdd(&tab[((size_t)p * 8 + arm[node]) * 12 + b], c);
         node = p;
     }
 }
@@ -343,9 +342,10 @@ struct pmcts_ctx {
     size_t scratch_cap = 0, scratch_used = 0;
     int64_t launches = 0;
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
-    double timed_ms = 0.0;
+    double timed_ms[4] = {0, 0, 0, 0};  // per PMCTS_KERNEL_* kind
     std::mutex mu;
 };
 
@@ -443,7 +443,8 @@ size_t al(size_t bytes) { return Stager::align(bytes); }
 struct LaunchTimer {
     pmcts_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
-    explicit LaunchTimer(pmcts_ctx *c) : ctx(c) {
+    int kind;
+    explicit LaunchTimer(pmcts_ctx *c, int kind_ = PMCTS_KERNEL_OTHER) : ctx(c), kind(kind_) {
         ctx->launches++;
         if (!ctx->timing) return;
         if (!ctx->event_pool.empty()) {
@@ -459,7 +460,7 @@ struct LaunchTimer {
     ~LaunchTimer() {
         if (!a) return;
         cudaEventRecord(b, ctx->stream);
-        ctx->timed.push_back({a, b});
+        ctx->timed.push_back({a, b, kind});
     }
 };
 
@@ -531,7 +532,7 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->scratch) cudaFree(ctx->scratch);
-    for (auto &p : ctx->timed) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : ctx->timed) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto &p : ctx->event_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -571,18 +572,29 @@ int pmcts_enable_timing(pmcts_ctx *ctx, int on) {
     return PMCTS_OK;
 }
 
-double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset) {
-    if (!ctx) return -1.0;
-    DeviceGuard g(ctx->device);
+static void drain_timers(pmcts_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->timed) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->timed_ms += ms;
-        ctx->event_pool.push_back(p);
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->timed_ms[p.kind & 3] += ms;
+        ctx->event_pool.push_back({p.a, p.b});
     }
     ctx->timed.clear();
-    const double r = ctx->timed_ms;
-    if (reset) ctx->timed_ms = 0.0;
+}
+
+double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset) {
+    if (!ctx || kind < 0 || kind > 3) return -1.0;
+    DeviceGuard g(ctx->device);
+    drain_timers(ctx);
+    const double r = ctx->timed_ms[kind];
+    if (reset) ctx->timed_ms[kind] = 0.0;
+    return r;
+}
+
+double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset) {
+    if (!ctx) return -1.0;
+    double r = 0.0;
+    for (int kind = 0; kind < 4; ++kind) r += pmcts_kernel_ms(ctx, kind, reset);
     return r;
 }
 
@@ -782,7 +794,7 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         return rc;
     if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)nsteps * n))) return rc;
     {
-        LaunchTimer lt(ctx);
+        LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
         if (ctx->precision == PMCTS_PREC_FAST)
             step_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(
                 sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
@@ -815,10 +827,11 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
     NoiseView nz = noise_view(noise);
     const int max_steps = sc->view.nT;
     if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
+    const bool acc = (flags & PMCTS_ROLL_ACCUMULATE) && !(flags & PMCTS_MEM_HOST);
     Stager st(ctx, flags & PMCTS_MEM_HOST);
     const size_t traj_bytes = al((size_t)traj_stride * n * 8);
     rc = st.reserve(al((size_t)n_leaf * prefix_stride * 8) + al(n_leaf * 4) + 6 * al(n * 8) + 2 * al(n * 4) + al(n) +
-                    (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(n_leaf * 48) + al(32) +
+                    (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(n_leaf * 48) + al(64) +
                     (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)max_steps * n * 8) : 0));
     if (rc) return rc;
     if ((rc = st.in(prefix, (size_t)n_leaf * prefix_stride)) || (rc = st.in(prefix_len, n_leaf)) ||
@@ -827,7 +840,7 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
         (rc = st.out(final_lat, n)) || (rc = st.out(final_lon, n)) ||
         (rc = st.out(traj_lat, (size_t)traj_stride * n, 0xFF)) ||
         (rc = st.out(traj_lon, (size_t)traj_stride * n, 0xFF)) ||
-        (rc = st.out(leaf_bins, (size_t)n_leaf * 12, 0)) || (rc = st.out(stats, 4, 0)))
+        (rc = st.out(leaf_bins, (size_t)n_leaf * 12, acc ? -1 : 0)) || (rc = st.out(stats, 8, acc ? -1 : 0)))
         return rc;
     if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)max_steps * n))) return rc;
     RolloutArgs a{};
@@ -857,7 +870,7 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
     a.stats = stats;
     a.flags = flags;
     {
-        LaunchTimer lt(ctx);
+        LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
         if (ctx->precision == PMCTS_PREC_FAST)
             rollout_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, ctx->params, nz, a);
         else
@@ -867,18 +880,20 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
     return st.finish();
 }
 
-int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, const int32_t *parent, const int8_t *arm,
-                 int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
+int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, const int32_t *parent,
+                 const int8_t *arm, int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
                  const uint32_t *leaf_bins, int flags) {
     if (!ctx || !table || !parent || !arm || !leaf_node || !leaf_slot || !leaf_bins)
         return fail(PMCTS_ERR_ARG, "NULL argument");
     if (flags & PMCTS_MEM_HOST) return fail(PMCTS_ERR_ARG, "pmcts_backup works on a device-resident table");
+    if (n_scen < 1 || n_scen > 65535 || n_nodes < 1) return fail(PMCTS_ERR_ARG, "bad sizes");
     if (n_leaf <= 0) return PMCTS_OK;
     DeviceGuard g(ctx->device);
     {
-        LaunchTimer lt(ctx);
-        backup_kernel<<<grid_for(n_leaf * 12), kBlock, 0, ctx->stream>>>(table, parent, arm, n_leaf, leaf_node,
-                                                                        leaf_slot, leaf_bins);
+        LaunchTimer lt(ctx, PMCTS_KERNEL_BACKUP);
+        dim3 grid(grid_for(n_leaf * 12), n_scen);
+        backup_kernel<<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
+                                                       leaf_slot, leaf_bins);
     }
     CUDA_TRY(cudaGetLastError());
     return PMCTS_OK;

@@ -122,8 +122,11 @@ class Engine:
     def enable_timing(self, on=True):
         N.check(self._lib.pmcts_enable_timing(self._h, int(bool(on))))
 
-    def kernel_ms(self, reset=True):
-        return float(self._lib.pmcts_kernel_ms_total(self._h, int(bool(reset))))
+    def kernel_ms(self, reset=True, kind=None):
+        """Device milliseconds of the launches timed since the last reset (all kernels or one kind)."""
+        if kind is None:
+            return float(self._lib.pmcts_kernel_ms_total(self._h, int(bool(reset))))
+        return float(self._lib.pmcts_kernel_ms(self._h, int(kind), int(bool(reset))))
 
     def set_params(self, polar, wind_max, pofsail_min, pofsail_max, sigma_coeff, dest_angle, earth_radius):
         pol = np.ascontiguousarray(polar, dtype=np.float64).reshape(36)
@@ -198,7 +201,7 @@ class Engine:
                 g("bin", "i32", n), g("frac", "f64", n), g("final_lat", "f64", n), g("final_lon", "f64", n),
                 g("traj_lat", "f64", traj_stride * n), g("traj_lon", "f64", traj_stride * n)]
         plb = g("leaf_bins", "u32", n_leaf * 12)
-        pstats = g("stats", "f64", 4)
+        pstats = g("stats", "f64", 8)
         nz = make_noise(a, z, seed, stream, id0)
         N.check(self._lib.pmcts_rollout_batch(self._h, int(scen), int(n_leaf), int(replicas), root.ctypes.data,
                                               dest.ctypes.data, float(tmin), ppre, plen, int(prefix_stride),
@@ -213,7 +216,7 @@ class Engine:
                          "leaf_bins", "stats")
         spec = dict(reward=(np.float64, n), t_arr=(np.float64, n), steps=(np.int32, n), status=(np.uint8, n),
                     bin=(np.int32, n), frac=(np.float64, n), final_lat=(np.float64, n),
-                    final_lon=(np.float64, n), leaf_bins=(np.uint32, n_leaf * 12), stats=(np.float64, 4))
+                    final_lon=(np.float64, n), leaf_bins=(np.uint32, n_leaf * 12), stats=(np.float64, 8))
         out = {nm: np.empty(spec[nm][1], spec[nm][0]) for nm in names}
         if traj_steps:
             out["traj_lat"] = np.full((traj_steps, n), np.nan)
@@ -234,12 +237,15 @@ class Engine:
         return out
 
     # ---- K3 / statistics --------------------------------------------------------------------------
-    def backup(self, table, parent, arm, leaf_node, leaf_slot, leaf_bins):
+    def backup(self, table, n_nodes, parent, arm, leaf_node, leaf_slot, leaf_bins, n_scen=1):
+        """table[n_scen][n_nodes][8][12] += per-leaf bins along every ancestor chain (device arrays)."""
         a = _Args()
-        n_leaf = leaf_node.numel()
-        N.check(self._lib.pmcts_backup(self._h, a.ptr(table, "u32"), a.ptr(parent, "i32"), a.ptr(arm, "i8"),
-                                       n_leaf, a.ptr(leaf_node, "i32", n_leaf), a.ptr(leaf_slot, "i8", n_leaf),
-                                       a.ptr(leaf_bins, "u32", n_leaf * 12), a.mem_flag))
+        n_leaf = leaf_node.numel() // n_scen
+        N.check(self._lib.pmcts_backup(self._h, a.ptr(table, "u32", n_scen * n_nodes * 96), int(n_nodes),
+                                       int(n_scen), a.ptr(parent, "i32", n_nodes), a.ptr(arm, "i8", n_nodes),
+                                       n_leaf, a.ptr(leaf_node, "i32", n_scen * n_leaf),
+                                       a.ptr(leaf_slot, "i8", n_scen * n_leaf),
+                                       a.ptr(leaf_bins, "u32", n_scen * n_leaf * 12), a.mem_flag))
 
     def hist_stats(self, table, n_nodes, mean=None, visits=None):
         a = _Args()

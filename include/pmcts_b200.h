@@ -50,6 +50,7 @@ typedef struct pmcts_ctx pmcts_ctx;
 #define PMCTS_STEP_STOP_BEFORE_TERMINAL 0x1 /* step_batch: fixed-heading sweep of initialize_simulators (forest.py:239) */
 #define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
 #define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
+#define PMCTS_ROLL_ACCUMULATE 0x8           /* rollout_batch, device arrays only: add to leaf_bins / stats instead of zeroing them first */
 #define PMCTS_MEM_HOST 0x100                /* array arguments are host memory */
 
 /* arithmetic mode */
@@ -80,10 +81,16 @@ int pmcts_synchronize(pmcts_ctx *ctx);
 int pmcts_set_precision(pmcts_ctx *ctx, int mode);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);
-/* milliseconds the last timed kernel took on the ctx stream (cudaEvent pair recorded around every
- * launch while timing is enabled); returns <0 if nothing was timed. */
+/* While timing is enabled every kernel launch is bracketed by a cudaEvent pair on the ctx stream;
+ * pmcts_kernel_ms* synchronise the stream and return the accumulated device milliseconds (all
+ * kernels, or one PMCTS_KERNEL_* kind). */
 int pmcts_enable_timing(pmcts_ctx *ctx, int on);
 double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset);
+#define PMCTS_KERNEL_STEP 0
+#define PMCTS_KERNEL_ROLLOUT 1
+#define PMCTS_KERNEL_BACKUP 2
+#define PMCTS_KERNEL_OTHER 3
+double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset);
 
 /* Module globals the reference reads at call time -- Boat.FIT_VELOCITY / POLAR_* /
  * UNCERTAINTY_COEFF (simulatorTLKT.py:454-471), DESTINATION_ANGLE (:43), EARTH_RADIUS (:40). */
@@ -123,7 +130,8 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
  * mode), steps, status, bin (Hist bin of the reward, utils.py:34-47), frac, final_lat, final_lon;
  * traj_lat/traj_lon [traj_stride][n] positions after each transition (NaN where not reached).
  * leaf_bins (optional) [n_leaf][12] uint32: per-leaf histogram of the replicas' reward bins.
- * stats (optional) [4] doubles: {count, sum t_arr, sum t_arr^2, arrived} over all rollouts. */
+ * stats (optional) [8] doubles over all rollouts: {rollouts with an arrival time, sum t_arr,
+ * sum t_arr^2, arrived, transitions, rollouts, 0, 0}. */
 int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],
                         const double dest[2], double tmin, const double *prefix,
                         const int32_t *prefix_len, int prefix_stride, const pmcts_noise *noise,
@@ -132,12 +140,18 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
                         double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
                         int flags);
 
-/* ---- K3: Node.back_up (worker.py:55-70) / MasterNode.add_reward* (master_node.py:34-54) --------
- * table[node][8][12] uint32 visit counts.  For every leaf l: table[leaf_node[l]][leaf_slot[l]] +=
- * leaf_bins[l], then for every ancestor chain node x -> parent[x]: table[parent[x]][arm[x]] +=
- * leaf_bins[l] (arm[x] = index in ACTIONS of the action that expanded x). */
-int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, const int32_t *parent, const int8_t *arm,
-                 int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
+/* ---- K3: Node.back_up (worker.py:55-70) / MasterNode.add_reward* + the ancestor walk of
+ * Tree.integrate_buffer (master_node.py:34-54, worker.py:358-378) -------------------------------
+ * table[scen][node][8][12] uint32 visit counts for n_scen scenarios of n_nodes nodes each (a worker
+ * tree is the n_scen = 1 case; the replicated master table has one slice per scenario).  The tree
+ * shape is shared: parent[node] (-1 for the root) and arm[node] = index in ACTIONS of the action
+ * that expanded `node`.  For scenario s and leaf l, with c = leaf_bins[s][l][0..12):
+ *   table[s][leaf_node[s][l]][leaf_slot[s][l]] += c        (the random slot of worker.py:62-63)
+ *   table[s][parent[x]][arm[x]] += c  for x = leaf, parent(leaf), ... up to the root's child.
+ * One launch covers all scenarios; additions are integer atomics, so the result is exact and
+ * independent of the order. */
+int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, const int32_t *parent,
+                 const int8_t *arm, int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
                  const uint32_t *leaf_bins, int flags);
 
 /* Per-(node, action) binned means and visit totals of a histogram table (Hist.get_mean,

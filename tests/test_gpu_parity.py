@@ -282,7 +282,7 @@ def test_device_pointer_path_and_backup(eng):
     slot = np.random.default_rng(0).integers(0, 8, n_leaf).astype(np.int8)
     table = torch.zeros(n_nodes * 96, dtype=torch.int32, device=dev)
     t = lambda a: torch.as_tensor(a, device=dev)  # noqa: E731
-    eng.backup(table, t(parent), t(arm), t(leaf_node), t(slot), out["leaf_bins"])
+    eng.backup(table, n_nodes, t(parent), t(arm), t(leaf_node), t(slot), out["leaf_bins"])
     want = np.zeros((n_nodes, 8, 12), np.int64)
     for l in range(n_leaf):
         node = leaf_node[l]
