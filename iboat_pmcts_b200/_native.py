@@ -24,7 +24,7 @@ ERR_NO_DEVICE = -3
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
-    "pmcts_synchronize", "pmcts_set_precision", "pmcts_launch_count", "pmcts_enable_timing",
+    "pmcts_synchronize", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_launch_count", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_backup", "pmcts_hist_stats",
 ]
@@ -65,6 +65,9 @@ def lib():
     L.pmcts_reset_stream.argtypes = [vp]
     L.pmcts_synchronize.argtypes = [vp]
     L.pmcts_set_precision.argtypes = [vp, i32]
+    L.pmcts_set_fast_margins.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
+    L.pmcts_last_redo_count.argtypes = [vp]
+    L.pmcts_last_redo_count.restype = i64
     L.pmcts_launch_count.argtypes = [vp]
     L.pmcts_launch_count.restype = i64
     L.pmcts_enable_timing.argtypes = [vp, i32]

@@ -4,6 +4,7 @@
 //        (see __graft_entry__.build()).  Depends on the CUDA runtime only.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -14,6 +15,8 @@
 #include <vector>
 
 #include "pmcts_device.cuh"
+#include "pmcts_fast.cuh"
+#include "pmcts_host.h"
 
 namespace pmcts {
 
@@ -60,24 +63,33 @@ __global__ void get_wind_kernel(ScenarioView sc, int64_t n, const int32_t *__res
 // K1 -- Simulator.doStep for n boats, nsteps transitions fused in one launch.
 // One thread per boat; state lives in registers across the steps; headings are re-read once per
 // segment (coalesced, [segment][boat]).
-template <int kMode>
 __global__ void __launch_bounds__(kBlock)
 step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
                   double *__restrict__ lat_io, double *__restrict__ lon_io,
                   double *__restrict__ prev_lat, double *__restrict__ prev_lon,
                   const double *__restrict__ heading, int seg_len, NoiseView nz,
                   uint8_t *__restrict__ status_io, double *__restrict__ traj_lat,
-                  double *__restrict__ traj_lon, int flags) {
+                  double *__restrict__ traj_lon, int flags, const int32_t *__restrict__ j_resume,
+                  const uint32_t *__restrict__ any_resume) {
+    // Resume mode (j_resume != NULL): only the boats the mixed-precision kernel handed over
+    // (status kStNeedsLiteral) run, each from the step it stopped at.
+    if (any_resume && *any_resume == 0) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    int st = status_io ? status_io[i] : PMCTS_ST_OK;
+    int j0 = 0;
+    if (j_resume) {
+        if (st != fast::kStNeedsLiteral) return;
+        st = PMCTS_ST_OK;
+        j0 = j_resume[i];
+    }
     int k = k_io[i];
     double lat = lat_io[i], lon = lon_io[i];
     double pla = prev_lat ? prev_lat[i] : lat, plo = prev_lon ? prev_lon[i] : lon;
-    int st = status_io ? status_io[i] : PMCTS_ST_OK;
     NoiseStream ns;
     double h = 0.0;
-    for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) {
-        if (j % seg_len == 0) h = heading[(size_t)(j / seg_len) * n + i];
+    for (int j = j0; j < nsteps && st == PMCTS_ST_OK; ++j) {
+        if (j % seg_len == 0 || j == j0) h = heading[(size_t)(j / seg_len) * n + i];
         if (flags & PMCTS_STEP_STOP_BEFORE_TERMINAL) {  // forest.py:239
             if (k + 1 >= sc.nT) { st = PMCTS_ST_PAST_HORIZON; break; }
             if (is_terminal(sc, k + 1, lat, lon)) {
@@ -85,7 +97,7 @@ step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t
                 break;
             }
         }
-        const double z = ns.draw<kMode == PMCTS_PREC_FAST>(nz, n, i, j);
+        const double z = ns.draw<false>(nz, n, i, j);
         const double la0 = lat, lo0 = lon;
         st = do_step_literal(sc, bp, k, lat, lon, h, z);
         if (st == PMCTS_ST_OK) {
@@ -103,33 +115,57 @@ step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t
     if (status_io) status_io[i] = (uint8_t)st;
 }
 
-struct RolloutArgs {
-    int64_t n_leaf;
-    int replicas;
-    double root_k, root_lat, root_lon, dest_lat, dest_lon, tmin;
-    const double *prefix;
-    const int32_t *prefix_len;
-    int prefix_stride;
-    double *reward, *t_arr;
-    int32_t *steps;
-    uint8_t *status;
-    int32_t *bin;
-    double *frac, *final_lat, *final_lon, *traj_lat, *traj_lon;
-    int traj_stride;
-    uint32_t *leaf_bins;
-    double *stats;
-    int flags;
-};
+// Per-leaf reduction of the reward bins and the plan-evaluation statistics, shared by the literal and
+// the mixed-precision rollout kernels.  Lanes holding the same (leaf, bin) find each other with one
+// MATCH; the lowest lane of each group adds the group's size to leaf_bins[leaf][bin].
+__device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned warp_mask, bool counted,
+                                                int64_t leaf, int bin, int st, int nstep, double ta) {
+    const int lane = threadIdx.x & 31;
+    if (a.leaf_bins) {
+        const unsigned long long key =
+            counted ? ((unsigned long long)leaf << 4) | (unsigned)bin : ~0ull - (unsigned)lane;
+        const unsigned peers = __match_any_sync(warp_mask, key);
+        if (counted && lane == __ffs(peers) - 1)
+            atomicAdd(&a.leaf_bins[leaf * 12 + bin], (uint32_t)__popc(peers));
+    }
+    if (a.stats) {
+        const bool has_t = counted && !isnan(ta);
+        const int c_t = __reduce_add_sync(warp_mask, has_t ? 1 : 0);
+        const int c_arr = __reduce_add_sync(warp_mask, (counted && st == PMCTS_ST_ARRIVED) ? 1 : 0);
+        const int c_steps = __reduce_add_sync(warp_mask, counted ? nstep : 0);
+        const int c_roll = __reduce_add_sync(warp_mask, counted ? 1 : 0);
+        double s1 = has_t ? ta : 0.0, s2 = has_t ? ta * ta : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(warp_mask, s1, off);
+            s2 += __shfl_xor_sync(warp_mask, s2, off);
+        }
+        if (lane == __ffs(warp_mask) - 1) {
+            if (c_t) {
+                atomicAdd(&a.stats[0], (double)c_t);
+                atomicAdd(&a.stats[1], s1);
+                atomicAdd(&a.stats[2], s2);
+            }
+            if (c_arr) atomicAdd(&a.stats[3], (double)c_arr);
+            atomicAdd(&a.stats[4], (double)c_steps);
+            atomicAdd(&a.stats[5], (double)c_roll);
+        }
+    }
+}
 
-// K2 / K4 / K5 -- one default-policy rollout per thread (worker.py:255-300), reward binned and
-// reduced per leaf with warp votes, optional (count, sum t, sum t^2, arrived) reduction for plan
-// evaluation (isochrones.py:537-550).
-template <int kMode>
+// K2 / K4 / K5, literal fp64 -- one default-policy rollout per thread (worker.py:255-300), reward
+// binned and reduced per leaf, optional (count, sum t, sum t^2, arrived) reduction for plan
+// evaluation (isochrones.py:537-550).  With a work list (a.work_list) the kernel runs only the listed
+// rollouts, grid-striding over *a.work_count: that is how the rollouts the mixed-precision kernel
+// could not decide are finished.
 __global__ void __launch_bounds__(kBlock)
 rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a) {
     const int64_t n = a.n_leaf * a.replicas;
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = r < n;
+    const int64_t total = a.work_list ? (int64_t)*a.work_count : n;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = base + threadIdx.x;
+    const bool live = t < total;
+    const int64_t r = live ? (a.work_list ? (int64_t)a.work_list[t] : t) : 0;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     int bin = 0, st = PMCTS_ST_OK, nstep_out = 0;
     int64_t leaf = 0;
@@ -147,7 +183,7 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
         const int plen = a.prefix_len ? a.prefix_len[leaf] : 0;
 
         auto step = [&](double action) {
-            const double z = ns.draw<kMode == PMCTS_PREC_FAST>(nz, n, r, nstep);
+            const double z = ns.draw<false>(nz, n, r, nstep);
             const double la0 = blat, lo0 = blon;
             st = do_step_literal(sc, bp, k, blat, blon, action, z);
             if (st == PMCTS_ST_OK) {
@@ -216,33 +252,98 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
         if (a.final_lat) a.final_lat[r] = blat;
         if (a.final_lon) a.final_lon[r] = blon;
     }
-    // ---- per-leaf reduction of the reward bins: lanes of the same leaf vote, one lane adds -------
-    if (a.leaf_bins && warp_mask) {
-        if (live) {
-            const unsigned peers = __match_any_sync(warp_mask, leaf);
-            const int leader = __ffs(peers) - 1;
-            const int lane = threadIdx.x & 31;
-#pragma unroll
-            for (int b = 0; b < 12; ++b) {
-                const unsigned votes = __ballot_sync(warp_mask, bin == b) & peers;
-                if (lane == leader && votes) atomicAdd(&a.leaf_bins[leaf * 12 + b], (uint32_t)__popc(votes));
-            }
+    reduce_rollouts(a, warp_mask, live, leaf, bin, st, nstep_out, ta);
+    }
+}
+
+// K2 / K4 / K5, mixed precision -- same contract; the arithmetic is pmcts_fast.cuh.  A rollout whose
+// decisions fell inside the error margins writes nothing: its id goes to a.redo_list and the literal
+// kernel above finishes it (same stream, next launch).
+__global__ void __launch_bounds__(kBlock)
+rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a) {
+    const int64_t n = a.n_leaf * a.replicas;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < n;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
+    fast::RollOut o;
+    o.st = PMCTS_ST_OK; o.nstep = 0; o.bin = 0; o.why = 0; o.ta = NAN;
+    bool counted = false;
+    if (live) {
+        fast::rollout_one(sc, bp, nz, a, n, r, o);
+        if (o.why) {
+            a.redo_list[atomicAdd(a.redo_count, 1u)] = (uint32_t)r;
+        } else {
+            counted = true;
+            if (a.reward) a.reward[r] = o.rw;
+            if (a.t_arr) a.t_arr[r] = o.ta;
+            if (a.steps) a.steps[r] = o.nstep;
+            if (a.status) a.status[r] = (uint8_t)o.st;
+            if (a.bin) a.bin[r] = o.bin;
+            if (a.frac) a.frac[r] = (o.st == PMCTS_ST_ARRIVED) ? o.frac : NAN;
+            if (a.final_lat) a.final_lat[r] = o.lat;
+            if (a.final_lon) a.final_lon[r] = o.lon;
         }
     }
-    if (a.stats && warp_mask) {
-        if (live) {
-            const bool has_t = !isnan(ta);
-            double v[6] = {has_t ? 1.0 : 0.0, has_t ? ta : 0.0, has_t ? ta * ta : 0.0,
-                           (st == PMCTS_ST_ARRIVED) ? 1.0 : 0.0, (double)nstep_out, 1.0};
-#pragma unroll
-            for (int q = 0; q < 6; ++q)
-                for (int off = 16; off > 0; off >>= 1) v[q] += __shfl_xor_sync(warp_mask, v[q], off);
-            if ((threadIdx.x & 31) == (__ffs(warp_mask) - 1)) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) atomicAdd(&a.stats[q], v[q]);
+    reduce_rollouts(a, warp_mask, counted, r / a.replicas, o.bin, o.st, o.nstep, o.ta);
+}
+
+// K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
+// step_batch_kernel).  A boat the fp32 formulas do not cover (heading outside [0, 360), a step longer
+// than fast::kMaxStepAngle) stops with the internal status kStNeedsLiteral and its step index in
+// j_resume; step_batch_kernel then finishes it.
+__global__ void __launch_bounds__(kBlock)
+step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
+                 double *__restrict__ lat_io, double *__restrict__ lon_io, double *__restrict__ prev_lat,
+                 double *__restrict__ prev_lon, const double *__restrict__ heading, int seg_len, NoiseView nz,
+                 uint8_t *__restrict__ status_io, double *__restrict__ traj_lat, double *__restrict__ traj_lon,
+                 int flags, int32_t *__restrict__ j_resume, uint32_t *__restrict__ any_resume) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = k_io[i];
+    double lat = lat_io[i], lon = lon_io[i];
+    double pla = prev_lat ? prev_lat[i] : lat, plo = prev_lon ? prev_lon[i] : lon;
+    int st = status_io ? status_io[i] : PMCTS_ST_OK;
+    fast::Noise ns;
+    float sh = 0.0f, ch = 1.0f;
+    int seg_left = 0;
+    const double *hp = heading + i;
+    for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) {
+        if (seg_left == 0) {
+            seg_left = seg_len;
+            const bool ok = fast::heading_unit(*hp, sh, ch);
+            hp += n;
+            if (!ok) { st = fast::kStNeedsLiteral; j_resume[i] = j; break; }
+        }
+        --seg_left;
+        if (flags & PMCTS_STEP_STOP_BEFORE_TERMINAL) {  // forest.py:239
+            if (k + 1 >= sc.nT) { st = PMCTS_ST_PAST_HORIZON; break; }
+            if (is_terminal(sc, k + 1, lat, lon)) {
+                st = (k + 1 >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
+                break;
             }
         }
+        float s, c;
+        fast::sincos_lat(lat, s, c);
+        const fast::GridPos g = fast::grid_pos(sc, lat, lon);
+        const float z = ns.draw(nz, n, i, j);
+        const double la0 = lat, lo0 = lon;
+        fast::Move m;
+        st = fast::fast_step(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
+        if (st == fast::kStNeedsLiteral) { j_resume[i] = j; break; }
+        if (st == PMCTS_ST_OK) {
+            pla = la0;
+            plo = lo0;
+            if (traj_lat) traj_lat[(size_t)j * n + i] = lat;
+            if (traj_lon) traj_lon[(size_t)j * n + i] = lon;
+        }
     }
+    if (st == fast::kStNeedsLiteral) *any_resume = 1u;
+    k_io[i] = k;
+    lat_io[i] = lat;
+    lon_io[i] = lon;
+    if (prev_lat) prev_lat[i] = pla;
+    if (prev_lon) prev_lon[i] = plo;
+    if (status_io) status_io[i] = (uint8_t)st;
 }
 
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
@@ -340,6 +441,11 @@ struct pmcts_ctx {
     // grow-only device scratch for PMCTS_MEM_HOST calls
     char *scratch = nullptr;
     size_t scratch_cap = 0, scratch_used = 0;
+    // grow-only device work area of the mixed-precision kernels: [0] redo / resume counter,
+    // then the rollout ids (uint32) or per-boat resume steps (int32) and a status byte per boat
+    char *work = nullptr;
+    size_t work_cap = 0;
+    bool margins_set = false;
     int64_t launches = 0;
     bool timing = false;
     struct Timed { cudaEvent_t a, b; int kind; };
@@ -466,6 +572,28 @@ struct LaunchTimer {
 
 int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 
+// Work area of the mixed-precision kernels: 256 B header (counter) + `bytes` payload.
+int ensure_work(pmcts_ctx *ctx, size_t bytes) {
+    const size_t need = 256 + bytes;
+    if (need > ctx->work_cap) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->work) CUDA_TRY(cudaFree(ctx->work));
+        ctx->work = nullptr;
+        ctx->work_cap = 0;
+        const size_t cap = need + need / 4;
+        CUDA_TRY(cudaMalloc((void **)&ctx->work, cap));
+        ctx->work_cap = cap;
+    }
+    return PMCTS_OK;
+}
+
+// Can this launch run on the fp32 kernels?  (Otherwise the literal fp64 kernels run: still the GPU.)
+bool fast_eligible(const pmcts_ctx *ctx, const Scenario *sc) {
+    const BoatParams &p = ctx->params;
+    return ctx->precision == PMCTS_PREC_FAST && sc->view.fast_ok && p.pofsail_min >= 0.0 &&
+           p.pofsail_min <= 90.0 && p.pofsail_max >= 90.0 && p.pofsail_max <= 180.0 && p.wind_max > 0.0;
+}
+
 int find_scenario(pmcts_ctx *ctx, int scen, Scenario **out) {
     auto it = ctx->scenarios.find(scen);
     if (it == ctx->scenarios.end()) return fail(PMCTS_ERR_SCENARIO, "scenario slot %d not uploaded", scen);
@@ -532,6 +660,7 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->work) cudaFree(ctx->work);
     for (auto &p : ctx->timed) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto &p : ctx->event_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaStreamDestroy(ctx->own_stream);
@@ -602,10 +731,7 @@ int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, do
                      double pofsail_max, double sigma_coeff, double dest_angle, double earth_radius) {
     if (!ctx || !polar) return fail(PMCTS_ERR_ARG, "NULL argument");
     BoatParams &p = ctx->params;
-    for (int i = 0; i < 36; ++i) {
-        p.polar[i] = polar[i];
-        p.polar_f[i] = (float)polar[i];
-    }
+    for (int i = 0; i < 36; ++i) p.polar[i] = polar[i];
     p.wind_max = wind_max;
     p.pofsail_min = pofsail_min;
     p.pofsail_max = pofsail_max;
@@ -614,7 +740,35 @@ int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, do
     p.earth_radius = earth_radius;
     p.cos_pmin = std::cos(kPi * pofsail_min / 180.0);
     p.cos_pmax = std::cos(kPi * pofsail_max / 180.0);
+    derive_fast_params(p);
+    if (!ctx->margins_set) default_fast_margins(p);
     return PMCTS_OK;
+}
+
+int pmcts_set_fast_margins(pmcts_ctx *ctx, double angle, double along, double near_miss2, double box, double bin) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    BoatParams &p = ctx->params;
+    if (angle < 0 && along < 0 && near_miss2 < 0 && box < 0 && bin < 0) {
+        default_fast_margins(p);
+        ctx->margins_set = false;
+        return PMCTS_OK;
+    }
+    if (angle >= 0) p.margin_angle = (float)angle;
+    if (along >= 0) p.margin_along = (float)along;
+    if (near_miss2 >= 0) p.near_miss2 = (float)near_miss2;
+    if (box >= 0) p.margin_box = (float)box;
+    if (bin >= 0) p.margin_bin = bin;
+    ctx->margins_set = true;
+    return PMCTS_OK;
+}
+
+int64_t pmcts_last_redo_count(pmcts_ctx *ctx) {
+    if (!ctx || !ctx->work) return 0;
+    DeviceGuard g(ctx->device);
+    uint32_t c = 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&c, ctx->work, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)c;
 }
 
 int pmcts_scenario_free(pmcts_ctx *ctx, int scen) {
@@ -645,24 +799,10 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     if (rc) return rc;
 
     // per-instant time cell and weight (SciPy find_indices semantics on the time axis)
-    std::vector<int> it(nT);
-    std::vector<double> wt(nT), dt(nT, 0.0);
-    std::vector<uint8_t> valid(nT);
-    for (int k = 0; k < nT; ++k) {
-        const double t = sim_times[k];
-        valid[k] = (t >= wtime[0] && t <= wtime[nt - 1]) ? 1 : 0;
-        int lo = 0, hi = nt;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (wtime[mid] <= t) lo = mid + 1; else hi = mid;
-        }
-        int i = lo - 1;
-        if (i < 0) i = 0;
-        if (i > nt - 2) i = nt - 2;
-        it[k] = i;
-        wt[k] = valid[k] ? (t - wtime[i]) / (wtime[i + 1] - wtime[i]) : 0.0;
-        if (k + 1 < nT) dt[k] = (sim_times[k + 1] - sim_times[k]) * 86400.0;
-    }
+    const TimeCells tc = time_cells(wtime, nt, sim_times, nT);
+    const std::vector<int> &it = tc.it;
+    const std::vector<double> &wt = tc.wt, &dt = tc.dt;
+    const std::vector<uint8_t> &valid = tc.valid;
 
     const size_t plane = (size_t)nlat * nlon, cells = plane * nT;
     const size_t esz = dtype == 0 ? 8 : 4;
@@ -671,7 +811,8 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     const size_t o_times = o_slab32 + al(cells * sizeof(float2));
     const size_t o_dt = o_times + al(nT * sizeof(double));
     const size_t o_valid = o_dt + al(nT * sizeof(double));
-    const size_t total = o_valid + al(nT);
+    const size_t o_dt32 = o_valid + al(nT);
+    const size_t total = o_dt32 + al(nT * sizeof(float));
     // temporaries: raw grid + time cells
     const size_t raw = (size_t)nt * plane * esz;
     const size_t t_u = 0, t_v = al(raw), t_it = t_v + al(raw), t_wt = t_it + al(nT * sizeof(int));
@@ -703,6 +844,7 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     UP_TRY(cudaMemcpyAsync(base + o_times, sim_times, nT * sizeof(double), cudaMemcpyHostToDevice, s));
     UP_TRY(cudaMemcpyAsync(base + o_dt, dt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
     UP_TRY(cudaMemcpyAsync(base + o_valid, valid.data(), nT, cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_dt32, tc.dt32.data(), nT * sizeof(float), cudaMemcpyHostToDevice, s));
     {
         LaunchTimer lt(ctx);
         const int grid = (int)((cells + 255) / 256);
@@ -742,6 +884,18 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.box_lon_lo = box[2];
     vw.box_lon_hi = box[3];
     vw.tmax = sim_times[nT - 1];
+    vw.dt_sec32 = (const float *)(base + o_dt32);
+    vw.kv_lo = tc.kv_lo;
+    vw.kv_hi = tc.kv_hi;
+    vw.max_abs_lat = (float)std::fmax(std::fabs(wlat[0]), std::fabs(wlat[nlat - 1]));
+    vw.dt_max = tc.dt_max;
+    vw.box_fa_lo = (float)((box[0] - vw.lat0) * inv_dlat);
+    vw.box_fa_hi = (float)((box[1] - vw.lat0) * inv_dlat);
+    vw.box_fo_lo = (float)((box[2] - vw.lon0) * inv_dlon);
+    vw.box_fo_hi = (float)((box[3] - vw.lon0) * inv_dlon);
+    // the fp32 kernels assume |lat| <= 90 on the grid (their sin / cos kernels cover [-pi/2, pi/2])
+    // and one contiguous run of valid instants
+    vw.fast_ok = (tc.contiguous && vw.max_abs_lat <= 90.0f) ? 1 : 0;
     ctx->scenarios[scen] = sc;
     return PMCTS_OK;
 }
@@ -793,16 +947,36 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         (rc = st.out(traj_lat, (size_t)nsteps * n, 0xFF)) || (rc = st.out(traj_lon, (size_t)nsteps * n, 0xFF)))
         return rc;
     if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)nsteps * n))) return rc;
-    {
+    if (fast_eligible(ctx, sc)) {
+        // work area: counter | j_resume[n] | status[n] (when the caller passes no status array)
+        const size_t o_status = al(n * sizeof(int32_t));
+        if ((rc = ensure_work(ctx, o_status + al(n)))) return rc;
+        uint32_t *any_resume = (uint32_t *)ctx->work;
+        int32_t *j_resume = (int32_t *)(ctx->work + 256);
+        uint8_t *status_dev = status;
+        CUDA_TRY(cudaMemsetAsync(any_resume, 0, sizeof(uint32_t), ctx->stream));
+        if (!status_dev) {
+            status_dev = (uint8_t *)(ctx->work + 256 + o_status);
+            CUDA_TRY(cudaMemsetAsync(status_dev, 0, n, ctx->stream));
+        }
+        {
+            LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
+            step_fast_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
+                status_dev, traj_lat, traj_lon, flags, j_resume, any_resume);
+        }
+        CUDA_TRY(cudaGetLastError());
+        {
+            LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
+            step_batch_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
+                status_dev, traj_lat, traj_lon, flags, j_resume, any_resume);
+        }
+    } else {
         LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
-        if (ctx->precision == PMCTS_PREC_FAST)
-            step_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(
-                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
-                status, traj_lat, traj_lon, flags);
-        else
-            step_batch_kernel<PMCTS_PREC_F64><<<grid_for(n), kBlock, 0, ctx->stream>>>(
-                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
-                status, traj_lat, traj_lon, flags);
+        step_batch_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(
+            sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz, status,
+            traj_lat, traj_lon, flags, nullptr, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
     return st.finish();
@@ -869,12 +1043,34 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
     a.leaf_bins = leaf_bins;
     a.stats = stats;
     a.flags = flags;
-    {
+    // the fp32 kernels also need the destination within 90 degrees of every grid point (their
+    // sin / cos kernels cover [-pi/2, pi/2] for latD - lat and lonD - lon)
+    const ScenarioView &vw = sc->view;
+    const bool dest_ok = std::fabs(dest[0]) <= 90.0 && std::fabs(dest[0] - vw.lat0) <= 89.0 &&
+                         std::fabs(dest[0] - vw.lat_last) <= 89.0 && std::fabs(dest[1] - vw.lon0) <= 89.0 &&
+                         std::fabs(dest[1] - vw.lon_last) <= 89.0;
+    if (fast_eligible(ctx, sc) && dest_ok && n < (int64_t)1 << 31) {
+        if ((rc = ensure_work(ctx, (size_t)n * sizeof(uint32_t)))) return rc;
+        a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
+        a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
+        a.redo_count = (uint32_t *)ctx->work;
+        a.redo_list = (uint32_t *)(ctx->work + 256);
+        CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
+        {
+            LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
+            rollout_fast_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
+        }
+        CUDA_TRY(cudaGetLastError());
+        a.work_list = a.redo_list;
+        a.work_count = a.redo_count;
+        {
+            LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
+            const int grid = (int)std::min<int64_t>(grid_for(n), 2 * 148);
+            rollout_batch_kernel<<<grid, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
+        }
+    } else {
         LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
-        if (ctx->precision == PMCTS_PREC_FAST)
-            rollout_batch_kernel<PMCTS_PREC_FAST><<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, ctx->params, nz, a);
-        else
-            rollout_batch_kernel<PMCTS_PREC_F64><<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, ctx->params, nz, a);
+        rollout_batch_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
     }
     CUDA_TRY(cudaGetLastError());
     return st.finish();

@@ -10,41 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/pmcts_b200.h"
+#include "pmcts_types.h"
 
 namespace pmcts {
-
-constexpr double kPi = 3.141592653589793;
-constexpr double kDegToRad = kPi / 180.0;
-
-// Device view of one uploaded scenario (see pmcts_scenario_upload): one time-blended (u, v) slab per
-// simulator instant, so a transition gathers 4 grid corners instead of 8 and needs no time weight.
-struct ScenarioView {
-    const double2 *slab64;  // [nT][nlat][nlon] (u, v) fp64
-    const float2 *slab32;   // same, rounded to fp32 (Fast mode)
-    const double *times;    // [nT] simulator instants, days
-    const double *dt_sec;   // [nT] (times[k+1]-times[k])*86400, last entry unused
-    const uint8_t *k_valid; // [nT] 1 if times[k] lies inside the weather time axis
-    int nT, nlat, nlon;
-    double lat0, lon0, inv_dlat, inv_dlon, lat_last, lon_last;
-    double box_lat_lo, box_lat_hi, box_lon_lo, box_lon_hi;
-    double tmax;
-};
-
-// Boat.* / module constants (pmcts_set_params), plus values derived once on the host.
-struct BoatParams {
-    double polar[36];
-    double wind_max, pofsail_min, pofsail_max, sigma_coeff;
-    double dest_angle, earth_radius;
-    double cos_pmin, cos_pmax;  // cos(pi * POLAR_{MIN,MAX}_POFSAIL / 180)
-    float polar_f[36];
-};
-
-struct NoiseView {
-    int mode;
-    const double *z;
-    uint64_t seed, stream, id0;
-};
 
 // ---- Philox4x32-10 (Salmon et al. 2011); counter layout documented in oracle/pmcts_oracle.c ----
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

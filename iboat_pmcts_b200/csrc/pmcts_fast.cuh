@@ -1,0 +1,554 @@
+// pmcts_b200 mixed-precision ("fast") simulator: the same transition as pmcts_device.cuh, re-derived
+// so that an fp32 datapath is enough.
+//
+// The reference (code/model/simulatorTLKT.py:132-216, code/solver/worker.py:255-300, 380-415) works
+// on absolute latitudes / longitudes through full-range fp64 transcendentals.  Evaluated in fp32 those
+// formulas lose the answer to cancellation (a step moves the boat by 1e-4 .. 1e-2 rad on top of a
+// position of ~1 rad).  Here every quantity that is small is computed *as a small quantity*:
+//
+//   * the position is kept in fp64 degrees, but a step only produces the increments
+//         sin(dlat) = a - s g,   sin(dlon) = b / H,     with a = sin(d) cos(hdg), b = sin(d) sin(hdg),
+//         A = c cos(d) - s a,  H = sqrt(A^2 + b^2) = cos(lat'),  g = b^2 / (H + A),  (s, c) = sin/cos(lat)
+//     which is Simulator.getDestination (simulatorTLKT.py:132-166) rewritten exactly (no series in d);
+//     (s, c) only scale small numbers, so fp32 is enough for them;
+//   * the bearing to the destination (simulatorTLKT.py:124-128) and the arrival test of
+//     Tree.is_state_at_dest (worker.py:380-415, including its latitude-as-colatitude mapping,
+//     simulatorTLKT.py:233-238) are written in differences to the current position:
+//         y = sin(latD - lat) + s cD (1 - cos(lonD - lon)),  x = cD sin(lonD - lon)
+//         D.(A x B) = dBy r + dDy q,  |A x B|^2 = dBy^2 + q^2        (see fast_at_dest)
+//   * the point of sail is the angle between the heading and the wind vector (a dot / cross
+//     product), so the wind direction never goes through atan2 / mod 360 / abs;
+//   * the polar polynomial is evaluated in variables centred on its domain (BoatParams::pc).
+//
+// What fp32 cannot guarantee is the *decision* of a test whose two sides are closer than the
+// rounding noise (arrival angle against DESTINATION_ANGLE, overshoot test, terminal box, histogram
+// bin edges).  Every such test carries a margin; a rollout that lands inside one is not decided here:
+// it is queued (RolloutArgs::redo_list) and re-run by the literal fp64 kernel.
+//
+// Everything is PMCTS_HD so that tests/fastmodel can compile the same code for the host and measure
+// its error against the oracle without a GPU (the product never runs the host build).
+#pragma once
+#include <math.h>
+
+#include "pmcts_types.h"
+
+namespace pmcts {
+namespace fast {
+
+// ---- hardware approximations (MUFU) with host stand-ins ------------------------------------------
+PMCTS_HD float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+PMCTS_HD float rsqrt_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+PMCTS_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+PMCTS_HD int imin(int a, int b) { return a < b ? a : b; }
+PMCTS_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ---- polynomial kernels (minimax fits, coefficients rounded to fp32; max abs error after rounding:
+// sinc 8e-9, cosc 3e-9 on |x| <= pi/2, atan 4e-8 on [0, 1]) -----------------------------------------
+// sin(x) = x * sinc_poly(x^2), 1 - cos(x) = x^2 * cosc_poly(x^2), |x| <= pi/2
+PMCTS_HD float sinc_poly(float y) {
+    float p = 2.605224902e-06f;
+    p = fma_(p, y, -1.980907528e-04f);
+    p = fma_(p, y, 8.333051063e-03f);
+    p = fma_(p, y, -1.666665799e-01f);
+    return fma_(p, y, 1.0f);
+}
+PMCTS_HD float cosc_poly(float y) {
+    float p = 2.633458343e-07f;
+    p = fma_(p, y, -2.477660893e-05f);
+    p = fma_(p, y, 1.388868840e-03f);
+    p = fma_(p, y, -4.166666179e-02f);
+    return fma_(p, y, 0.5f);
+}
+// short forms for a step length |x| <= 0.1 rad (next terms: 2e-10 and 3e-11 relative)
+PMCTS_HD float sinc_small(float y) { return fma_(fma_(8.3333333e-03f, y, -1.6666667e-01f), y, 1.0f); }
+PMCTS_HD float cosc_small(float y) { return fma_(fma_(1.3888889e-03f, y, -4.1666667e-02f), y, 0.5f); }
+// asin(x) = x * asinc_small(x^2), |x| <= 0.12 (next term 3e-10 relative)
+PMCTS_HD float asinc_small(float y) {
+    return fma_(fma_(fma_(4.4642857e-02f, y, 7.5e-02f), y, 1.6666667e-01f), y, 1.0f);
+}
+// atan2(s, c) for s >= 0, result in [0, pi]
+PMCTS_HD float atan2_pos(float s, float c) {
+    const float ac = fabsf(c);
+    const float mx = fmaxf(s, ac), mn = fminf(s, ac);
+    const float t = mn * rcp_approx(mx);
+    const float y = t * t;
+    float p = 2.903537903e-03f;
+    p = fma_(p, y, -1.628295011e-02f);
+    p = fma_(p, y, 4.303927486e-02f);
+    p = fma_(p, y, -7.533668294e-02f);
+    p = fma_(p, y, 1.065467381e-01f);
+    p = fma_(p, y, -1.420713276e-01f);
+    p = fma_(p, y, 1.999305400e-01f);
+    p = fma_(p, y, -3.333309395e-01f);
+    p = fma_(p, y, 1.0f);
+    float r = t * p;
+    if (s > ac) r = 1.57079632679f - r;
+    if (c < 0.0f) r = 3.14159265359f - r;
+    return r;
+}
+
+// ---- noise: Philox4x32-10 + Box-Muller in fp32 (same counter layout as oracle/pmcts_oracle.c) ------
+PMCTS_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                            uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+PMCTS_HD void box_muller(uint32_t x0, uint32_t x1, float &z0, float &z1) {
+    // u = (x + 0.5) * 2^-32 in (0, 1); the angle is taken about pi so the hardware sin / cos stay in
+    // their accurate range: cos(2 pi u) = -cos(2 pi u - pi)
+    const float u0 = fminf(fma_((float)x0, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
+    const float th = fma_((float)x1, 1.4629180792671596e-09f, -3.14159265359f + 7.3145904e-10f);
+#if defined(__CUDA_ARCH__)
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u0));  // -2 ln(u0)
+    float s, c;
+    __sincosf(th, &s, &c);
+#else
+    const float r = sqrtf(-2.0f * logf(u0));
+    const float s = sinf(th), c = cosf(th);
+#endif
+    z0 = -r * c;
+    z1 = -r * s;
+}
+
+struct Noise {
+    float cache[4];
+    int cached_block;
+    PMCTS_HD Noise() : cached_block(-1) {}
+    PMCTS_HD float draw(const NoiseView &nz, int64_t n, int64_t i, int step) {
+        if (nz.mode == PMCTS_NOISE_INJECTED) return (float)nz.z[(size_t)step * n + i];
+        if (nz.mode == PMCTS_NOISE_NONE) return 0.0f;
+        const int block = step >> 2;
+        if (block != cached_block) {
+            const uint64_t boat = nz.id0 + (uint64_t)i;
+            uint32_t x[4];
+            philox4x32_10((uint32_t)boat, (uint32_t)(boat >> 32), (uint32_t)block, (uint32_t)nz.stream,
+                          (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), x);
+            box_muller(x[0], x[1], cache[0], cache[1]);
+            box_muller(x[2], x[3], cache[2], cache[3]);
+            cached_block = block;
+        }
+        const int q = step & 3;
+        return q == 0 ? cache[0] : q == 1 ? cache[1] : q == 2 ? cache[2] : cache[3];
+    }
+};
+
+// ---- position on the wind grid -------------------------------------------------------------------
+// Cell index and weights of SciPy's linear RegularGridInterpolator (weatherTLKT.py:377-378; cell
+// clipped to n-2 so that the last node is reached with weight 1); the index is taken in fp64, the
+// in-cell weight is an fp32 number in [0, 1].
+struct GridPos {
+    int ia, io;
+    float wa, wo;
+    float fa, fo;  // fractional index (terminal-box test)
+    bool inside;   // SciPy bounds_error=True
+};
+
+PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
+    GridPos g;
+    g.inside = lat >= sc.lat0 && lat <= sc.lat_last && lon >= sc.lon0 && lon <= sc.lon_last;
+    const double fa = (lat - sc.lat0) * sc.inv_dlat, fo = (lon - sc.lon0) * sc.inv_dlon;
+    g.ia = imin(imax((int)fa, 0), sc.nlat - 2);
+    g.io = imin(imax((int)fo, 0), sc.nlon - 2);
+    g.wa = (float)(fa - (double)g.ia);
+    g.wo = (float)(fo - (double)g.io);
+    g.fa = (float)fa;
+    g.fo = (float)fo;
+    return g;
+}
+
+// Simulator.getWind (simulatorTLKT.py:168-179) on the time-blended fp32 slab of instant k.
+PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u, float &v) {
+    const float2 *row0 = sc.slab32 + ((size_t)k * sc.nlat + g.ia) * sc.nlon + g.io;
+    const float2 *row1 = row0 + sc.nlon;
+#if defined(__CUDA_ARCH__)
+    const float2 c00 = __ldg(row0), c01 = __ldg(row0 + 1), c10 = __ldg(row1), c11 = __ldg(row1 + 1);
+#else
+    const float2 c00 = row0[0], c01 = row0[1], c10 = row1[0], c11 = row1[1];
+#endif
+    const float u0 = fma_(g.wo, c01.x - c00.x, c00.x), u1 = fma_(g.wo, c11.x - c10.x, c10.x);
+    const float v0 = fma_(g.wo, c01.y - c00.y, c00.y), v1 = fma_(g.wo, c11.y - c10.y, c10.y);
+    u = fma_(g.wa, u1 - u0, u0);
+    v = fma_(g.wa, v1 - v0, v0);
+}
+
+// ---- Boat.getDeterDyn (simulatorTLKT.py:473-502) ----------------------------------------------------
+PMCTS_HD float polar_centred(const BoatParams &bp, float x, float y) {
+    const float *c = bp.pc;
+    if (bp.polar_tri) {
+        // column j (power of y) has degree 5 - j in x
+        float c0 = c[30];
+        c0 = fma_(c0, x, c[24]); c0 = fma_(c0, x, c[18]); c0 = fma_(c0, x, c[12]); c0 = fma_(c0, x, c[6]); c0 = fma_(c0, x, c[0]);
+        float c1 = c[25];
+        c1 = fma_(c1, x, c[19]); c1 = fma_(c1, x, c[13]); c1 = fma_(c1, x, c[7]); c1 = fma_(c1, x, c[1]);
+        float c2 = c[20];
+        c2 = fma_(c2, x, c[14]); c2 = fma_(c2, x, c[8]); c2 = fma_(c2, x, c[2]);
+        float c3 = c[15];
+        c3 = fma_(c3, x, c[9]); c3 = fma_(c3, x, c[3]);
+        float c4 = fma_(c[10], x, c[4]);
+        float acc = c[5];
+        acc = fma_(acc, y, c4); acc = fma_(acc, y, c3); acc = fma_(acc, y, c2); acc = fma_(acc, y, c1);
+        return fma_(acc, y, c0);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 5; j >= 0; --j) {
+        float col = c[30 + j];
+#pragma unroll
+        for (int i = 4; i >= 0; --i) col = fma_(col, x, c[i * 6 + j]);
+        acc = fma_(acc, y, col);
+    }
+    return acc;
+}
+
+// Boat speed for wind (u, v) and the unit heading vector (sh, ch) = (sin, cos)(heading):
+// Weather.returnPolarVel (weatherTLKT.py:148-163) + point of sail (simulatorTLKT.py:203) +
+// Boat.getDeterDyn.  The wind blows *to* (u, v); the point of sail is the angle between the heading
+// and the direction the wind comes *from*, folded to [0, 180] -- i.e. the plain angle between the
+// two unit vectors (the reference's abs / 360 - p fold is that angle for headings in [0, 360)).
+PMCTS_HD float boat_speed(const BoatParams &bp, float u, float v, float sh, float ch) {
+    const float m2 = fma_(u, u, v * v);
+    float du = 0.0f, dv = 1.0f, mag = 0.0f;  // atan2(0, 0) = 0: a calm wind "blows north"
+    if (m2 > 0.0f) {
+        const float rm = rsqrt_approx(m2);
+        mag = m2 * rm;
+        du = u * rm;
+        dv = v * rm;
+    }
+    const float cosp = -fma_(du, sh, dv * ch);
+    const float sinp = fabsf(fma_(du, ch, -dv * sh));
+    const float p = atan2_pos(sinp, cosp) * 57.2957795131f;
+    const float w = fminf(mag, bp.wind_max_f);
+    const float pe = fminf(fmaxf(p, bp.pmin_f), bp.pmax_f);
+    float sp = polar_centred(bp, (pe - bp.p_mid) * bp.p_ihalf, fma_(w, bp.w_ihalf, -1.0f));
+    if (p < bp.pmin_f) sp *= bp.cos_pmin_f * rcp_approx(cosp);
+    else if (p > bp.pmax_f) sp *= bp.cos_pmax_f * rcp_approx(cosp);
+    return sp;
+}
+
+// ---- Simulator.getDestination (simulatorTLKT.py:132-166) in increments ---------------------------
+struct Move {
+    float sin_dlat;  // sin(lat' - lat)
+    float sin_dlon;  // sin(lon' - lon)
+    float h_dlon;    // 1 - cos(lon' - lon)
+    float cm1_dlat;  // cos(lat' - lat) - 1
+    float dlat, dlon;  // radians
+};
+
+// d = angular distance (rad, may be negative), (sh, ch) heading, (s, c) = sin/cos(lat).
+PMCTS_HD Move move_increments(float d, float sh, float ch, float s, float c) {
+    Move m;
+    const float d2 = d * d;
+    const float sd = d * sinc_small(d2);
+    const float e = d2 * cosc_small(d2);  // 1 - cos(d)
+    const float a = sd * ch, b = sd * sh;
+    const float cd = 1.0f - e;
+    const float A = fma_(c, cd, -s * a);
+    const float b2 = b * b;
+    const float n2 = fma_(A, A, b2);
+    const float rH = rsqrt_approx(n2);
+    const float H = n2 * rH;
+    const float g = b2 * rcp_approx(H + A);
+    m.sin_dlon = b * rH;
+    m.h_dlon = g * rH;
+    m.sin_dlat = fma_(-s, g, a);
+    m.cm1_dlat = fma_(c, g, -e);
+    m.dlat = m.sin_dlat * asinc_small(m.sin_dlat * m.sin_dlat);
+    m.dlon = m.sin_dlon * asinc_small(m.sin_dlon * m.sin_dlon);
+    return m;
+}
+
+// sin / cos of a latitude given in fp64 degrees
+PMCTS_HD void sincos_lat(double lat_deg, float &s, float &c) {
+    const float x = (float)(lat_deg * kDegToRad);
+    const float y = x * x;
+    s = x * sinc_poly(y);
+    c = fma_(-y, cosc_poly(y), 1.0f);
+}
+
+// Destination seen from the current position: the three numbers the bearing and the arrival test need.
+struct DestRel {
+    float sin_dlat;  // sin(latD - lat)
+    float sin_dlon;  // sin(lonD - lon)
+    float h_dlon;    // 1 - cos(lonD - lon)
+    float x_dlat;    // latD - lat, radians (for 1 - cos(latD - lat) in the arrival branch)
+};
+
+PMCTS_HD DestRel dest_rel(double lat, double lon, double dlat, double dlon) {
+    DestRel r;
+    const float xa = (float)((dlat - lat) * kDegToRad), xo = (float)((dlon - lon) * kDegToRad);
+    const float ya = xa * xa, yo = xo * xo;
+    r.sin_dlat = xa * sinc_poly(ya);
+    r.sin_dlon = xo * sinc_poly(yo);
+    r.h_dlon = yo * cosc_poly(yo);
+    r.x_dlat = xa;
+    return r;
+}
+
+// Unit vector of the initial bearing to the destination (simulatorTLKT.py:124-128):
+// (x, y) = (cD sin(dlon), c sD - s cD cos(dlon)) with y rewritten as sin(latD - lat) + s cD (1 - cos(dlon)).
+PMCTS_HD void bearing_unit(const DestRel &r, float s, float sD, float cD, float &sh, float &ch) {
+    (void)sD;
+    const float x = cD * r.sin_dlon;
+    const float y = fma_(s * cD, r.h_dlon, r.sin_dlat);
+    const float n2 = fma_(x, x, y * y);
+    if (n2 > 0.0f) {
+        const float rn = rsqrt_approx(n2);
+        sh = x * rn;
+        ch = y * rn;
+    } else {  // atan2(0, 0) = 0
+        sh = 0.0f;
+        ch = 1.0f;
+    }
+}
+
+// ---- Tree.is_state_at_dest (worker.py:380-415) -----------------------------------------------------
+// Points are mapped by Simulator.fromGeoToCartesian (simulatorTLKT.py:233-238), which uses the
+// latitude as a colatitude: P = (s cos(lon), s sin(lon), c) with (s, c) = sin/cos(lat).  Rotating
+// about the z axis so that A sits at longitude 0 leaves the test unchanged and gives, with B and D
+// written relative to A,
+//     dB = (sA cm1B + cA sdB - sB hB,  sB sin(dlonB),  cA cm1B - sA sdB)     (B - A)
+//     dD = (sA cm1D + cA sdD - sD hD,  sD sin(dlonD),  cA cm1D - sA sdD)     (D - A)
+//     D . (A x B) = dBy r + dDy q,   |A x B|^2 = dBy^2 + q^2,
+//     q = sdB - cA sB hB,   r = -sdD + cA sD hD
+// (sdX = sin(latX - latA), cm1X = cos(latX - latA) - 1, hX = 1 - cos(lonX - lonA)).
+// The distance of D to the plane (O, A, B) is |D . (A x B)| / |A x B|; the reference takes its asin
+// and compares with DESTINATION_ANGLE, then asks for (D - A).(B - D) >= 0 and reports
+// frac = (D - A).(B - A) / |B - A|^2.
+// Returns 1 arrived, 0 not arrived; *uncertain is set when a comparison is closer than its margin
+// (or the plane is degenerate: the reference raises ZeroDivisionError there).
+// Why a rollout was left to the literal kernel (RollOut::why bits).
+enum : int { kWhyAngle = 1, kWhyAlong = 2, kWhyBox = 4, kWhyBin = 8, kWhyDegenerate = 16, kWhyStep = 32, kWhyNearMiss = 64 };
+
+// The margins live in BoatParams (margin_*; defaults in pmcts_host.h, pmcts_set_fast_margins overrides).
+
+PMCTS_HD int fast_at_dest(const BoatParams &bp, const DestRel &rd, const Move &m, float sA, float cA, float sB,
+                          float sD, float &frac, int &why) {
+    const float dBy = sB * m.sin_dlon;
+    const float q = fma_(-cA * sB, m.h_dlon, m.sin_dlat);
+    const float r = fma_(cA * sD, rd.h_dlon, -rd.sin_dlat);
+    const float dDy = sD * rd.sin_dlon;
+    const float T = fma_(dBy, r, dDy * q);
+    const float N2 = fma_(dBy, dBy, q * q);
+    const float lhs = T * T, rhs = bp.sin2_dest_angle * N2;
+    if (!(N2 > 0.0f)) {  // A == B
+        why |= kWhyDegenerate;
+        return 0;
+    }
+    if (fabsf(lhs - rhs) <= bp.margin_angle * rhs) why |= kWhyAngle;
+    if (lhs > rhs) return 0;
+    const float dBx = fma_(sA, m.cm1_dlat, fma_(cA, m.sin_dlat, -sB * m.h_dlon));
+    const float dBz = fma_(cA, m.cm1_dlat, -sA * m.sin_dlat);
+    const float cm1D = -(rd.x_dlat * rd.x_dlat) * cosc_poly(rd.x_dlat * rd.x_dlat);
+    const float dDx = fma_(sA, cm1D, fma_(cA, rd.sin_dlat, -sD * rd.h_dlon));
+    const float dDz = fma_(cA, cm1D, -sA * rd.sin_dlat);
+    const float ab = fma_(dDx, dBx, fma_(dDy, dBy, dDz * dBz));
+    const float dd = fma_(dDx, dDx, fma_(dDy, dDy, dDz * dDz));
+    const float bb = fma_(dBx, dBx, fma_(dBy, dBy, dBz * dBz));
+    const float p = ab - dd;  // (D - A).(B - D)
+    if (fabsf(p) <= bp.margin_along * bb) why |= kWhyAlong;
+    if (p < 0.0f) {
+        // B stopped short of D by less than kNearMiss of a step: the next bearing is taken almost on top
+        // of the destination and amplifies the (tiny) position error by step / distance
+        if (dd - 2.0f * ab + bb < bp.near_miss2 * bb) why |= kWhyNearMiss;
+        return 0;
+    }
+    frac = ab * rcp_approx(bb);
+    // frac feeds the arrival time; the approximate reciprocal costs ~1e-7 relative
+    return 1;
+}
+
+// ---- one transition -------------------------------------------------------------------------------
+// The short series (sinc_small, cosc_small, asinc_small) hold to 3e-10 for angles below 0.12 rad; a
+// longer step (|speed * dt / R| or the longitude increment above kMaxStepAngle) is not taken here.
+constexpr float kMaxStepAngle = 0.12f;
+constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout continues in the fp64 kernel
+// Simulator.doStep (simulatorTLKT.py:181-216).  g = grid position of (lat, lon); (sh, ch) heading;
+// (s, c) = sin/cos(lat); z standard normal.  On PMCTS_ST_OK the state is advanced and m holds the
+// increments; otherwise nothing changes.
+PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
+                       const GridPos &g, float sh, float ch, float s, float c, float z, Move &m) {
+    if (k < 0 || k >= sc.nT) return PMCTS_ST_PAST_HORIZON;
+    if (!g.inside || k < sc.kv_lo || k > sc.kv_hi) return PMCTS_ST_OUT_OF_GRID;
+    float u, v;
+    wind_at(sc, k, g, u, v);
+    float speed = boat_speed(bp, u, v, sh, ch);
+    speed = fma_(z, speed * bp.sigma_f, speed);  // Boat.addUncertainty (:504-517)
+    if (k + 1 >= sc.nT) return PMCTS_ST_PAST_HORIZON;
+#if defined(__CUDA_ARCH__)
+    const float dt = __ldg(sc.dt_sec32 + k);
+#else
+    const float dt = sc.dt_sec32[k];
+#endif
+    const float d = speed * dt * bp.inv_radius_f;
+    if (!(fabsf(d) <= kMaxStepAngle)) return kStNeedsLiteral;
+    m = move_increments(d, sh, ch, s, c);
+    if (!(fabsf(m.sin_dlon) <= kMaxStepAngle)) return kStNeedsLiteral;  // high latitude: dlon = b / cos(lat)
+    lat = fma((double)m.dlat, 180.0 / kPi, lat);
+    lon = fma((double)m.dlon, 180.0 / kPi, lon);
+    k += 1;
+    return PMCTS_ST_OK;
+}
+
+// Heading given in degrees (an action of the tree, a plan, a K1 heading segment).  The dot-product
+// point of sail equals the reference's abs / fold only for headings in [0, 360).
+PMCTS_HD bool heading_unit(double deg, float &sh, float &ch) {
+    if (!(deg >= 0.0 && deg < 360.0)) return false;
+    // reduce to [-90, 90] exactly (multiples of 90 are exact in fp64), then the lat kernels
+    double a = deg;
+    int quad = 0;
+    if (a > 315.0) { a -= 360.0; }
+    else if (a > 225.0) { a -= 270.0; quad = 3; }
+    else if (a > 135.0) { a -= 180.0; quad = 2; }
+    else if (a > 45.0) { a -= 90.0; quad = 1; }
+    float s, c;
+    sincos_lat(a, s, c);
+    switch (quad) {
+        case 0: sh = s; ch = c; break;
+        case 1: sh = c; ch = -s; break;
+        case 2: sh = -s; ch = -c; break;
+        default: sh = -c; ch = s; break;
+    }
+    return true;
+}
+
+// Hist.add bin (utils.py:34-47) of a reward, flagging values closer than `margin` to a bin edge.
+PMCTS_HD int hist_bin_checked(const BoatParams &bp, double r, int &why) {
+    const double r8 = r * 8.0;
+    const double c = ceil(r8);
+    if (r8 > 0.0 && r8 < 11.5 && (c - r8 < bp.margin_bin || r8 - (c - 1.0) < bp.margin_bin)) why |= kWhyBin;
+    const int b = (int)c - 1;
+    return b < 0 ? 0 : (b > 11 ? 11 : b);
+}
+
+
+// Tree.is_state_terminal (worker.py:417-436) on the fp32 grid coordinates of the position.
+PMCTS_HD bool fast_terminal(const ScenarioView &sc, const BoatParams &bp, int k, const GridPos &g, int &why) {
+    if (k >= sc.nT - 1) return true;
+    const float m = bp.margin_box * (1.0f + fmaxf(fabsf(g.fa), fabsf(g.fo)) * 0.01f);
+    const float da0 = g.fa - sc.box_fa_lo, da1 = sc.box_fa_hi - g.fa;
+    const float do0 = g.fo - sc.box_fo_lo, do1 = sc.box_fo_hi - g.fo;
+    const float lo = fminf(fminf(da0, da1), fminf(do0, do1));
+    if (fabsf(lo) <= m) why |= kWhyBox;  // only the binding edge can flip
+    return lo < 0.0f;
+}
+
+// Result of one rollout.
+struct RollOut {
+    int st, nstep, bin;
+    int why;  // 0, or the kWhy* reasons this rollout is left to the literal kernel
+    double ta, rw, frac, lat, lon;
+};
+
+// Tree.get_sim_to_estimate_state + Tree.default_policy (worker.py:255-300), estimate_perfomance_plan's
+// inner loop (isochrones.py:498-530).  One loop serves every mode:
+//   step j uses heading prefix[j] while j < n_fixed, the bearing to the destination afterwards;
+//   the arrival / terminal tests run after step j once j + 1 >= n_unchecked.
+PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const NoiseView &nz, const RolloutArgs &a,
+                          int64_t n, int64_t r, RollOut &o) {
+    const int64_t leaf = r / a.replicas;
+    int k = (int)a.root_k;
+    double lat = a.root_lat, lon = a.root_lon;
+    const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
+    const int plen = a.prefix_len ? a.prefix_len[leaf] : 0;
+    const bool plan = (a.flags & PMCTS_ROLL_PLAN_EVAL) != 0;
+    const int n_fixed = plan ? plen : ((a.flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) ? plen : imin(plen, 1));
+    const int n_unchecked = plan ? imax(plen, 1) : 1;
+    const float sD = a.sin_dest_lat, cD = a.cos_dest_lat;
+    o.st = PMCTS_ST_OK;
+    o.nstep = 0;
+    o.why = 0;
+    o.frac = 0.0;
+    int at = 0;
+    float frac = 0.0f;
+    if (!plan && plen == 0) {
+        // worker.py:264-265 on prevState == state: the plane is degenerate (ZeroDivisionError)
+        o.st = PMCTS_ST_DEGENERATE;
+    } else if (a.root_lat == 0.0 || a.root_lon == 0.0) {
+        o.why = kWhyDegenerate;  // ya == 0 in worker.py:396: left to the literal kernel
+    } else {
+        Noise ns;
+        float sA, cA;
+        sincos_lat(lat, sA, cA);
+        DestRel rd = dest_rel(lat, lon, a.dest_lat, a.dest_lon);
+        GridPos g = grid_pos(sc, lat, lon);
+        for (;;) {
+            float sh, ch;
+            if (o.nstep < n_fixed) {
+                if (!heading_unit(pre[o.nstep], sh, ch)) {
+                    o.why |= kWhyStep;
+                    break;
+                }
+            } else {
+                bearing_unit(rd, sA, sD, cD, sh, ch);
+            }
+            const float z = ns.draw(nz, n, r, o.nstep);
+            Move m;
+            o.st = fast_step(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
+            if (o.st == kStNeedsLiteral) {
+                o.st = PMCTS_ST_OK;
+                o.why |= kWhyStep;
+                break;
+            }
+            if (o.st != PMCTS_ST_OK) break;
+            if (a.traj_lat && o.nstep < a.traj_stride) a.traj_lat[(size_t)o.nstep * n + r] = lat;
+            if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = lon;
+            ++o.nstep;
+            float sB, cB;
+            sincos_lat(lat, sB, cB);
+            g = grid_pos(sc, lat, lon);
+            if (o.nstep >= n_unchecked) {
+                at = fast_at_dest(bp, rd, m, sA, cA, sB, sD, frac, o.why);
+                if (at || o.why) break;
+                if (fast_terminal(sc, bp, k, g, o.why)) break;
+                if (o.why) break;
+            }
+            sA = sB;
+            cA = cB;
+            rd = dest_rel(lat, lon, a.dest_lat, a.dest_lon);
+        }
+    }
+    o.ta = NAN;
+    o.rw = 0.0;
+    if (o.st == PMCTS_ST_OK && !o.why) {
+        if (at) {
+            const double tk = sc.times[k];
+            o.frac = (double)frac;
+            o.ta = tk - (1.0 - o.frac) * (tk - sc.times[k - 1]);  // worker.py:274-275
+            o.rw = (exp((sc.tmax * 1.001 - o.ta) / (sc.tmax * 1.001 - a.tmin)) - 1.0) / (exp(1.0) - 1.0);
+            o.st = PMCTS_ST_ARRIVED;
+        } else {
+            o.st = (k >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
+            if (plan) o.ta = sc.tmax;  // isochrones.py:527-530
+        }
+    }
+    o.bin = hist_bin_checked(bp, o.rw, o.why);
+    o.lat = lat;
+    o.lon = lon;
+}
+
+}  // namespace fast
+}  // namespace pmcts

@@ -1,0 +1,102 @@
+// pmcts_b200 shared plain-data types: device views of a scenario, boat parameters, noise and launch
+// arguments.  Included by the literal fp64 kernels (pmcts_device.cuh), the mixed-precision kernels
+// (pmcts_fast.cuh) and the host-compiled numerics model of the latter (tests/fastmodel).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/pmcts_b200.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define PMCTS_HD __host__ __device__ __forceinline__
+#else
+#define PMCTS_HD inline
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+#endif
+
+namespace pmcts {
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kDegToRad = kPi / 180.0;
+
+// Device view of one uploaded scenario (see pmcts_scenario_upload): one time-blended (u, v) slab per
+// simulator instant, so a transition gathers 4 grid corners instead of 8 and needs no time weight.
+struct ScenarioView {
+    const double2 *slab64;  // [nT][nlat][nlon] (u, v) fp64
+    const float2 *slab32;   // same, rounded to fp32 (Fast mode)
+    const double *times;    // [nT] simulator instants, days
+    const double *dt_sec;   // [nT] (times[k+1]-times[k])*86400, last entry unused
+    const uint8_t *k_valid; // [nT] 1 if times[k] lies inside the weather time axis
+    int nT, nlat, nlon;
+    double lat0, lon0, inv_dlat, inv_dlon, lat_last, lon_last;
+    double box_lat_lo, box_lat_hi, box_lon_lo, box_lon_hi;
+    double tmax;
+    // ---- mixed-precision ("fast") view ----
+    const float *dt_sec32;  // [nT] dt_sec rounded to fp32
+    int kv_lo, kv_hi;       // k_valid[k] == 1 exactly for kv_lo <= k <= kv_hi
+    int fast_ok;            // 0: this scenario must run on the literal fp64 kernels
+    float max_abs_lat;      // max(|lat0|, |lat_last|), degrees
+    double dt_max;          // max_k dt_sec[k]
+    float box_fa_lo, box_fa_hi, box_fo_lo, box_fo_hi;  // terminal box in grid-index units
+};
+
+// Boat.* / module constants (pmcts_set_params), plus values derived once on the host.
+struct BoatParams {
+    double polar[36];
+    double wind_max, pofsail_min, pofsail_max, sigma_coeff;
+    double dest_angle, earth_radius;
+    double cos_pmin, cos_pmax;  // cos(pi * POLAR_{MIN,MAX}_POFSAIL / 180)
+    // ---- mixed-precision ("fast") copy, derived in pmcts_set_params ----
+    // The same polynomial re-expanded about the centre of its domain, P(p, w) = sum pc[i][j] x^i y^j
+    // with x = (p - p_mid) * p_ihalf in [-1, 1] over [POLAR_MIN, POLAR_MAX] and y = w * w_ihalf - 1
+    // in [-1, 1] over [0, wind_max]: O(1) coefficients, so an fp32 Horner loses no digits to
+    // cancellation (the raw monomial form cancels from ~30 down to ~1 m/s).
+    float pc[36];
+    int polar_tri;  // 1 if pc[i][j] == 0 for i + j > 5 (the reference's fit): 20-FMA triangular Horner
+    float p_mid, p_ihalf, w_ihalf;
+    float wind_max_f, pmin_f, pmax_f, cos_pmin_f, cos_pmax_f, sigma_f, inv_radius_f;
+    float sin2_dest_angle;  // sin(DESTINATION_ANGLE)^2
+    float speed_bound;      // upper bound of |P| over the domain
+    // decision margins of the mixed-precision path: a test closer than its margin is not decided in
+    // fp32, the rollout is re-run by the literal kernel (pmcts_fast.cuh)
+    float margin_angle;  // relative, on sin^2(angle to the plane) vs sin^2(DESTINATION_ANGLE)
+    float margin_along;  // position of D along A -> B, in units of |B - A|
+    float near_miss2;    // (|D - B| / |B - A|)^2 below which the next bearing is ill-conditioned
+    float margin_box;    // terminal box edges, grid-index units
+    double margin_bin;   // reward * 8 against the integer bin edges
+};
+
+struct NoiseView {
+    int mode;
+    const double *z;
+    uint64_t seed, stream, id0;
+};
+
+// Arguments of one rollout launch (pmcts_rollout_batch).
+struct RolloutArgs {
+    int64_t n_leaf;
+    int replicas;
+    double root_k, root_lat, root_lon, dest_lat, dest_lon, tmin;
+    const double *prefix;
+    const int32_t *prefix_len;
+    int prefix_stride;
+    double *reward, *t_arr;
+    int32_t *steps;
+    uint8_t *status;
+    int32_t *bin;
+    double *frac, *final_lat, *final_lon, *traj_lat, *traj_lon;
+    int traj_stride;
+    uint32_t *leaf_bins;
+    double *stats;
+    int flags;
+    // mixed-precision path: destination trigonometry (host, fp64 -> fp32) and the work list of
+    // rollouts whose decisions fell inside the error margins (re-run by the literal fp64 kernel)
+    float sin_dest_lat, cos_dest_lat;
+    uint32_t *redo_list;
+    uint32_t *redo_count;
+    const uint32_t *work_list;   // literal kernel: rollout ids to run (NULL = all)
+    const uint32_t *work_count;
+};
+
+}  // namespace pmcts

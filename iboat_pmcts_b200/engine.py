@@ -105,6 +105,15 @@ class Engine:
         N.check(self._lib.pmcts_set_precision(self._h, int(mode)))
         self.precision = int(mode)
 
+    def set_fast_margins(self, angle=-1.0, along=-1.0, near_miss2=-1.0, box=-1.0, bin=-1.0):
+        """Decision margins of the mixed-precision kernels (negative = keep; all negative = defaults)."""
+        N.check(self._lib.pmcts_set_fast_margins(self._h, float(angle), float(along), float(near_miss2),
+                                                 float(box), float(bin)))
+
+    def last_redo_count(self):
+        """Rollouts the last FAST launch handed to the fp64 kernel (synchronises)."""
+        return int(self._lib.pmcts_last_redo_count(self._h))
+
     def use_torch_stream(self):
         """Orders the engine's work on torch's current stream of this device."""
         s = torch.cuda.current_stream(self.device).cuda_stream

@@ -55,7 +55,9 @@ typedef struct pmcts_ctx pmcts_ctx;
 
 /* arithmetic mode */
 #define PMCTS_PREC_F64 0   /* literal fp64 transcription of the reference formulas */
-#define PMCTS_PREC_FAST 1  /* fp32 wind / polar / noise, re-derived fp64 geodesy; same results within 1e-6 relative */
+#define PMCTS_PREC_FAST 1  /* fp32 arithmetic on re-derived, difference-form formulas; positions within 1e-6
+                              relative of the fp64 path; every decision (arrival, terminal box, histogram bin)
+                              closer than its error margin is re-taken by the fp64 kernel (pmcts_fast.cuh) */
 
 /* noise source for Boat.addUncertainty (simulatorTLKT.py:504-517): speed + z * (speed * sigma) */
 #define PMCTS_NOISE_INJECTED 0 /* z[step * n + i], fp64 (parity tests) */
@@ -79,6 +81,15 @@ int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream);
 int pmcts_reset_stream(pmcts_ctx *ctx);
 int pmcts_synchronize(pmcts_ctx *ctx);
 int pmcts_set_precision(pmcts_ctx *ctx, int mode);
+/* Decision margins of PMCTS_PREC_FAST (a negative value keeps the current one; all negative restores
+ * the defaults): relative margin on sin^2 of the arrival angle vs sin^2(DESTINATION_ANGLE); margin on the
+ * position of the destination along the last step (units of the step); (distance to the destination /
+ * step)^2 under which a missed arrival is re-run; terminal-box margin in grid cells; margin on reward * 8
+ * against the histogram bin edges.  Huge margins send every rollout through the fp64 kernel. */
+int pmcts_set_fast_margins(pmcts_ctx *ctx, double angle, double along, double near_miss2, double box,
+                           double bin);
+/* Rollouts (or K1 hand-over flag) the last FAST launch left to the fp64 kernel; synchronises the stream. */
+int64_t pmcts_last_redo_count(pmcts_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);
 /* While timing is enabled every kernel launch is bracketed by a cudaEvent pair on the ctx stream;

@@ -1,0 +1,153 @@
+"""Arithmetic of the mixed-precision kernels (csrc/pmcts_fast.cuh) against the fp64 oracle, on the CPU.
+
+tests/fastmodel compiles the very header the CUDA kernels are built from with g++ (MUFU approximations
+replaced by IEEE operations), so these tests pin the *formulas* -- the difference-form geodesy, the
+dot-product point of sail, the centred polar polynomial, the decision margins -- without a GPU.  The
+kernels themselves are compared with the oracle in test_gpu_parity.py.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import pmcts_helpers as H
+from iboat_pmcts_b200 import synth
+from oracle import cport
+import fastmodel
+
+DEST, TMIN = [46.77751005, 355.0], 2.0223605
+
+
+def model(scen, times=None):
+    t, la, lo, u, v = synth.wind_fields(scen)
+    if times is None:
+        times, lats, lons = H.sim_axes(la, lo)
+    else:
+        lats, lons = la, lo
+    return fastmodel.FastModel(t, la, lo, u, v, times, lats, lons)
+
+
+def test_boat_speed_matches_get_deter_dyn():
+    """Weather.returnPolarVel + point of sail + Boat.getDeterDyn: absolute error below 1e-6 m/s
+    over the whole (wind, heading) domain, including the tack / gybe cosine extensions, calm wind and
+    the wind clamp."""
+    f, o = model(0), H.oracle_sim(0)
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(20000):
+        mag, hd, wd = rng.uniform(0.0, 25.0), rng.uniform(0, 360), rng.uniform(0, 360)
+        u = float(np.float32(mag * np.sin(np.radians(wd))))
+        v = float(np.float32(mag * np.cos(np.radians(wd))))
+        m, ang = cport.polar_vel(u, v)
+        want = o.deter_dyn(abs((ang + 180) % 360 - hd), m)
+        worst = max(worst, abs(f.boat_speed(u, v, hd) - want))
+    assert worst < 1e-6
+    # calm wind: atan2(0, 0) = 0, point of sail |180 - heading|
+    for hd in (0.0, 45.0, 200.0, 359.0):
+        assert abs(f.boat_speed(0.0, 0.0, hd) - o.deter_dyn(abs(180.0 - hd), 0.0)) < 1e-6
+
+
+def test_move_and_bearing_building_blocks():
+    L = fastmodel.lib()
+    o = H.oracle_sim(0)
+    rng = np.random.default_rng(1)
+    e_lat = e_lon = e_brg = 0.0
+    for _ in range(20000):
+        lat, lon, hd = rng.uniform(-70, 70), rng.uniform(0, 360), rng.uniform(0, 360)
+        dist = rng.uniform(-10e3, 60e3)
+        a, b = C.c_double(), C.c_double()
+        L.fm_move(C.c_float(dist / 6371e3), C.c_double(hd), C.c_double(lat), C.c_double(lon), C.byref(a), C.byref(b))
+        want = o.get_destination(dist, hd, lat, lon)
+        step_deg = abs(dist) / 6371e3 * 180 / np.pi
+        e_lat = max(e_lat, abs(a.value - want[0]) / max(step_deg, 1e-3))
+        e_lon = max(e_lon, abs(b.value - want[1]) * np.cos(np.radians(lat)) / max(step_deg, 1e-3))
+        dl, do = lat + rng.uniform(-8, 8), lon + rng.uniform(-12, 12)
+        sh, ch = C.c_float(), C.c_float()
+        L.fm_bearing(C.c_double(lat), C.c_double(lon), C.c_double(dl), C.c_double(do), C.byref(sh), C.byref(ch))
+        brg = o.dist_bearing(lat, lon, dl, do)[1]
+        e = np.arctan2(sh.value, ch.value) - np.radians(brg)
+        e_brg = max(e_brg, abs((e + np.pi) % (2 * np.pi) - np.pi))
+    # increments are exact to fp32 relative accuracy *of the increment*
+    assert e_lat < 1e-6 and e_lon < 1e-6 and e_brg < 1e-6
+
+
+def test_raw_steps_golden_and_seeded():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "raw_steps_c3.npz"))
+    f = model(0, times=g["times"])
+    nsteps, n = g["traj_lat"].shape
+    head = synth.octagon_headings(g["h0"], nsteps)
+    r = f.step_batch(0, g["lat0"], g["lon0"], head, nsteps=nsteps, seg_len=25, z=g["z"], traj=True)
+    assert (r["status"] == 0).all() and (r["k"] == nsteps).all() and not r["needs_literal"].any()
+    assert np.max(np.abs(r["traj_lat"] - g["traj_lat"]) / g["traj_lat"]) < 2e-8
+    assert np.max(np.abs(r["traj_lon"] - g["traj_lon"]) / g["traj_lon"]) < 2e-8
+    # what the fp32 formulas do not cover is handed over, not approximated
+    head2 = head.copy()
+    head2[2, 0] = -45.0
+    z2 = g["z"].copy()
+    z2[60, 1] = 5000.0
+    r = f.step_batch(0, g["lat0"], g["lon0"], head2, nsteps=nsteps, seg_len=25, z=z2)
+    assert r["needs_literal"][0] == 1 and r["k"][0] == 50
+    assert r["needs_literal"][1] == 1 and r["k"][1] == 60
+    assert not r["needs_literal"][2:].any()
+
+
+@pytest.mark.parametrize("scen,flags", [(4, 0), (0, 0), (7, 2)])
+def test_rollout_decisions_outside_margins_agree(scen, flags):
+    """Every rollout the fp32 path decides itself takes the decisions of the oracle (steps, status,
+    histogram bin), its trajectory stays within 2e-7 relative, and few rollouts are left undecided."""
+    f, o = model(scen), H.oracle_sim(scen)
+    rng = np.random.default_rng(100 + scen)
+    n_leaf, rep = 256, 128
+    n = n_leaf * rep
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 4))
+    plen = rng.integers(1, 5, n_leaf).astype(np.int32)
+    z = rng.standard_normal((13, n))
+    got = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags,
+                          traj_steps=13)
+    want = o.rollout_batch(n, H.STATE0, DEST, TMIN, prefix=np.repeat(prefix, rep, 0),
+                           prefix_len=np.repeat(plen, rep), replay_full=bool(flags & 2), z=z, nthreads=8,
+                           traj_steps=13)
+    ok = got["uncertain"] == 0
+    assert 0.0 < (~ok).mean() < 0.01
+    for key in ("steps", "status", "bin"):
+        assert np.array_equal(got[key][ok], want[key][ok]), key
+    el = np.abs(got["traj_lat"] - want["traj_lat"])[:, ok] / np.abs(want["traj_lat"][:, ok])
+    eo = np.abs(got["traj_lon"] - want["traj_lon"])[:, ok] / np.abs(want["traj_lon"][:, ok])
+    assert np.nanmax(el) < 2e-7 and np.nanmax(eo) < 2e-7
+    assert np.array_equal(np.isnan(got["traj_lat"][:, ok]), np.isnan(want["traj_lat"][:, ok]))
+    arr = ok & (want["status"] == 1)
+    assert np.allclose(got["t_arr"][arr], want["t_arr"][arr], rtol=1e-6)
+    assert np.allclose(got["reward"][ok], want["reward"][ok], rtol=1e-6, atol=3e-6)
+    # with the margins closed the fp32 path would still be right almost always: the margins are slack
+    f.set_margins(angle=0.0, along=0.0, near_miss2=0.0, box=0.0, bin=0.0)
+    raw = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
+    bad = (raw["steps"] != want["steps"]) | (raw["status"] != want["status"]) | (raw["bin"] != want["bin"])
+    assert bad[raw["uncertain"] == 0].sum() <= 2
+
+
+def test_plan_evaluation_mode_and_golden_rollouts(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    pe = np.load(os.path.join(golden_dir, "plan_eval_c5.npz"))
+    dest, tmin = g["destination"].tolist(), float(g["timemin"])
+    S, nT, n = g["traj_lat"].shape
+    for si, scen in enumerate(g["scenarios"]):
+        f = model(int(scen))
+        z = np.ascontiguousarray(g["zroll"][si].T)
+        r = f.rollout_batch(n, 1, H.STATE0, dest, tmin, prefix=g["prefix"], prefix_len=g["prefix_len"], z=z,
+                            traj_steps=nT)
+        ok = r["uncertain"] == 0
+        assert ok.mean() > 0.95
+        assert np.array_equal(r["steps"][ok], g["steps"][si][ok])
+        assert np.array_equal(r["status"][ok] == 1, g["atdest"][si][ok] == 1)
+        assert np.nanmax(np.abs(r["traj_lat"] - g["traj_lat"][si])[:, ok] / g["traj_lat"][si][:, ok]) < 2e-7
+        # plan evaluation: arrival time or times[-1]
+        nt2 = int(pe["plan_ntra"])
+        plan = pe["plan_plan"].astype(np.float64)
+        zz = np.ascontiguousarray(pe["plan_z"][si * nt2:(si + 1) * nt2].T)
+        o = H.oracle_sim(int(scen))
+        want = o.rollout_batch(nt2, H.STATE0, dest, 0.0, prefix=np.tile(plan, (nt2, 1)), mode=1, z=zz)
+        got = f.rollout_batch(nt2, 1, H.STATE0, dest, 0.0, prefix=np.tile(plan, (nt2, 1)), z=zz, flags=4)
+        ok = got["uncertain"] == 0
+        assert np.array_equal(got["status"][ok], want["status"][ok])
+        assert np.allclose(got["t_arr"][ok], want["t_arr"][ok], rtol=1e-6)
