@@ -3,10 +3,11 @@
 
 Default workload ("c4-shard", BASELINE.json configs[3] per GPU): every rank owns 8 synthetic
 GFS-ensemble-shaped weather scenarios; one *step* is 10^6 leaf-batched default-policy rollouts per
-scenario, issued as 8 waves of 4096 leaves x 32 noise replicas, each wave followed by the per-leaf
-reward-bin reduction (in K2), one all-gather of the per-scenario update blocks (N > 1 only) and the
-back-up of every scenario's blocks into the replicated master table (K3).  Scenarios are the unit of
-sharding, so scaling is weak: per-GPU work is fixed as N grows.
+scenario (4096 leaves x 256 noise replicas), all 8 scenarios in ONE launch (pmcts_rollout_forest: K2
+with the per-leaf reward-bin reduction, plus the fp64 re-run of the rollouts the fp32 kernel leaves
+undecided), then one all-gather of the per-scenario update blocks (N > 1 only) and the back-up of
+every scenario's blocks into the replicated master table (K3).  Scenarios are the unit of sharding, so
+scaling is weak: per-GPU work is fixed as N grows.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3] [--impl reference]
 
@@ -17,9 +18,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -33,8 +32,8 @@ from iboat_pmcts_b200 import synth  # noqa: E402
 # ---- workload constants ------------------------------------------------------------
 SCEN_PER_GPU = 8
 N_LEAF = 4096          # a complete depth-4 tree over the 8 headings has 8^4 leaves
-REPLICAS = 32
-WAVES = 8
+REPLICAS = 256
+WAVES = 1
 STATE0 = (0, 44.0, 355.0)
 DEST = (46.77751005, 355.0)   # initialize_simulators on scenarios 0-2 (tests/golden/rollouts_c1.npz)
 TMIN = 2.022360548788055
@@ -69,55 +68,58 @@ def depth4_tree():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML every few milliseconds while the
+    timed region runs (the timed region of this path is tens of milliseconds, below nvidia-smi's -lms floor)."""
 
-    def __init__(self, index):
-        self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period_s=0.004):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            self._nv = None
+            return
+        self._period = period_s
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        nv = self._nv
+        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self._thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            # "under load": the upper half of the samples (idle samples before/after the timed region drop out)
-            sm_sorted = sorted(sm)
-            out["sm_mhz"] = statistics.median(sm_sorted[len(sm_sorted) // 2:])
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
+            out["samples"] = len(self.samples)
+        out["reasons"] = sorted(self.reasons)
+        out["source"] = "NVML, polled every %d ms during the timed region" % round(self._period * 1e3)
         return out
 
 
@@ -219,7 +221,7 @@ def workload_config(workload, n_gpus):
                 scenarios_per_gpu=SCEN_PER_GPU, scenarios_total=SCEN_PER_GPU * n_gpus, leaves=N_LEAF,
                 replicas=REPLICAS, waves=WAVES, rollouts_per_scenario_per_step=N_LEAF * REPLICAS * WAVES,
                 sim_axis="6-hourly over 3 days (13 instants)", grid="41x21x31 (t, lat, lon), 0.5 deg, 3-hourly",
-                sharding="scenario s on GPU s // 8; master table replicated; one all-gather per wave",
+                sharding="scenario s on GPU s // 8; master table replicated; one all-gather per step",
                 l2="L2 flushed (256 MiB write) between timed steps", noise="philox4x32-10 seed 42")
 
 
@@ -279,13 +281,13 @@ def main():
     for i in range(warm):
         run["device_step"](i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     eng.enable_timing(True)
     eng.kernel_ms(reset=True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     run["reset_counters"]()
     barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush_l2()
@@ -294,6 +296,7 @@ def main():
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
     launches = eng.launch_count() - launches0
     dom_kernel_ms = eng.kernel_ms(reset=False, kind=run["dominant"]["kind"])
     kernel_ms = eng.kernel_ms(reset=True)
@@ -331,7 +334,6 @@ def main():
         sm = e2e_stat.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         e2e_s, e2e_tr = float(mx[0]), float(sm[1])
-    clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         per_launch_units = run["dominant"]["units_per_launch"]
@@ -354,7 +356,7 @@ def main():
                     rollouts_per_s=rollouts / (dev_ms * 1e-3) if rollouts else None,
                     config=workload_config(args.workload, world), precision_mode="f64" if prec == N.PREC_F64 else "fast",
                     e2e=dict(value=e2e_tr / e2e_s, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             steps=e2e_steps, api="pmcts_rollout_batch / pmcts_step_batch with PMCTS_MEM_HOST"),
+                             steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST")),
                     gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
                     roofline=roofline)
         if not args.no_cpu_baseline:
@@ -386,18 +388,17 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     master = torch.zeros(S_total * n_nodes * 96, dtype=torch.int32, device=dev)
     bins_local = torch.zeros(S_local * N_LEAF * 12, dtype=torch.int32, device=dev)
     bins_all = torch.zeros(S_total * N_LEAF * 12, dtype=torch.int32, device=dev) if world > 1 else bins_local
-    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    stats = torch.zeros(S_local * 8, dtype=torch.float64, device=dev)
     plen_h = np.full(N_LEAF, 4, np.int32)
+
+    scen_slots = np.arange(S_local, dtype=np.int32)
 
     def device_step(i):
         for w in range(WAVES):
             bins_local.zero_()
-            for j in range(S_local):
-                g = rank * S_local + j
-                eng.rollout_batch(j, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, seed=SEED, stream=g,
-                                  id0=(i * WAVES + w) * n,
-                                  out=dict(leaf_bins=bins_local[j * N_LEAF * 12:(j + 1) * N_LEAF * 12], stats=stats),
-                                  flags=N.ROLL_ACCUMULATE)
+            eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, prefix_shared=True,
+                               seed=SEED, stream=rank * S_local, id0=(i * WAVES + w) * n,
+                               out=dict(leaf_bins=bins_local, stats=stats), flags=N.ROLL_ACCUMULATE)
             if world > 1:
                 dist.all_gather_into_tensor(bins_all, bins_local)
             eng.backup(master, n_nodes, parent, arm, leaf_node, slots, bins_all, n_scen=S_total)
@@ -407,28 +408,28 @@ def setup_c4(eng, torch, dist, dev, rank, world):
         master.zero_()
 
     def read_counters():
-        s = stats.cpu().numpy()
+        s = stats.cpu().numpy().reshape(S_local, 8).sum(0)
         root_visits = int(master.view(S_total, n_nodes, 96)[:, 0].sum().item())
-        assert root_visits == int(round(s[5])) * world or world > 1, (root_visits, s[5])
+        assert root_visits == int(round(s[5])) * world, (root_visits, s[5])
         return float(s[4]), float(s[5])
 
     def e2e_step(i):
         tr = 0
         for w in range(WAVES):
-            for j in range(S_local):
-                g = rank * S_local + j
-                r = eng.rollout_batch_host(j, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix=prefix_h, prefix_len=plen_h,
-                                           seed=SEED, stream=g, id0=(1000 + i * WAVES + w) * n,
-                                           want=("leaf_bins", "stats"))
-                tr += int(r["stats"][4])
-        calls = WAVES * S_local
-        return tr, calls * (prefix_h.nbytes + plen_h.nbytes), calls * (N_LEAF * 12 * 4 + 64)
+            out = dict(leaf_bins=np.empty(S_local * N_LEAF * 12, np.uint32), stats=np.empty(S_local * 8))
+            eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix_h.reshape(-1), plen_h, 4,
+                               prefix_shared=True, seed=SEED, stream=rank * S_local, id0=(1000 + i * WAVES + w) * n,
+                               out=out)
+            tr += int(out["stats"].reshape(S_local, 8)[:, 4].sum())
+        return tr, WAVES * (prefix_h.nbytes + plen_h.nbytes), WAVES * (S_local * N_LEAF * 12 * 4 + S_local * 64)
 
     return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
                 e2e_step=e2e_step,
-                dominant=dict(kernel="rollout_batch_kernel", launches_per_step=WAVES * S_local, units_per_launch=None,
+                dominant=dict(kernel="rollout_fast_kernel (+ rollout_batch_kernel on its work list)",
+                              launches_per_step=WAVES, units_per_launch=None,
                               flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
-                              hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + N_LEAF * 48 + n * 0))
+                              api="pmcts_rollout_forest with PMCTS_MEM_HOST (host prefix in, host leaf_bins / stats out)",
+                              hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))
 
 
 def setup_c3(eng, torch, dev, rank, world):
@@ -470,8 +471,9 @@ def setup_c3(eng, torch, dev, rank, world):
 
     return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
                 e2e_step=e2e_step,
-                dominant=dict(kernel="step_batch_kernel", launches_per_step=1, units_per_launch=None,
+                dominant=dict(kernel="step_fast_kernel", launches_per_step=1, units_per_launch=None,
                               flop_per_unit=F_ALG_RAW, kind=0,
+                              api="pmcts_step_batch with PMCTS_MEM_HOST (host state / headings in, host state out)",
                               hbm_bytes_per_launch=n * (21 + 21) + head_h.nbytes))
 
 

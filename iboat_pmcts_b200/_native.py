@@ -26,7 +26,7 @@ EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_synchronize", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_launch_count", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
-    "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_backup", "pmcts_hist_stats",
+    "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
 ]
 
 
@@ -83,6 +83,8 @@ def lib():
                                    vp, vp, vp, i32]
     L.pmcts_rollout_batch.argtypes = [vp, i32, i64, i32, vp, vp, dbl, vp, vp, i32, C.POINTER(Noise),
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32]
+    L.pmcts_rollout_forest.argtypes = [vp, i32, vp, i64, i32, vp, vp, dbl, vp, vp, i32, i32, C.POINTER(Noise),
+                                       vp, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_backup.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp, vp, vp, i32]
     L.pmcts_hist_stats.argtypes = [vp, vp, i64, vp, vp, i32]
     _lib = L

@@ -115,20 +115,72 @@ step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t
     if (status_io) status_io[i] = (uint8_t)st;
 }
 
+// Several scenarios in one launch (pmcts_rollout_forest): the scenarios share their geometry (axes,
+// box, simulator instants); only the wind slabs differ.  select_scenario turns the launch-wide
+// arguments into those of scenario s: slabs, noise stream, and every per-scenario array offset.
+constexpr int kMaxForest = 16;
+struct ForestSlabs {
+    const float2 *s32[kMaxForest];
+    const double2 *s64[kMaxForest];
+    int n_scen, prefix_shared;
+};
+
+__device__ __forceinline__ void select_scenario(int s, int64_t n, const ForestSlabs &fs, ScenarioView &sc,
+                                                NoiseView &nz, RolloutArgs &a) {
+    sc.slab32 = fs.s32[s];
+    sc.slab64 = fs.s64[s];
+    nz.stream += (uint64_t)s;
+    if (nz.z) nz.z += (size_t)s * sc.nT * n;
+    const size_t on = (size_t)s * n, ol = (size_t)s * a.n_leaf;
+    if (!fs.prefix_shared) {
+        if (a.prefix) a.prefix += ol * a.prefix_stride;
+        if (a.prefix_len) a.prefix_len += ol;
+    }
+    if (a.reward) a.reward += on;
+    if (a.t_arr) a.t_arr += on;
+    if (a.steps) a.steps += on;
+    if (a.status) a.status += on;
+    if (a.bin) a.bin += on;
+    if (a.frac) a.frac += on;
+    if (a.final_lat) a.final_lat += on;
+    if (a.final_lon) a.final_lon += on;
+    if (a.traj_lat) a.traj_lat += on * a.traj_stride;
+    if (a.traj_lon) a.traj_lon += on * a.traj_stride;
+    if (a.leaf_bins) a.leaf_bins += ol * 12;
+    if (a.stats) a.stats += (size_t)s * 8;
+}
+
+// Work-list entry of the mixed-precision kernels: scenario index in the top 4 bits, rollout id below.
+constexpr int kRedoShift = 28;
+
 // Per-leaf reduction of the reward bins and the plan-evaluation statistics, shared by the literal and
 // the mixed-precision rollout kernels.  Lanes holding the same (leaf, bin) find each other with one
 // MATCH; the lowest lane of each group adds the group's size to leaf_bins[leaf][bin].
-__device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned warp_mask, bool counted,
+// `a` is the lane's own (scenario-offset) argument block; with kUniform every lane of the warp belongs
+// to the same scenario (the stats of a warp go to one place), otherwise lanes add their own.
+template <bool kUniform>
+__device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned warp_mask, bool counted, int scen,
                                                 int64_t leaf, int bin, int st, int nstep, double ta) {
     const int lane = threadIdx.x & 31;
     if (a.leaf_bins) {
         const unsigned long long key =
-            counted ? ((unsigned long long)leaf << 4) | (unsigned)bin : ~0ull - (unsigned)lane;
+            counted ? ((unsigned long long)(scen * a.n_leaf + leaf) << 4) | (unsigned)bin : ~0ull - (unsigned)lane;
         const unsigned peers = __match_any_sync(warp_mask, key);
         if (counted && lane == __ffs(peers) - 1)
             atomicAdd(&a.leaf_bins[leaf * 12 + bin], (uint32_t)__popc(peers));
     }
-    if (a.stats) {
+    if (a.stats && !kUniform) {
+        if (counted) {
+            if (!isnan(ta)) {
+                atomicAdd(&a.stats[0], 1.0);
+                atomicAdd(&a.stats[1], ta);
+                atomicAdd(&a.stats[2], ta * ta);
+            }
+            if (st == PMCTS_ST_ARRIVED) atomicAdd(&a.stats[3], 1.0);
+            atomicAdd(&a.stats[4], (double)nstep);
+            atomicAdd(&a.stats[5], 1.0);
+        }
+    } else if (a.stats) {
         const bool has_t = counted && !isnan(ta);
         const int c_t = __reduce_add_sync(warp_mask, has_t ? 1 : 0);
         const int c_arr = __reduce_add_sync(warp_mask, (counted && st == PMCTS_ST_ARRIVED) ? 1 : 0);
@@ -159,13 +211,23 @@ __device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned w
 // rollouts, grid-striding over *a.work_count: that is how the rollouts the mixed-precision kernel
 // could not decide are finished.
 __global__ void __launch_bounds__(kBlock)
-rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a) {
-    const int64_t n = a.n_leaf * a.replicas;
-    const int64_t total = a.work_list ? (int64_t)*a.work_count : n;
+rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs a0, ForestSlabs fs) {
+    const int64_t n = a0.n_leaf * a0.replicas;
+    const int64_t total = a0.work_list ? (int64_t)*a0.work_count : n;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = base + threadIdx.x;
     const bool live = t < total;
-    const int64_t r = live ? (a.work_list ? (int64_t)a.work_list[t] : t) : 0;
+    int64_t r = live ? t : 0;
+    int scen = blockIdx.y;
+    if (live && a0.work_list) {
+        const uint32_t e = a0.work_list[t];
+        scen = (int)(e >> kRedoShift);
+        r = (int64_t)(e & ((1u << kRedoShift) - 1));
+    }
+    ScenarioView sc = sc0;
+    NoiseView nz = nz0;
+    RolloutArgs a = a0;
+    select_scenario(scen, n, fs, sc, nz, a);
     const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     int bin = 0, st = PMCTS_ST_OK, nstep_out = 0;
     int64_t leaf = 0;
@@ -252,7 +314,8 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
         if (a.final_lat) a.final_lat[r] = blat;
         if (a.final_lon) a.final_lon[r] = blon;
     }
-    reduce_rollouts(a, warp_mask, live, leaf, bin, st, nstep_out, ta);
+    if (a0.work_list) reduce_rollouts<false>(a, warp_mask, live, scen, leaf, bin, st, nstep_out, ta);
+    else reduce_rollouts<true>(a, warp_mask, live, scen, leaf, bin, st, nstep_out, ta);
     }
 }
 
@@ -260,9 +323,11 @@ rollout_batch_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a
 // decisions fell inside the error margins writes nothing: its id goes to a.redo_list and the literal
 // kernel above finishes it (same stream, next launch).
 __global__ void __launch_bounds__(kBlock)
-rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a) {
+rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
     const int64_t n = a.n_leaf * a.replicas;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int scen = blockIdx.y;
+    select_scenario(scen, n, fs, sc, nz, a);
     const bool live = r < n;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     fast::RollOut o;
@@ -271,7 +336,7 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a)
     if (live) {
         fast::rollout_one(sc, bp, nz, a, n, r, o);
         if (o.why) {
-            a.redo_list[atomicAdd(a.redo_count, 1u)] = (uint32_t)r;
+            a.redo_list[atomicAdd(a.redo_count, 1u)] = ((uint32_t)scen << kRedoShift) | (uint32_t)r;
         } else {
             counted = true;
             if (a.reward) a.reward[r] = o.rw;
@@ -284,7 +349,7 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a)
             if (a.final_lon) a.final_lon[r] = o.lon;
         }
     }
-    reduce_rollouts(a, warp_mask, counted, r / a.replicas, o.bin, o.st, o.nstep, o.ta);
+    reduce_rollouts<true>(a, warp_mask, counted, scen, r / a.replicas, o.bin, o.st, o.nstep, o.ta);
 }
 
 // K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
@@ -425,6 +490,7 @@ static int fail(int code, const char *fmt, ...) {
 struct Scenario {
     ScenarioView view{};
     void *blob = nullptr;  // one allocation holding slabs + axes
+    uint64_t times_hash = 0;  // FNV-1a of the simulator instants (launches over several scenarios need equal axes)
 };
 
 }  // namespace pmcts
@@ -896,6 +962,12 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     // the fp32 kernels assume |lat| <= 90 on the grid (their sin / cos kernels cover [-pi/2, pi/2])
     // and one contiguous run of valid instants
     vw.fast_ok = (tc.contiguous && vw.max_abs_lat <= 90.0f) ? 1 : 0;
+    {
+        uint64_t h = 1469598103934665603ull;
+        const unsigned char *bytes = (const unsigned char *)sim_times;
+        for (size_t i = 0; i < (size_t)nT * sizeof(double); ++i) h = (h ^ bytes[i]) * 1099511628211ull;
+        sc.times_hash = h;
+    }
     ctx->scenarios[scen] = sc;
     return PMCTS_OK;
 }
@@ -982,41 +1054,59 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
     return st.finish();
 }
 
-int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],
-                        const double dest[2], double tmin, const double *prefix,
-                        const int32_t *prefix_len, int prefix_stride, const pmcts_noise *noise,
-                        double *reward, double *t_arr, int32_t *steps, uint8_t *status, int32_t *bin,
-                        double *frac, double *final_lat, double *final_lon, double *traj_lat,
-                        double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
-                        int flags) {
-    if (!ctx || !root || !dest) return fail(PMCTS_ERR_ARG, "NULL argument");
+static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int prefix_shared, int64_t n_leaf,
+                        int replicas, const double root[3], const double dest[2], double tmin,
+                        const double *prefix, const int32_t *prefix_len, int prefix_stride,
+                        const pmcts_noise *noise, double *reward, double *t_arr, int32_t *steps, uint8_t *status,
+                        int32_t *bin, double *frac, double *final_lat, double *final_lon, double *traj_lat,
+                        double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats, int flags) {
+    if (!ctx || !root || !dest || !scens) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n_scen < 1 || n_scen > kMaxForest) return fail(PMCTS_ERR_ARG, "1 .. %d scenarios per launch", kMaxForest);
     if (n_leaf < 0 || replicas < 1 || prefix_stride < 0 || traj_stride < 0) return fail(PMCTS_ERR_ARG, "bad sizes");
     if ((prefix == nullptr) != (prefix_len == nullptr)) return fail(PMCTS_ERR_ARG, "prefix and prefix_len go together");
     if (n_leaf == 0) return PMCTS_OK;
     DeviceGuard g(ctx->device);
     Scenario *sc;
-    int rc = find_scenario(ctx, scen, &sc);
+    int rc = find_scenario(ctx, scens[0], &sc);
     if (rc) return rc;
+    ForestSlabs fs{};
+    fs.n_scen = n_scen;
+    fs.prefix_shared = prefix_shared;
+    bool all_fast = true;
+    for (int i = 0; i < n_scen; ++i) {
+        Scenario *si;
+        if ((rc = find_scenario(ctx, scens[i], &si))) return rc;
+        const ScenarioView &x = si->view, &y = sc->view;
+        if (x.nT != y.nT || x.nlat != y.nlat || x.nlon != y.nlon || x.lat0 != y.lat0 || x.lon0 != y.lon0 ||
+            x.inv_dlat != y.inv_dlat || x.inv_dlon != y.inv_dlon || x.box_lat_lo != y.box_lat_lo ||
+            x.box_lat_hi != y.box_lat_hi || x.box_lon_lo != y.box_lon_lo || x.box_lon_hi != y.box_lon_hi ||
+            x.tmax != y.tmax || x.kv_lo != y.kv_lo || x.kv_hi != y.kv_hi || si->times_hash != sc->times_hash)
+            return fail(PMCTS_ERR_SCENARIO, "scenarios of one launch must share their axes, box and simulator instants "
+                                            "(slot %d differs from slot %d)", scens[i], scens[0]);
+        fs.s32[i] = x.slab32;
+        fs.s64[i] = x.slab64;
+        all_fast = all_fast && x.fast_ok;
+    }
     const int64_t n = n_leaf * replicas;
+    const size_t S = (size_t)n_scen, P = prefix_shared ? 1 : S;
     NoiseView nz = noise_view(noise);
     const int max_steps = sc->view.nT;
     if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
     const bool acc = (flags & PMCTS_ROLL_ACCUMULATE) && !(flags & PMCTS_MEM_HOST);
     Stager st(ctx, flags & PMCTS_MEM_HOST);
-    const size_t traj_bytes = al((size_t)traj_stride * n * 8);
-    rc = st.reserve(al((size_t)n_leaf * prefix_stride * 8) + al(n_leaf * 4) + 6 * al(n * 8) + 2 * al(n * 4) + al(n) +
-                    (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(n_leaf * 48) + al(64) +
-                    (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)max_steps * n * 8) : 0));
+    const size_t traj_bytes = al(S * traj_stride * n * 8);
+    rc = st.reserve(al(P * n_leaf * prefix_stride * 8) + al(P * n_leaf * 4) + 6 * al(S * n * 8) + 2 * al(S * n * 4) +
+                    al(S * n) + (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(S * n_leaf * 48) +
+                    al(S * 64) + (nz.mode == PMCTS_NOISE_INJECTED ? al(S * max_steps * n * 8) : 0));
     if (rc) return rc;
-    if ((rc = st.in(prefix, (size_t)n_leaf * prefix_stride)) || (rc = st.in(prefix_len, n_leaf)) ||
-        (rc = st.out(reward, n)) || (rc = st.out(t_arr, n)) || (rc = st.out(steps, n)) ||
-        (rc = st.out(status, n)) || (rc = st.out(bin, n)) || (rc = st.out(frac, n)) ||
-        (rc = st.out(final_lat, n)) || (rc = st.out(final_lon, n)) ||
-        (rc = st.out(traj_lat, (size_t)traj_stride * n, 0xFF)) ||
-        (rc = st.out(traj_lon, (size_t)traj_stride * n, 0xFF)) ||
-        (rc = st.out(leaf_bins, (size_t)n_leaf * 12, acc ? -1 : 0)) || (rc = st.out(stats, 8, acc ? -1 : 0)))
+    if ((rc = st.in(prefix, P * n_leaf * prefix_stride)) || (rc = st.in(prefix_len, P * n_leaf)) ||
+        (rc = st.out(reward, S * n)) || (rc = st.out(t_arr, S * n)) || (rc = st.out(steps, S * n)) ||
+        (rc = st.out(status, S * n)) || (rc = st.out(bin, S * n)) || (rc = st.out(frac, S * n)) ||
+        (rc = st.out(final_lat, S * n)) || (rc = st.out(final_lon, S * n)) ||
+        (rc = st.out(traj_lat, S * traj_stride * n, 0xFF)) || (rc = st.out(traj_lon, S * traj_stride * n, 0xFF)) ||
+        (rc = st.out(leaf_bins, S * n_leaf * 12, acc ? -1 : 0)) || (rc = st.out(stats, S * 8, acc ? -1 : 0)))
         return rc;
-    if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)max_steps * n))) return rc;
+    if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, S * max_steps * n))) return rc;
     RolloutArgs a{};
     a.n_leaf = n_leaf;
     a.replicas = replicas;
@@ -1049,8 +1139,9 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
     const bool dest_ok = std::fabs(dest[0]) <= 90.0 && std::fabs(dest[0] - vw.lat0) <= 89.0 &&
                          std::fabs(dest[0] - vw.lat_last) <= 89.0 && std::fabs(dest[1] - vw.lon0) <= 89.0 &&
                          std::fabs(dest[1] - vw.lon_last) <= 89.0;
-    if (fast_eligible(ctx, sc) && dest_ok && n < (int64_t)1 << 31) {
-        if ((rc = ensure_work(ctx, (size_t)n * sizeof(uint32_t)))) return rc;
+    const dim3 grid_all(grid_for(n), n_scen);
+    if (fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift)) {
+        if ((rc = ensure_work(ctx, S * n * sizeof(uint32_t)))) return rc;
         a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
         a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
         a.redo_count = (uint32_t *)ctx->work;
@@ -1058,22 +1149,45 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
         CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
-            rollout_fast_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
+            rollout_fast_kernel<<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
         }
         CUDA_TRY(cudaGetLastError());
         a.work_list = a.redo_list;
         a.work_count = a.redo_count;
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
-            const int grid = (int)std::min<int64_t>(grid_for(n), 2 * 148);
-            rollout_batch_kernel<<<grid, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
+            const int grid = (int)std::min<int64_t>((int64_t)grid_for(n) * n_scen, 2 * 148);
+            rollout_batch_kernel<<<grid, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
         }
     } else {
         LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
-        rollout_batch_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a);
+        rollout_batch_kernel<<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
     }
     CUDA_TRY(cudaGetLastError());
     return st.finish();
+}
+
+int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],
+                        const double dest[2], double tmin, const double *prefix,
+                        const int32_t *prefix_len, int prefix_stride, const pmcts_noise *noise,
+                        double *reward, double *t_arr, int32_t *steps, uint8_t *status, int32_t *bin,
+                        double *frac, double *final_lat, double *final_lon, double *traj_lat,
+                        double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
+                        int flags) {
+    const int32_t one = scen;
+    return rollout_impl(ctx, 1, &one, 1, n_leaf, replicas, root, dest, tmin, prefix, prefix_len, prefix_stride, noise,
+                        reward, t_arr, steps, status, bin, frac, final_lat, final_lon, traj_lat, traj_lon, traj_stride,
+                        leaf_bins, stats, flags);
+}
+
+int pmcts_rollout_forest(pmcts_ctx *ctx, int n_scen, const int32_t *scen, int64_t n_leaf, int replicas,
+                         const double root[3], const double dest[2], double tmin, const double *prefix,
+                         const int32_t *prefix_len, int prefix_stride, int prefix_shared,
+                         const pmcts_noise *noise, double *reward, double *t_arr, int32_t *steps,
+                         uint8_t *status, int32_t *bin, uint32_t *leaf_bins, double *stats, int flags) {
+    return rollout_impl(ctx, n_scen, scen, prefix_shared ? 1 : 0, n_leaf, replicas, root, dest, tmin, prefix,
+                        prefix_len, prefix_stride, noise, reward, t_arr, steps, status, bin, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, 0, leaf_bins, stats, flags);
 }
 
 int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, const int32_t *parent,

@@ -217,6 +217,31 @@ class Engine:
                                               C.byref(nz), *ptrs, int(traj_stride), plb, pstats,
                                               int(flags) | a.mem_flag))
 
+    def rollout_forest(self, scens, n_leaf, replicas, root, dest, tmin, prefix=None, prefix_len=None,
+                       prefix_stride=0, prefix_shared=True, z=None, seed=None, stream=0, id0=0, out=None, flags=0):
+        """K2 for the scenario slots ``scens`` in one launch (``pmcts_rollout_forest``).  ``out`` maps
+        reward / t_arr / steps / status / bin ([S][n]), leaf_bins ([S][n_leaf][12]) and stats ([S][8]) to
+        preallocated arrays."""
+        out = out or {}
+        a = _Args()
+        scens = np.ascontiguousarray(scens, np.int32)
+        S = scens.size
+        n = int(n_leaf) * int(replicas)
+        P = 1 if prefix_shared else S
+        root = np.ascontiguousarray(root, np.float64).reshape(3)
+        dest = np.ascontiguousarray(dest, np.float64).reshape(2)
+        ppre = a.ptr(prefix, "f64", P * n_leaf * prefix_stride) if prefix is not None else None
+        plen = a.ptr(prefix_len, "i32", P * n_leaf) if prefix_len is not None else None
+        g = lambda name, dt, size: a.ptr(out.get(name), dt, size, True)  # noqa: E731
+        ptrs = [g("reward", "f64", S * n), g("t_arr", "f64", S * n), g("steps", "i32", S * n),
+                g("status", "u8", S * n), g("bin", "i32", S * n), g("leaf_bins", "u32", S * n_leaf * 12),
+                g("stats", "f64", S * 8)]
+        nz = make_noise(a, z, seed, stream, id0)
+        N.check(self._lib.pmcts_rollout_forest(self._h, S, scens.ctypes.data, int(n_leaf), int(replicas),
+                                               root.ctypes.data, dest.ctypes.data, float(tmin), ppre, plen,
+                                               int(prefix_stride), int(bool(prefix_shared)), C.byref(nz), *ptrs,
+                                               int(flags) | a.mem_flag))
+
     def rollout_batch_host(self, scen, n_leaf, replicas, root, dest, tmin, prefix=None, prefix_len=None,
                            z=None, seed=None, stream=0, id0=0, traj_steps=0, flags=0, want=None):
         """Convenience wrapper: allocates NumPy outputs and returns them as a dict."""

@@ -151,6 +151,19 @@ int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, 
                         double *traj_lon, int traj_stride, uint32_t *leaf_bins, double *stats,
                         int flags);
 
+/* K2 for several scenarios in ONE launch -- what Forest.launch_search (forest.py:45-81) spreads over one
+ * process per scenario: rollouts of the scenario slots scen[0 .. n_scen) (a HOST array, n_scen <= 16; the
+ * slots must share their axes, terminal box and simulator instants), n_leaf * replicas rollouts each,
+ * same root / dest / tmin.  Arrays carry a leading scenario dimension: prefix [n_scen][n_leaf][stride]
+ * and prefix_len [n_scen][n_leaf] (or one copy for all when prefix_shared != 0), outputs [n_scen][n],
+ * leaf_bins [n_scen][n_leaf][12], stats [n_scen][8], injected noise z [n_scen][nT][n].  Scenario i draws
+ * its Philox noise from stream noise->stream + i. */
+int pmcts_rollout_forest(pmcts_ctx *ctx, int n_scen, const int32_t *scen, int64_t n_leaf, int replicas,
+                         const double root[3], const double dest[2], double tmin, const double *prefix,
+                         const int32_t *prefix_len, int prefix_stride, int prefix_shared,
+                         const pmcts_noise *noise, double *reward, double *t_arr, int32_t *steps,
+                         uint8_t *status, int32_t *bin, uint32_t *leaf_bins, double *stats, int flags);
+
 /* ---- K3: Node.back_up (worker.py:55-70) / MasterNode.add_reward* + the ancestor walk of
  * Tree.integrate_buffer (master_node.py:34-54, worker.py:358-378) -------------------------------
  * table[scen][node][8][12] uint32 visit counts for n_scen scenarios of n_nodes nodes each (a worker

@@ -287,7 +287,9 @@ def test_fast_mode_hands_over_what_it_does_not_cover(eng):
     n, nsteps = 1000, 40
     lat0, lon0, h0 = synth.octagon_fleet(n, seed=4)
     head = synth.octagon_headings(h0, nsteps, seg_len=5)
-    head[3:, ::7] -= 360.0   # negative headings from the 4th segment on, every 7th boat
+    # 360.0 is outside [0, 360) (the fast path declines it) yet physically sane: the reference's fold of
+    # |wind_from - 360| gives the same point of sail as heading 0
+    head[3:, ::7] = 360.0
     z = np.random.default_rng(8).standard_normal((nsteps, n))
     z[17, ::11] = 4000.0      # one absurd gust: a step of ~0.5 rad
     res = {}
@@ -305,6 +307,50 @@ def test_fast_mode_hands_over_what_it_does_not_cover(eng):
     ok = stl == 0
     assert ok.sum() > n // 2
     assert relerr(laf[ok], lal[ok]) < RTOL and relerr(lof[ok], lol[ok]) < RTOL
+    eng.set_precision(N.PREC_F64)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_rollout_forest_equals_per_scenario_launches(eng, mode):
+    """One launch over several scenarios (pmcts_rollout_forest) == one pmcts_rollout_batch per scenario, with
+    shared and with per-scenario leaf sets, Philox streams stream + s."""
+    eng.set_precision(mode)
+    scen_ids = [2, 5, 9]
+    for slot, sid in enumerate(scen_ids):
+        upload(eng, 10 + slot, sid)
+    dest, tmin = [46.77751005, 355.0], 2.0223605
+    n_leaf, rep = 40, 50
+    n = n_leaf * rep
+    S = len(scen_ids)
+    rng = np.random.default_rng(5)
+    for shared in (True, False):
+        P = 1 if shared else S
+        prefix = 45.0 * rng.integers(0, 8, (P, n_leaf, 2))
+        plen = rng.integers(1, 3, (P, n_leaf)).astype(np.int32)
+        out = dict(steps=np.empty(S * n, np.int32), status=np.empty(S * n, np.uint8), reward=np.empty(S * n),
+                   leaf_bins=np.empty(S * n_leaf * 12, np.uint32), stats=np.empty(S * 8))
+        eng.rollout_forest([10, 11, 12], n_leaf, rep, H.STATE0, dest, tmin, prefix.reshape(-1), plen.reshape(-1), 2,
+                           prefix_shared=shared, seed=77, stream=5, id0=1000, out=out)
+        for s in range(S):
+            one = eng.rollout_batch_host(10 + s, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix[0 if shared else s],
+                                         prefix_len=plen[0 if shared else s], seed=77, stream=5 + s, id0=1000)
+            assert np.array_equal(out["steps"][s * n:(s + 1) * n], one["steps"])
+            assert np.array_equal(out["status"][s * n:(s + 1) * n], one["status"])
+            assert np.array_equal(out["reward"][s * n:(s + 1) * n], one["reward"])
+            assert np.array_equal(out["leaf_bins"].reshape(S, n_leaf, 12)[s], one["leaf_bins"])
+            assert np.array_equal(out["stats"].reshape(S, 8)[s][[0, 3, 4, 5]], one["stats"][[0, 3, 4, 5]])
+            assert np.isclose(out["stats"].reshape(S, 8)[s][1], one["stats"][1], rtol=1e-12)
+        # against the oracle: integer outputs exact
+        o = H.oracle_sim(scen_ids[1])
+        want = o.rollout_batch(n, H.STATE0, dest, tmin, prefix=np.repeat(prefix[0 if shared else 1], rep, 0),
+                               prefix_len=np.repeat(plen[0 if shared else 1], rep), seed=77, stream=6, id0=1000)
+        if mode == N.PREC_F64:
+            assert np.array_equal(out["steps"][n:2 * n], want["steps"])
+            assert np.array_equal(out["status"][n:2 * n], want["status"])
+    # scenarios with different simulator axes cannot share a launch
+    upload(eng, 13, 1, times=np.linspace(0, 5, 41))
+    with pytest.raises(N.PmctsError):
+        eng.rollout_forest([10, 13], n_leaf, rep, H.STATE0, dest, tmin, out=dict(stats=np.empty(16)))
     eng.set_precision(N.PREC_F64)
 
 
