@@ -26,7 +26,7 @@ EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_synchronize", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_launch_count", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
-    "pmcts_get_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
+    "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
     L.pmcts_scenario_upload.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, vp]
     L.pmcts_scenario_free.argtypes = [vp, i32]
     L.pmcts_get_wind.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32]
+    L.pmcts_interp_wind.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_step_batch.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32, C.POINTER(Noise),
                                    vp, vp, vp, i32]
     L.pmcts_rollout_batch.argtypes = [vp, i32, i64, i32, vp, vp, dbl, vp, vp, i32, C.POINTER(Noise),

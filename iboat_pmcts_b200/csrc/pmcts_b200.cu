@@ -46,6 +46,62 @@ __global__ void blend_time_slabs_kernel(const T *__restrict__ u, const T *__rest
     slab32[idx] = make_float2((float)uu, (float)vv);
 }
 
+// Weather.uInterpolator / vInterpolator (weatherTLKT.py:369-378): SciPy's linear RegularGridInterpolator
+// at arbitrary (t, lat, lon), on the raw grid kept from the upload.  Evaluation order of
+// scipy/interpolate/_rgi.py:520-549 -- corners in product order (time slowest, lon fastest), weight
+// ((1 * wt) * wlat) * wlon, accumulated from 0 -- with explicitly unfused multiplies and adds, so the
+// result equals SciPy's bit for bit.
+__device__ __forceinline__ int axis_cell(const double *__restrict__ g, int n, double x, double &w) {
+    int lo = 0, hi = n;  // first index with g[idx] > x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    int i = min(max(lo - 1, 0), n - 2);
+    w = __ddiv_rn(__dsub_rn(x, g[i]), __dsub_rn(g[i + 1], g[i]));
+    return i;
+}
+
+template <typename T>
+__global__ void interp_wind_kernel(const T *__restrict__ u, const T *__restrict__ v, const double *__restrict__ gt,
+                                   int nt, const double *__restrict__ ga, int nlat, const double *__restrict__ go,
+                                   int nlon, int64_t n, const double *__restrict__ t, const double *__restrict__ lat,
+                                   const double *__restrict__ lon, double *__restrict__ ou, double *__restrict__ ov,
+                                   uint8_t *__restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double tt = t[i], la = lat[i], lo = lon[i];
+    const bool ok = gt[0] <= tt && tt <= gt[nt - 1] && ga[0] <= la && la <= ga[nlat - 1] && go[0] <= lo &&
+                    lo <= go[nlon - 1];
+    double su = NAN, sv = NAN;
+    if (ok) {
+        double w[3][2];
+        double y;
+        const int it = axis_cell(gt, nt, tt, y);
+        w[0][0] = __dsub_rn(1.0, y); w[0][1] = y;
+        const int ia = axis_cell(ga, nlat, la, y);
+        w[1][0] = __dsub_rn(1.0, y); w[1][1] = y;
+        const int io = axis_cell(go, nlon, lo, y);
+        w[2][0] = __dsub_rn(1.0, y); w[2][1] = y;
+        su = 0.0;
+        sv = 0.0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const double weight = __dmul_rn(__dmul_rn(__dmul_rn(1.0, w[0][a]), w[1][b]), w[2][c]);
+                    const size_t idx = ((size_t)(it + a) * nlat + (ia + b)) * nlon + (io + c);
+                    su = __dadd_rn(su, __dmul_rn((double)u[idx], weight));
+                    sv = __dadd_rn(sv, __dmul_rn((double)v[idx], weight));
+                }
+    }
+    ou[i] = su;
+    ov[i] = sv;
+    if (status) status[i] = ok ? PMCTS_ST_OK : PMCTS_ST_OUT_OF_GRID;
+}
+
 __global__ void get_wind_kernel(ScenarioView sc, int64_t n, const int32_t *__restrict__ k,
                                 const double *__restrict__ lat, const double *__restrict__ lon,
                                 double *__restrict__ u, double *__restrict__ v,
@@ -491,6 +547,10 @@ struct Scenario {
     ScenarioView view{};
     void *blob = nullptr;  // one allocation holding slabs + axes
     uint64_t times_hash = 0;  // FNV-1a of the simulator instants (launches over several scenarios need equal axes)
+    // raw weather grid kept for Weather.*Interpolator queries at arbitrary times
+    const void *raw_u = nullptr, *raw_v = nullptr;
+    const double *wtime = nullptr, *wlat = nullptr, *wlon = nullptr;
+    int nt = 0, raw_dtype = 0;
 };
 
 }  // namespace pmcts
@@ -660,9 +720,11 @@ bool fast_eligible(const pmcts_ctx *ctx, const Scenario *sc) {
            p.pofsail_min <= 90.0 && p.pofsail_max >= 90.0 && p.pofsail_max <= 180.0 && p.wind_max > 0.0;
 }
 
-int find_scenario(pmcts_ctx *ctx, int scen, Scenario **out) {
+int find_scenario(pmcts_ctx *ctx, int scen, Scenario **out, bool need_axis = true) {
     auto it = ctx->scenarios.find(scen);
     if (it == ctx->scenarios.end()) return fail(PMCTS_ERR_SCENARIO, "scenario slot %d not uploaded", scen);
+    if (need_axis && it->second.view.nT < 1)
+        return fail(PMCTS_ERR_SCENARIO, "scenario slot %d holds a weather grid only (uploaded without simulator instants)", scen);
     *out = &it->second;
     return PMCTS_OK;
 }
@@ -851,9 +913,11 @@ int pmcts_scenario_free(pmcts_ctx *ctx, int scen) {
 int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt, const double *wlat,
                           int nlat, const double *wlon, int nlon, const void *u, const void *v,
                           int dtype, const double *sim_times, int nT, const double box[4]) {
-    if (!ctx || !wtime || !wlat || !wlon || !u || !v || !sim_times || !box)
-        return fail(PMCTS_ERR_ARG, "NULL argument");
-    if (nt < 2 || nlat < 2 || nlon < 2 || nT < 1) return fail(PMCTS_ERR_ARG, "axes too short");
+    if (!ctx || !wtime || !wlat || !wlon || !u || !v) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (nT < 0 || (nT > 0 && (!sim_times || !box))) return fail(PMCTS_ERR_ARG, "a simulator axis needs sim_times and box");
+    if (nt < 2 || nlat < 2 || nlon < 2) return fail(PMCTS_ERR_ARG, "axes too short");
+    static const double no_box[4] = {0, 0, 0, 0};
+    if (nT == 0) box = no_box;
     if (dtype != 0 && dtype != 1) return fail(PMCTS_ERR_ARG, "dtype must be 0 (f64) or 1 (f32)");
     double inv_dlat, inv_dlon;
     if (!uniform_axis(wlat, nlat, &inv_dlat) || !uniform_axis(wlon, nlon, &inv_dlon))
@@ -878,11 +942,16 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     const size_t o_dt = o_times + al(nT * sizeof(double));
     const size_t o_valid = o_dt + al(nT * sizeof(double));
     const size_t o_dt32 = o_valid + al(nT);
-    const size_t total = o_dt32 + al(nT * sizeof(float));
-    // temporaries: raw grid + time cells
     const size_t raw = (size_t)nt * plane * esz;
-    const size_t t_u = 0, t_v = al(raw), t_it = t_v + al(raw), t_wt = t_it + al(nT * sizeof(int));
-    const size_t tmp_total = t_wt + al(nT * sizeof(double));
+    const size_t o_u = o_dt32 + al(nT * sizeof(float));
+    const size_t o_v = o_u + al(raw);
+    const size_t o_wtime = o_v + al(raw);
+    const size_t o_wlat = o_wtime + al(nt * sizeof(double));
+    const size_t o_wlon = o_wlat + al(nlat * sizeof(double));
+    const size_t total = o_wlon + al(nlon * sizeof(double));
+    // temporaries: time cells
+    const size_t t_it = 0, t_wt = al(nT * sizeof(int));
+    const size_t tmp_total = t_wt + al(nT * sizeof(double)) + 256;
 
     Scenario sc;
     char *tmp = nullptr;
@@ -903,25 +972,30 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
             return fail(PMCTS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e2_));         \
         }                                                                                         \
     } while (0)
-    UP_TRY(cudaMemcpyAsync(tmp + t_u, u, raw, cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(tmp + t_v, v, raw, cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(tmp + t_it, it.data(), nT * sizeof(int), cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(tmp + t_wt, wt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(base + o_times, sim_times, nT * sizeof(double), cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(base + o_dt, dt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(base + o_valid, valid.data(), nT, cudaMemcpyHostToDevice, s));
-    UP_TRY(cudaMemcpyAsync(base + o_dt32, tc.dt32.data(), nT * sizeof(float), cudaMemcpyHostToDevice, s));
-    {
+    UP_TRY(cudaMemcpyAsync(base + o_u, u, raw, cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_v, v, raw, cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_wtime, wtime, nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_wlat, wlat, nlat * sizeof(double), cudaMemcpyHostToDevice, s));
+    UP_TRY(cudaMemcpyAsync(base + o_wlon, wlon, nlon * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nT > 0) {
+        UP_TRY(cudaMemcpyAsync(tmp + t_it, it.data(), nT * sizeof(int), cudaMemcpyHostToDevice, s));
+        UP_TRY(cudaMemcpyAsync(tmp + t_wt, wt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
+        UP_TRY(cudaMemcpyAsync(base + o_times, sim_times, nT * sizeof(double), cudaMemcpyHostToDevice, s));
+        UP_TRY(cudaMemcpyAsync(base + o_dt, dt.data(), nT * sizeof(double), cudaMemcpyHostToDevice, s));
+        UP_TRY(cudaMemcpyAsync(base + o_valid, valid.data(), nT, cudaMemcpyHostToDevice, s));
+        UP_TRY(cudaMemcpyAsync(base + o_dt32, tc.dt32.data(), nT * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    if (nT > 0) {
         LaunchTimer lt(ctx);
         const int grid = (int)((cells + 255) / 256);
         if (dtype == 0)
             blend_time_slabs_kernel<double><<<grid, 256, 0, s>>>(
-                (const double *)(tmp + t_u), (const double *)(tmp + t_v), (const int *)(tmp + t_it),
+                (const double *)(base + o_u), (const double *)(base + o_v), (const int *)(tmp + t_it),
                 (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
                 (float2 *)(base + o_slab32));
         else
             blend_time_slabs_kernel<float><<<grid, 256, 0, s>>>(
-                (const float *)(tmp + t_u), (const float *)(tmp + t_v), (const int *)(tmp + t_it),
+                (const float *)(base + o_u), (const float *)(base + o_v), (const int *)(tmp + t_it),
                 (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
                 (float2 *)(base + o_slab32));
     }
@@ -949,7 +1023,14 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.box_lat_hi = box[1];
     vw.box_lon_lo = box[2];
     vw.box_lon_hi = box[3];
-    vw.tmax = sim_times[nT - 1];
+    vw.tmax = nT > 0 ? sim_times[nT - 1] : 0.0;
+    sc.raw_u = base + o_u;
+    sc.raw_v = base + o_v;
+    sc.wtime = (const double *)(base + o_wtime);
+    sc.wlat = (const double *)(base + o_wlat);
+    sc.wlon = (const double *)(base + o_wlon);
+    sc.nt = nt;
+    sc.raw_dtype = dtype;
     vw.dt_sec32 = (const float *)(base + o_dt32);
     vw.kv_lo = tc.kv_lo;
     vw.kv_hi = tc.kv_hi;
@@ -961,7 +1042,7 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.box_fo_hi = (float)((box[3] - vw.lon0) * inv_dlon);
     // the fp32 kernels assume |lat| <= 90 on the grid (their sin / cos kernels cover [-pi/2, pi/2])
     // and one contiguous run of valid instants
-    vw.fast_ok = (tc.contiguous && vw.max_abs_lat <= 90.0f) ? 1 : 0;
+    vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f) ? 1 : 0;
     {
         uint64_t h = 1469598103934665603ull;
         const unsigned char *bytes = (const unsigned char *)sim_times;
@@ -989,6 +1070,36 @@ int pmcts_get_wind(pmcts_ctx *ctx, int scen, int64_t n, const int32_t *k, const 
     {
         LaunchTimer lt(ctx);
         get_wind_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(sc->view, n, k, lat, lon, u, v, status);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return st.finish();
+}
+
+int pmcts_interp_wind(pmcts_ctx *ctx, int scen, int64_t n, const double *t, const double *lat, const double *lon,
+                      double *u, double *v, uint8_t *status, int flags) {
+    if (!ctx || !t || !lat || !lon || !u || !v) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n <= 0) return PMCTS_OK;
+    DeviceGuard g(ctx->device);
+    Scenario *sc;
+    int rc = find_scenario(ctx, scen, &sc, false);
+    if (rc) return rc;
+    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    rc = st.reserve(5 * al(n * 8) + al(n));
+    if (rc) return rc;
+    if ((rc = st.in(t, n)) || (rc = st.in(lat, n)) || (rc = st.in(lon, n)) || (rc = st.out(u, n)) ||
+        (rc = st.out(v, n)) || (rc = st.out(status, n)))
+        return rc;
+    {
+        LaunchTimer lt(ctx);
+        const ScenarioView &vw = sc->view;
+        if (sc->raw_dtype == 0)
+            interp_wind_kernel<double><<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                (const double *)sc->raw_u, (const double *)sc->raw_v, sc->wtime, sc->nt, sc->wlat, vw.nlat, sc->wlon,
+                vw.nlon, n, t, lat, lon, u, v, status);
+        else
+            interp_wind_kernel<float><<<grid_for(n), kBlock, 0, ctx->stream>>>(
+                (const float *)sc->raw_u, (const float *)sc->raw_v, sc->wtime, sc->nt, sc->wlat, vw.nlat, sc->wlon,
+                vw.nlon, n, t, lat, lon, u, v, status);
     }
     CUDA_TRY(cudaGetLastError());
     return st.finish();

@@ -144,7 +144,7 @@ class Engine:
                                            float(earth_radius)))
 
     # ---- scenarios ----------------------------------------------------------------------------
-    def upload_scenario(self, scen, wtime, wlat, wlon, u, v, sim_times, box):
+    def upload_scenario(self, scen, wtime, wlat, wlon, u, v, sim_times=None, box=None):
         wtime = np.ascontiguousarray(wtime, np.float64)
         wlat = np.ascontiguousarray(wlat, np.float64)
         wlon = np.ascontiguousarray(wlon, np.float64)
@@ -155,6 +155,12 @@ class Engine:
         v = np.ascontiguousarray(v, dt)
         if u.shape != (wtime.size, wlat.size, wlon.size) or v.shape != u.shape:
             raise ValueError("u, v must have shape (ntime, nlat, nlon)")
+        if sim_times is None:  # weather only: serves interp_wind
+            N.check(self._lib.pmcts_scenario_upload(
+                self._h, int(scen), wtime.ctypes.data, wtime.size, wlat.ctypes.data, wlat.size,
+                wlon.ctypes.data, wlon.size, u.ctypes.data, v.ctypes.data, 1 if dt == np.float32 else 0,
+                None, 0, None))
+            return
         sim_times = np.ascontiguousarray(sim_times, np.float64)
         box = np.ascontiguousarray(box, np.float64).reshape(4)
         N.check(self._lib.pmcts_scenario_upload(
@@ -174,6 +180,17 @@ class Engine:
         u, v, st = np.empty(n), np.empty(n), np.empty(n, np.uint8)
         N.check(self._lib.pmcts_get_wind(self._h, int(scen), n, k.ctypes.data, lat.ctypes.data, lon.ctypes.data,
                                          u.ctypes.data, v.ctypes.data, st.ctypes.data, N.MEM_HOST))
+        return u, v, st
+
+    def interp_wind(self, scen, t, lat, lon):
+        """SciPy-exact trilinear interpolation of the raw grid at arbitrary (t, lat, lon) points."""
+        lat = np.ascontiguousarray(lat, np.float64).ravel()
+        lon = np.ascontiguousarray(lon, np.float64).ravel()
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float64), lat.shape))
+        n = lat.size
+        u, v, st = np.empty(n), np.empty(n), np.empty(n, np.uint8)
+        N.check(self._lib.pmcts_interp_wind(self._h, int(scen), n, t.ctypes.data, lat.ctypes.data, lon.ctypes.data,
+                                            u.ctypes.data, v.ctypes.data, st.ctypes.data, N.MEM_HOST))
         return u, v, st
 
     # ---- K1 ---------------------------------------------------------------------------------------
@@ -289,10 +306,39 @@ class Engine:
 
 
 _default = {}
+_default_device = None
 
 
-def default_engine(device=0):
+def set_default_device(device):
+    """Device used by the reference-API mirror (Weather / Simulator / Tree / Forest ...); by default
+    LOCAL_RANK when launched by torchrun, else 0."""
+    global _default_device
+    _default_device = int(device)
+
+
+def default_engine(device=None):
     """Process-wide engine per device, created on first use."""
+    import os
+    if device is None:
+        device = _default_device if _default_device is not None else int(os.environ.get("LOCAL_RANK", "0"))
     if device not in _default:
         _default[device] = Engine(device)
     return _default[device]
+
+
+class Slot:
+    """A scenario slot of an engine, freed when the last Python object that uses it goes away."""
+    _next = {}
+
+    def __init__(self, engine):
+        self.engine = engine
+        key = id(engine)
+        Slot._next[key] = Slot._next.get(key, 1 << 20) + 1
+        self.id = Slot._next[key]
+
+    def __del__(self):
+        try:
+            if self.engine._h:
+                self.engine.free_scenario(self.id)
+        except Exception:
+            pass

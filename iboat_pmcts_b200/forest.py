@@ -1,0 +1,288 @@
+"""Drop-in mirror of ``code/solver/forest.py`` (reference): ``Forest``, ``create_simulators`` and
+``initialize_simulators``.  (Scenario download / pickle loading / plotting are out of scope.)
+
+The reference runs one ``multiprocessing.Process`` per scenario around a ``Manager().dict()``
+(forest.py:45-81).  Here the scenarios of this process are rolled out together on its GPU
+(``pmcts_rollout_forest``: all local scenarios in one launch), scenarios are sharded over the ranks of a
+``torch.distributed`` job, and the per-scenario update blocks of a wave are all-gathered so that every
+rank applies the same updates, in the same order, to its replica of the master dictionary.
+"""
+import random as rand
+from copy import deepcopy
+
+import numpy as np
+
+from . import _native as N
+from . import worker as mt
+from .master_node import MasterNode
+from .simulatorTLKT import A_DICT, ACTIONS, HOURS_TO_DAY, Simulator
+
+ROOT_HASH = hash(tuple([]))
+MAX_DEPTH = 32  # fixed width of a leaf's action path in the all-gathered update block
+
+
+class Forest:
+    """Coordinates the worker trees and the master dictionary of a parallel search (forest.py:14-81)."""
+
+    def __init__(self, listsimulators=[], destination=[], timemin=0, budget=100):
+        self.workers = dict()
+        nscenario = len(listsimulators)
+        self.nscenario = nscenario
+        self.destination = list(destination)
+        self.timemin = timemin
+        for i, sim in enumerate(listsimulators):
+            self.workers[i] = mt.Tree(workerid=i, nscenario=nscenario, ite=0, budget=budget,
+                                      simulator=deepcopy(sim), destination=deepcopy(destination), TimeMin=timemin)
+
+    # ------------------------------------------------------------------------------------------------
+    def launch_search(self, root_state, frequency, mode="batched", leaves=64, replicas=32, seed=0,
+                      replay_full_prefix=False, group=None):
+        """Runs the search and returns the master dictionary ``{hash(tuple(origins)): MasterNode}`` (deep
+        copy it with ``master_node.deepcopy_dict`` before use, as with the reference).
+
+        ``mode="sequential"``: every worker runs the reference's ``Tree.uct_search`` (one rollout per
+        iteration, ``frequency`` iterations between pushes to the master), one worker after the other --
+        what the reference's processes do when they do not interleave; reproducible from
+        ``random.seed`` / ``np.random.seed``.
+
+        ``mode="batched"`` (default): waves of ``leaves`` leaves per tree, ``replicas`` noise replicas per
+        leaf (Philox noise from ``seed``), all local scenarios in one launch; the master is updated after
+        every wave (the role ``frequency`` plays in the reference).  With ``torch.distributed`` initialised
+        (``group``), worker ``i`` lives on rank ``i % world`` and the waves' update blocks are all-gathered.
+        """
+        Master_nodes = dict()
+        Master_nodes[ROOT_HASH] = MasterNode(len(self.workers), nodehash=ROOT_HASH)
+        if mode == "sequential":
+            for worker in self.workers.values():
+                worker.replay_full_prefix = replay_full_prefix
+                worker.uct_search(deepcopy(root_state), frequency, Master_nodes)
+            return Master_nodes
+        if mode != "batched":
+            raise ValueError("mode must be 'sequential' or 'batched'")
+        return self._search_batched(list(root_state), Master_nodes, int(leaves), int(replicas), int(seed),
+                                    bool(replay_full_prefix), group)
+
+    # ------------------------------------------------------------------------------------------------
+    def _search_batched(self, root_state, Master_nodes, B, K, seed, replay_full, group):
+        dist = None
+        rank, world = 0, 1
+        try:
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized():
+                dist, rank, world = tdist, tdist.get_rank(group), tdist.get_world_size(group)
+        except ImportError:
+            pass
+        S = len(self.workers)
+        if S % world:
+            raise ValueError("the number of scenarios (%d) must be a multiple of the world size (%d)" % (S, world))
+        local_ids = [i for i in range(S) if i % world == rank]
+        trees = [self.workers[i] for i in local_ids]
+        for t in trees:
+            t._make_root(root_state)
+        budget = trees[0].budget
+        eng, slots = None, []
+        for t in trees:
+            e, s = t.Simulator.scenario()
+            eng = e
+            slots.append(s)
+        eng.set_precision(N.PREC_FAST)
+        flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
+        S_loc = len(trees)
+        wave = 0
+        while trees[0].ite < budget:
+            b = min(B, budget - trees[0].ite)
+            leaves = [t.select_leaves(b, Master_nodes) for t in trees]
+            depth = max(1, max(len(l.origins) for ls in leaves for l in ls))
+            if depth > MAX_DEPTH:
+                raise ValueError("tree deeper than %d" % MAX_DEPTH)
+            prefix = np.zeros((S_loc, b, depth), np.float64)
+            plen = np.zeros((S_loc, b), np.int32)
+            for si, ls in enumerate(leaves):
+                for li, leaf in enumerate(ls):
+                    plen[si, li] = len(leaf.origins)
+                    prefix[si, li, :plen[si, li]] = leaf.origins
+            bins = np.zeros((S_loc, b, 12), np.uint32)
+            eng.rollout_forest(slots, b, K, root_state, self.destination, self.timemin, prefix.reshape(-1),
+                               plen.reshape(-1), depth, prefix_shared=False, seed=seed,
+                               stream=wave * S + rank * S_loc, id0=0,
+                               out=dict(leaf_bins=bins.reshape(-1)), flags=flags)
+            # random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward (master_node.py:42)
+            slot_w = np.random.randint(len(ACTIONS), size=(S_loc, b))
+            slot_m = np.random.randint(len(ACTIONS), size=(S_loc, b))
+            for t, ls, bb, sw in zip(trees, leaves, bins, slot_w):
+                t.back_up_leaves(ls, bb, sw)
+            # update block of this rank: action paths, slots and histograms of its leaves
+            paths = np.full((S_loc, b, MAX_DEPTH), -1, np.int32)
+            paths[:, :, :depth] = np.where(np.arange(depth)[None, None, :] < plen[:, :, None], prefix, -1).astype(np.int32)
+            block = dict(ids=np.asarray(local_ids, np.int32), paths=paths, slots=slot_m.astype(np.int32), bins=bins)
+            blocks = _all_gather_blocks(block, dist, group, world)
+            for blk in blocks:  # rank order, then scenario order, then leaf order: identical on every rank
+                for si, scen_id in enumerate(blk["ids"]):
+                    for li in range(b):
+                        path = [a for a in blk["paths"][si, li] if a >= 0]
+                        _master_add(Master_nodes, S, int(scen_id), path, int(blk["slots"][si, li]), blk["bins"][si, li])
+            wave += 1
+        return Master_nodes
+
+
+def _master_add(Master_nodes, nscen, scen_id, path, slot, bins):
+    """``Tree.integrate_buffer`` (worker.py:348-378) for one leaf and a whole histogram of rewards."""
+    actions = [int(a) for a in path]
+    key = hash(tuple(actions))
+    node = Master_nodes.get(key, 0)
+    if node == 0:
+        # ancestors first (a leaf of a later wave may sit several levels below the last known node)
+        parent = Master_nodes[ROOT_HASH]
+        for d in range(1, len(actions) + 1):
+            k = hash(tuple(actions[:d]))
+            nxt = Master_nodes.get(k, 0)
+            if nxt == 0:
+                nxt = MasterNode(nscen, nodehash=k, parentNode=parent, action=actions[d - 1])
+                Master_nodes[k] = nxt
+            parent = nxt
+        node = Master_nodes[key]
+    node.add_bins(scen_id, slot, bins)
+    while node.parentNode is not None:
+        node.parentNode.add_bins(scen_id, A_DICT[node.arm], bins)
+        node = node.parentNode
+
+
+def _all_gather_blocks(block, dist, group, world):
+    """One all-gather of the fixed-size update block per wave (NCCL on the GPUs; gloo in the CPU tests)."""
+    if dist is None or world == 1:
+        return [block]
+    import torch
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    flat = np.concatenate([block["ids"].ravel(), block["paths"].ravel(), block["slots"].ravel(),
+                           block["bins"].astype(np.int64).astype(np.int32).ravel()]).astype(np.int32)
+    send = torch.from_numpy(flat).to(dev)
+    recv = torch.empty(world * flat.size, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, -1)
+    out = []
+    s_loc, b = block["paths"].shape[:2]
+    for r in range(world):
+        o = 0
+        blk = {}
+        for name, shape in (("ids", (s_loc,)), ("paths", (s_loc, b, MAX_DEPTH)), ("slots", (s_loc, b)),
+                            ("bins", (s_loc, b, 12))):
+            size = int(np.prod(shape))
+            blk[name] = recv[r, o:o + size].reshape(shape)
+            o += size
+        blk["bins"] = blk["bins"].astype(np.uint32)
+        out.append(blk)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def create_simulators(weathers, numberofsim, simtimestep=6, stateinit=(0, 47.5, -3.5 + 360),
+                      ndaysim=8, deltalatlon=0.5):
+    """One ``Simulator`` per weather scenario (forest.py:154-187).  Shifts each ``weather.time`` to start
+    at 0 in place, as the reference does."""
+    sims = []
+    for jj in range(numberofsim):
+        weathers[jj].time = weathers[jj].time - weathers[jj].time[0]
+        times = np.arange(0, ndaysim + simtimestep * HOURS_TO_DAY, simtimestep * HOURS_TO_DAY)
+        lats = np.arange(weathers[jj].lat[0], weathers[jj].lat[-1], deltalatlon)
+        lons = np.arange(weathers[jj].lon[0], weathers[jj].lon[-1], deltalatlon)
+        sims.append(Simulator(times, lats, lons, weathers[jj], list(stateinit)))
+    return sims
+
+
+def _reference_noise(n_steps):
+    """n_steps standard normals from Python's global generator, and a function that leaves the generator
+    where ``used`` calls of ``random.gauss`` would have."""
+    state = rand.getstate()
+    z = np.array([rand.gauss(0.0, 1.0) for _ in range(n_steps)], np.float64)
+
+    def consume(used):
+        rand.setstate(state)
+        for _ in range(used):
+            rand.gauss(0.0, 1.0)
+    return z, consume
+
+
+def initialize_simulators(sims, ntra, stateinit, missionheading, plot=False, seed=None):
+    """Destination point and reference time of a search (forest.py:210-331).
+
+    Phase 1: per scenario, ``ntra`` boats hold ``missionheading`` until their next state would be terminal;
+    the destination lies at the smallest of the scenarios' mean distances.  Phase 2: per scenario, ``ntra``
+    default-policy runs to that destination; ``timemin`` is the smallest arrival time.
+
+    ``seed=None``: the noise comes from ``random.gauss`` in the reference's order (one launch per
+    trajectory), so a seeded script gets the reference's numbers.  ``seed=int``: Philox noise, one launch
+    per scenario and phase.
+    """
+    if plot:
+        raise NotImplementedError("plotting is outside the scope of pmcts_b200")
+    k0, lat0, lon0 = int(stateinit[0]), float(stateinit[1]), float(stateinit[2])
+    meanarrivaldistances = []
+    for si, sim in enumerate(sims):
+        eng, scen = sim.scenario()
+        nT = len(sim.times)
+        prec = eng.precision
+        eng.set_precision(N.PREC_F64 if seed is None else N.PREC_FAST)
+        try:
+            if seed is None:
+                ends = []
+                for _ in range(ntra):
+                    z, consume = _reference_noise(nT)
+                    k, la, lo = np.array([k0], np.int32), np.array([lat0]), np.array([lon0])
+                    st = np.zeros(1, np.uint8)
+                    eng.step_batch(scen, k, la, lo, np.array([[float(missionheading)]]), nsteps=nT, seg_len=nT,
+                                   status=st, z=z.reshape(nT, 1), flags=N.STEP_STOP_BEFORE_TERMINAL)
+                    consume(int(k[0]) - k0)
+                    _raise_unless(st, (N.ST_HORIZON, N.ST_OUT_OF_BOX))
+                    ends.append((float(la[0]), float(lo[0])))
+            else:
+                k, la, lo = np.full(ntra, k0, np.int32), np.full(ntra, lat0), np.full(ntra, lon0)
+                st = np.zeros(ntra, np.uint8)
+                eng.step_batch(scen, k, la, lo, np.full((1, ntra), float(missionheading)), nsteps=nT, seg_len=nT,
+                               status=st, seed=seed, stream=2 * si, flags=N.STEP_STOP_BEFORE_TERMINAL)
+                _raise_unless(st, (N.ST_HORIZON, N.ST_OUT_OF_BOX))
+                ends = list(zip(la.tolist(), lo.tolist()))
+        finally:
+            eng.set_precision(prec)
+        arrivaldistances = [sim.getDistAndBearing([lat0, lon0], list(p))[0] for p in ends]
+        meanarrivaldistances.append(np.mean(arrivaldistances))
+    mindist = np.min(meanarrivaldistances)
+    destination = sims[-1].getDestination(mindist, missionheading, [lat0, lon0])
+
+    min_arrival_times = []
+    for si, sim in enumerate(sims):
+        eng, scen = sim.scenario()
+        nT = len(sim.times)
+        prec = eng.precision
+        eng.set_precision(N.PREC_F64 if seed is None else N.PREC_FAST)
+        try:
+            if seed is None:
+                arrivaltimes = []
+                for _ in range(ntra):
+                    z, consume = _reference_noise(nT)
+                    r = eng.rollout_batch_host(scen, 1, 1, [k0, lat0, lon0], destination, 0.0, z=z.reshape(nT, 1),
+                                               flags=N.ROLL_PLAN_EVAL, want=("t_arr", "steps", "status"))
+                    consume(int(r["steps"][0]))
+                    _raise_unless(r["status"], (N.ST_ARRIVED, N.ST_HORIZON, N.ST_OUT_OF_BOX))
+                    if r["status"][0] == N.ST_ARRIVED:
+                        arrivaltimes.append(float(r["t_arr"][0]))
+            else:
+                r = eng.rollout_batch_host(scen, ntra, 1, [k0, lat0, lon0], destination, 0.0, seed=seed,
+                                           stream=2 * si + 1, flags=N.ROLL_PLAN_EVAL, want=("t_arr", "status"))
+                _raise_unless(r["status"], (N.ST_ARRIVED, N.ST_HORIZON, N.ST_OUT_OF_BOX))
+                arrivaltimes = r["t_arr"][r["status"] == N.ST_ARRIVED].tolist()
+        finally:
+            eng.set_precision(prec)
+        if arrivaltimes:
+            min_arrival_times.append(min(arrivaltimes))
+        else:
+            print("Scenario num : " + str(si) + " did not reach destination")
+    timemin = min(min_arrival_times)
+    return [destination, timemin]
+
+
+def _raise_unless(status, allowed):
+    from .simulatorTLKT import raise_for_status
+    for s in np.asarray(status).ravel():
+        if int(s) not in allowed and int(s) != N.ST_OK:
+            raise_for_status(int(s))

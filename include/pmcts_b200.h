@@ -114,7 +114,9 @@ int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, do
  * Weather axes ascending and uniformly spaced; u, v are [nt][nlat][nlon] host arrays, fp64
  * (dtype 0) or fp32 (dtype 1).  sim_times[nT] is the simulator axis in days; box = {lats[0],
  * lats[-1], lons[0], lons[-1]} of the Simulator (the terminal box of worker.py:430-434).
- * On the device the scenario is stored as one time-blended (u, v) slab per simulator instant. */
+ * On the device the scenario is stored as one time-blended (u, v) slab per simulator instant, plus the
+ * raw grid (for pmcts_interp_wind).  nT = 0 (sim_times / box may be NULL) uploads the weather alone:
+ * such a slot serves pmcts_interp_wind only. */
 int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt, const double *wlat,
                           int nlat, const double *wlon, int nlon, const void *u, const void *v,
                           int dtype, const double *sim_times, int nT, const double box[4]);
@@ -122,6 +124,12 @@ int pmcts_scenario_free(pmcts_ctx *ctx, int scen);
 /* Simulator.getWind (simulatorTLKT.py:168-179) for n query points at time index k[i]. */
 int pmcts_get_wind(pmcts_ctx *ctx, int scen, int64_t n, const int32_t *k, const double *lat,
                    const double *lon, double *u, double *v, uint8_t *status, int flags);
+
+/* Weather.uInterpolator / vInterpolator (weatherTLKT.py:369-378) at n arbitrary points (t days, lat, lon):
+ * SciPy's linear RegularGridInterpolator, same evaluation order, bit-for-bit; out-of-bounds points get
+ * NaN and PMCTS_ST_OUT_OF_GRID (SciPy raises ValueError). */
+int pmcts_interp_wind(pmcts_ctx *ctx, int scen, int64_t n, const double *t, const double *lat,
+                      const double *lon, double *u, double *v, uint8_t *status, int flags);
 
 /* ---- K1: Simulator.doStep (simulatorTLKT.py:181-216) for n boats, nsteps fused ---------------
  * State is structure-of-arrays: k[n] time index, lat[n], lon[n] degrees, prev_lat/prev_lon[n]

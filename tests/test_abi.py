@@ -1,0 +1,58 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/pmcts_b200.h declares; the product
+has no CPU path (creating a context without a CUDA device fails loudly)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from iboat_pmcts_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "pmcts_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmcts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 24
+    lib = N.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(N.EXPORTS) == names  # the ctypes binding lists exactly the header's functions
+    assert b"sm_100a" in lib.pmcts_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    rc = N.lib().pmcts_create(0, C.byref(h))
+    assert rc == N.ERR_NO_DEVICE and not h.value
+    assert b"no CPU path" in N.lib().pmcts_last_error()
+    from iboat_pmcts_b200.engine import Engine
+    with pytest.raises(N.PmctsError):
+        Engine(0)
+    # the reference-API mirror goes through the same engine: no silent host implementation of doStep
+    from iboat_pmcts_b200 import synth
+    from iboat_pmcts_b200.forest import create_simulators
+    from iboat_pmcts_b200.weatherTLKT import Weather
+    t, la, lo, u, v = synth.wind_fields(0)
+    with pytest.raises(N.PmctsError):
+        sims = create_simulators([Weather(la, lo, t, u, v)], 1, stateinit=(0, 44.0, 355.0), ndaysim=3)
+        sims[0].doStep(0)
+
+
+def test_product_does_not_import_test_infrastructure():
+    pkg = os.path.join(ROOT, "iboat_pmcts_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in text and "from oracle" not in text, fn
+                assert "fastmodel" not in text.replace("tests/fastmodel", "") or fn.endswith((".cuh", ".h")), fn

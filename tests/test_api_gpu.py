@@ -1,0 +1,227 @@
+"""The reference's Python API on top of the CUDA engine (GPU): Weather interpolators, Simulator.doStep and
+its exceptions, initialize_simulators, estimate_perfomance_plan, a seeded Tree.uct_search that must grow
+the reference's tree, and the leaf-batched Forest search.  Expected values are the golden fixtures
+recorded from the reference itself (oracle/gen_golden.py) or the oracle on the same inputs.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import pmcts_helpers as H
+from iboat_pmcts_b200 import forest as ft
+from iboat_pmcts_b200 import isochrones as iso
+from iboat_pmcts_b200 import master_node as mn
+from iboat_pmcts_b200 import simulatorTLKT as SimC
+from iboat_pmcts_b200 import synth, worker
+from iboat_pmcts_b200.master import MasterTree
+from iboat_pmcts_b200.weatherTLKT import Weather
+
+pytestmark = pytest.mark.gpu
+
+STATE0 = [0, 44.0, 355.0]
+
+
+def make_sims(scenarios):
+    ws = []
+    for s in scenarios:
+        t, la, lo, u, v = synth.wind_fields(s)
+        ws.append(Weather(la, lo, t, u, v))
+    return ft.create_simulators(ws, len(ws), simtimestep=6, stateinit=tuple(STATE0), ndaysim=3)
+
+
+class Feeder:
+    """Stands in for the ``random`` module: gauss(mu, s) = mu + z[row, j] * s, one row per trajectory (a
+    row starts at every getstate(), which the mirror calls once per trajectory)."""
+
+    def __init__(self, z):
+        self.z, self.i, self.j = np.asarray(z), -1, 0
+
+    def getstate(self):
+        self.i += 1
+        self.j = 0
+        return (self.i, 0)
+
+    def setstate(self, st):
+        self.i, self.j = st
+
+    def gauss(self, mu, sigma):
+        zz = float(self.z[self.i, self.j])
+        self.j += 1
+        return mu + zz * sigma
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "kat.json")) as f:
+        return json.load(f)
+
+
+def test_weather_interpolators_are_scipy_exact(kat):
+    t, la, lo, u, v = synth.wind_fields(0)
+    w = Weather(la, lo, t, u, v)
+    w.Interpolators()
+    pts = np.array(kat["getWind_scenario0"])
+    assert np.array_equal(w.uInterpolator(pts[:, :3]), pts[:, 3])   # bit for bit
+    assert np.array_equal(w.vInterpolator(pts[:, :3]), pts[:, 4])
+    one = w.uInterpolator(list(pts[0, :3]))
+    assert one.shape == (1,) and one[0] == pts[0, 3]
+    # grid nodes and the far corner
+    assert w.uInterpolator([t[3], la[5], lo[7]])[0] == u[3, 5, 7]
+    assert w.vInterpolator([t[-1], la[-1], lo[-1]])[0] == v[-1, -1, -1]
+    with pytest.raises(ValueError):
+        w.uInterpolator([0.0, 39.99, 350.0])
+    with pytest.raises(ValueError):
+        w.vInterpolator([5.01, 45.0, 350.0])
+    assert Weather.returnPolarVel(3, 4) == (5.0, 36.86989764584402)
+    c = w.crop(latBound=[41, 49], lonBound=[346, 359], timeSteps=[0, 10])
+    assert c.lat[0] == 41.5 and c.lon[-1] == 358.5 and c.u.shape == (10, 15, 25)
+
+
+def test_simulator_do_step_follows_the_reference(kat):
+    sim = make_sims([0])[0]
+    o = H.oracle_sim(0)
+    random.seed(11)
+    zs = []
+    state = random.getstate()
+    for _ in range(12):
+        zs.append(random.gauss(0.0, 1.0))
+    random.setstate(state)
+    sim.reset(STATE0)
+    k, la, lo = 0, 44.0, 355.0
+    for j, action in enumerate([0, 45, 90, 315, 0, 0, 270, 0, 45, 0, 0, 0]):
+        want = o.step_batch(k, [la], [lo], [[float(action)]], z=[[zs[j]]])
+        prev = list(sim.state)
+        st = sim.doStep(action)
+        assert st is sim.state and sim.prevState == prev
+        k, la, lo = int(want["k"][0]), float(want["lat"][0]), float(want["lon"][0])
+        assert st[0] == k and abs(st[1] - la) < 1e-11 * la and abs(st[2] - lo) < 1e-11 * lo
+    assert isinstance(st[0], int) and isinstance(st[1], float)
+    with pytest.raises(IndexError):   # times[k + 1] past the axis (simulatorTLKT.py:208)
+        sim.doStep(0)
+    sim.reset([0, 49.9, 359.9])
+    with pytest.raises(ValueError):   # SciPy bounds_error
+        for _ in range(12):
+            sim.doStep(45)
+    # scalar helpers and KATs
+    for d, b, la_, lo_, want in kat["getDestination"]:
+        assert sim.getDestination(d, b, [la_, lo_]) == want
+    for a, b, want in kat["getDistAndBearing"]:
+        assert list(sim.getDistAndBearing(a, b)) == want
+    for p, w, want in kat["getDeterDyn"]:
+        assert float(SimC.Boat.getDeterDyn(p, w, SimC.Boat.FIT_VELOCITY)) == want
+    sim.reset(STATE0)
+    u, v = sim.getWind()
+    assert u.shape == (1,) and (float(u[0]), float(v[0])) == o.interp(0.0, 44.0, 355.0)
+    # Boat.UNCERTAINTY_COEFF is read at call time (Tutorial.py:81 sets it to 0 for the isochrones)
+    saved = SimC.Boat.UNCERTAINTY_COEFF
+    try:
+        SimC.Boat.UNCERTAINTY_COEFF = 0
+        sim.reset(STATE0)
+        a = list(sim.doStep(0))
+        sim.reset(STATE0)
+        b = list(sim.doStep(0))
+        assert a == b
+        want = o.step_batch(0, [44.0], [355.0], [[0.0]], z=[[0.0]])
+        assert abs(a[1] - want["lat"][0]) < 1e-10
+    finally:
+        SimC.Boat.UNCERTAINTY_COEFF = saved
+
+
+def test_initialize_simulators_and_plan_evaluation_golden(golden_dir, monkeypatch):
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    pe = np.load(os.path.join(golden_dir, "plan_eval_c5.npz"))
+    sims = make_sims([int(s) for s in g["scenarios"]])
+    assert np.array_equal(sims[0].times, g["times"]) and np.array_equal(sims[0].lats, g["lats"])
+    monkeypatch.setattr(ft, "rand", Feeder(g["zinit"]))
+    destination, timemin = ft.initialize_simulators(sims, int(g["ntra"]), STATE0, 0)
+    assert np.allclose(destination, g["destination"], rtol=1e-11, atol=0)
+    assert abs(timemin - float(g["timemin"])) < 1e-10
+    for name in ("plan", "empty"):
+        monkeypatch.setattr(ft, "rand", Feeder(pe[name + "_z"]))
+        mean, var = iso.estimate_perfomance_plan(sims, int(pe[name + "_ntra"]), STATE0, g["destination"].tolist(),
+                                                 plan=pe[name + "_plan"].tolist(), verbose=False)
+        assert np.allclose(mean, pe[name + "_mean"], rtol=1e-10) and np.allclose(var, pe[name + "_var"], rtol=1e-7, atol=1e-14)
+    # Philox / batched variants: same statistics within Monte-Carlo noise
+    dest2, tmin2 = ft.initialize_simulators(sims, 2000, STATE0, 0, seed=3)
+    assert abs(dest2[0] - destination[0]) < 0.05 and dest2[1] == pytest.approx(355.0, abs=1e-9)
+    assert tmin2 <= timemin + 0.05
+    mean2, var2 = iso.estimate_perfomance_plan(sims, 4000, STATE0, g["destination"].tolist(),
+                                               plan=pe["plan_plan"].tolist(), verbose=False, seed=4)
+    assert np.allclose(mean2, pe["plan_mean"], atol=0.06)
+
+
+def test_seeded_uct_search_grows_the_reference_tree(golden_dir, monkeypatch):
+    """random.seed(1); np.random.seed(1); Tree.uct_search(...) -- the same leaves in the same order, the same
+    rewards, the same visit counts and the same best policy as the reference's run."""
+    with open(os.path.join(golden_dir, "tree_replay_c1.json")) as f:
+        replay = json.load(f)
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    sims = make_sims([0])
+    random.seed(1)
+    np.random.seed(1)
+    monkeypatch.setattr(worker, "RHO", replay["rho"])
+    monkeypatch.setattr(worker, "UCT_COEFF", replay["uct_coeff"])
+    tree = worker.Tree(workerid=0, nscenario=1, budget=replay["budget"], simulator=sims[0],
+                       destination=[float(x) for x in g["destination"]], TimeMin=float(g["timemin"]))
+    master = {ft.ROOT_HASH: mn.MasterNode(1, nodehash=ft.ROOT_HASH)}
+    seen = []
+    orig = worker.Node.back_up
+
+    def rec(self, reward):
+        seen.append(([int(a) for a in self.origins], reward))
+        return orig(self, reward)
+
+    monkeypatch.setattr(worker.Node, "back_up", rec)
+    tree.uct_search(STATE0, replay["frequency"], master)
+    assert [s[0] for s in seen] == [it["origins"] for it in replay["iterations"]]
+    assert np.allclose([s[1] for s in seen], [it["reward"] for it in replay["iterations"]], rtol=1e-9, atol=1e-12)
+    for node, want in zip(tree.Nodes, replay["nodes"]):
+        assert np.array_equal(np.array([h.h for h in node.Values]), np.array(want["hist"]))
+    for k, node in master.items():
+        assert np.array_equal(np.array([h.h for h in node.rewards[0]]), np.array(replay["master_nodes"][str(k)]))
+    nodes = mn.deepcopy_dict(master)
+    mt = MasterTree(sims, tree.destination, nodes=nodes)
+    mt.get_best_policy(verbose=False)
+    assert {str(k): [int(a) for a in v] for k, v in mt.best_policy.items()} == replay["best_policy"]
+    # the scalar path of get_sim_to_estimate_state replays one action only (quirk Q1) ...
+    tree.get_sim_to_estimate_state(tree.Nodes[-1])
+    assert sims[0].state[0] == 1
+    # ... unless asked to replay the whole prefix
+    tree.replay_full_prefix = True
+    deep = max(tree.Nodes, key=lambda n: n.depth)
+    tree.get_sim_to_estimate_state(deep)
+    assert sims[0].state[0] == deep.depth
+
+
+def test_forest_batched_search_decides_like_the_sequential_one(golden_dir):
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    destination, timemin = [float(x) for x in g["destination"]], float(g["timemin"])
+    sims = make_sims([0, 1, 2])
+    np.random.seed(5)
+    random.seed(5)
+    forest = ft.Forest(listsimulators=sims, destination=destination, timemin=timemin, budget=256)
+    master = forest.launch_search(STATE0, 10, mode="batched", leaves=32, replicas=64, seed=9)
+    root = master[ft.ROOT_HASH]
+    for s in range(3):
+        assert root._table[s].sum() == 256 * 64
+        assert forest.workers[s].rootNode.visits() == 256 * 64 and forest.workers[s].ite == 256
+    nodes = mn.deepcopy_dict(master)
+    mt = MasterTree(sims, destination, nodes=nodes)
+    mt.get_best_policy(verbose=False)
+    assert len(mt.best_policy[-1]) >= 1
+    # every first heading was tried by every scenario; the preferred ones point towards the destination (north)
+    assert len(nodes[ft.ROOT_HASH].children) == 8
+    assert int(mt.best_policy[-1][0]) in (0, 45, 315)
+    for s in range(3):
+        assert int(mt.best_policy[s][0]) in (0, 45, 315)
+    # a sequential (reference-order) search on scenario 0 prefers the same first heading family
+    random.seed(1)
+    np.random.seed(1)
+    f2 = ft.Forest(listsimulators=sims[:1], destination=destination, timemin=timemin, budget=120)
+    m2 = f2.launch_search(STATE0, 10, mode="sequential")
+    mt2 = MasterTree(sims[:1], destination, nodes=mn.deepcopy_dict(m2))
+    mt2.get_best_policy(verbose=False)
+    assert int(mt2.best_policy[-1][0]) in (0, 45, 315)

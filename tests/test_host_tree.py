@@ -1,0 +1,162 @@
+"""Host side of the search (no GPU): reward histograms, worker-tree back-up, master updates and the
+master-tree post-processing, replayed on the leaf / slot / reward sequence recorded from a seeded run of
+the reference's own ``Tree.uct_search`` (tests/golden/tree_replay_c1.json, oracle/gen_golden.py).
+Visit counts must be bit-exact; the best policy must be the reference's.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from iboat_pmcts_b200 import master_node as mn
+from iboat_pmcts_b200 import worker
+from iboat_pmcts_b200.forest import ROOT_HASH, _master_add
+from iboat_pmcts_b200.master import MasterTree
+from iboat_pmcts_b200.utils import Hist
+
+
+@pytest.fixture(scope="module")
+def replay(golden_dir):
+    with open(os.path.join(golden_dir, "tree_replay_c1.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "kat.json")) as f:
+        return json.load(f)
+
+
+class _Sim:
+    """What Tree needs from a Simulator when no rollout is launched."""
+    times = np.arange(0, 3 + 6 / 24, 6 * (1 / 24))
+
+
+def test_hist_bins_and_means(kat):
+    for value, want in kat["hist_bin"]:
+        assert Hist.bin_of(value) == want
+        h = Hist()
+        h.add(value)
+        assert h.h[want] == 1 and h.h.sum() == 1
+    assert Hist().get_mean() == 0 and Hist().is_empty()
+    h = Hist([0, 2, 0, 1, 0, 0, 0, 0, 0, 0, 0, 3])
+    assert h.get_mean() == np.dot(h.h, Hist.MEANS) / 6
+    assert np.array_equal(Hist.MEANS, (np.arange(12) + 0.5) * 0.125)
+    # a Hist can be a live view of a table row
+    table = np.zeros((3, 12), dtype=int)
+    v = Hist(store=table[1])
+    v.add(0.5)
+    assert table[1, 3] == 1
+
+
+def _replay_tree(replay, monkeypatch):
+    """Feeds the recorded iterations into a fresh Tree + master dictionary."""
+    monkeypatch.setattr(worker, "RHO", replay["rho"])
+    monkeypatch.setattr(worker, "UCT_COEFF", replay["uct_coeff"])
+    tree = worker.Tree(workerid=0, nscenario=1, budget=replay["budget"], simulator=_Sim(), destination=[46.7, 355.0],
+                       TimeMin=2.0)
+    tree._make_root([0, 44.0, 355.0])
+    master = {ROOT_HASH: mn.MasterNode(1, nodehash=ROOT_HASH)}
+    by_path = {(): tree.rootNode}
+    slots = iter([])
+    feed = {"queue": []}
+    monkeypatch.setattr(np.random, "randint", lambda *a, **k: feed["queue"].pop(0))
+    mslots = list(replay["master_slots"])
+    freq = replay["frequency"]
+    for i, it in enumerate(replay["iterations"]):
+        origins = it["origins"]
+        parent = by_path[tuple(origins[:-1])]
+        # the expansion the reference's tree policy made at this iteration
+        assert origins[-1] in [int(a) for a in parent.actions]
+        parent.actions.remove(origins[-1])
+        row = tree._new_row()
+        leaf = worker.Node(parent=parent, origins=origins, depth=parent.depth + 1, store=row)
+        parent.children.append(leaf)
+        tree.Nodes.append(leaf)
+        tree.depth = max(tree.depth, leaf.depth)
+        by_path[tuple(origins)] = leaf
+        feed["queue"] = [it["slot"]]
+        leaf.back_up(it["reward"])
+        tree.buffer.append([0, hash(tuple(origins)), hash(tuple(origins[:-1])), origins[-1], it["reward"]])
+        if (i + 1) % freq == 0:
+            feed["queue"] = [mslots.pop(0) for _ in range(freq)]
+            tree.integrate_buffer(master)
+            tree.buffer = []
+            assert not feed["queue"]
+    del slots
+    return tree, master
+
+
+def test_replayed_search_visit_counts_are_bit_exact(replay, monkeypatch):
+    tree, master = _replay_tree(replay, monkeypatch)
+    assert len(tree.Nodes) == len(replay["nodes"]) and tree.depth == replay["depth"]
+    for node, want in zip(tree.Nodes, replay["nodes"]):
+        assert [int(a) for a in node.origins] == want["origins"]
+        assert np.array_equal(np.array([h.h for h in node.Values]), np.array(want["hist"]))
+    # the table behind the nodes is the same numbers
+    assert np.array_equal(tree.table[:len(tree.Nodes)], np.array([n["hist"] for n in replay["nodes"]]))
+    assert tree.rootNode.visits() == replay["budget"]
+    # master dictionary: same keys (CPython tuple hashes), same histograms
+    assert {str(k) for k in master} == set(replay["master_nodes"])
+    for k, node in master.items():
+        assert np.array_equal(np.array([h.h for h in node.rewards[0]]), np.array(replay["master_nodes"][str(k)]))
+
+
+def test_master_tree_best_policy_matches_reference(replay, monkeypatch):
+    _, master = _replay_tree(replay, monkeypatch)
+    import iboat_pmcts_b200.master as master_mod
+    # MasterTree binds UCT_COEFF at import (quirk Q4); the recorded run had set worker.UCT_COEFF *after* import,
+    # so the reference's post-processing used the import-time value: keep it
+    nodes = mn.deepcopy_dict(master)
+    assert len(master) == 0  # emptied, like the reference's
+    root = nodes[ROOT_HASH]
+    assert root.depth == 0 and root.parentNode is None and len(root.children) == 8
+    assert max(n.depth for n in nodes.values()) == replay["depth"]
+    mt = MasterTree([_Sim()], [46.7, 355.0], nodes=nodes)
+    mt.get_best_policy(verbose=False)
+    for key, want in replay["best_policy"].items():
+        assert [int(a) for a in mt.best_policy[int(key)]] == want
+    assert master_mod.UCT_COEFF == 1 / 5 * 1 / 2 ** 0.5
+
+
+def test_batched_master_update_equals_integrate_buffer(replay, monkeypatch):
+    """forest._master_add with one-reward histograms == Tree.integrate_buffer on the same updates."""
+    _, master = _replay_tree(replay, monkeypatch)
+    batched = {ROOT_HASH: mn.MasterNode(1, nodehash=ROOT_HASH)}
+    mslots = list(replay["master_slots"])
+    for it, slot in zip(replay["iterations"], mslots):
+        bins = np.zeros(12, np.uint32)
+        bins[Hist.bin_of(it["reward"])] = 1
+        _master_add(batched, 1, 0, it["origins"], slot, bins)
+    assert set(batched) == set(master)
+    for k in master:
+        assert np.array_equal(batched[k]._table, master[k]._table)
+        assert batched[k].arm == master[k].arm
+        assert (batched[k].parentNode.hash if batched[k].parentNode else None) == \
+               (master[k].parentNode.hash if master[k].parentNode else None)
+
+
+def test_leaf_batched_selection_spreads_and_backs_up(monkeypatch):
+    """select_leaves puts virtual visits on the paths of a wave (so the wave spreads over the tree) and
+    back_up_leaves removes them while adding whole histograms."""
+    import random
+    random.seed(3)
+    np.random.seed(3)
+    tree = worker.Tree(workerid=0, nscenario=1, budget=100, simulator=_Sim(), destination=[46.7, 355.0], TimeMin=2.0)
+    tree._make_root([0, 44.0, 355.0])
+    master = {ROOT_HASH: mn.MasterNode(1, nodehash=ROOT_HASH)}
+    for wave in range(6):
+        leaves = tree.select_leaves(16, master)
+        assert len({tuple(l.origins) for l in leaves}) == 16  # all distinct
+        assert tree.rootNode.pending == 16
+        bins = np.zeros((16, 12), np.uint32)
+        bins[np.arange(16), np.random.randint(12, size=16)] = 32
+        tree.back_up_leaves(leaves, bins, np.random.randint(8, size=16))
+        assert all(n.pending == 0 for n in tree.Nodes)
+    assert tree.ite == 96 and tree.rootNode.visits() == 96 * 32
+    assert tree.depth >= 2
+    # every node holds its own wave's rollouts (in a random slot, quirk Q2) plus those of all nodes below it
+    for node in tree.Nodes[1:]:
+        below = sum(1 for n in tree.Nodes if n.origins[:len(node.origins)] == node.origins)
+        assert node._table.sum() == below * 32
