@@ -181,6 +181,7 @@ struct ForestSlabs {
     int n_scen, prefix_shared;
 };
 
+template <bool kLean = false>
 __device__ __forceinline__ void select_scenario(int s, int64_t n, const ForestSlabs &fs, ScenarioView &sc,
                                                 NoiseView &nz, RolloutArgs &a) {
     sc.slab32 = fs.s32[s];
@@ -192,6 +193,9 @@ __device__ __forceinline__ void select_scenario(int s, int64_t n, const ForestSl
         if (a.prefix) a.prefix += ol * a.prefix_stride;
         if (a.prefix_len) a.prefix_len += ol;
     }
+    if (a.leaf_bins) a.leaf_bins += ol * 12;
+    if (a.stats) a.stats += (size_t)s * 8;
+    if (kLean) return;  // a lean launch has no per-rollout outputs
     if (a.reward) a.reward += on;
     if (a.t_arr) a.t_arr += on;
     if (a.steps) a.steps += on;
@@ -202,8 +206,6 @@ __device__ __forceinline__ void select_scenario(int s, int64_t n, const ForestSl
     if (a.final_lon) a.final_lon += on;
     if (a.traj_lat) a.traj_lat += on * a.traj_stride;
     if (a.traj_lon) a.traj_lon += on * a.traj_stride;
-    if (a.leaf_bins) a.leaf_bins += ol * 12;
-    if (a.stats) a.stats += (size_t)s * 8;
 }
 
 // Work-list entry of the mixed-precision kernels: scenario index in the top 4 bits, rollout id below.
@@ -377,32 +379,36 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
 
 // K2 / K4 / K5, mixed precision -- same contract; the arithmetic is pmcts_fast.cuh.  A rollout whose
 // decisions fell inside the error margins writes nothing: its id goes to a.redo_list and the literal
-// kernel above finishes it (same stream, next launch).
+// kernel above finishes it (same stream, next launch).  kNoise fixes the noise source at compile time;
+// kLean is the throughput form: per-leaf histograms and statistics only, no per-rollout outputs.
+template <int kNoise, bool kLean>
 __global__ void __launch_bounds__(kBlock)
 rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
     const int64_t n = a.n_leaf * a.replicas;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int scen = blockIdx.y;
-    select_scenario(scen, n, fs, sc, nz, a);
+    select_scenario<kLean>(scen, n, fs, sc, nz, a);
     const bool live = r < n;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     fast::RollOut o;
     o.st = PMCTS_ST_OK; o.nstep = 0; o.bin = 0; o.why = 0; o.ta = NAN;
     bool counted = false;
     if (live) {
-        fast::rollout_one(sc, bp, nz, a, n, r, o);
+        fast::rollout_one<kNoise, kLean>(sc, bp, nz, a, n, r, o);
         if (o.why) {
             a.redo_list[atomicAdd(a.redo_count, 1u)] = ((uint32_t)scen << kRedoShift) | (uint32_t)r;
         } else {
             counted = true;
-            if (a.reward) a.reward[r] = o.rw;
-            if (a.t_arr) a.t_arr[r] = o.ta;
-            if (a.steps) a.steps[r] = o.nstep;
-            if (a.status) a.status[r] = (uint8_t)o.st;
-            if (a.bin) a.bin[r] = o.bin;
-            if (a.frac) a.frac[r] = (o.st == PMCTS_ST_ARRIVED) ? o.frac : NAN;
-            if (a.final_lat) a.final_lat[r] = o.lat;
-            if (a.final_lon) a.final_lon[r] = o.lon;
+            if (!kLean) {
+                if (a.reward) a.reward[r] = o.rw;
+                if (a.t_arr) a.t_arr[r] = o.ta;
+                if (a.steps) a.steps[r] = o.nstep;
+                if (a.status) a.status[r] = (uint8_t)o.st;
+                if (a.bin) a.bin[r] = o.bin;
+                if (a.frac) a.frac[r] = (o.st == PMCTS_ST_ARRIVED) ? o.frac : NAN;
+                if (a.final_lat) a.final_lat[r] = o.lat;
+                if (a.final_lon) a.final_lon[r] = o.lon;
+            }
         }
     }
     reduce_rollouts<true>(a, warp_mask, counted, scen, r / a.replicas, o.bin, o.st, o.nstep, o.ta);
@@ -411,7 +417,11 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
 // K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
 // step_batch_kernel).  A boat the fp32 formulas do not cover (heading outside [0, 360), a step longer
 // than fast::kMaxStepAngle) stops with the internal status kStNeedsLiteral and its step index in
-// j_resume; step_batch_kernel then finishes it.
+// j_resume; step_batch_kernel then finishes it.  kLean: no trajectory / previous-state output and no
+// stop-before-terminal mode -- the raw sweep of BASELINE config 3.
+constexpr int kRefreshTrig = 16;  // steps between re-evaluations of sin / cos(lat) from the fp64 latitude
+
+template <int kNoise, bool kLean>
 __global__ void __launch_bounds__(kBlock)
 step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
                  double *__restrict__ lat_io, double *__restrict__ lon_io, double *__restrict__ prev_lat,
@@ -422,11 +432,15 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
     if (i >= n) return;
     int k = k_io[i];
     double lat = lat_io[i], lon = lon_io[i];
-    double pla = prev_lat ? prev_lat[i] : lat, plo = prev_lon ? prev_lon[i] : lon;
-    int st = status_io ? status_io[i] : PMCTS_ST_OK;
+    double pla = lat, plo = lon;
+    if (!kLean) {
+        if (prev_lat) pla = prev_lat[i];
+        if (prev_lon) plo = prev_lon[i];
+    }
+    int st = status_io[i];
     fast::Noise ns;
-    float sh = 0.0f, ch = 1.0f;
-    int seg_left = 0;
+    float sh = 0.0f, ch = 1.0f, s = 0.0f, c = 1.0f;
+    int seg_left = 0, trig_left = 0;
     const double *hp = heading + i;
     for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) {
         if (seg_left == 0) {
@@ -436,35 +450,47 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
             if (!ok) { st = fast::kStNeedsLiteral; j_resume[i] = j; break; }
         }
         --seg_left;
-        if (flags & PMCTS_STEP_STOP_BEFORE_TERMINAL) {  // forest.py:239
+        if (!kLean && (flags & PMCTS_STEP_STOP_BEFORE_TERMINAL)) {  // forest.py:239
             if (k + 1 >= sc.nT) { st = PMCTS_ST_PAST_HORIZON; break; }
             if (is_terminal(sc, k + 1, lat, lon)) {
                 st = (k + 1 >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
                 break;
             }
         }
-        float s, c;
-        fast::sincos_lat(lat, s, c);
+        // sin / cos(lat): exact from the latitude every kRefreshTrig steps, carried by the step's own
+        // identities (s' = s cos d + c a, c' = H) in between -- they only scale increments, and the drift of
+        // a few fp32 roundings is re-set before it matters
+        if (trig_left == 0) {
+            trig_left = kRefreshTrig;
+            fast::sincos_lat(lat, s, c);
+        }
+        --trig_left;
         const fast::GridPos g = fast::grid_pos(sc, lat, lon);
-        const float z = ns.draw(nz, n, i, j);
+        const float z = ns.draw<kNoise>(nz, n, i, j);
         const double la0 = lat, lo0 = lon;
         fast::Move m;
         st = fast::fast_step(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
         if (st == fast::kStNeedsLiteral) { j_resume[i] = j; break; }
         if (st == PMCTS_ST_OK) {
-            pla = la0;
-            plo = lo0;
-            if (traj_lat) traj_lat[(size_t)j * n + i] = lat;
-            if (traj_lon) traj_lon[(size_t)j * n + i] = lon;
+            s = m.s_new;
+            c = m.c_new;
+            if (!kLean) {
+                pla = la0;
+                plo = lo0;
+                if (traj_lat) traj_lat[(size_t)j * n + i] = lat;
+                if (traj_lon) traj_lon[(size_t)j * n + i] = lon;
+            }
         }
     }
     if (st == fast::kStNeedsLiteral) *any_resume = 1u;
     k_io[i] = k;
     lat_io[i] = lat;
     lon_io[i] = lon;
-    if (prev_lat) prev_lat[i] = pla;
-    if (prev_lon) prev_lon[i] = plo;
-    if (status_io) status_io[i] = (uint8_t)st;
+    if (!kLean) {
+        if (prev_lat) prev_lat[i] = pla;
+        if (prev_lon) prev_lon[i] = plo;
+    }
+    status_io[i] = (uint8_t)st;
 }
 
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
@@ -1042,7 +1068,11 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.box_fo_hi = (float)((box[3] - vw.lon0) * inv_dlon);
     // the fp32 kernels assume |lat| <= 90 on the grid (their sin / cos kernels cover [-pi/2, pi/2])
     // and one contiguous run of valid instants
-    vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f) ? 1 : 0;
+    vw.fa_c0 = -vw.lat0 * inv_dlat;
+    vw.fo_c0 = -vw.lon0 * inv_dlon;
+    vw.ks_lo = std::max(0, tc.kv_lo);
+    vw.ks_hi = std::min(nT - 2, tc.kv_hi);
+    vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f && cells < ((size_t)1 << 31)) ? 1 : 0;
     {
         uint64_t h = 1469598103934665603ull;
         const unsigned char *bytes = (const unsigned char *)sim_times;
@@ -1144,9 +1174,18 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         }
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
-            step_fast_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(
-                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,
-                status_dev, traj_lat, traj_lon, flags, j_resume, any_resume);
+            const bool lean = !prev_lat && !prev_lon && !traj_lat && !traj_lon && !(flags & PMCTS_STEP_STOP_BEFORE_TERMINAL);
+#define PMCTS_LAUNCH_STEP(NOISE, LEAN)                                                                      \
+            step_fast_kernel<NOISE, LEAN><<<grid_for(n), kBlock, 0, ctx->stream>>>(                         \
+                sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,    \
+                status_dev, traj_lat, traj_lon, flags, j_resume, any_resume)
+            if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, true);
+            else if (lean && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, true);
+            else if (lean) PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, true);
+            else if (nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, false);
+            else if (nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, false);
+            else PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, false);
+#undef PMCTS_LAUNCH_STEP
         }
         CUDA_TRY(cudaGetLastError());
         {
@@ -1258,9 +1297,21 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         a.redo_count = (uint32_t *)ctx->work;
         a.redo_list = (uint32_t *)(ctx->work + 256);
         CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
+        a.rw_t0 = vw.tmax * 1.001;
+        a.rw_inv = (float)(1.0 / (vw.tmax * 1.001 - tmin));
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
-            rollout_fast_kernel<<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
+            const bool lean = !reward && !t_arr && !steps && !status && !bin && !frac && !final_lat && !final_lon &&
+                              !traj_lat && !traj_lon;
+#define PMCTS_LAUNCH_ROLL(NOISE, LEAN) \
+            rollout_fast_kernel<NOISE, LEAN><<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs)
+            if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true);
+            else if (lean && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true);
+            else if (lean) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true);
+            else if (nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, false);
+            else if (nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, false);
+            else PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, false);
+#undef PMCTS_LAUNCH_ROLL
         }
         CUDA_TRY(cudaGetLastError());
         a.work_list = a.redo_list;

@@ -54,6 +54,15 @@ PMCTS_HD float rsqrt_approx(float x) {
     return 1.0f / sqrtf(x);
 #endif
 }
+PMCTS_HD float exp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+#else
+    return expf(x);
+#endif
+}
 PMCTS_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 PMCTS_HD int imin(int a, int b) { return a < b ? a : b; }
 PMCTS_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -123,7 +132,8 @@ PMCTS_HD void box_muller(uint32_t x0, uint32_t x1, float &z0, float &z1) {
     const float u0 = fminf(fma_((float)x0, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
     const float th = fma_((float)x1, 1.4629180792671596e-09f, -3.14159265359f + 7.3145904e-10f);
 #if defined(__CUDA_ARCH__)
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u0));  // -2 ln(u0)
+    const float t = -1.3862943611198906f * __log2f(u0);  // -2 ln(u0) > 0
+    const float r = t * rsqrt_approx(t);
     float s, c;
     __sincosf(th, &s, &c);
 #else
@@ -138,9 +148,12 @@ struct Noise {
     float cache[4];
     int cached_block;
     PMCTS_HD Noise() : cached_block(-1) {}
+    // kMode: PMCTS_NOISE_* known at compile time, or -1 to read nz.mode
+    template <int kMode>
     PMCTS_HD float draw(const NoiseView &nz, int64_t n, int64_t i, int step) {
-        if (nz.mode == PMCTS_NOISE_INJECTED) return (float)nz.z[(size_t)step * n + i];
-        if (nz.mode == PMCTS_NOISE_NONE) return 0.0f;
+        const int mode = kMode >= 0 ? kMode : nz.mode;
+        if (mode == PMCTS_NOISE_INJECTED) return (float)nz.z[(size_t)step * n + i];
+        if (mode == PMCTS_NOISE_NONE) return 0.0f;
         const int block = step >> 2;
         if (block != cached_block) {
             const uint64_t boat = nz.id0 + (uint64_t)i;
@@ -170,9 +183,10 @@ struct GridPos {
 PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
     GridPos g;
     g.inside = lat >= sc.lat0 && lat <= sc.lat_last && lon >= sc.lon0 && lon <= sc.lon_last;
-    const double fa = (lat - sc.lat0) * sc.inv_dlat, fo = (lon - sc.lon0) * sc.inv_dlon;
-    g.ia = imin(imax((int)fa, 0), sc.nlat - 2);
-    g.io = imin(imax((int)fo, 0), sc.nlon - 2);
+    // (lat - lat0) / dlat as one fma; inside the grid it is >= -1e-13, so truncation needs no lower clamp
+    const double fa = fma(lat, sc.inv_dlat, sc.fa_c0), fo = fma(lon, sc.inv_dlon, sc.fo_c0);
+    g.ia = imin((int)fa, sc.nlat - 2);
+    g.io = imin((int)fo, sc.nlon - 2);
     g.wa = (float)(fa - (double)g.ia);
     g.wo = (float)(fo - (double)g.io);
     g.fa = (float)fa;
@@ -182,7 +196,7 @@ PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
 
 // Simulator.getWind (simulatorTLKT.py:168-179) on the time-blended fp32 slab of instant k.
 PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u, float &v) {
-    const float2 *row0 = sc.slab32 + ((size_t)k * sc.nlat + g.ia) * sc.nlon + g.io;
+    const float2 *row0 = sc.slab32 + ((k * sc.nlat + g.ia) * sc.nlon + g.io);  // < 2^31 cells (checked at upload)
     const float2 *row1 = row0 + sc.nlon;
 #if defined(__CUDA_ARCH__)
     const float2 c00 = __ldg(row0), c01 = __ldg(row0 + 1), c10 = __ldg(row1), c11 = __ldg(row1 + 1);
@@ -256,6 +270,7 @@ struct Move {
     float h_dlon;    // 1 - cos(lon' - lon)
     float cm1_dlat;  // cos(lat' - lat) - 1
     float dlat, dlon;  // radians
+    float s_new, c_new;  // sin / cos of the new latitude (exact identities: s cd + c a, H)
 };
 
 // d = angular distance (rad, may be negative), (sh, ch) heading, (s, c) = sin/cos(lat).
@@ -273,6 +288,8 @@ PMCTS_HD Move move_increments(float d, float sh, float ch, float s, float c) {
     const float H = n2 * rH;
     const float g = b2 * rcp_approx(H + A);
     m.sin_dlon = b * rH;
+    m.s_new = fma_(s, cd, c * a);
+    m.c_new = H;
     m.h_dlon = g * rH;
     m.sin_dlat = fma_(-s, g, a);
     m.cm1_dlat = fma_(c, g, -e);
@@ -391,13 +408,18 @@ constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout co
 // increments; otherwise nothing changes.
 PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
                        const GridPos &g, float sh, float ch, float s, float c, float z, Move &m) {
-    if (k < 0 || k >= sc.nT) return PMCTS_ST_PAST_HORIZON;
-    if (!g.inside || k < sc.kv_lo || k > sc.kv_hi) return PMCTS_ST_OUT_OF_GRID;
+    // instants a step can start from: inside the weather time axis and not the last one
+    if ((unsigned)(k - sc.ks_lo) > (unsigned)(sc.ks_hi - sc.ks_lo) || sc.ks_hi < sc.ks_lo || !g.inside) {
+        // which error the reference raises: IndexError before anything for a bad index, ValueError from the
+        // wind query (simulatorTLKT.py:176-177), IndexError from times[k + 1] (:208)
+        if (k < 0 || k >= sc.nT) return PMCTS_ST_PAST_HORIZON;
+        if (!g.inside || k < sc.kv_lo || k > sc.kv_hi) return PMCTS_ST_OUT_OF_GRID;
+        return PMCTS_ST_PAST_HORIZON;
+    }
     float u, v;
     wind_at(sc, k, g, u, v);
     float speed = boat_speed(bp, u, v, sh, ch);
     speed = fma_(z, speed * bp.sigma_f, speed);  // Boat.addUncertainty (:504-517)
-    if (k + 1 >= sc.nT) return PMCTS_ST_PAST_HORIZON;
 #if defined(__CUDA_ARCH__)
     const float dt = __ldg(sc.dt_sec32 + k);
 #else
@@ -467,6 +489,8 @@ struct RollOut {
 // inner loop (isochrones.py:498-530).  One loop serves every mode:
 //   step j uses heading prefix[j] while j < n_fixed, the bearing to the destination afterwards;
 //   the arrival / terminal tests run after step j once j + 1 >= n_unchecked.
+// kNoise: PMCTS_NOISE_* or -1 (runtime); kLean: no trajectory output.
+template <int kNoise, bool kLean>
 PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const NoiseView &nz, const RolloutArgs &a,
                           int64_t n, int64_t r, RollOut &o) {
     const int64_t leaf = r / a.replicas;
@@ -505,7 +529,7 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             } else {
                 bearing_unit(rd, sA, sD, cD, sh, ch);
             }
-            const float z = ns.draw(nz, n, r, o.nstep);
+            const float z = ns.draw<kNoise>(nz, n, r, o.nstep);
             Move m;
             o.st = fast_step(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
             if (o.st == kStNeedsLiteral) {
@@ -514,8 +538,10 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
                 break;
             }
             if (o.st != PMCTS_ST_OK) break;
-            if (a.traj_lat && o.nstep < a.traj_stride) a.traj_lat[(size_t)o.nstep * n + r] = lat;
-            if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = lon;
+            if (!kLean) {
+                if (a.traj_lat && o.nstep < a.traj_stride) a.traj_lat[(size_t)o.nstep * n + r] = lat;
+                if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = lon;
+            }
             ++o.nstep;
             float sB, cB;
             sincos_lat(lat, sB, cB);
@@ -538,7 +564,8 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             const double tk = sc.times[k];
             o.frac = (double)frac;
             o.ta = tk - (1.0 - o.frac) * (tk - sc.times[k - 1]);  // worker.py:274-275
-            o.rw = (exp((sc.tmax * 1.001 - o.ta) / (sc.tmax * 1.001 - a.tmin)) - 1.0) / (exp(1.0) - 1.0);
+            // reward (worker.py:276-277): the difference of times in fp64, the exponential in fp32
+            o.rw = (double)((exp_approx((float)(a.rw_t0 - o.ta) * a.rw_inv) - 1.0f) * 0.58197670686932642f);
             o.st = PMCTS_ST_ARRIVED;
         } else {
             o.st = (k >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;

@@ -54,7 +54,7 @@ inline void default_fast_margins(BoatParams &p) {
     p.margin_along = 2e-5f;
     p.near_miss2 = 1e-5f;
     p.margin_box = 3e-5f;
-    p.margin_bin = 2e-5;
+    p.margin_bin = 1e-4;  // the fp32 reward is good to ~1e-5 in these units
 }
 
 // Time cell / weight of every simulator instant on the weather time axis (SciPy find_indices

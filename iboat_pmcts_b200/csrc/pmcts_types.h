@@ -39,6 +39,8 @@ struct ScenarioView {
     float max_abs_lat;      // max(|lat0|, |lat_last|), degrees
     double dt_max;          // max_k dt_sec[k]
     float box_fa_lo, box_fa_hi, box_fo_lo, box_fo_hi;  // terminal box in grid-index units
+    double fa_c0, fo_c0;    // -lat0 * inv_dlat, -lon0 * inv_dlon: fractional index = fma(lat, inv_dlat, fa_c0)
+    int ks_lo, ks_hi;       // instants a transition can start from: max(0, kv_lo) .. min(nT - 2, kv_hi)
 };
 
 // Boat.* / module constants (pmcts_set_params), plus values derived once on the host.
@@ -93,6 +95,8 @@ struct RolloutArgs {
     // mixed-precision path: destination trigonometry (host, fp64 -> fp32) and the work list of
     // rollouts whose decisions fell inside the error margins (re-run by the literal fp64 kernel)
     float sin_dest_lat, cos_dest_lat;
+    double rw_t0;  // 1.001 * TimeMax
+    float rw_inv;  // 1 / (1.001 * TimeMax - TimeMin)
     uint32_t *redo_list;
     uint32_t *redo_count;
     const uint32_t *work_list;   // literal kernel: rollout ids to run (NULL = all)

@@ -74,6 +74,10 @@ void *fm_create(const double *wtime, int nt, const double *wlat, int nlat, const
     s.box_fa_hi = (float)((box[1] - s.lat0) * s.inv_dlat);
     s.box_fo_lo = (float)((box[2] - s.lon0) * s.inv_dlon);
     s.box_fo_hi = (float)((box[3] - s.lon0) * s.inv_dlon);
+    s.fa_c0 = -s.lat0 * s.inv_dlat;
+    s.fo_c0 = -s.lon0 * s.inv_dlon;
+    s.ks_lo = m->tc.kv_lo > 0 ? m->tc.kv_lo : 0;
+    s.ks_hi = m->tc.kv_hi < nT - 2 ? m->tc.kv_hi : nT - 2;
     s.tmax = sim_times[nT - 1];
     BoatParams &p = m->bp;
     std::memcpy(p.polar, kFit, sizeof kFit);
@@ -116,12 +120,14 @@ void fm_rollout_batch(void *h, int64_t n_leaf, int replicas, const double root[3
     a.flags = flags;
     a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
     a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
+    a.rw_t0 = m->sc.tmax * 1.001;
+    a.rw_inv = (float)(1.0 / (m->sc.tmax * 1.001 - tmin));
     NoiseView nz{};
     nz.mode = noise_mode; nz.z = z; nz.seed = seed; nz.stream = stream; nz.id0 = id0;
     const int64_t n = n_leaf * replicas;
     for (int64_t r = 0; r < n; ++r) {
         fast::RollOut o;
-        fast::rollout_one(m->sc, m->bp, nz, a, n, r, o);
+        fast::rollout_one<-1, false>(m->sc, m->bp, nz, a, n, r, o);
         if (reward) reward[r] = o.rw;
         if (t_arr) t_arr[r] = o.ta;
         if (steps) steps[r] = o.nstep;
@@ -150,17 +156,19 @@ void fm_step_batch(void *h, int64_t n, int nsteps, int32_t *k, double *lat, doub
         float sh = 0.f, ch = 1.f;
         bool hok = true;
         if (needs_literal) needs_literal[i] = 0;
+        float s = 0.f, c = 1.f;
         for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) {
             if (j % seg_len == 0) hok = fast::heading_unit(heading[(size_t)(j / seg_len) * n + i], sh, ch);
             if (!hok) { if (needs_literal) needs_literal[i] = 1; break; }
-            float s, c;
-            fast::sincos_lat(la, s, c);
+            if (j % 16 == 0) fast::sincos_lat(la, s, c);  // as step_fast_kernel: refreshed every 16 steps
             const fast::GridPos g = fast::grid_pos(m->sc, la, lo);
-            const float zz = ns.draw(nz, n, i, j);
+            const float zz = ns.draw<-1>(nz, n, i, j);
             fast::Move mv;
             st = fast::fast_step(m->sc, m->bp, kk, la, lo, g, sh, ch, s, c, zz, mv);
             if (st == fast::kStNeedsLiteral) { st = 0; if (needs_literal) needs_literal[i] = 1; break; }
             if (st == PMCTS_ST_OK) {
+                s = mv.s_new;
+                c = mv.c_new;
                 if (traj_lat) traj_lat[(size_t)j * n + i] = la;
                 if (traj_lon) traj_lon[(size_t)j * n + i] = lo;
             }

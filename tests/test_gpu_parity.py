@@ -126,7 +126,11 @@ def test_raw_steps_vs_oracle_seeded(eng, mode):
     a2, o2 = lat0.copy(), lon0.copy()
     for j in range(20):
         eng.step_batch(3, k2, a2, o2, head[0], nsteps=1, z=z[j:j + 1])
-    assert np.array_equal(a1, a2) and np.array_equal(o1, o2) and np.array_equal(k1, k2)
+    assert np.array_equal(k1, k2)
+    if mode == N.PREC_F64:
+        assert np.array_equal(a1, a2) and np.array_equal(o1, o2)
+    else:  # the fused launch carries sin / cos(lat) between steps (refreshed every 16): last-bit differences
+        assert relerr(a1, a2) < 1e-9 and relerr(o1, o2) < 1e-9
     w = o.step_batch(0, lat0, lon0, head, nsteps=20, seg_len=25, z=z, nthreads=8)
     assert relerr(a1, w["lat"]) < rtol_for(mode) and relerr(o1, w["lon"]) < rtol_for(mode)
 
