@@ -175,6 +175,10 @@ step_batch_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t
 // box, simulator instants); only the wind slabs differ.  select_scenario turns the launch-wide
 // arguments into those of scenario s: slabs, noise stream, and every per-scenario array offset.
 constexpr int kMaxForest = 16;
+// Statistics are accumulated into kStatsCopies sets of partial sums per scenario (picked by block index)
+// and folded into the caller's stats[8] by stats_finish_kernel: a single set of six addresses hit by every
+// warp of the grid serialises in one L2 slice and stalls every other access that maps to it.
+constexpr int kStatsCopies = 64;
 struct ForestSlabs {
     const float2 *s32[kMaxForest];
     const double2 *s64[kMaxForest];
@@ -194,7 +198,7 @@ __device__ __forceinline__ void select_scenario(int s, int64_t n, const ForestSl
         if (a.prefix_len) a.prefix_len += ol;
     }
     if (a.leaf_bins) a.leaf_bins += ol * 12;
-    if (a.stats) a.stats += (size_t)s * 8;
+    if (a.stats) a.stats += (size_t)s * (kStatsCopies * 8);  // a.stats is the launch's partial-sum area
     if (kLean) return;  // a lean launch has no per-rollout outputs
     if (a.reward) a.reward += on;
     if (a.t_arr) a.t_arr += on;
@@ -227,18 +231,19 @@ __device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned w
         if (counted && lane == __ffs(peers) - 1)
             atomicAdd(&a.leaf_bins[leaf * 12 + bin], (uint32_t)__popc(peers));
     }
-    if (a.stats && !kUniform) {
+    double *stats = a.stats ? a.stats + ((blockIdx.x + (threadIdx.x >> 5)) & (kStatsCopies - 1)) * 8 : nullptr;
+    if (stats && !kUniform) {
         if (counted) {
             if (!isnan(ta)) {
-                atomicAdd(&a.stats[0], 1.0);
-                atomicAdd(&a.stats[1], ta);
-                atomicAdd(&a.stats[2], ta * ta);
+                atomicAdd(&stats[0], 1.0);
+                atomicAdd(&stats[1], ta);
+                atomicAdd(&stats[2], ta * ta);
             }
-            if (st == PMCTS_ST_ARRIVED) atomicAdd(&a.stats[3], 1.0);
-            atomicAdd(&a.stats[4], (double)nstep);
-            atomicAdd(&a.stats[5], 1.0);
+            if (st == PMCTS_ST_ARRIVED) atomicAdd(&stats[3], 1.0);
+            atomicAdd(&stats[4], (double)nstep);
+            atomicAdd(&stats[5], 1.0);
         }
-    } else if (a.stats) {
+    } else if (stats) {
         const bool has_t = counted && !isnan(ta);
         const int c_t = __reduce_add_sync(warp_mask, has_t ? 1 : 0);
         const int c_arr = __reduce_add_sync(warp_mask, (counted && st == PMCTS_ST_ARRIVED) ? 1 : 0);
@@ -252,14 +257,27 @@ __device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned w
         }
         if (lane == __ffs(warp_mask) - 1) {
             if (c_t) {
-                atomicAdd(&a.stats[0], (double)c_t);
-                atomicAdd(&a.stats[1], s1);
-                atomicAdd(&a.stats[2], s2);
+                atomicAdd(&stats[0], (double)c_t);
+                atomicAdd(&stats[1], s1);
+                atomicAdd(&stats[2], s2);
             }
-            if (c_arr) atomicAdd(&a.stats[3], (double)c_arr);
-            atomicAdd(&a.stats[4], (double)c_steps);
-            atomicAdd(&a.stats[5], (double)c_roll);
+            if (c_arr) atomicAdd(&stats[3], (double)c_arr);
+            atomicAdd(&stats[4], (double)c_steps);
+            atomicAdd(&stats[5], (double)c_roll);
         }
+    }
+}
+
+// Folds the partial sums of a launch into the caller's stats[n_scen][8] (always adds: the caller's array
+// was zeroed first unless PMCTS_ROLL_ACCUMULATE).  One block per scenario, one thread per copy.
+__global__ void stats_finish_kernel(const double *__restrict__ part, double *__restrict__ stats) {
+    const int s = blockIdx.x, c = threadIdx.x;
+    const double *p = part + ((size_t)s * kStatsCopies + c) * 8;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        double v = p[q];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((c & 31) == 0 && v != 0.0) atomicAdd(&stats[s * 8 + q], v);
     }
 }
 
@@ -1281,8 +1299,15 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     a.traj_lon = traj_lon;
     a.traj_stride = traj_stride;
     a.leaf_bins = leaf_bins;
-    a.stats = stats;
     a.flags = flags;
+    // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list
+    const size_t part_bytes = al(S * kStatsCopies * 8 * sizeof(double));
+    if ((rc = ensure_work(ctx, part_bytes + S * n * sizeof(uint32_t)))) return rc;
+    double *stats_part = (double *)(ctx->work + 256);
+    if (stats) {
+        a.stats = stats_part;
+        CUDA_TRY(cudaMemsetAsync(stats_part, 0, S * kStatsCopies * 8 * sizeof(double), ctx->stream));
+    }
     // the fp32 kernels also need the destination within 90 degrees of every grid point (their
     // sin / cos kernels cover [-pi/2, pi/2] for latD - lat and lonD - lon)
     const ScenarioView &vw = sc->view;
@@ -1291,11 +1316,10 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
                          std::fabs(dest[1] - vw.lon_last) <= 89.0;
     const dim3 grid_all(grid_for(n), n_scen);
     if (fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift)) {
-        if ((rc = ensure_work(ctx, S * n * sizeof(uint32_t)))) return rc;
         a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
         a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
         a.redo_count = (uint32_t *)ctx->work;
-        a.redo_list = (uint32_t *)(ctx->work + 256);
+        a.redo_list = (uint32_t *)(ctx->work + 256 + part_bytes);
         CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
         a.rw_t0 = vw.tmax * 1.001;
         a.rw_inv = (float)(1.0 / (vw.tmax * 1.001 - tmin));
@@ -1326,6 +1350,11 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         rollout_batch_kernel<<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
     }
     CUDA_TRY(cudaGetLastError());
+    if (stats) {
+        LaunchTimer lt(ctx, PMCTS_KERNEL_OTHER);
+        stats_finish_kernel<<<n_scen, kStatsCopies, 0, ctx->stream>>>(stats_part, stats);
+        CUDA_TRY(cudaGetLastError());
+    }
     return st.finish();
 }
 

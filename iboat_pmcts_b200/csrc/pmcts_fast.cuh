@@ -497,6 +497,8 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
     int k = (int)a.root_k;
     double lat = a.root_lat, lon = a.root_lon;
     const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
+    // both loads are issued back to back: the first heading does not wait for the prefix length
+    double fixed_heading = (pre && a.prefix_stride > 0) ? pre[0] : 0.0;
     const int plen = a.prefix_len ? a.prefix_len[leaf] : 0;
     const bool plan = (a.flags & PMCTS_ROLL_PLAN_EVAL) != 0;
     const int n_fixed = plan ? plen : ((a.flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) ? plen : imin(plen, 1));
@@ -522,10 +524,11 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
         for (;;) {
             float sh, ch;
             if (o.nstep < n_fixed) {
-                if (!heading_unit(pre[o.nstep], sh, ch)) {
+                if (!heading_unit(fixed_heading, sh, ch)) {
                     o.why |= kWhyStep;
                     break;
                 }
+                if (o.nstep + 1 < n_fixed) fixed_heading = pre[o.nstep + 1];
             } else {
                 bearing_unit(rd, sA, sD, cD, sh, ch);
             }
