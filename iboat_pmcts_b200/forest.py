@@ -48,7 +48,8 @@ class Forest:
         ``mode="batched"`` (default): waves of ``leaves`` leaves per tree, ``replicas`` noise replicas per
         leaf (Philox noise from ``seed``), all local scenarios in one launch; the master is updated after
         every wave (the role ``frequency`` plays in the reference).  With ``torch.distributed`` initialised
-        (``group``), worker ``i`` lives on rank ``i % world`` and the waves' update blocks are all-gathered.
+        (``group``; ``False`` = ignore it), rank ``r`` owns workers ``r * S/world .. (r+1) * S/world - 1`` and the waves' update blocks are
+        all-gathered; seeded alike, the ranks return the same dictionary as a single process would.
         """
         Master_nodes = dict()
         Master_nodes[ROOT_HASH] = MasterNode(len(self.workers), nodehash=ROOT_HASH)
@@ -68,16 +69,18 @@ class Forest:
         rank, world = 0, 1
         try:
             import torch.distributed as tdist
-            if tdist.is_available() and tdist.is_initialized():
+            if group is not False and tdist.is_available() and tdist.is_initialized():
                 dist, rank, world = tdist, tdist.get_rank(group), tdist.get_world_size(group)
         except ImportError:
             pass
         S = len(self.workers)
         if S % world:
             raise ValueError("the number of scenarios (%d) must be a multiple of the world size (%d)" % (S, world))
-        local_ids = [i for i in range(S) if i % world == rank]
+        S_loc = S // world
+        local_ids = list(range(rank * S_loc, (rank + 1) * S_loc))  # contiguous block: Philox stream = scenario id
         trees = [self.workers[i] for i in local_ids]
         for t in trees:
+            t.rng = rand.Random(1000003 * seed + t.id)  # per-tree action orders: independent of the sharding
             t._make_root(root_state)
         budget = trees[0].budget
         eng, slots = None, []
@@ -87,7 +90,6 @@ class Forest:
             slots.append(s)
         eng.set_precision(N.PREC_FAST)
         flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
-        S_loc = len(trees)
         wave = 0
         while trees[0].ite < budget:
             b = min(B, budget - trees[0].ite)
@@ -106,9 +108,11 @@ class Forest:
                                plen.reshape(-1), depth, prefix_shared=False, seed=seed,
                                stream=wave * S + rank * S_loc, id0=0,
                                out=dict(leaf_bins=bins.reshape(-1)), flags=flags)
-            # random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward (master_node.py:42)
-            slot_w = np.random.randint(len(ACTIONS), size=(S_loc, b))
-            slot_m = np.random.randint(len(ACTIONS), size=(S_loc, b))
+            # random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward (master_node.py:42):
+            # drawn for ALL scenarios on every rank (ranks seeded alike draw alike), so the search does not
+            # depend on the number of ranks
+            slot_w = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc]
+            slot_m = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc]
             for t, ls, bb, sw in zip(trees, leaves, bins, slot_w):
                 t.back_up_leaves(ls, bb, sw)
             # update block of this rank: action paths, slots and histograms of its leaves

@@ -6,7 +6,7 @@ Selection and expansion stay on the host, as in the reference; the default-polic
 * ``Tree.uct_search`` -- the reference's sequential loop, one rollout per iteration.  The rollout is one
   literal-fp64 launch whose noise is taken from Python's ``random.gauss`` stream in the reference's
   order, and ``back_up`` / ``integrate_buffer`` consume ``np.random.randint`` as the reference does: a
-  seeded search reproduces the reference's tree, visit count by visit count (tests/test_tree_replay.py).
+  seeded search reproduces the reference's tree, visit count by visit count (tests/test_host_tree.py, tests/test_api_gpu.py).
 * ``Tree.select_leaves`` / ``Tree.back_up_leaves`` -- the leaf-batched form used by ``forest.Forest``:
   ``B`` leaves per wave (virtual visits keep them apart), ``K`` noise replicas per leaf, per-leaf reward
   histograms reduced in the rollout kernel and added along the ancestor chains.
@@ -35,13 +35,13 @@ RHO = 0.3
 class Node:
     """Node of a worker ``Tree`` (worker.py:27-104)."""
 
-    def __init__(self, state=None, parent=None, origins=[], children=[], depth=0, store=None):
+    def __init__(self, state=None, parent=None, origins=[], children=[], depth=0, store=None, rng=None):
         self.state = tuple(state) if state is not None else None  # root only
         self.parent = parent
         self.origins = list(origins)
         self.children = list(children)
         self.actions = list(SimC.ACTIONS)
-        rand.shuffle(self.actions)
+        (rng or rand).shuffle(self.actions)  # the reference shuffles with the global generator (worker.py:51)
         self._table = store if store is not None else np.zeros((len(SimC.ACTIONS), Hist.N_BINS), dtype=int)
         self.Values = np.array([Hist(store=self._table[i]) for i in range(len(SimC.ACTIONS))])
         self.depth = depth
@@ -107,6 +107,8 @@ class Tree:
             self.probability = np.array([1 / nscenario for _ in range(nscenario)])
         else:
             self.probability = probability
+        self.rng = None  # generator of the nodes' action order; None = Python's global one, as in the reference
+        self.vectorized = False  # leaf-batched search: NumPy forms of the UCT sums (same values up to rounding)
         self.replay_full_prefix = False  # True fixes quirk Q1 (worker.py:297 never replays past the first action)
         self._cap = 0
         self.table = np.zeros((0, len(SimC.ACTIONS), Hist.N_BINS), dtype=int)
@@ -128,7 +130,7 @@ class Tree:
         return self.table[idx]
 
     def _make_root(self, rootState):
-        rootNode = Node(state=rootState, store=self._new_row())
+        rootNode = Node(state=rootState, store=self._new_row(), rng=self.rng)
         self.rootNode = rootNode
         self.Nodes.append(rootNode)
         return rootNode
@@ -161,7 +163,7 @@ class Tree:
     def expand(self, node):
         row = self._new_row()  # before Node(): growing the table re-points existing views
         action = node.actions.pop()
-        newNode = Node(parent=node, origins=node.origins + [action], depth=node.depth + 1, store=row)
+        newNode = Node(parent=node, origins=node.origins + [action], depth=node.depth + 1, store=row, rng=self.rng)
         self.depth = max(self.depth, newNode.depth)
         node.children.append(newNode)
         self.Nodes.append(newNode)
@@ -171,11 +173,45 @@ class Tree:
         """Child with the largest score: its own UCT, mixed with the master's when the master knows the
         node (worker.py:224-253); first maximum wins."""
         best_score, best_id = -1, -1
+        if self.vectorized:
+            return self._best_child_vectorized(node, Master_nodes)
         num_node = node.visits() + node.pending
         for i, child in enumerate(node.children):
             uct_master = self.get_master_uct(hash(tuple(child.origins)), Master_nodes)
             own = self._child_uct(child, num_node)
             score = own if uct_master == 0 else (1 - RHO) * own + RHO * uct_master
+            if score > best_score:
+                best_score, best_id = score, i
+        return node.children[best_id]
+
+    def _best_child_vectorized(self, node, Master_nodes):
+        """best_child with the histogram sums done by NumPy on the nodes' tables (leaf-batched search)."""
+        means_c = Hist.MEANS
+        num_parent = int(node._table.sum()) + node.pending
+        log_parent = 2 * math.log(num_parent)
+        prob = np.asarray(self.probability, dtype=np.float64)
+        best_score, best_id = -1, -1
+        for i, child in enumerate(node.children):
+            t = child._table
+            tot = t.sum(1)
+            mean = np.divide(t @ means_c, tot, out=np.zeros(len(tot)), where=tot > 0)
+            own = mean.max() + UCT_COEFF * (log_parent / (int(tot.sum()) + child.pending)) ** 0.5
+            score = own
+            key = getattr(child, "_hash", None)
+            if key is None:
+                key = child._hash = hash(tuple(child.origins))
+            m = Master_nodes.get(key, 0)
+            if m != 0:
+                mt, pt = m._table, m.parentNode._table
+                n_node, n_par = mt.sum((1, 2)), pt.sum((1, 2))
+                ok = (n_node != 0) & (n_par != 0)
+                if ok.any():
+                    tot_m = mt.sum(2)
+                    mean_m = np.divide(mt @ means_c, tot_m, out=np.zeros(tot_m.shape), where=tot_m > 0).max(1)
+                    uct = mean_m[ok] + UCT_COEFF * (2 * np.log(n_par[ok]) / n_node[ok]) ** 0.5
+                    uct_master = float(np.dot(uct, prob[ok]))
+                    if uct_master != 0:
+                        score = (1 - RHO) * own + RHO * uct_master
             if score > best_score:
                 best_score, best_id = score, i
         return node.children[best_id]
@@ -286,6 +322,7 @@ class Tree:
         virtual visit on its path (exploration term only), so the runs spread over the tree instead of
         piling on one child.  Returns the list of leaf nodes."""
         leaves = []
+        self.vectorized = True
         for _ in range(n_leaves):
             leaf = self.tree_policy(self.rootNode, master_nodes)
             node = leaf
@@ -293,6 +330,7 @@ class Tree:
                 node.pending += 1
                 node = node.parent
             leaves.append(leaf)
+        self.vectorized = False
         return leaves
 
     def back_up_leaves(self, leaves, leaf_bins, slots):

@@ -57,11 +57,11 @@ def _rank_main(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        local = [s for s in range(S) if s % world == rank]
+        local = list(range(rank * (S // world), (rank + 1) * (S // world)))
         master = {ROOT_HASH: mn.MasterNode(S, nodehash=ROOT_HASH)}
         for wave in range(WAVES):
             blocks = _all_gather_blocks(_wave_block(local, wave), dist, None, world)
-            assert [list(b["ids"]) for b in blocks] == [[s for s in range(S) if s % world == r] for r in range(world)]
+            assert [list(b["ids"]) for b in blocks] == [list(range(r * (S // world), (r + 1) * (S // world))) for r in range(world)]
             _apply(master, blocks)
         with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as f:
             pickle.dump(_tables(master), f)
@@ -81,7 +81,7 @@ def test_two_ranks_build_the_same_master_as_one_process():
     # single process, same (rank, scenario, leaf) order
     master = {ROOT_HASH: mn.MasterNode(S, nodehash=ROOT_HASH)}
     for wave in range(WAVES):
-        _apply(master, [_wave_block([s for s in range(S) if s % world == r], wave) for r in range(world)])
+        _apply(master, [_wave_block(list(range(r * (S // world), (r + 1) * (S // world))), wave) for r in range(world)])
     want = _tables(master)
     for g in got:
         assert set(g) == set(want)
@@ -93,7 +93,7 @@ def test_two_ranks_build_the_same_master_as_one_process():
     # integer adds commute: any order of the blocks gives the same counts
     master2 = {ROOT_HASH: mn.MasterNode(S, nodehash=ROOT_HASH)}
     for wave in reversed(range(WAVES)):
-        _apply(master2, [_wave_block([s for s in range(S) if s % world == r], wave) for r in reversed(range(world))])
+        _apply(master2, [_wave_block(list(range(r * (S // world), (r + 1) * (S // world))), wave) for r in reversed(range(world))])
     for k, v in _tables(master2).items():
         assert np.array_equal(v[0], want[k][0])
 
