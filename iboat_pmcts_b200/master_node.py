@@ -25,8 +25,20 @@ class MasterNode:
             self._table = np.zeros((numscenarios, len(ACTIONS), Hist.N_BINS), dtype=int)
         else:
             self._table = np.array([[np.asarray(h.h) for h in row] for row in rewards], dtype=int)
-        self.rewards = np.array([[Hist(store=self._table[s, a]) for a in range(self._table.shape[1])]
-                                 for s in range(self._table.shape[0])])
+        self._rewards = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_rewards"] = None  # views of _table: rebuilt on first use after unpickling
+        return d
+
+    @property
+    def rewards(self):
+        """Array of ``Hist`` (scenarios x actions), views of this node's table (built on first use)."""
+        if self._rewards is None:
+            self._rewards = np.array([[Hist(store=self._table[s, a]) for a in range(self._table.shape[1])]
+                                      for s in range(self._table.shape[0])])
+        return self._rewards
 
     def add_reward(self, idscenario, reward):
         """Adds a reward to a uniformly random action slot of one scenario (master_node.py:34-44)."""
@@ -42,14 +54,14 @@ class MasterNode:
         self._table[idscenario, slot] += np.asarray(bins, dtype=self._table.dtype)
 
     def is_expanded(self, idscenario):
-        return not all(hist.is_empty() for hist in self.rewards[idscenario, :])
+        return bool(self._table[idscenario].any())
 
 
 def deepcopy_dict(nodes):
     """Deep copy of the dictionary the search returns, rewired with ``parentNode``, ``children`` and
     ``depth`` (master_node.py:66-109).  Empties ``nodes`` as the reference does."""
     root_key = hash(tuple([]))
-    n = len(nodes[root_key].rewards)
+    n = nodes[root_key]._table.shape[0]
     new_dict = dict()
     for k, node in list(nodes.items()):
         new_node = MasterNode(n, nodehash=node.hash, parentNode=None, action=node.arm, rewards=node.rewards)

@@ -43,9 +43,22 @@ class Node:
         self.actions = list(SimC.ACTIONS)
         (rng or rand).shuffle(self.actions)  # the reference shuffles with the global generator (worker.py:51)
         self._table = store if store is not None else np.zeros((len(SimC.ACTIONS), Hist.N_BINS), dtype=int)
-        self.Values = np.array([Hist(store=self._table[i]) for i in range(len(SimC.ACTIONS))])
+        self._values = None
         self.depth = depth
         self.pending = 0  # virtual visits of the wave being assembled (leaf-batched search)
+
+    @property
+    def Values(self):
+        """Array of 8 ``Hist``, views of this node's rows of the tree table (built on first use)."""
+        if self._values is None:
+            self._values = np.array([Hist(store=self._table[i]) for i in range(self._table.shape[0])])
+        return self._values
+
+    def _rebind(self, rows):
+        self._table = rows
+        if self._values is not None:
+            for a, hist in enumerate(self._values):
+                hist.h = rows[a]
 
     def back_up(self, reward):
         """Adds the reward to a random action slot of this node (worker.py:62-63) and, up to the root, to
@@ -87,6 +100,18 @@ class Node:
         return best + exploration
 
 
+def memo_counts(memo, node):
+    """(visit count, max over actions of the binned mean) of a node, once per wave."""
+    got = memo.get(id(node))
+    if got is None:
+        t = node._table
+        tot = t.sum(1)
+        visits = int(tot.sum())
+        value = float(np.divide(t @ Hist.MEANS, tot, out=np.zeros(len(tot)), where=tot > 0).max()) if visits else 0.0
+        got = memo[id(node)] = (visits, value)
+    return got
+
+
 class Tree:
     """MCTS-UCT on one weather scenario (worker.py:107-445)."""
 
@@ -124,9 +149,7 @@ class Tree:
             table[:self._cap] = self.table[:self._cap]
             self.table, self._cap = table, cap
             for i, node in enumerate(self.Nodes):
-                node._table = table[i]
-                for a, hist in enumerate(node.Values):
-                    hist.h = table[i, a]
+                node._rebind(table[i])
         return self.table[idx]
 
     def _make_root(self, rootState):
@@ -185,36 +208,39 @@ class Tree:
         return node.children[best_id]
 
     def _best_child_vectorized(self, node, Master_nodes):
-        """best_child with the histogram sums done by NumPy on the nodes' tables (leaf-batched search)."""
-        means_c = Hist.MEANS
-        num_parent = int(node._table.sum()) + node.pending
+        """best_child for the leaf-batched search.  Within a wave neither the tree's counts nor the master
+        change (only the virtual visits do), so the exploitation value and visit count of a node, and the
+        master's UCT of a node, are computed once per wave (NumPy on the tables) and reused."""
+        memo = self._wave_memo
+        num_parent = memo_counts(memo, node)[0] + node.pending
         log_parent = 2 * math.log(num_parent)
-        prob = np.asarray(self.probability, dtype=np.float64)
         best_score, best_id = -1, -1
         for i, child in enumerate(node.children):
-            t = child._table
-            tot = t.sum(1)
-            mean = np.divide(t @ means_c, tot, out=np.zeros(len(tot)), where=tot > 0)
-            own = mean.max() + UCT_COEFF * (log_parent / (int(tot.sum()) + child.pending)) ** 0.5
-            score = own
-            key = getattr(child, "_hash", None)
+            visits, value = memo_counts(memo, child)
+            own = value + UCT_COEFF * (log_parent / (visits + child.pending)) ** 0.5
+            key = child.__dict__.get("_hash")
             if key is None:
                 key = child._hash = hash(tuple(child.origins))
-            m = Master_nodes.get(key, 0)
-            if m != 0:
-                mt, pt = m._table, m.parentNode._table
-                n_node, n_par = mt.sum((1, 2)), pt.sum((1, 2))
-                ok = (n_node != 0) & (n_par != 0)
-                if ok.any():
-                    tot_m = mt.sum(2)
-                    mean_m = np.divide(mt @ means_c, tot_m, out=np.zeros(tot_m.shape), where=tot_m > 0).max(1)
-                    uct = mean_m[ok] + UCT_COEFF * (2 * np.log(n_par[ok]) / n_node[ok]) ** 0.5
-                    uct_master = float(np.dot(uct, prob[ok]))
-                    if uct_master != 0:
-                        score = (1 - RHO) * own + RHO * uct_master
+            uct_master = memo.get(key)
+            if uct_master is None:
+                uct_master = memo[key] = self._master_uct_vectorized(Master_nodes.get(key, 0))
+            score = own if uct_master == 0 else (1 - RHO) * own + RHO * uct_master
             if score > best_score:
                 best_score, best_id = score, i
         return node.children[best_id]
+
+    def _master_uct_vectorized(self, m):
+        if m == 0:
+            return 0
+        mt, pt = m._table, m.parentNode._table
+        n_node, n_par = mt.sum((1, 2)), pt.sum((1, 2))
+        ok = (n_node != 0) & (n_par != 0)
+        if not ok.any():
+            return 0.0
+        tot = mt.sum(2)
+        mean = np.divide(mt @ Hist.MEANS, tot, out=np.zeros(tot.shape), where=tot > 0).max(1)
+        uct = mean[ok] + UCT_COEFF * (2 * np.log(n_par[ok]) / n_node[ok]) ** 0.5
+        return float(np.dot(uct, np.asarray(self.probability, dtype=np.float64)[ok]))
 
     @staticmethod
     def _child_uct(child, num_parent):
@@ -323,6 +349,7 @@ class Tree:
         piling on one child.  Returns the list of leaf nodes."""
         leaves = []
         self.vectorized = True
+        self._wave_memo = {}
         for _ in range(n_leaves):
             leaf = self.tree_policy(self.rootNode, master_nodes)
             node = leaf

@@ -225,3 +225,66 @@ def test_forest_batched_search_decides_like_the_sequential_one(golden_dir):
     mt2 = MasterTree(sims[:1], destination, nodes=mn.deepcopy_dict(m2))
     mt2.get_best_policy(verbose=False)
     assert int(mt2.best_policy[-1][0]) in (0, 45, 315)
+
+
+def test_device_backup_equals_host_tree_backup(golden_dir):
+    """K3 (pmcts_backup on a device table) adds a wave's histograms exactly where worker.Tree.back_up_leaves
+    does on the host table, and pmcts_hist_stats returns Hist.get_mean / visit totals of every node."""
+    import torch
+    from iboat_pmcts_b200 import _native as N
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    destination, timemin = [float(x) for x in g["destination"]], float(g["timemin"])
+    sims = make_sims([3])
+    random.seed(2)
+    np.random.seed(2)
+    tree = worker.Tree(workerid=0, nscenario=1, budget=10 ** 6, simulator=sims[0], destination=destination,
+                       TimeMin=timemin)
+    tree._make_root(STATE0)
+    master = {ft.ROOT_HASH: mn.MasterNode(1, nodehash=ft.ROOT_HASH)}
+    eng, scen = sims[0].scenario()
+    eng.set_precision(N.PREC_FAST)
+    eng.use_torch_stream()
+    dev = torch.device("cuda:0")
+    cap = 600
+    table = torch.zeros(cap * 96, dtype=torch.int32, device=dev)
+    index = {id(tree.rootNode): 0}
+    try:
+        for wave in range(6):
+            b, K = 48, 64
+            leaves = tree.select_leaves(b, master)
+            for node in tree.Nodes:
+                index.setdefault(id(node), len(index))
+            n_nodes = len(tree.Nodes)
+            parent = np.full(n_nodes, -1, np.int32)
+            arm = np.zeros(n_nodes, np.int8)
+            for node in tree.Nodes[1:]:
+                parent[index[id(node)]] = index[id(node.parent)]
+                arm[index[id(node)]] = worker.A_DICT[node.origins[-1]]
+            depth = max(len(l.origins) for l in leaves)
+            prefix = np.zeros((b, depth))
+            plen = np.zeros(b, np.int32)
+            for i, l in enumerate(leaves):
+                plen[i] = len(l.origins)
+                prefix[i, :plen[i]] = l.origins
+            t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)  # noqa: E731
+            bins_d = torch.zeros(b * 12, dtype=torch.int32, device=dev)
+            eng.rollout_batch(scen, b, K, STATE0, destination, timemin, t(prefix).reshape(-1), t(plen), depth,
+                              seed=13, stream=wave, out=dict(leaf_bins=bins_d))
+            slots = np.random.randint(8, size=b).astype(np.int8)
+            leaf_idx = np.array([index[id(l)] for l in leaves], np.int32)
+            eng.backup(table, n_nodes, t(parent), t(arm), t(leaf_idx), t(slots), bins_d)
+            torch.cuda.synchronize()
+            tree.back_up_leaves(leaves, bins_d.cpu().numpy().astype(np.uint32).reshape(b, 12), slots)
+        n_nodes = len(tree.Nodes)
+        got = table.cpu().numpy().reshape(cap, 8, 12)[:n_nodes]
+        assert np.array_equal(got, tree.table[:n_nodes]) and got[0].sum() == 6 * 48 * 64
+        mean = torch.empty(n_nodes * 8, dtype=torch.float64, device=dev)
+        visits = torch.empty(n_nodes, dtype=torch.int32, device=dev)
+        eng.hist_stats(table, n_nodes, mean, visits)
+        torch.cuda.synchronize()
+        want_mean = np.array([[h.get_mean() for h in node.Values] for node in tree.Nodes], dtype=np.float64)
+        assert np.allclose(mean.cpu().numpy().reshape(n_nodes, 8), want_mean, rtol=1e-15, atol=0)
+        assert np.array_equal(visits.cpu().numpy(), np.array([int(node.visits()) for node in tree.Nodes]))
+    finally:
+        eng.use_own_stream()
+        eng.set_precision(N.PREC_F64)

@@ -160,3 +160,20 @@ def test_leaf_batched_selection_spreads_and_backs_up(monkeypatch):
     for node in tree.Nodes[1:]:
         below = sum(1 for n in tree.Nodes if n.origins[:len(node.origins)] == node.origins)
         assert node._table.sum() == below * 32
+
+
+def test_master_tree_pickle_round_trip(replay, monkeypatch, tmp_path):
+    """MasterTree.save_tree / load_tree (master.py:390-410): histograms, wiring and policy survive."""
+    _, master = _replay_tree(replay, monkeypatch)
+    mt = MasterTree([_Sim()], [46.7, 355.0], nodes=mn.deepcopy_dict(master))
+    mt.get_best_policy(verbose=False)
+    mt.Simulators = []  # (simulators hold device handles; the reference pickles them with the tree)
+    mt.save_tree("tree", directory=str(tmp_path) + "/")
+    back = MasterTree.load_tree("tree", directory=str(tmp_path) + "/")
+    assert set(back.nodes) == set(mt.nodes) and back.best_policy == mt.best_policy
+    for k, node in mt.nodes.items():
+        other = back.nodes[k]
+        assert np.array_equal(other._table, node._table) and other.depth == node.depth
+        assert np.array_equal(other.rewards[0, 3].h, node.rewards[0, 3].h)
+        other.rewards[0, 0].add(0.3)           # the Hist views alias the unpickled table again
+        assert other._table[0, 0].sum() == node._table[0, 0].sum() + 1
