@@ -297,9 +297,41 @@ def tree_replay(R, destination, timemin, budget=300, frequency=10):
                 depth=int(tree.depth))
 
 
+def isochrone_fixture(R, destination):
+    """The reference's deterministic isochrone solver (isochrones.py:24-464) on scenario 0 with
+    Boat.UNCERTAINTY_COEFF = 0 (Tutorial.py:81): every isochrone it keeps, and its solution."""
+    simc, iso = R.simulatorTLKT, R.isochrones
+    sims = make_sims(R, [0])
+    saved = simc.Boat.UNCERTAINTY_COEFF
+    simc.Boat.UNCERTAINTY_COEFF = 0
+    random.seed(3)
+    try:
+        import io
+        import contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            solver = iso.Isochrone(sims[0], [0, 44.0, 355.0], list(destination), delta_cap=5, increment_cap=9,
+                                   nb_secteur=300, resolution=100)  # Tutorial.py:90-91
+            temps, actions, caps_fin, positions = solver.isochrone_methode()
+    finally:
+        simc.Boat.UNCERTAINTY_COEFF = saved
+    return dict(destination=[float(x) for x in destination], temps_transit=float(temps),
+                liste_actions=[float(a) for a in actions], liste_caps_fin=[float(a) for a in caps_fin],
+                liste_positions=[[float(p[0]), float(p[1])] for p in positions], C0=float(solver.C0),
+                isochrone_stock=[[[int(st[0]), float(st[1]), float(st[2])] for st in front]
+                                 for front in solver.isochrone_stock])
+
+
 def main():
     R = refshim.load_reference()
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-isochrone" in sys.argv:
+        g = np.load(os.path.join(GOLD, "rollouts_c1.npz"))
+        fx = isochrone_fixture(R, g["destination"])
+        with open(os.path.join(GOLD, "isochrone_c1.json"), "w") as f:
+            json.dump(fx, f)
+        print("isochrone: transit", fx["temps_transit"], "actions", fx["liste_actions"], "fronts",
+              [len(x) for x in fx["isochrone_stock"]])
+        return
     with open(os.path.join(GOLD, "kat.json"), "w") as f:
         json.dump(kat(R), f, indent=1)
     np.savez(os.path.join(GOLD, "raw_steps_c3.npz"), **raw_steps(R))
@@ -311,6 +343,8 @@ def main():
     tr = tree_replay(R, [float(x) for x in g["destination"]], float(g["timemin"]))
     with open(os.path.join(GOLD, "tree_replay_c1.json"), "w") as f:
         json.dump(tr, f)
+    with open(os.path.join(GOLD, "isochrone_c1.json"), "w") as f:
+        json.dump(isochrone_fixture(R, g["destination"]), f)
     print("destination", g["destination"], "timemin", g["timemin"])
     print("best_policy", tr["best_policy"], "depth", tr["depth"])
     for fn in sorted(os.listdir(GOLD)):

@@ -288,3 +288,36 @@ def test_device_backup_equals_host_tree_backup(golden_dir):
     finally:
         eng.use_own_stream()
         eng.set_precision(N.PREC_F64)
+
+
+def test_isochrone_solver_matches_the_reference(golden_dir):
+    """Isochrone.isochrone_methode with the tutorial's parameters (Tutorial.py:81-92): every isochrone kept
+    by the reference, its headings, positions and travel time; each front is one batched doStep launch."""
+    with open(os.path.join(golden_dir, "isochrone_c1.json")) as f:
+        want = json.load(f)
+    sims = make_sims([0])
+    saved = SimC.Boat.UNCERTAINTY_COEFF
+    SimC.Boat.UNCERTAINTY_COEFF = 0
+    random.seed(3)
+    try:
+        eng, _ = sims[0].scenario()
+        before = eng.launch_count()
+        solver = iso.Isochrone(sims[0], STATE0, want["destination"], delta_cap=5, increment_cap=9, nb_secteur=300,
+                               resolution=100)
+        temps, actions, caps_fin, positions = solver.isochrone_methode()
+        launches = eng.launch_count() - before
+    finally:
+        SimC.Boat.UNCERTAINTY_COEFF = saved
+    assert solver.C0 == want["C0"]
+    assert [len(f) for f in solver.isochrone_stock] == [len(f) for f in want["isochrone_stock"]]
+    for got_front, want_front in zip(solver.isochrone_stock, want["isochrone_stock"]):
+        g, w = np.array(got_front, dtype=np.float64), np.array(want_front, dtype=np.float64)
+        assert np.array_equal(g[:, 0], w[:, 0]) and np.allclose(g[:, 1:], w[:, 1:], rtol=1e-11, atol=0)
+    assert abs(temps - want["temps_transit"]) < 1e-10
+    assert np.allclose(actions, want["liste_actions"], rtol=0, atol=1e-8)
+    assert np.allclose(caps_fin, want["liste_caps_fin"], rtol=0, atol=1e-6)
+    assert np.allclose(positions, want["liste_positions"], rtol=1e-11)
+    # ~45 000 (node, heading) transitions of the fronts in 9 launches; only the last leg of the few hundred
+    # nodes within 20 km of the arrival is stepped one by one (Isochrone.aller_point_arrivee)
+    assert launches < 2000
+    assert len(solver.positions_to_states()) == len(positions)
