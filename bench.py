@@ -351,7 +351,8 @@ def main():
         units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
         achieved = units * f_alg / (dom_ms * 1e-3) / 1e12
         roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=FP32_PEAK_TFLOPS,
-                        unit="TFLOP/s", frac=achieved / FP32_PEAK_TFLOPS, traffic=None,
+                        unit="TFLOP/s", frac=achieved / FP32_PEAK_TFLOPS, traffic=run["dominant"].get("traffic"),
+                        traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture under profiles/ (round 1)",
                         peak_source="nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has "
                                     "HBM and bf16-tensor entries only; the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
                         algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
@@ -438,6 +439,7 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                               launches_per_step=WAVES, units_per_launch=None,
                               flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
                               api="pmcts_rollout_forest with PMCTS_MEM_HOST (host prefix in, host leaf_bins / stats out)",
+                              traffic=1801984 + 1559808,  # profiles/r01_c4_forest_full.txt: main kernel + fp64 finisher
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))
 
 
@@ -483,6 +485,7 @@ def setup_c3(eng, torch, dev, rank, world):
                 dominant=dict(kernel="step_fast_kernel", launches_per_step=1, units_per_launch=None,
                               flop_per_unit=F_ALG_RAW, kind=0,
                               api="pmcts_step_batch with PMCTS_MEM_HOST (host state / headings in, host state out)",
+                              traffic=182030848 + 15603456,  # profiles/r01_c3_step_fast_full.txt
                               hbm_bytes_per_launch=n * (21 + 21) + head_h.nbytes))
 
 
