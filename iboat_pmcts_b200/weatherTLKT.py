@@ -1,7 +1,7 @@
 """Drop-in mirror of ``code/model/weatherTLKT.py`` (reference) for the rollout path.
 
 ``Weather`` keeps the reference's attributes (``lat, lon, time, u, v``) and methods on the path:
-``Interpolators`` (weatherTLKT.py:369-378), ``returnPolarVel`` (:148-163), ``crop`` (:165-218).  The two
+``Interpolators`` (weatherTLKT.py:369-378), ``returnPolarVel`` (:148-163), ``crop`` (:165-218), ``load`` (:51-78).  The two
 interpolators are callables with SciPy's ``RegularGridInterpolator`` call convention, evaluated on the GPU
 by ``pmcts_interp_wind`` (same evaluation order as SciPy, bit for bit).  Download and plotting methods of
 the reference are out of scope.
@@ -56,6 +56,17 @@ class Weather:
         self.time = time
         self.u = u
         self.v = v
+
+    @classmethod
+    def load(cls, path, latBound=[-90, 90], lonBound=[0, 360], timeSteps=[0, 64]):
+        """Loads a pickled ``Weather`` (as saved by the reference's ``Weather.download``,
+        weatherTLKT.py:51-78, 128-133) and crops it.  Pickles written by the reference name the module
+        ``weatherTLKT``: alias it first (``sys.modules['weatherTLKT'] = iboat_pmcts_b200.weatherTLKT``,
+        INTEGRATION.md) so that they unpickle into this class."""
+        import pickle
+        with open(path, 'rb') as f:
+            obj = pickle.load(f)
+        return obj.crop(latBound, lonBound, timeSteps)
 
     # the device copies are caches, not state: they are dropped on copy / pickle
     def __getstate__(self):

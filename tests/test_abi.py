@@ -56,3 +56,31 @@ def test_product_does_not_import_test_infrastructure():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, fn
                 assert "fastmodel" not in text.replace("tests/fastmodel", "") or fn.endswith((".cuh", ".h")), fn
+
+
+def test_weather_pickle_ingest(tmp_path):
+    """Weather.load: a pickle written under the reference's module name unpickles into the mirror class and
+    is cropped like the reference's (strict bounds)."""
+    import pickle
+    import sys
+    import numpy as np
+    from iboat_pmcts_b200 import synth, weatherTLKT
+    t, la, lo, u, v = synth.wind_fields(1)
+    sys.modules["weatherTLKT"] = weatherTLKT
+    try:
+        w = weatherTLKT.Weather(la, lo, t, u.astype(np.float32), v.astype(np.float32))
+        weatherTLKT.Weather.__module__ = "weatherTLKT"      # what a pickle written by the reference says
+        try:
+            blob = pickle.dumps(w)
+        finally:
+            weatherTLKT.Weather.__module__ = "iboat_pmcts_b200.weatherTLKT"
+        assert b"iboat_pmcts_b200" not in blob
+        path = tmp_path / "20180108_gep_0100z.obj"
+        path.write_bytes(blob)
+        got = weatherTLKT.Weather.load(str(path), latBound=[40, 50], lonBound=[345, 360], timeSteps=[0, 24])
+    finally:
+        del sys.modules["weatherTLKT"]
+    assert isinstance(got, weatherTLKT.Weather)
+    assert got.lat[0] == 40.5 and got.lat[-1] == 49.5 and got.lon[0] == 345.5 and got.time.size == 24
+    assert got.u.dtype == np.float64 and got.u.shape == (24, 19, 29)
+    assert np.array_equal(got.u, u[:24, 1:-1, 1:-1])
