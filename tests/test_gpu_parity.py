@@ -437,3 +437,77 @@ def test_device_pointer_path_and_backup(eng):
     assert np.array_equal(mean.cpu().numpy().reshape(n_nodes, 8), wmean)
     assert np.array_equal(visits.cpu().numpy(), want.sum((1, 2)))
     eng.use_own_stream()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_no_writes_outside_the_callers_arrays(eng, mode):
+    """compute-sanitizer is closed on this pool, so bounds are checked the hard way: every device array is
+    carved out of a larger buffer filled with a sentinel, sizes are awkward (not multiples of the warp /
+    block size), and the guard zones must come back untouched."""
+    import torch
+    eng.set_precision(mode)
+    times = upload(eng, 0, 8)
+    nT = times.size
+    dev = torch.device("cuda:0")
+    eng.use_torch_stream()
+    G = 64  # guard elements on each side
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=dev)
+        return buf, buf[G:G + n]
+
+    def check(buf, n, fill, name):
+        b = buf.cpu()
+        if b.dtype.is_floating_point:
+            assert bool((b[:G] == fill).all()) and bool((b[G + n:] == fill).all()), name
+        else:
+            assert bool((b[:G] == fill).all()) and bool((b[G + n:] == fill).all()), name
+
+    try:
+        for n_leaf, rep in ((1, 1), (3, 37), (7, 129), (33, 31)):
+            n = n_leaf * rep
+            stride = 3
+            rng = np.random.default_rng(n)
+            prefix = torch.tensor(45.0 * rng.integers(0, 8, (n_leaf, stride)), device=dev).reshape(-1)
+            plen = torch.tensor(rng.integers(1, stride + 1, n_leaf).astype(np.int32), device=dev)
+            bufs = {}
+            out = {}
+            for name, dt, size, fill in (("reward", torch.float64, n, -7.0), ("t_arr", torch.float64, n, -7.0),
+                                         ("steps", torch.int32, n, -7), ("status", torch.uint8, n, 201),
+                                         ("bin", torch.int32, n, -7), ("frac", torch.float64, n, -7.0),
+                                         ("final_lat", torch.float64, n, -7.0), ("final_lon", torch.float64, n, -7.0),
+                                         ("traj_lat", torch.float64, 5 * n, -7.0), ("traj_lon", torch.float64, 5 * n, -7.0),
+                                         ("leaf_bins", torch.int32, n_leaf * 12, -7), ("stats", torch.float64, 8, -7.0)):
+                bufs[name], out[name] = guarded(size, dt, fill)
+                bufs[name + "_meta"] = (size, fill)
+            eng.rollout_batch(0, n_leaf, rep, H.STATE0, [46.77751005, 355.0], 2.0223605, prefix, plen, stride,
+                              seed=3, stream=n, out=out, traj_stride=5,
+                              flags=N.ROLL_REPLAY_FULL_PREFIX)
+            torch.cuda.synchronize()
+            for name in out:
+                size, fill = bufs[name + "_meta"]
+                check(bufs[name], size, fill, "%s n_leaf=%d rep=%d" % (name, n_leaf, rep))
+            assert int(out["leaf_bins"].sum()) == n and float(out["stats"][5]) == n
+            assert bool((out["status"] >= 1).all()) and bool((out["status"] <= 3).all())
+        for n in (1, 31, 129, 1000):
+            lat0, lon0, h0 = synth.octagon_fleet(n, seed=n)
+            head = torch.tensor(synth.octagon_headings(h0, 12, seg_len=5), device=dev).reshape(-1)
+            kb, k = guarded(n, torch.int32, -7)
+            k.zero_()
+            lab, lat = guarded(n, torch.float64, -7.0)
+            lob, lon = guarded(n, torch.float64, -7.0)
+            lat.copy_(torch.tensor(lat0, device=dev))
+            lon.copy_(torch.tensor(lon0, device=dev))
+            stb, st = guarded(n, torch.uint8, 201)
+            st.zero_()
+            plb, pl = guarded(n, torch.float64, -7.0)
+            tlb, tl = guarded(12 * n, torch.float64, -7.0)
+            eng.step_batch(0, k, lat, lon, head, nsteps=12, seg_len=5, prev_lat=pl, status=st, seed=9, traj_lat=tl)
+            torch.cuda.synchronize()
+            for buf, size, fill, name in ((kb, n, -7, "k"), (lab, n, -7.0, "lat"), (lob, n, -7.0, "lon"),
+                                          (stb, n, 201, "status"), (plb, n, -7.0, "prev_lat"), (tlb, 12 * n, -7.0, "traj")):
+                check(buf, size, fill, "%s n=%d" % (name, n))
+            assert bool((k == 12).all())
+    finally:
+        eng.use_own_stream()
+        eng.set_precision(N.PREC_F64)
