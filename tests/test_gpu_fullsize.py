@@ -1,0 +1,127 @@
+"""BASELINE.json's full sizes on the GPU, checked through size-independent properties (the oracle would
+need minutes for them): conservation of counts, determinism, invariance to how a batch is cut into
+launches, and agreement with the oracle on a random subset.
+"""
+import numpy as np
+import pytest
+
+import pmcts_helpers as H
+from iboat_pmcts_b200 import _native as N
+from iboat_pmcts_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from iboat_pmcts_b200.engine import Engine
+    e = Engine(0, precision=N.PREC_FAST)
+    e.use_torch_stream()
+    yield e
+    e.close()
+
+
+def test_config3_million_boats_500_steps(eng):
+    import torch
+    dev = torch.device("cuda:0")
+    n, nsteps = 1_000_000, 500
+    times = np.linspace(0, 5, nsteps + 1)
+    t, la, lo, u, v = synth.wind_fields(0)
+    eng.upload_scenario(0, t, la, lo, u, v, times, [la[0], la[-1], lo[0], lo[-1]])
+    lat0, lon0, h0 = synth.octagon_fleet(n)
+    head_h = synth.octagon_headings(h0, nsteps)
+    head = torch.tensor(head_h, device=dev)
+
+    def run(lo_i, hi_i):
+        m = hi_i - lo_i
+        k = torch.zeros(m, dtype=torch.int32, device=dev)
+        lat = torch.tensor(lat0[lo_i:hi_i], device=dev)
+        lon = torch.tensor(lon0[lo_i:hi_i], device=dev)
+        st = torch.zeros(m, dtype=torch.uint8, device=dev)
+        eng.step_batch(0, k, lat, lon, head[:, lo_i:hi_i].contiguous().reshape(-1), nsteps=nsteps, seg_len=25, status=st,
+                       seed=42, stream=0, id0=lo_i)
+        torch.cuda.synchronize()
+        return k.cpu().numpy(), lat.cpu().numpy(), lon.cpu().numpy(), st.cpu().numpy()
+
+    k, lat, lon, st = run(0, n)
+    assert (st == 0).all() and (k == nsteps).all()          # nobody leaves the grid, everybody reaches the horizon
+    assert np.isfinite(lat).all() and np.isfinite(lon).all()
+    assert lat.min() > la[0] and lat.max() < la[-1] and lon.min() > lo[0] and lon.max() < lo[-1]
+    # determinism, and invariance to how the fleet is cut into launches (counter-based noise: boat id = id0 + i)
+    k2, lat2, lon2, _ = run(0, n)
+    assert np.array_equal(lat, lat2) and np.array_equal(lon, lon2)
+    cut = 333_337
+    _, la_a, lo_a, _ = run(0, cut)
+    _, la_b, lo_b, _ = run(cut, n)
+    assert np.array_equal(np.concatenate([la_a, la_b]), lat) and np.array_equal(np.concatenate([lo_a, lo_b]), lon)
+    # a random subset against the oracle (same Philox counters)
+    idx = np.sort(np.random.default_rng(0).choice(n, 1500, replace=False))
+    o = H.oracle_sim(0, times=times)
+    want_lat, want_lon = np.empty(idx.size), np.empty(idx.size)
+    for j, i in enumerate(idx):
+        r = o.step_batch(0, lat0[i:i + 1], lon0[i:i + 1], head_h[:, i:i + 1], nsteps=nsteps, seg_len=25, seed=42,
+                         stream=0, id0=int(i))
+        want_lat[j], want_lon[j] = r["lat"][0], r["lon"][0]
+    assert np.max(np.abs(lat[idx] - want_lat) / want_lat) < 1e-6
+    assert np.max(np.abs(lon[idx] - want_lon) / want_lon) < 1e-6
+    # the noise does its job: mean displacement matches, boats are spread
+    assert np.std(lat - lat0) > 0.05
+
+
+def test_config4_shard_eight_million_rollouts(eng):
+    import torch
+    dev = torch.device("cuda:0")
+    S, n_leaf, rep = 8, 4096, 256
+    n = n_leaf * rep
+    for s in range(S):
+        t, la, lo, u, v = synth.wind_fields(s)
+        times, lats, lons = H.sim_axes(la, lo)
+        eng.upload_scenario(10 + s, t, la, lo, u.astype(np.float32), v.astype(np.float32), times,
+                            [lats[0], lats[-1], lons[0], lons[-1]])
+    dest, tmin = [46.77751005, 355.0], 2.022360548788055
+    paths = np.stack(np.meshgrid(*[np.arange(8)] * 4, indexing="ij"), -1).reshape(-1, 4) * 45.0
+    prefix = torch.tensor(paths, device=dev).reshape(-1)
+    plen = torch.full((n_leaf,), 4, dtype=torch.int32, device=dev)
+    slots = np.arange(10, 10 + S, dtype=np.int32)
+
+    def run(seed):
+        bins = torch.zeros(S * n_leaf * 12, dtype=torch.int32, device=dev)
+        stats = torch.zeros(S * 8, dtype=torch.float64, device=dev)
+        eng.rollout_forest(slots, n_leaf, rep, H.STATE0, dest, tmin, prefix, plen, 4, prefix_shared=True, seed=seed,
+                           stream=0, out=dict(leaf_bins=bins, stats=stats))
+        redo = eng.last_redo_count()
+        return bins.cpu().numpy().reshape(S, n_leaf, 12).astype(np.int64), stats.cpu().numpy().reshape(S, 8), redo
+
+    bins, stats, redo = run(42)
+    assert (bins.sum(2) == rep).all()                       # every rollout lands in exactly one bin of its leaf
+    assert (stats[:, 5] == n).all() and (stats[:, 0] == stats[:, 3]).all()
+    assert (bins[:, :, 0].sum(1) >= n - stats[:, 3]).all()  # a rollout that does not arrive has reward 0: bin 0
+    assert ((stats[:, 4] >= 8 * stats[:, 5]) & (stats[:, 4] <= 12 * stats[:, 5])).all()   # 8..12 transitions each
+    assert 0 < redo < 0.01 * S * n                          # the fp64 kernel finished a small share
+    # quirk Q1: only the first action of a leaf is replayed, so leaves sharing it are draws of one distribution
+    per_first = bins.reshape(S, 8, 512, 12).sum(2)
+    share = per_first / per_first.sum(2, keepdims=True)
+    leaf_share = bins.reshape(S, 8, 512, 12) / rep
+    assert np.abs(leaf_share - share[:, :, None, :]).max() < 0.25
+    # determinism; a different seed gives different draws with the same totals
+    bins2, stats2, _ = run(42)
+    assert np.array_equal(bins, bins2) and np.array_equal(stats[:, [0, 3, 4, 5]], stats2[:, [0, 3, 4, 5]])
+    bins3, stats3, _ = run(43)
+    assert not np.array_equal(bins, bins3) and (bins3.sum(2) == rep).all()
+    assert np.abs(stats3[:, 4] / stats[:, 4] - 1).max() < 2e-3
+    # one leaf per scenario against the oracle: the fp64 mode must match it exactly, the fast mode within the
+    # few rollouts whose fp32 noise lands on the other side of a bin edge
+    eng.set_precision(N.PREC_F64)
+    try:
+        for s in (0, 5):
+            o = H.oracle_sim(s)
+            leaf = 1234 + s
+            want = o.rollout_batch(rep, H.STATE0, dest, tmin, prefix=np.repeat(paths[leaf:leaf + 1], rep, 0), seed=42,
+                                   stream=s, id0=leaf * rep, nthreads=8)
+            want_bins = np.bincount(want["bin"], minlength=12)
+            one = eng.rollout_batch_host(10 + s, 1, rep, H.STATE0, dest, tmin, prefix=paths[leaf:leaf + 1], seed=42,
+                                         stream=s, id0=leaf * rep, want=("leaf_bins", "steps"))
+            assert np.array_equal(one["leaf_bins"][0], want_bins) and np.array_equal(one["steps"], want["steps"])
+            assert np.abs(bins[s, leaf] - want_bins).sum() <= 2
+    finally:
+        eng.set_precision(N.PREC_FAST)
