@@ -6,8 +6,10 @@ GFS-ensemble-shaped weather scenarios; one *step* is 10^6 leaf-batched default-p
 scenario (4096 leaves x 256 noise replicas), all 8 scenarios in ONE launch (pmcts_rollout_forest: K2
 with the per-leaf reward-bin reduction, plus the fp64 re-run of the rollouts the fp32 kernel leaves
 undecided), then one all-gather of the per-scenario update blocks (N > 1 only) and the back-up of
-every scenario's blocks into the replicated master table (K3).  Scenarios are the unit of sharding, so
-scaling is weak: per-GPU work is fixed as N grows.
+every scenario's blocks into the replicated master table (K3).  The fp64 finisher of step i runs on a side
+stream and overlaps the main kernel of step i + 1 (its histograms are gathered and backed up one launch
+later; the last timed step drains the pipeline inside its own window).  Scenarios are the unit of sharding,
+so scaling is weak: per-GPU work is fixed as N grows.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3] [--impl reference]
 
@@ -282,7 +284,7 @@ def main():
 
     # ---- device-resident timing: W warm-up steps, then K steps, each bracketed by CUDA events ------
     for i in range(warm):
-        run["device_step"](i)
+        run["device_step"](i)  # (the c4 step drains its pipeline: last=True)
     barrier()
     eng.enable_timing(True)
     eng.kernel_ms(reset=True)
@@ -297,13 +299,17 @@ def main():
     for i in range(args.steps):
         flush_l2()
         ev[i][0].record()
-        run["device_step"](warm + i)
+        if args.workload == "c4":
+            run["device_step"](warm + i, last=(i == args.steps - 1))
+        else:
+            run["device_step"](warm + i)
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count() - launches0
     dom_kernel_ms = eng.kernel_ms(reset=False, kind=run["dominant"]["kind"])
+    fin_kernel_ms = eng.kernel_ms(reset=False, kind=N.KERNEL_FINISHER)
     kernel_ms = eng.kernel_ms(reset=True)
     eng.enable_timing(False)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -345,7 +351,7 @@ def main():
     if rank == 0:
         per_launch_units = run["dominant"]["units_per_launch"]
         n_dom = run["dominant"]["launches_per_step"] * args.steps
-        dom_ms = dom_kernel_ms / n_dom
+        dom_ms = (dom_kernel_ms + fin_kernel_ms) / n_dom  # main kernel + its fp64 finisher: all the transitions
         f_alg = run["dominant"]["flop_per_unit"]
         # units per launch are transitions: measured, averaged over the timed launches of this rank
         units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
@@ -355,6 +361,7 @@ def main():
                         traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture under profiles/ (round 1)",
                         peak_source="nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has "
                                     "HBM and bf16-tensor entries only; the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
+                        main_kernel_ms_per_launch=dom_kernel_ms / n_dom, finisher_ms_per_launch=fin_kernel_ms / n_dom,
                         algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
                         hbm_bytes_per_launch=run["dominant"]["hbm_bytes_per_launch"],
                         hbm_gbs=run["dominant"]["hbm_bytes_per_launch"] / (dom_ms * 1e-3) / 1e9)
@@ -365,7 +372,7 @@ def main():
                     config=workload_config(args.workload, world), precision_mode="f64" if prec == N.PREC_F64 else "fast",
                     e2e=dict(value=e2e_tr / e2e_s, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST")),
-                    gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
+                    gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, finisher_kernel_ms=fin_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
                     roofline=roofline)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
@@ -395,22 +402,38 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     slots = torch.tensor(np.random.default_rng(3).integers(0, 8, S_total * N_LEAF).astype(np.int8), device=dev)
     master = torch.zeros(S_total * n_nodes * 96, dtype=torch.int32, device=dev)
     bins_local = torch.zeros(S_local * N_LEAF * 12, dtype=torch.int32, device=dev)
-    bins_all = torch.zeros(S_total * N_LEAF * 12, dtype=torch.int32, device=dev) if world > 1 else bins_local
+    bins_all = torch.zeros(S_total * N_LEAF * 12, dtype=torch.int32, device=dev) if world > 1 else None
     stats = torch.zeros(S_local * 8, dtype=torch.float64, device=dev)
     plen_h = np.full(N_LEAF, 4, np.int32)
 
     scen_slots = np.arange(S_local, dtype=np.int32)
+    # Two histogram buffers: the fp64 finisher of step i (side stream, PMCTS_ROLL_DEFER_REDO) overlaps the
+    # main kernel of step i + 1, so step i's histograms are complete -- and gathered / backed up -- one
+    # launch later.  The last step of a run drains the pipeline inside its own timed window.
+    bins_ring = [bins_local, torch.zeros_like(bins_local)]
+    pending = []
 
-    def device_step(i):
+    def complete(keep_last):
+        eng.join(keep_last)
+        while len(pending) > keep_last:
+            buf = pending.pop(0)
+            src = buf
+            if world > 1:
+                if not os.environ.get("PMCTS_BENCH_NO_AG"):
+                    dist.all_gather_into_tensor(bins_all, buf)
+                src = bins_all
+            if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
+                eng.backup(master, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S_total)
+
+    def device_step(i, last=True):
         for w in range(WAVES):
-            bins_local.zero_()
+            buf = bins_ring[(i * WAVES + w) % 2]
+            buf.zero_()
             eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, prefix_shared=True,
                                seed=SEED, stream=rank * S_local, id0=(i * WAVES + w) * n,
-                               out=dict(leaf_bins=bins_local, stats=stats), flags=N.ROLL_ACCUMULATE)
-            if world > 1 and not os.environ.get("PMCTS_BENCH_NO_AG"):
-                dist.all_gather_into_tensor(bins_all, bins_local)
-            if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
-                eng.backup(master, n_nodes, parent, arm, leaf_node, slots, bins_all, n_scen=S_total)
+                               out=dict(leaf_bins=buf, stats=stats), flags=N.ROLL_ACCUMULATE | N.ROLL_DEFER_REDO)
+            pending.append(buf)
+            complete(0 if (last and w == WAVES - 1) else 1)
 
     def reset_counters():
         stats.zero_()

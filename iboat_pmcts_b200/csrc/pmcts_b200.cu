@@ -616,12 +616,23 @@ struct pmcts_ctx {
     char *work = nullptr;
     size_t work_cap = 0;
     bool margins_set = false;
+    // PMCTS_ROLL_DEFER_REDO: the fp64 finisher of a rollout launch runs on a side stream so that it overlaps
+    // the next launch; two work areas alternate, each guarded by the events of the launch that used it last
+    cudaStream_t side_stream = nullptr;
+    struct Deferred {
+        char *work = nullptr;
+        size_t cap = 0;
+        cudaEvent_t main_done = nullptr, redo_done = nullptr;
+        bool pending = false;
+        uint64_t seq = 0;
+    } defer[2];
+    uint64_t defer_seq = 0;
     int64_t launches = 0;
     bool timing = false;
     struct Timed { cudaEvent_t a, b; int kind; };
     std::vector<Timed> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
-    double timed_ms[4] = {0, 0, 0, 0};  // per PMCTS_KERNEL_* kind
+    double timed_ms[5] = {0, 0, 0, 0, 0};  // per PMCTS_KERNEL_* kind
     std::mutex mu;
 };
 
@@ -720,7 +731,9 @@ struct LaunchTimer {
     pmcts_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
     int kind;
-    explicit LaunchTimer(pmcts_ctx *c, int kind_ = PMCTS_KERNEL_OTHER) : ctx(c), kind(kind_) {
+    cudaStream_t stream;
+    explicit LaunchTimer(pmcts_ctx *c, int kind_ = PMCTS_KERNEL_OTHER, cudaStream_t s = nullptr)
+        : ctx(c), kind(kind_), stream(s ? s : c->stream) {
         ctx->launches++;
         if (!ctx->timing) return;
         if (!ctx->event_pool.empty()) {
@@ -731,11 +744,11 @@ struct LaunchTimer {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
         }
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, stream);
     }
     ~LaunchTimer() {
         if (!a) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, stream);
         ctx->timed.push_back({a, b, kind});
     }
 };
@@ -833,6 +846,13 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work) cudaFree(ctx->work);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+    for (auto &d : ctx->defer) {
+        if (d.work) cudaFree(d.work);
+        if (d.main_done) cudaEventDestroy(d.main_done);
+        if (d.redo_done) cudaEventDestroy(d.redo_done);
+    }
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     for (auto &p : ctx->timed) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto &p : ctx->event_pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaStreamDestroy(ctx->own_stream);
@@ -855,6 +875,7 @@ int pmcts_synchronize(pmcts_ctx *ctx) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
     DeviceGuard g(ctx->device);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
     return PMCTS_OK;
 }
 
@@ -875,16 +896,17 @@ int pmcts_enable_timing(pmcts_ctx *ctx, int on) {
 
 static void drain_timers(pmcts_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     for (auto &p : ctx->timed) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->timed_ms[p.kind & 3] += ms;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->timed_ms[p.kind < 5 ? p.kind : 3] += ms;
         ctx->event_pool.push_back({p.a, p.b});
     }
     ctx->timed.clear();
 }
 
 double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset) {
-    if (!ctx || kind < 0 || kind > 3) return -1.0;
+    if (!ctx || kind < 0 || kind > 4) return -1.0;
     DeviceGuard g(ctx->device);
     drain_timers(ctx);
     const double r = ctx->timed_ms[kind];
@@ -895,7 +917,7 @@ double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset) {
 double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset) {
     if (!ctx) return -1.0;
     double r = 0.0;
-    for (int kind = 0; kind < 4; ++kind) r += pmcts_kernel_ms(ctx, kind, reset);
+    for (int kind = 0; kind < 5; ++kind) r += pmcts_kernel_ms(ctx, kind, reset);
     return r;
 }
 
@@ -1300,26 +1322,59 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     a.traj_stride = traj_stride;
     a.leaf_bins = leaf_bins;
     a.flags = flags;
-    // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list
-    const size_t part_bytes = al(S * kStatsCopies * 8 * sizeof(double));
-    if ((rc = ensure_work(ctx, part_bytes + S * n * sizeof(uint32_t)))) return rc;
-    double *stats_part = (double *)(ctx->work + 256);
-    if (stats) {
-        a.stats = stats_part;
-        CUDA_TRY(cudaMemsetAsync(stats_part, 0, S * kStatsCopies * 8 * sizeof(double), ctx->stream));
-    }
     // the fp32 kernels also need the destination within 90 degrees of every grid point (their
     // sin / cos kernels cover [-pi/2, pi/2] for latD - lat and lonD - lon)
     const ScenarioView &vw = sc->view;
     const bool dest_ok = std::fabs(dest[0]) <= 90.0 && std::fabs(dest[0] - vw.lat0) <= 89.0 &&
                          std::fabs(dest[0] - vw.lat_last) <= 89.0 && std::fabs(dest[1] - vw.lon0) <= 89.0 &&
                          std::fabs(dest[1] - vw.lon_last) <= 89.0;
+    const bool fast = fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift);
+    const bool defer = fast && (flags & PMCTS_ROLL_DEFER_REDO) && !(flags & PMCTS_MEM_HOST);
+    // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list
+    const size_t part_bytes = al(S * kStatsCopies * 8 * sizeof(double));
+    const size_t work_bytes = part_bytes + S * n * sizeof(uint32_t);
+    char *work = nullptr;
+    pmcts_ctx::Deferred *slot = nullptr;
+    if (defer) {
+        slot = &ctx->defer[ctx->defer_seq & 1];
+        if (!ctx->side_stream) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        }
+        if (!slot->main_done) {
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->redo_done, cudaEventDisableTiming));
+        }
+        // the launch that used this work area two calls ago must have finished with it
+        if (slot->pending) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
+        if (256 + work_bytes > slot->cap) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
+            if (slot->work) CUDA_TRY(cudaFree(slot->work));
+            slot->work = nullptr;
+            slot->cap = 0;
+            const size_t cap = 256 + work_bytes + work_bytes / 4;
+            CUDA_TRY(cudaMalloc((void **)&slot->work, cap));
+            slot->cap = cap;
+        }
+        work = slot->work;
+    } else {
+        if ((rc = ensure_work(ctx, work_bytes))) return rc;
+        work = ctx->work;
+    }
+    double *stats_part = (double *)(work + 256);
+    if (stats) {
+        a.stats = stats_part;
+        CUDA_TRY(cudaMemsetAsync(stats_part, 0, S * kStatsCopies * 8 * sizeof(double), ctx->stream));
+    }
     const dim3 grid_all(grid_for(n), n_scen);
-    if (fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift)) {
+    cudaStream_t tail_stream = ctx->stream;  // where the fp64 finisher and the statistics fold run
+    if (fast) {
         a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
         a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
-        a.redo_count = (uint32_t *)ctx->work;
-        a.redo_list = (uint32_t *)(ctx->work + 256 + part_bytes);
+        a.redo_count = (uint32_t *)work;
+        a.redo_list = (uint32_t *)(work + 256 + part_bytes);
         CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
         a.rw_t0 = vw.tmax * 1.001;
         a.rw_inv = (float)(1.0 / (vw.tmax * 1.001 - tmin));
@@ -1338,12 +1393,17 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
 #undef PMCTS_LAUNCH_ROLL
         }
         CUDA_TRY(cudaGetLastError());
+        if (defer) {
+            CUDA_TRY(cudaEventRecord(slot->main_done, ctx->stream));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->side_stream, slot->main_done, 0));
+            tail_stream = ctx->side_stream;
+        }
         a.work_list = a.redo_list;
         a.work_count = a.redo_count;
         {
-            LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
+            LaunchTimer lt(ctx, PMCTS_KERNEL_FINISHER, tail_stream);
             const int grid = (int)std::min<int64_t>((int64_t)grid_for(n) * n_scen, 2 * 148);
-            rollout_batch_kernel<<<grid, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
+            rollout_batch_kernel<<<grid, kBlock, 0, tail_stream>>>(vw, ctx->params, nz, a, fs);
         }
     } else {
         LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
@@ -1351,11 +1411,29 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     }
     CUDA_TRY(cudaGetLastError());
     if (stats) {
-        LaunchTimer lt(ctx, PMCTS_KERNEL_OTHER);
-        stats_finish_kernel<<<n_scen, kStatsCopies, 0, ctx->stream>>>(stats_part, stats);
+        LaunchTimer lt(ctx, PMCTS_KERNEL_OTHER, tail_stream);
+        stats_finish_kernel<<<n_scen, kStatsCopies, 0, tail_stream>>>(stats_part, stats);
         CUDA_TRY(cudaGetLastError());
     }
+    if (defer) {
+        CUDA_TRY(cudaEventRecord(slot->redo_done, ctx->side_stream));
+        slot->pending = true;
+        slot->seq = ctx->defer_seq++;
+    }
     return st.finish();
+}
+
+int pmcts_join(pmcts_ctx *ctx, int keep_last) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    if (keep_last < 0) keep_last = 0;
+    DeviceGuard g(ctx->device);
+    for (auto &d : ctx->defer) {
+        if (d.pending && d.seq + (uint64_t)keep_last < ctx->defer_seq) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, d.redo_done, 0));
+            d.pending = false;
+        }
+    }
+    return PMCTS_OK;
 }
 
 int pmcts_rollout_batch(pmcts_ctx *ctx, int scen, int64_t n_leaf, int replicas, const double root[3],

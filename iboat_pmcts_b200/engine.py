@@ -125,6 +125,10 @@ class Engine:
     def synchronize(self):
         N.check(self._lib.pmcts_synchronize(self._h))
 
+    def join(self, keep_last=0):
+        """Orders the ctx stream after the deferred finishers of all but the ``keep_last`` latest launches."""
+        N.check(self._lib.pmcts_join(self._h, int(keep_last)))
+
     def launch_count(self):
         return int(self._lib.pmcts_launch_count(self._h))
 

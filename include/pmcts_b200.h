@@ -51,6 +51,10 @@ typedef struct pmcts_ctx pmcts_ctx;
 #define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
 #define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
 #define PMCTS_ROLL_ACCUMULATE 0x8           /* rollout_batch, device arrays only: add to leaf_bins / stats instead of zeroing them first */
+#define PMCTS_ROLL_DEFER_REDO 0x10          /* rollout_batch / rollout_forest, device arrays, PMCTS_PREC_FAST: the fp64
+                                               finisher (and the statistics fold) run on a side stream, so they
+                                               overlap the NEXT launch on this ctx; the outputs of this call are
+                                               complete only after pmcts_join (or pmcts_synchronize) */
 #define PMCTS_MEM_HOST 0x100                /* array arguments are host memory */
 
 /* arithmetic mode */
@@ -80,6 +84,9 @@ const char *pmcts_version(void);
 int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream);
 int pmcts_reset_stream(pmcts_ctx *ctx);
 int pmcts_synchronize(pmcts_ctx *ctx);
+/* Makes the ctx stream wait for the deferred finishers (PMCTS_ROLL_DEFER_REDO) of all but the `keep_last`
+ * most recent launches: work enqueued on the stream afterwards sees their complete outputs. */
+int pmcts_join(pmcts_ctx *ctx, int keep_last);
 int pmcts_set_precision(pmcts_ctx *ctx, int mode);
 /* Decision margins of PMCTS_PREC_FAST (a negative value keeps the current one; all negative restores
  * the defaults): relative margin on sin^2 of the arrival angle vs sin^2(DESTINATION_ANGLE); margin on the
@@ -101,6 +108,7 @@ double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset);
 #define PMCTS_KERNEL_ROLLOUT 1
 #define PMCTS_KERNEL_BACKUP 2
 #define PMCTS_KERNEL_OTHER 3
+#define PMCTS_KERNEL_FINISHER 4 /* the fp64 kernel on the work list of a PMCTS_PREC_FAST rollout launch */
 double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset);
 
 /* Module globals the reference reads at call time -- Boat.FIT_VELOCITY / POLAR_* /

@@ -358,6 +358,51 @@ def test_rollout_forest_equals_per_scenario_launches(eng, mode):
     eng.set_precision(N.PREC_F64)
 
 
+def test_deferred_finisher_gives_the_same_results(eng):
+    """PMCTS_ROLL_DEFER_REDO: the fp64 finisher runs on a side stream and overlaps the next launch; after
+    pmcts_join the outputs equal those of the ordinary (in-order) call, launch after launch."""
+    import torch
+    eng.set_precision(N.PREC_FAST)
+    for slot, sid in enumerate((1, 4)):
+        upload(eng, 20 + slot, sid)
+    dev = torch.device("cuda:0")
+    eng.use_torch_stream()
+    try:
+        dest, tmin = [46.77751005, 355.0], 2.0223605
+        n_leaf, rep, S = 256, 128, 2
+        prefix = torch.tensor(45.0 * (np.arange(n_leaf) % 8).astype(np.float64), device=dev)
+        plen = torch.ones(n_leaf, dtype=torch.int32, device=dev)
+
+        def call(seed, flags, bins, stats):
+            eng.rollout_forest([20, 21], n_leaf, rep, H.STATE0, dest, tmin, prefix, plen, 1, prefix_shared=True,
+                               seed=seed, out=dict(leaf_bins=bins, stats=stats), flags=flags)
+
+        want = []
+        for seed in range(5):
+            b = torch.zeros(S * n_leaf * 12, dtype=torch.int32, device=dev)
+            st = torch.zeros(S * 8, dtype=torch.float64, device=dev)
+            call(seed, 0, b, st)
+            torch.cuda.synchronize()
+            assert eng.last_redo_count() > 0
+            want.append((b.cpu().numpy(), st.cpu().numpy()))
+        got = []
+        for seed in range(5):   # five deferred launches back to back: the two work areas are reused
+            b = torch.zeros(S * n_leaf * 12, dtype=torch.int32, device=dev)
+            st = torch.zeros(S * 8, dtype=torch.float64, device=dev)
+            call(seed, N.ROLL_DEFER_REDO, b, st)
+            eng.join(keep_last=1)
+            got.append((b, st))
+        eng.join()
+        snap = [(b.cpu().numpy(), st.cpu().numpy()) for b, st in got]  # on torch's stream, after the join
+        for (b, st), (wb, wst) in zip(snap, want):
+            assert np.array_equal(b, wb) and int(b.sum()) == S * n_leaf * rep
+            assert np.array_equal(st[[0, 3, 4, 5, 8, 11, 12, 13]], wst[[0, 3, 4, 5, 8, 11, 12, 13]])
+            assert np.allclose(st, wst, rtol=1e-12)
+    finally:
+        eng.use_own_stream()
+        eng.set_precision(N.PREC_F64)
+
+
 def test_edge_cases(eng):
     eng.set_precision(N.PREC_F64)
     times = upload(eng, 0, 2)
