@@ -28,6 +28,9 @@ EXPORTS = [
     "pmcts_synchronize", "pmcts_join", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_launch_count", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
+    "pmcts_forest_create", "pmcts_forest_destroy", "pmcts_forest_last_error", "pmcts_forest_set_coefficients",
+    "pmcts_forest_select", "pmcts_forest_backup", "pmcts_forest_master_apply", "pmcts_forest_tree_size",
+    "pmcts_forest_master_size", "pmcts_forest_export_tree", "pmcts_forest_export_master",
 ]
 
 
@@ -90,6 +93,20 @@ def lib():
                                        vp, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_backup.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp, vp, vp, i32]
     L.pmcts_hist_stats.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.pmcts_forest_create.argtypes = [i32, i32, vp, i32, vp, dbl, dbl, vp, i64, C.POINTER(vp)]
+    L.pmcts_forest_destroy.argtypes = [vp]
+    L.pmcts_forest_destroy.restype = None
+    L.pmcts_forest_last_error.restype = C.c_char_p
+    L.pmcts_forest_set_coefficients.argtypes = [vp, dbl, dbl]
+    L.pmcts_forest_select.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.pmcts_forest_backup.argtypes = [vp, i32, vp, vp]
+    L.pmcts_forest_master_apply.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp]
+    L.pmcts_forest_tree_size.argtypes = [vp, i32]
+    L.pmcts_forest_tree_size.restype = i64
+    L.pmcts_forest_master_size.argtypes = [vp]
+    L.pmcts_forest_master_size.restype = i64
+    L.pmcts_forest_export_tree.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.pmcts_forest_export_master.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -97,3 +114,8 @@ def lib():
 def check(rc):
     if rc != 0:
         raise PmctsError(rc, lib().pmcts_last_error().decode("utf-8", "replace"))
+
+
+def check_forest(rc):
+    if rc != 0:
+        raise PmctsError(rc, lib().pmcts_forest_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,358 @@
+// pmcts_b200 host runtime of the leaf-batched forest search: array-based worker trees and the replicated
+// master tree, with the selection / expansion / back-up logic of the reference's Python classes
+// (code/solver/worker.py:27-253, 302-378; code/solver/master_node.py:10-63) restated over
+// structure-of-arrays storage.  Pure host code (no CUDA): it decides *which* rollouts the GPU runs and
+// files their histograms; it never computes a rollout.
+//
+// Semantics are those of iboat_pmcts_b200/worker.py's batched path (Tree.select_leaves /
+// back_up_leaves, forest._master_add), which tests/test_host_forest.py compares it with leaf by leaf and
+// counter by counter:
+//   * a node's untried actions are a permutation handed in by the caller (the reference shuffles them with
+//     Python's generator, worker.py:51) and are consumed from the end (list.pop());
+//   * children are kept in expansion order and the best child is the FIRST maximum of
+//       own            = max_a mean_a + C sqrt(2 ln(N_parent + pending) / (N_child + pending))
+//       score          = own                      if the master has no value for the child
+//                      = (1 - rho) own + rho m    otherwise            (worker.py:224-253)
+//     with m = sum over scenarios that visited the node and its parent of probability[s] * (max_a mean_a +
+//     C sqrt(2 ln N_parent / N_node)) (worker.py:302-346), evaluated once per wave;
+//   * mean_a is the binned mean of utils.Hist (utils.py:49-59): sum h[b] (b + 0.5) / 8 / sum h[b] -- exact in
+//     fp64 whatever the summation order;
+//   * a leaf's wave histogram goes to a random action slot of the leaf (worker.py:62-63,
+//     master_node.py:42-44) and to the slot of the action taken at every ancestor.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pmcts_b200.h"
+
+namespace {
+
+constexpr int kA = 8;    // actions
+constexpr int kB = 12;   // histogram bins
+constexpr int kRow = kA * kB;
+
+thread_local std::string g_err;
+
+int fail(int code, const char *msg) {
+    g_err = msg;
+    return code;
+}
+
+// (visit count, max over actions of the binned mean) of one node's 8 x 12 counters
+template <typename T>
+inline void node_value(const T *row, int64_t &visits, double &best) {
+    visits = 0;
+    best = 0.0;
+    for (int a = 0; a < kA; ++a) {
+        int64_t tot = 0, acc = 0;  // acc = sum h[b] * (2b + 1): the mean is acc / 16 / tot
+        for (int b = 0; b < kB; ++b) {
+            tot += (int64_t)row[a * kB + b];
+            acc += (int64_t)row[a * kB + b] * (2 * b + 1);
+        }
+        visits += tot;
+        if (tot > 0) {
+            const double mean = ((double)acc * 0.0625) / (double)tot;
+            if (mean > best) best = mean;
+        }
+    }
+}
+
+struct Tree {
+    int scen = 0;  // global scenario id
+    std::vector<int32_t> parent, mnode, pending;
+    std::vector<int8_t> arm;
+    std::vector<int16_t> depth;
+    std::vector<int32_t> child;       // [node][kA] in expansion order, -1 beyond n_child
+    std::vector<uint8_t> n_child, n_untried;
+    std::vector<uint8_t> untried;     // [node][kA] action indices, consumed from the end
+    std::vector<int64_t> table;       // [node][kA][kB]
+    std::vector<int64_t> visits;      // cached
+    std::vector<double> best;         // cached
+    const uint8_t *perms = nullptr;   // caller-owned [max_nodes][kA]
+    int64_t max_nodes = 0;
+    std::vector<int32_t> wave_leaves;
+
+    int32_t size() const { return (int32_t)parent.size(); }
+
+    int32_t add_node(int32_t par, int a) {
+        const int32_t idx = size();
+        parent.push_back(par);
+        arm.push_back((int8_t)a);
+        depth.push_back(par < 0 ? 0 : (int16_t)(depth[par] + 1));
+        mnode.push_back(-1);
+        pending.push_back(0);
+        child.insert(child.end(), kA, -1);
+        n_child.push_back(0);
+        n_untried.push_back(kA);
+        untried.insert(untried.end(), perms + (size_t)idx * kA, perms + (size_t)idx * kA + kA);
+        table.insert(table.end(), kRow, 0);
+        visits.push_back(0);
+        best.push_back(0.0);
+        return idx;
+    }
+};
+
+struct Master {
+    int n_scen = 0;
+    std::vector<int32_t> parent, child;  // child [node][kA] by action index
+    std::vector<int8_t> arm;
+    std::vector<uint32_t> table;         // [node][n_scen][kA][kB]
+    std::vector<int64_t> visits;         // [node][n_scen] cached
+    std::vector<double> best;            // [node][n_scen] cached
+    std::vector<double> memo;            // master UCT per node, valid when stamp == wave
+    std::vector<int64_t> stamp;
+
+    int32_t size() const { return (int32_t)parent.size(); }
+
+    int32_t add_node(int32_t par, int a) {
+        const int32_t idx = size();
+        parent.push_back(par);
+        arm.push_back((int8_t)a);
+        child.insert(child.end(), kA, -1);
+        table.insert(table.end(), (size_t)n_scen * kRow, 0u);
+        visits.insert(visits.end(), n_scen, 0);
+        best.insert(best.end(), n_scen, 0.0);
+        memo.push_back(0.0);
+        stamp.push_back(-1);
+        if (par >= 0) child[(size_t)par * kA + a] = idx;
+        return idx;
+    }
+
+    // node reached by a path of action indices, created on the way (ancestors first)
+    int32_t descend(const int8_t *path, int len) {
+        int32_t node = 0;
+        for (int d = 0; d < len; ++d) {
+            int32_t nxt = child[(size_t)node * kA + path[d]];
+            if (nxt < 0) nxt = add_node(node, path[d]);
+            node = nxt;
+        }
+        return node;
+    }
+
+    void add(int32_t node, int s, int slot, const uint32_t *bins) {
+        uint32_t *row = table.data() + ((size_t)node * n_scen + s) * kRow;
+        for (int b = 0; b < kB; ++b) row[slot * kB + b] += bins[b];
+        node_value(row, visits[(size_t)node * n_scen + s], best[(size_t)node * n_scen + s]);
+    }
+};
+
+}  // namespace
+
+struct pmcts_forest {
+    int n_scen = 0, n_local = 0, max_depth = 0;
+    double uct_coeff = 0.0, rho = 0.0;
+    std::vector<double> probability;
+    std::vector<Tree> trees;
+    Master master;
+    int64_t wave = 0;
+
+    double master_uct(int32_t m) {
+        if (m < 0) return 0.0;
+        if (master.stamp[m] == wave) return master.memo[m];
+        const int32_t p = master.parent[m];
+        double acc = 0.0;
+        bool any = false;
+        for (int s = 0; s < n_scen; ++s) {
+            const int64_t n_node = master.visits[(size_t)m * n_scen + s];
+            const int64_t n_par = p >= 0 ? master.visits[(size_t)p * n_scen + s] : 0;
+            if (n_node != 0 && n_par != 0) {
+                const double uct = master.best[(size_t)m * n_scen + s] +
+                                   uct_coeff * std::pow(2.0 * std::log((double)n_par) / (double)n_node, 0.5);
+                acc += uct * probability[s];
+                any = true;
+            }
+        }
+        master.stamp[m] = wave;
+        master.memo[m] = any ? acc : 0.0;
+        return master.memo[m];
+    }
+
+    // master node of a worker node (by its action path), or -1 when the master does not know it yet
+    int32_t master_of(Tree &t, int32_t node) {
+        if (t.mnode[node] >= 0) return t.mnode[node];
+        if (t.parent[node] < 0) return t.mnode[node] = 0;
+        const int32_t pm = master_of(t, t.parent[node]);
+        if (pm < 0) return -1;
+        const int32_t m = master.child[(size_t)pm * kA + t.arm[node]];
+        if (m >= 0) t.mnode[node] = m;
+        return m;
+    }
+
+    int32_t best_child(Tree &t, int32_t node) {
+        const int64_t num_parent = t.visits[node] + t.pending[node];
+        const double log_parent = 2.0 * std::log((double)num_parent);
+        double best_score = -1.0;
+        int32_t best = -1;
+        for (int j = 0; j < t.n_child[node]; ++j) {
+            const int32_t c = t.child[(size_t)node * kA + j];
+            const double own = t.best[c] + uct_coeff * std::pow(log_parent / (double)(t.visits[c] + t.pending[c]), 0.5);
+            const double um = master_uct(master_of(t, c));
+            const double score = um == 0.0 ? own : (1.0 - rho) * own + rho * um;
+            if (score > best_score) {
+                best_score = score;
+                best = c;
+            }
+        }
+        return best;
+    }
+
+    int32_t tree_policy(Tree &t) {
+        int32_t node = 0;
+        while (t.depth[node] != max_depth) {
+            if (t.n_untried[node] > 0) {
+                if (t.size() >= t.max_nodes) return -1;
+                const int a = t.untried[(size_t)node * kA + --t.n_untried[node]];
+                const int32_t nn = t.add_node(node, a);
+                t.child[(size_t)node * kA + t.n_child[node]++] = nn;
+                return nn;
+            }
+            node = best_child(t, node);
+        }
+        return node;
+    }
+};
+
+extern "C" {
+
+const char *pmcts_forest_last_error(void) { return g_err.c_str(); }
+
+int pmcts_forest_create(int n_scen, int n_local, const int32_t *local_ids, int max_depth,
+                        const double *probability, double uct_coeff, double rho, const uint8_t *perms,
+                        int64_t max_nodes, pmcts_forest **out) {
+    if (!out || !local_ids || !probability || !perms) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n_scen < 1 || n_local < 1 || n_local > n_scen || max_depth < 1 || max_nodes < 1)
+        return fail(PMCTS_ERR_ARG, "bad sizes");
+    pmcts_forest *f = new pmcts_forest();
+    f->n_scen = n_scen;
+    f->n_local = n_local;
+    f->max_depth = max_depth;
+    f->uct_coeff = uct_coeff;
+    f->rho = rho;
+    f->probability.assign(probability, probability + n_scen);
+    f->trees.resize(n_local);
+    for (int i = 0; i < n_local; ++i) {
+        Tree &t = f->trees[i];
+        t.scen = local_ids[i];
+        t.perms = perms + (size_t)i * max_nodes * kA;
+        t.max_nodes = max_nodes;
+        t.add_node(-1, 0);
+    }
+    f->master.n_scen = n_scen;
+    f->master.add_node(-1, 0);
+    *out = f;
+    return PMCTS_OK;
+}
+
+void pmcts_forest_destroy(pmcts_forest *f) { delete f; }
+
+int pmcts_forest_set_coefficients(pmcts_forest *f, double uct_coeff, double rho) {
+    if (!f) return fail(PMCTS_ERR_ARG, "forest is NULL");
+    f->uct_coeff = uct_coeff;
+    f->rho = rho;
+    return PMCTS_OK;
+}
+
+int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_t *leaf_node,
+                        int32_t *prefix_len, int8_t *prefix_act) {
+    if (!f || !leaf_node || !prefix_len || !prefix_act) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (n_leaves < 1 || prefix_stride < f->max_depth) return fail(PMCTS_ERR_ARG, "prefix_stride must hold max_depth actions");
+    for (int i = 0; i < f->n_local; ++i) {
+        Tree &t = f->trees[i];
+        t.wave_leaves.clear();
+        for (int l = 0; l < n_leaves; ++l) {
+            const int32_t leaf = f->tree_policy(t);
+            if (leaf < 0) return fail(PMCTS_ERR_ARG, "tree capacity (max_nodes) exhausted");
+            for (int32_t x = leaf; x >= 0; x = t.parent[x]) t.pending[x] += 1;
+            t.wave_leaves.push_back(leaf);
+            const size_t o = (size_t)i * n_leaves + l;
+            leaf_node[o] = leaf;
+            const int len = t.depth[leaf];
+            prefix_len[o] = len;
+            int8_t *p = prefix_act + o * prefix_stride;
+            std::memset(p, -1, prefix_stride);
+            int d = len;
+            for (int32_t x = leaf; t.parent[x] >= 0; x = t.parent[x]) p[--d] = t.arm[x];
+        }
+    }
+    return PMCTS_OK;
+}
+
+int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) {
+    if (!f || !leaf_bins || !slots) return fail(PMCTS_ERR_ARG, "NULL argument");
+    for (int i = 0; i < f->n_local; ++i) {
+        Tree &t = f->trees[i];
+        if ((int)t.wave_leaves.size() != n_leaves) return fail(PMCTS_ERR_ARG, "back-up does not match the last selection");
+        for (int l = 0; l < n_leaves; ++l) {
+            const int32_t leaf = t.wave_leaves[l];
+            const uint32_t *bins = leaf_bins + ((size_t)i * n_leaves + l) * kB;
+            int slot = slots[(size_t)i * n_leaves + l];
+            for (int32_t x = leaf; x >= 0; x = t.parent[x]) {
+                int64_t *row = t.table.data() + (size_t)x * kRow;
+                for (int b = 0; b < kB; ++b) row[slot * kB + b] += bins[b];
+                node_value(row, t.visits[x], t.best[x]);
+                t.pending[x] -= 1;
+                slot = t.arm[x];  // the ancestors take the histogram in the slot of the action that led here
+            }
+        }
+        t.wave_leaves.clear();
+    }
+    return PMCTS_OK;
+}
+
+int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t *scen_ids, int n_leaves,
+                              int prefix_stride, const int32_t *prefix_len, const int8_t *prefix_act,
+                              const int8_t *slots, const uint32_t *leaf_bins) {
+    if (!f || !scen_ids || !prefix_len || !prefix_act || !slots || !leaf_bins) return fail(PMCTS_ERR_ARG, "NULL argument");
+    Master &m = f->master;
+    for (int i = 0; i < n_blocks_scen; ++i) {
+        const int s = scen_ids[i];
+        if (s < 0 || s >= f->n_scen) return fail(PMCTS_ERR_ARG, "scenario id out of range");
+        for (int l = 0; l < n_leaves; ++l) {
+            const size_t o = (size_t)i * n_leaves + l;
+            const int8_t *path = prefix_act + o * prefix_stride;
+            const uint32_t *bins = leaf_bins + o * kB;
+            int32_t node = m.descend(path, prefix_len[o]);
+            m.add(node, s, slots[o], bins);
+            while (m.parent[node] >= 0) {
+                m.add(m.parent[node], s, m.arm[node], bins);
+                node = m.parent[node];
+            }
+        }
+    }
+    f->wave += 1;  // the master changed: its UCT values are recomputed on next use
+    return PMCTS_OK;
+}
+
+int64_t pmcts_forest_tree_size(pmcts_forest *f, int local_index) {
+    if (!f || local_index < 0 || local_index >= f->n_local) return -1;
+    return f->trees[local_index].size();
+}
+
+int64_t pmcts_forest_master_size(pmcts_forest *f) { return f ? f->master.size() : -1; }
+
+int pmcts_forest_export_tree(pmcts_forest *f, int local_index, int32_t *parent, int8_t *arm, int64_t *table,
+                             uint8_t *n_untried, uint8_t *untried) {
+    if (!f || local_index < 0 || local_index >= f->n_local) return fail(PMCTS_ERR_ARG, "bad tree index");
+    const Tree &t = f->trees[local_index];
+    const size_t n = t.parent.size();
+    if (parent) std::memcpy(parent, t.parent.data(), n * sizeof(int32_t));
+    if (arm) std::memcpy(arm, t.arm.data(), n);
+    if (table) std::memcpy(table, t.table.data(), n * kRow * sizeof(int64_t));
+    if (n_untried) std::memcpy(n_untried, t.n_untried.data(), n);
+    if (untried) std::memcpy(untried, t.untried.data(), n * kA);
+    return PMCTS_OK;
+}
+
+int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, uint32_t *table) {
+    if (!f) return fail(PMCTS_ERR_ARG, "forest is NULL");
+    const Master &m = f->master;
+    const size_t n = m.parent.size();
+    if (parent) std::memcpy(parent, m.parent.data(), n * sizeof(int32_t));
+    if (arm) std::memcpy(arm, m.arm.data(), n);
+    if (table) std::memcpy(table, m.table.data(), n * (size_t)m.n_scen * kRow * sizeof(uint32_t));
+    return PMCTS_OK;
+}
+
+}  // extern "C"

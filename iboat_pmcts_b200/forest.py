@@ -36,7 +36,7 @@ class Forest:
 
     # ------------------------------------------------------------------------------------------------
     def launch_search(self, root_state, frequency, mode="batched", leaves=64, replicas=32, seed=0,
-                      replay_full_prefix=False, group=None):
+                      replay_full_prefix=False, group=None, host="native"):
         """Runs the search and returns the master dictionary ``{hash(tuple(origins)): MasterNode}`` (deep
         copy it with ``master_node.deepcopy_dict`` before use, as with the reference).
 
@@ -50,6 +50,9 @@ class Forest:
         every wave (the role ``frequency`` plays in the reference).  With ``torch.distributed`` initialised
         (``group``; ``False`` = ignore it), rank ``r`` owns workers ``r * S/world .. (r+1) * S/world - 1`` and the waves' update blocks are
         all-gathered; seeded alike, the ranks return the same dictionary as a single process would.
+        ``host="native"`` keeps the trees and the master in the C++ host runtime (``pmcts_forest_*``) during
+        the search and turns them into ``Node`` / ``MasterNode`` objects afterwards; ``host="python"`` runs the
+        same search on the Python classes (same leaves, same counts: tests/test_host_forest.py).
         """
         Master_nodes = dict()
         Master_nodes[ROOT_HASH] = MasterNode(len(self.workers), nodehash=ROOT_HASH)
@@ -60,19 +63,15 @@ class Forest:
             return Master_nodes
         if mode != "batched":
             raise ValueError("mode must be 'sequential' or 'batched'")
+        if host == "native":
+            return self._search_native(list(root_state), int(leaves), int(replicas), int(seed),
+                                       bool(replay_full_prefix), group)
         return self._search_batched(list(root_state), Master_nodes, int(leaves), int(replicas), int(seed),
                                     bool(replay_full_prefix), group)
 
     # ------------------------------------------------------------------------------------------------
     def _search_batched(self, root_state, Master_nodes, B, K, seed, replay_full, group):
-        dist = None
-        rank, world = 0, 1
-        try:
-            import torch.distributed as tdist
-            if group is not False and tdist.is_available() and tdist.is_initialized():
-                dist, rank, world = tdist, tdist.get_rank(group), tdist.get_world_size(group)
-        except ImportError:
-            pass
+        dist, rank, world = _dist_env(group)
         S = len(self.workers)
         if S % world:
             raise ValueError("the number of scenarios (%d) must be a multiple of the world size (%d)" % (S, world))
@@ -127,6 +126,156 @@ class Forest:
                         _master_add(Master_nodes, S, int(scen_id), path, int(blk["slots"][si, li]), blk["bins"][si, li])
             wave += 1
         return Master_nodes
+
+
+    # ------------------------------------------------------------------------------------------------
+    def _search_native(self, root_state, B, K, seed, replay_full, group):
+        """The batched search with the trees and the master in the C++ host runtime."""
+        import ctypes as C
+        from . import worker as W
+        lib = N.lib()
+        dist, rank, world = _dist_env(group)
+        S = len(self.workers)
+        if S % world:
+            raise ValueError("the number of scenarios (%d) must be a multiple of the world size (%d)" % (S, world))
+        S_loc = S // world
+        local_ids = list(range(rank * S_loc, (rank + 1) * S_loc))
+        trees = [self.workers[i] for i in local_ids]
+        budget = trees[0].budget
+        nT = len(trees[0].Simulator.times)
+        max_depth = nT - 1
+        # every node's shuffled action list, drawn tree by tree in creation order with the tree's own generator
+        # (what Node.__init__ does, worker.py:50-51)
+        max_nodes = budget + 2
+        perms = np.empty((S_loc, max_nodes, len(ACTIONS)), np.uint8)
+        base = list(range(len(ACTIONS)))
+        for ti, t in enumerate(trees):
+            rng = rand.Random(1000003 * seed + t.id)
+            for j in range(max_nodes):
+                order = list(base)
+                rng.shuffle(order)
+                perms[ti, j] = order
+        ids = np.asarray(local_ids, np.int32)
+        prob = np.ascontiguousarray(trees[0].probability, np.float64)
+        handle = C.c_void_p()
+        N.check_forest(lib.pmcts_forest_create(S, S_loc, ids.ctypes.data, max_depth, prob.ctypes.data,
+                                               float(W.UCT_COEFF), float(W.RHO), perms.ctypes.data, max_nodes,
+                                               C.byref(handle)))
+        try:
+            eng, slots = None, []
+            for t in trees:
+                eng, s = t.Simulator.scenario()
+                slots.append(s)
+            eng.set_precision(N.PREC_FAST)
+            flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
+            done, wave = 0, 0
+            while done < budget:
+                b = min(B, budget - done)
+                leaf_node = np.empty((S_loc, b), np.int32)
+                plen = np.empty((S_loc, b), np.int32)
+                path = np.empty((S_loc, b, MAX_DEPTH), np.int8)
+                N.check_forest(lib.pmcts_forest_select(handle, b, MAX_DEPTH, leaf_node.ctypes.data, plen.ctypes.data,
+                                                       path.ctypes.data))
+                depth = max(1, int(plen.max()))
+                prefix = np.where(path[:, :, :depth] >= 0, path[:, :, :depth].astype(np.float64) * 45.0, 0.0)
+                bins = np.zeros((S_loc, b, 12), np.uint32)
+                eng.rollout_forest(slots, b, K, root_state, self.destination, self.timemin,
+                                   np.ascontiguousarray(prefix).reshape(-1), plen.reshape(-1), depth,
+                                   prefix_shared=False, seed=seed, stream=wave * S + rank * S_loc, id0=0,
+                                   out=dict(leaf_bins=bins.reshape(-1)), flags=flags)
+                slot_w = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc].astype(np.int8)
+                slot_m = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc].astype(np.int8)
+                slot_w = np.ascontiguousarray(slot_w)
+                N.check_forest(lib.pmcts_forest_backup(handle, b, bins.ctypes.data, slot_w.ctypes.data))
+                paths32 = np.where(path >= 0, path.astype(np.int32) * 45, -1).astype(np.int32)
+                block = dict(ids=ids, paths=paths32, slots=slot_m.astype(np.int32), bins=bins)
+                for blk in _all_gather_blocks(block, dist, group, world):
+                    bp = np.ascontiguousarray(np.where(blk["paths"] >= 0, blk["paths"] // 45, -1).astype(np.int8))
+                    bl = np.ascontiguousarray((blk["paths"] >= 0).sum(2).astype(np.int32))
+                    bs = np.ascontiguousarray(blk["slots"].astype(np.int8))
+                    bb = np.ascontiguousarray(blk["bins"].astype(np.uint32))
+                    bi = np.ascontiguousarray(blk["ids"].astype(np.int32))
+                    N.check_forest(lib.pmcts_forest_master_apply(handle, bi.size, bi.ctypes.data, b, MAX_DEPTH,
+                                                                 bl.ctypes.data, bp.ctypes.data, bs.ctypes.data,
+                                                                 bb.ctypes.data))
+                done += b
+                wave += 1
+            for ti, t in enumerate(trees):
+                _import_tree(lib, handle, ti, t, root_state, done)
+            return _import_master(lib, handle, S)
+        finally:
+            lib.pmcts_forest_destroy(handle)
+
+
+def _dist_env(group):
+    try:
+        import torch.distributed as tdist
+        if group is not False and tdist.is_available() and tdist.is_initialized():
+            return tdist, tdist.get_rank(group), tdist.get_world_size(group)
+    except ImportError:
+        pass
+    return None, 0, 1
+
+
+def _import_tree(lib, handle, ti, tree, root_state, iterations):
+    """Rebuilds ``tree.Nodes`` (``worker.Node`` objects over one table) from the native arrays."""
+    n = int(lib.pmcts_forest_tree_size(handle, ti))
+    parent = np.empty(n, np.int32)
+    arm = np.empty(n, np.int8)
+    table = np.empty((n, len(ACTIONS), 12), np.int64)
+    n_untried = np.empty(n, np.uint8)
+    untried = np.empty((n, len(ACTIONS)), np.uint8)
+    N.check_forest(lib.pmcts_forest_export_tree(handle, ti, parent.ctypes.data, arm.ctypes.data, table.ctypes.data,
+                                                n_untried.ctypes.data, untried.ctypes.data))
+    tree.table, tree._cap = table.astype(int, copy=False), n
+    tree.Nodes = []
+    tree.ite = iterations
+    nodes = []
+    for i in range(n):
+        node = mt.Node.__new__(mt.Node)
+        p = nodes[parent[i]] if parent[i] >= 0 else None
+        node.state = tuple(root_state) if p is None else None
+        node.parent = p
+        node.origins = [] if p is None else p.origins + [ACTIONS[arm[i]]]
+        node.children = []
+        node.actions = [ACTIONS[a] for a in untried[i, :n_untried[i]]]
+        node._table = tree.table[i]
+        node._values = None
+        node.depth = 0 if p is None else p.depth + 1
+        node.pending = 0
+        if p is not None:
+            p.children.append(node)
+        nodes.append(node)
+    tree.Nodes = nodes
+    tree.rootNode = nodes[0]
+    tree.depth = max(nd.depth for nd in nodes)
+
+
+def _import_master(lib, handle, nscen):
+    """The master dictionary ``{hash(tuple(origins)): MasterNode}`` from the native master tree."""
+    n = int(lib.pmcts_forest_master_size(handle))
+    parent = np.empty(n, np.int32)
+    arm = np.empty(n, np.int8)
+    table = np.empty((n, nscen, len(ACTIONS), 12), np.uint32)
+    N.check_forest(lib.pmcts_forest_export_master(handle, parent.ctypes.data, arm.ctypes.data, table.ctypes.data))
+    table = table.astype(int)
+    out, nodes, paths = dict(), [], []
+    for i in range(n):
+        p = nodes[parent[i]] if parent[i] >= 0 else None
+        path = [] if p is None else paths[parent[i]] + [int(ACTIONS[arm[i]])]
+        node = MasterNode.__new__(MasterNode)
+        node.hash = hash(tuple(path))
+        node.arm = None if p is None else ACTIONS[arm[i]]
+        node.parentNode = p
+        node.children = []
+        node.depth = None
+        node.guessed_rewards = dict()
+        node._table = table[i]
+        node._rewards = None
+        nodes.append(node)
+        paths.append(path)
+        out[node.hash] = node
+    return out
 
 
 def _master_add(Master_nodes, nscen, scen_id, path, slot, bins):

@@ -107,7 +107,11 @@ def memo_counts(memo, node):
         t = node._table
         tot = t.sum(1)
         visits = int(tot.sum())
-        value = float(np.divide(t @ Hist.MEANS, tot, out=np.zeros(len(tot)), where=tot > 0).max()) if visits else 0.0
+        acc16 = t @ (2 * np.arange(Hist.N_BINS) + 1)
+        value = 0.0
+        for a in range(len(tot)):
+            if tot[a] > 0:
+                value = max(value, (float(acc16[a]) * 0.0625) / float(tot[a]))
         got = memo[id(node)] = (visits, value)
     return got
 
@@ -217,7 +221,7 @@ class Tree:
         best_score, best_id = -1, -1
         for i, child in enumerate(node.children):
             visits, value = memo_counts(memo, child)
-            own = value + UCT_COEFF * (log_parent / (visits + child.pending)) ** 0.5
+            own = value + UCT_COEFF * (log_parent / float(visits + child.pending)) ** 0.5
             key = child.__dict__.get("_hash")
             if key is None:
                 key = child._hash = hash(tuple(child.origins))
@@ -230,17 +234,27 @@ class Tree:
         return node.children[best_id]
 
     def _master_uct_vectorized(self, m):
+        """get_master_uct on the master node's table: counts by NumPy, then scalar libm arithmetic summed in
+        scenario order (the same operations, in the same order, as csrc/pmcts_forest_host.cpp)."""
         if m == 0:
             return 0
         mt, pt = m._table, m.parentNode._table
         n_node, n_par = mt.sum((1, 2)), pt.sum((1, 2))
-        ok = (n_node != 0) & (n_par != 0)
-        if not ok.any():
-            return 0.0
         tot = mt.sum(2)
-        mean = np.divide(mt @ Hist.MEANS, tot, out=np.zeros(tot.shape), where=tot > 0).max(1)
-        uct = mean[ok] + UCT_COEFF * (2 * np.log(n_par[ok]) / n_node[ok]) ** 0.5
-        return float(np.dot(uct, np.asarray(self.probability, dtype=np.float64)[ok]))
+        acc16 = mt @ (2 * np.arange(Hist.N_BINS) + 1)   # sum h[b] (2b + 1): the binned mean is acc16 / 16 / tot
+        total, any_ok = 0.0, False
+        for s in range(mt.shape[0]):
+            if n_node[s] != 0 and n_par[s] != 0:
+                best = 0.0
+                for a in range(mt.shape[1]):
+                    if tot[s, a] > 0:
+                        mean = (float(acc16[s, a]) * 0.0625) / float(tot[s, a])
+                        if mean > best:
+                            best = mean
+                uct = best + UCT_COEFF * (2.0 * math.log(float(n_par[s])) / float(n_node[s])) ** 0.5
+                total += uct * float(self.probability[s])
+                any_ok = True
+        return total if any_ok else 0.0
 
     @staticmethod
     def _child_uct(child, num_parent):

@@ -200,6 +200,47 @@ int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, c
 int pmcts_hist_stats(pmcts_ctx *ctx, const uint32_t *table, int64_t n_nodes, double *mean,
                      uint32_t *visits, int flags);
 
+/* ---- host runtime of the leaf-batched forest search -------------------------------------------------
+ * Array-based worker trees (one per local scenario) and the replicated master tree, with the selection /
+ * expansion / back-up rules of the reference's Python classes: Node, Tree.tree_policy / expand / best_child /
+ * get_master_uct (worker.py:27-253, 302-346), Node.back_up (worker.py:55-70), Tree.integrate_buffer and
+ * MasterNode.add_reward* (worker.py:348-378, master_node.py:34-54).  Host code: it picks the leaves the GPU
+ * rolls out (pmcts_rollout_forest) and files the histograms that come back.  All arrays are HOST memory.
+ * Actions are indices into ACTIONS (0..7).
+ *
+ * create: n_scen scenarios in total, n_local trees on this rank for the scenarios local_ids[]; a node at depth
+ *   max_depth is terminal (Tree.is_node_terminal, worker.py:438-445: len(times) - 1); perms[n_local][max_nodes][8]
+ *   gives every node, in creation order, its shuffled list of untried actions (worker.py:50-51; consumed from
+ *   the end like list.pop()); the caller keeps perms alive.
+ * select: n_leaves runs of the tree policy per local tree, a virtual visit left on each selected path;
+ *   outputs [n_local][n_leaves]: the leaf's node index, its depth, its action path (prefix_stride >= max_depth
+ *   entries, -1 padded).
+ * backup: the wave's histograms leaf_bins[n_local][n_leaves][12] and random action slots (worker.py:62) along
+ *   the ancestor chains; clears the virtual visits.
+ * master_apply: update blocks of any rank (scenario ids, paths, slots of master_node.py:42, histograms) into
+ *   the master tree, creating missing nodes ancestors first; call it with the same blocks in the same order
+ *   on every rank. */
+typedef struct pmcts_forest pmcts_forest;
+int pmcts_forest_create(int n_scen, int n_local, const int32_t *local_ids, int max_depth,
+                        const double *probability, double uct_coeff, double rho, const uint8_t *perms,
+                        int64_t max_nodes, pmcts_forest **out);
+void pmcts_forest_destroy(pmcts_forest *f);
+const char *pmcts_forest_last_error(void);
+int pmcts_forest_set_coefficients(pmcts_forest *f, double uct_coeff, double rho);
+int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_t *leaf_node,
+                        int32_t *prefix_len, int8_t *prefix_act);
+int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots);
+int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t *scen_ids, int n_leaves,
+                              int prefix_stride, const int32_t *prefix_len, const int8_t *prefix_act,
+                              const int8_t *slots, const uint32_t *leaf_bins);
+int64_t pmcts_forest_tree_size(pmcts_forest *f, int local_index);
+int64_t pmcts_forest_master_size(pmcts_forest *f);
+/* Copies of a worker tree (parent, arm, table[node][8][12] int64, untried actions) and of the master tree
+ * (parent, arm, table[node][n_scen][8][12] uint32); any pointer may be NULL. */
+int pmcts_forest_export_tree(pmcts_forest *f, int local_index, int32_t *parent, int8_t *arm, int64_t *table,
+                             uint8_t *n_untried, uint8_t *untried);
+int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, uint32_t *table);
+
 #ifdef __cplusplus
 }
 #endif
