@@ -72,3 +72,18 @@ def oracle_plan_eval(osims, ntra, stateinit, dest, plan, z):
         gv += (gm - val) ** 2
     gv /= len(all_t)
     return [gm] + means, [gv] + vars_
+
+
+def southern_world(seed=0):
+    """A different corner of the globe: southern hemisphere, negative longitudes, 0.25-degree grid, hourly
+    weather, 2-hour simulator steps, destination to the south-west."""
+    rng = np.random.default_rng(seed)
+    wt = np.arange(0, 2.0001, 1 / 24)
+    wlat = np.arange(-42.0, -33.99, 0.25)
+    wlon = np.arange(-60.0, -49.99, 0.25)
+    T, LAT, LON = np.meshgrid(wt, wlat, wlon, indexing="ij")
+    u = (7 * np.sin(0.4 * LAT + 2 * T) + 4 * np.cos(0.3 * LON) + rng.normal(0, 1, T.shape)).astype(np.float32).astype(np.float64)
+    v = (6 * np.cos(0.35 * LON - T) - 3 * np.sin(0.2 * LAT) + rng.normal(0, 1, T.shape)).astype(np.float32).astype(np.float64)
+    times = np.arange(0, 2.0001, 2 / 24)
+    lats, lons = wlat[:-1], wlon[:-1]
+    return wt, wlat, wlon, u, v, times, lats, lons

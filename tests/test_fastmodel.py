@@ -151,3 +151,41 @@ def test_plan_evaluation_mode_and_golden_rollouts(golden_dir):
         ok = got["uncertain"] == 0
         assert np.array_equal(got["status"][ok], want["status"][ok])
         assert np.allclose(got["t_arr"][ok], want["t_arr"][ok], rtol=1e-6)
+
+
+def test_other_hemisphere_and_grid():
+    wt, wlat, wlon, u, v, times, lats, lons = H.southern_world()
+    f = fastmodel.FastModel(wt, wlat, wlon, u, v, times, lats, lons)
+    o = cport.OracleSim(wt, wlat, wlon, u, v, times, lats, lons)
+    root, dest, tmin = (0, -36.0, -52.0), [-36.7, -52.9], 0.6
+    rng = np.random.default_rng(5)
+    n_leaf, rep = 64, 64
+    n = n_leaf * rep
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 3))
+    plen = rng.integers(1, 4, n_leaf).astype(np.int32)
+    z = rng.standard_normal((times.size, n))
+    for flags in (0, 2, 4):
+        got = f.rollout_batch(n_leaf, rep, root, dest, tmin, prefix=prefix, prefix_len=plen, z=z, flags=flags,
+                              traj_steps=times.size)
+        want = o.rollout_batch(n, root, dest, tmin, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep),
+                               replay_full=bool(flags & 2), mode=1 if flags & 4 else 0, z=z, nthreads=8,
+                               traj_steps=times.size)
+        ok = got["uncertain"] == 0
+        assert ok.mean() > 0.97
+        for key in ("steps", "status", "bin"):
+            assert np.array_equal(got[key][ok], want[key][ok]), (flags, key)
+        el = np.abs(got["traj_lat"] - want["traj_lat"])[:, ok] / np.abs(want["traj_lat"][:, ok])
+        eo = np.abs(got["traj_lon"] - want["traj_lon"])[:, ok] / np.abs(want["traj_lon"][:, ok])
+        assert np.nanmax(el) < 3e-7 and np.nanmax(eo) < 3e-7
+        assert (want["status"] == 1).mean() > 0.2   # a good share arrives, the rest runs out of time or leaves the box
+    # raw steps with arbitrary (non multiple-of-45) headings
+    nb = 512
+    lat0, lon0 = rng.uniform(-40, -36, nb), rng.uniform(-58, -52, nb)
+    head = rng.uniform(0, 360, (3, nb))
+    zz = rng.standard_normal((24, nb))
+    w = o.step_batch(0, lat0, lon0, head, nsteps=24, seg_len=8, z=zz, nthreads=8)
+    g = f.step_batch(0, lat0, lon0, head, nsteps=24, seg_len=8, z=zz)
+    same = w["status"] == 0
+    assert np.array_equal(g["status"], w["status"]) and np.array_equal(g["k"], w["k"]) and same.sum() > nb // 2
+    assert np.max(np.abs(g["lat"][same] - w["lat"][same]) / np.abs(w["lat"][same])) < 1e-7
+    assert np.max(np.abs(g["lon"][same] - w["lon"][same]) / np.abs(w["lon"][same])) < 1e-7

@@ -403,6 +403,47 @@ def test_deferred_finisher_gives_the_same_results(eng):
         eng.set_precision(N.PREC_F64)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_other_hemisphere_and_grid(eng, mode):
+    """Southern hemisphere, negative longitudes, 0.25-degree grid, hourly weather, 2-hour steps, arbitrary
+    headings: the kernels against the oracle, all three rollout modes."""
+    from oracle import cport
+    eng.set_precision(mode)
+    wt, wlat, wlon, u, v, times, lats, lons = H.southern_world()
+    eng.upload_scenario(30, wt, wlat, wlon, u, v, times, [lats[0], lats[-1], lons[0], lons[-1]])
+    o = cport.OracleSim(wt, wlat, wlon, u, v, times, lats, lons)
+    root, dest, tmin = (0, -36.0, -52.0), [-36.7, -52.9], 0.6
+    rng = np.random.default_rng(5)
+    n_leaf, rep = 64, 64
+    n = n_leaf * rep
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 3))
+    plen = rng.integers(1, 4, n_leaf).astype(np.int32)
+    z = rng.standard_normal((times.size, n))
+    for flags in (0, N.ROLL_REPLAY_FULL_PREFIX, N.ROLL_PLAN_EVAL):
+        got = eng.rollout_batch_host(30, n_leaf, rep, root, dest, tmin, prefix=prefix, prefix_len=plen, z=z, flags=flags)
+        want = o.rollout_batch(n, root, dest, tmin, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep),
+                               replay_full=bool(flags & N.ROLL_REPLAY_FULL_PREFIX),
+                               mode=1 if flags & N.ROLL_PLAN_EVAL else 0, z=z, nthreads=8)
+        for key in ("steps", "status", "bin"):
+            assert np.array_equal(got[key], want[key]), (flags, key)
+        assert relerr(got["final_lat"], want["final_lat"]) < rtol_for(mode)
+        assert relerr(got["final_lon"], want["final_lon"]) < rtol_for(mode)
+        assert (want["status"] == 1).mean() > 0.2
+    nb = 512
+    lat0, lon0 = rng.uniform(-40, -36, nb), rng.uniform(-58, -52, nb)
+    head = rng.uniform(0, 360, (3, nb))
+    zz = rng.standard_normal((24, nb))
+    w = o.step_batch(0, lat0, lon0, head, nsteps=24, seg_len=8, z=zz, nthreads=8)
+    k = np.zeros(nb, np.int32)
+    lat, lon = lat0.copy(), lon0.copy()
+    st = np.zeros(nb, np.uint8)
+    eng.step_batch(30, k, lat, lon, head, nsteps=24, seg_len=8, status=st, z=zz)
+    same = w["status"] == 0
+    assert np.array_equal(st, w["status"]) and np.array_equal(k, w["k"]) and same.sum() > nb // 2
+    assert relerr(lat[same], w["lat"][same]) < rtol_for(mode) and relerr(lon[same], w["lon"][same]) < rtol_for(mode)
+    eng.set_precision(N.PREC_F64)
+
+
 def test_edge_cases(eng):
     eng.set_precision(N.PREC_F64)
     times = upload(eng, 0, 2)
