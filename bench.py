@@ -266,6 +266,8 @@ def main():
     eng.use_torch_stream()
     prec = {"default": N.PREC_FAST, "f64": N.PREC_F64, "fast": N.PREC_FAST}[args.precision]
     eng.set_precision(prec)
+    if os.environ.get("PMCTS_NO_STAGE"):  # diagnostic: K1 without the shared-memory slab ring
+        eng.set_option(N.OPT_STAGE_SLABS, 0)
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

@@ -33,7 +33,7 @@ constexpr int kBlock = 128;
 template <typename T>
 __global__ void blend_time_slabs_kernel(const T *__restrict__ u, const T *__restrict__ v,
                                         const int *__restrict__ it, const double *__restrict__ wt,
-                                        int nT, int plane, double2 *__restrict__ slab64,
+                                        int nT, int plane, int stride32, double2 *__restrict__ slab64,
                                         float2 *__restrict__ slab32) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)nT * plane) return;
@@ -43,7 +43,7 @@ __global__ void blend_time_slabs_kernel(const T *__restrict__ u, const T *__rest
     const double uu = (double)u[lo] * (1.0 - w) + (double)u[hi] * w;
     const double vv = (double)v[lo] * (1.0 - w) + (double)v[hi] * w;
     slab64[idx] = make_double2(uu, vv);
-    slab32[idx] = make_float2((float)uu, (float)vv);
+    slab32[(size_t)k * stride32 + p] = make_float2((float)uu, (float)vv);
 }
 
 // Weather.uInterpolator / vInterpolator (weatherTLKT.py:369-378): SciPy's linear RegularGridInterpolator
@@ -511,6 +511,138 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
     status_io[i] = (uint8_t)st;
 }
 
+// ---- TMA bulk copy + mbarrier (PTX, sm_90+): global -> shared without passing through registers -------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// K1, mixed precision, wind slab staged in shared memory -- the raw sweep when every running boat of a block
+// stands at the same time index (BASELINE config 3: the whole fleet starts at k = 0).  At step j all of them
+// interpolate on slab k0 + j: one thread brings that slab (nlat * nlon * 8 bytes; 5.2 KB on the 0.5-degree
+// grid) into shared memory with ONE TMA bulk copy, two steps ahead, into a two-slot ring guarded by
+// mbarriers; the four corner gathers of every boat are then shared-memory loads.  Blocks whose boats do not
+// share a time index, and grids whose slab does not fit the ring, take the L1 / L2 path of step_fast_kernel.
+template <int kNoise>
+__global__ void __launch_bounds__(kBlock)
+step_fast_staged_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
+                        double *__restrict__ lat_io, double *__restrict__ lon_io,
+                        const double *__restrict__ heading, int seg_len, NoiseView nz,
+                        uint8_t *__restrict__ status_io, int32_t *__restrict__ j_resume,
+                        uint32_t *__restrict__ any_resume) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ int s_kb;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < n;
+    int k = 0, st = PMCTS_ST_HORIZON;
+    double lat = 0.0, lon = 0.0;
+    if (mine) {
+        k = k_io[i];
+        lat = lat_io[i];
+        lon = lon_io[i];
+        st = status_io[i];
+    }
+    // common time index of the running boats of this block
+    if (threadIdx.x == 0) s_kb = 0x7fffffff;
+    __syncthreads();
+    if (st == PMCTS_ST_OK) atomicMin(&s_kb, k);
+    __syncthreads();
+    const int kb = s_kb;
+    if (kb == 0x7fffffff) return;  // nobody runs
+    const bool staged = __syncthreads_and(st != PMCTS_ST_OK || k == kb) != 0;
+
+    fast::Noise ns;
+    float sh = 0.0f, ch = 1.0f, s = 0.0f, c = 1.0f;
+    int seg_left = 0, trig_left = 0;
+    const double *hp = heading + (mine ? i : 0);
+
+    // one transition of this thread's boat (lean form of step_fast_kernel's loop body)
+    auto advance = [&](int j, const float2 *slab) {
+        if (seg_left == 0) {
+            seg_left = seg_len;
+            const bool ok = fast::heading_unit(*hp, sh, ch);
+            hp += n;
+            if (!ok) { st = fast::kStNeedsLiteral; j_resume[i] = j; return; }
+        }
+        --seg_left;
+        if (trig_left == 0) {
+            trig_left = kRefreshTrig;
+            fast::sincos_lat(lat, s, c);
+        }
+        --trig_left;
+        const fast::GridPos g = fast::grid_pos(sc, lat, lon);
+        const float z = ns.draw<kNoise>(nz, n, i, j);
+        fast::Move m;
+        st = slab ? fast::fast_step<true>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m, slab)
+                  : fast::fast_step<false>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
+        if (st == fast::kStNeedsLiteral) { j_resume[i] = j; return; }
+        if (st == PMCTS_ST_OK) {
+            s = m.s_new;
+            c = m.c_new;
+        }
+    };
+
+    if (!staged) {
+        for (int j = 0; j < nsteps && st == PMCTS_ST_OK; ++j) advance(j, nullptr);
+    } else {
+        const int cells = sc.slab32_stride;
+        const uint32_t bytes = (uint32_t)cells * sizeof(float2);
+        float2 *const ring = reinterpret_cast<float2 *>(smem_raw);  // slot b at ring + b * cells
+        auto issue = [&](int j) {  // slab of step j into slot j & 1 (thread 0 only)
+            const int kj = kb + j;
+            if (j < nsteps && kj >= 0 && kj < sc.nT) {
+                mbar_expect_tx(&bars[j & 1], bytes);
+                tma_bulk_load(ring + (j & 1) * cells, sc.slab32 + (size_t)kj * cells, bytes, &bars[j & 1]);
+            }
+        };
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            issue(0);
+            issue(1);
+        }
+        __syncthreads();
+        for (int j = 0; j < nsteps; ++j) {
+            const int kj = kb + j;
+            if (kj >= 0 && kj < sc.nT) mbar_wait(&bars[j & 1], (uint32_t)(j >> 1) & 1u);
+            if (st == PMCTS_ST_OK) advance(j, ring + (j & 1) * cells);
+            // everybody is done with slot j & 1 (and learns whether anybody still runs) before it is refilled
+            if (!__syncthreads_or(st == PMCTS_ST_OK)) break;
+            if (threadIdx.x == 0) issue(j + 2);
+        }
+    }
+    if (!mine) return;
+    if (st == fast::kStNeedsLiteral) *any_resume = 1u;
+    k_io[i] = k;
+    lat_io[i] = lat;
+    lon_io[i] = lon;
+    status_io[i] = (uint8_t)st;
+}
+
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
 // blockIdx.y = scenario.
 __global__ void backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes,
@@ -616,6 +748,8 @@ struct pmcts_ctx {
     char *work = nullptr;
     size_t work_cap = 0;
     bool margins_set = false;
+    bool stage_slabs = false;  // K1: stage the step's wind slab in shared memory (pmcts_set_option); measured
+                               // 21 % slower than the L1 / L2 gathers on config 3 (profiles/README.md), so off
     // PMCTS_ROLL_DEFER_REDO: the fp64 finisher of a rollout launch runs on a side stream so that it overlaps
     // the next launch; two work areas alternate, each guarded by the events of the launch that used it last
     cudaStream_t side_stream = nullptr;
@@ -888,6 +1022,15 @@ int pmcts_set_precision(pmcts_ctx *ctx, int mode) {
 
 int64_t pmcts_launch_count(pmcts_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    if (option == PMCTS_OPT_STAGE_SLABS) {
+        ctx->stage_slabs = value != 0;
+        return PMCTS_OK;
+    }
+    return fail(PMCTS_ERR_ARG, "unknown option %d", option);
+}
+
 int pmcts_enable_timing(pmcts_ctx *ctx, int on) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
     ctx->timing = on != 0;
@@ -1004,7 +1147,8 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     const size_t esz = dtype == 0 ? 8 : 4;
     const size_t o_slab64 = 0;
     const size_t o_slab32 = o_slab64 + al(cells * sizeof(double2));
-    const size_t o_times = o_slab32 + al(cells * sizeof(float2));
+    const size_t stride32 = (plane + 1) & ~(size_t)1;  // every fp32 slab 16-byte aligned
+    const size_t o_times = o_slab32 + al(stride32 * nT * sizeof(float2));
     const size_t o_dt = o_times + al(nT * sizeof(double));
     const size_t o_valid = o_dt + al(nT * sizeof(double));
     const size_t o_dt32 = o_valid + al(nT);
@@ -1038,6 +1182,7 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
             return fail(PMCTS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e2_));         \
         }                                                                                         \
     } while (0)
+    UP_TRY(cudaMemsetAsync(base + o_slab32, 0, stride32 * nT * sizeof(float2), s));  // (the padding cell of odd planes)
     UP_TRY(cudaMemcpyAsync(base + o_u, u, raw, cudaMemcpyHostToDevice, s));
     UP_TRY(cudaMemcpyAsync(base + o_v, v, raw, cudaMemcpyHostToDevice, s));
     UP_TRY(cudaMemcpyAsync(base + o_wtime, wtime, nt * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1057,12 +1202,12 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
         if (dtype == 0)
             blend_time_slabs_kernel<double><<<grid, 256, 0, s>>>(
                 (const double *)(base + o_u), (const double *)(base + o_v), (const int *)(tmp + t_it),
-                (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
+                (const double *)(tmp + t_wt), nT, (int)plane, (int)stride32, (double2 *)(base + o_slab64),
                 (float2 *)(base + o_slab32));
         else
             blend_time_slabs_kernel<float><<<grid, 256, 0, s>>>(
                 (const float *)(base + o_u), (const float *)(base + o_v), (const int *)(tmp + t_it),
-                (const double *)(tmp + t_wt), nT, (int)plane, (double2 *)(base + o_slab64),
+                (const double *)(tmp + t_wt), nT, (int)plane, (int)stride32, (double2 *)(base + o_slab64),
                 (float2 *)(base + o_slab32));
     }
     UP_TRY(cudaGetLastError());
@@ -1108,11 +1253,12 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.box_fo_hi = (float)((box[3] - vw.lon0) * inv_dlon);
     // the fp32 kernels assume |lat| <= 90 on the grid (their sin / cos kernels cover [-pi/2, pi/2])
     // and one contiguous run of valid instants
+    vw.slab32_stride = (int)stride32;
     vw.fa_c0 = -vw.lat0 * inv_dlat;
     vw.fo_c0 = -vw.lon0 * inv_dlon;
     vw.ks_lo = std::max(0, tc.kv_lo);
     vw.ks_hi = std::min(nT - 2, tc.kv_hi);
-    vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f && cells < ((size_t)1 << 31)) ? 1 : 0;
+    vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f && stride32 * nT < ((size_t)1 << 31)) ? 1 : 0;
     {
         uint64_t h = 1469598103934665603ull;
         const unsigned char *bytes = (const unsigned char *)sim_times;
@@ -1219,13 +1365,25 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
             step_fast_kernel<NOISE, LEAN><<<grid_for(n), kBlock, 0, ctx->stream>>>(                         \
                 sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,    \
                 status_dev, traj_lat, traj_lon, flags, j_resume, any_resume)
-            if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, true);
+            // two slabs of the fp32 grid in shared memory: worth it when a block runs several steps and the ring
+            // leaves room for >= 8 blocks per SM
+            const size_t ring = 2 * (size_t)sc->view.slab32_stride * sizeof(float2);
+            const bool stage = lean && ctx->stage_slabs && nsteps >= 4 && ring <= 24 * 1024;
+#define PMCTS_LAUNCH_STAGED(NOISE)                                                                          \
+            step_fast_staged_kernel<NOISE><<<grid_for(n), kBlock, ring, ctx->stream>>>(                      \
+                sc->view, ctx->params, n, nsteps, k, lat, lon, heading, seg_len, nz, status_dev, j_resume,   \
+                any_resume)
+            if (stage && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_PHILOX);
+            else if (stage && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_INJECTED);
+            else if (stage) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_NONE);
+            else if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, true);
             else if (lean && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, true);
             else if (lean) PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, true);
             else if (nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, false);
             else if (nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, false);
             else PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, false);
 #undef PMCTS_LAUNCH_STEP
+#undef PMCTS_LAUNCH_STAGED
         }
         CUDA_TRY(cudaGetLastError());
         {

@@ -194,12 +194,20 @@ PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
     return g;
 }
 
-// Simulator.getWind (simulatorTLKT.py:168-179) on the time-blended fp32 slab of instant k.
-PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u, float &v) {
-    const float2 *row0 = sc.slab32 + ((k * sc.nlat + g.ia) * sc.nlon + g.io);  // < 2^31 cells (checked at upload)
+// Simulator.getWind (simulatorTLKT.py:168-179) on the time-blended fp32 slab of instant k.  kShared: the
+// slab has been staged in shared memory (`slab` points there); otherwise it is read through L1 / L2.
+template <bool kShared = false>
+PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u, float &v,
+                      const float2 *slab = nullptr) {
+    const float2 *row0 = (kShared ? slab : sc.slab32 + k * sc.slab32_stride) + (g.ia * sc.nlon + g.io);
     const float2 *row1 = row0 + sc.nlon;
 #if defined(__CUDA_ARCH__)
-    const float2 c00 = __ldg(row0), c01 = __ldg(row0 + 1), c10 = __ldg(row1), c11 = __ldg(row1 + 1);
+    float2 c00, c01, c10, c11;
+    if (kShared) {
+        c00 = row0[0]; c01 = row0[1]; c10 = row1[0]; c11 = row1[1];
+    } else {
+        c00 = __ldg(row0); c01 = __ldg(row0 + 1); c10 = __ldg(row1); c11 = __ldg(row1 + 1);
+    }
 #else
     const float2 c00 = row0[0], c01 = row0[1], c10 = row1[0], c11 = row1[1];
 #endif
@@ -406,8 +414,10 @@ constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout co
 // Simulator.doStep (simulatorTLKT.py:181-216).  g = grid position of (lat, lon); (sh, ch) heading;
 // (s, c) = sin/cos(lat); z standard normal.  On PMCTS_ST_OK the state is advanced and m holds the
 // increments; otherwise nothing changes.
+template <bool kShared = false>
 PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
-                       const GridPos &g, float sh, float ch, float s, float c, float z, Move &m) {
+                       const GridPos &g, float sh, float ch, float s, float c, float z, Move &m,
+                       const float2 *slab = nullptr) {
     // instants a step can start from: inside the weather time axis and not the last one
     if ((unsigned)(k - sc.ks_lo) > (unsigned)(sc.ks_hi - sc.ks_lo) || sc.ks_hi < sc.ks_lo || !g.inside) {
         // which error the reference raises: IndexError before anything for a bad index, ValueError from the
@@ -417,7 +427,7 @@ PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, dou
         return PMCTS_ST_PAST_HORIZON;
     }
     float u, v;
-    wind_at(sc, k, g, u, v);
+    wind_at<kShared>(sc, k, g, u, v, slab);
     float speed = boat_speed(bp, u, v, sh, ch);
     speed = fma_(z, speed * bp.sigma_f, speed);  // Boat.addUncertainty (:504-517)
 #if defined(__CUDA_ARCH__)

@@ -24,7 +24,7 @@ constexpr double kDegToRad = kPi / 180.0;
 // simulator instant, so a transition gathers 4 grid corners instead of 8 and needs no time weight.
 struct ScenarioView {
     const double2 *slab64;  // [nT][nlat][nlon] (u, v) fp64
-    const float2 *slab32;   // same, rounded to fp32 (Fast mode)
+    const float2 *slab32;   // same, rounded to fp32 (Fast mode); slab k starts at slab32 + k * slab32_stride
     const double *times;    // [nT] simulator instants, days
     const double *dt_sec;   // [nT] (times[k+1]-times[k])*86400, last entry unused
     const uint8_t *k_valid; // [nT] 1 if times[k] lies inside the weather time axis
@@ -41,6 +41,8 @@ struct ScenarioView {
     float box_fa_lo, box_fa_hi, box_fo_lo, box_fo_hi;  // terminal box in grid-index units
     double fa_c0, fo_c0;    // -lat0 * inv_dlat, -lon0 * inv_dlon: fractional index = fma(lat, inv_dlat, fa_c0)
     int ks_lo, ks_hi;       // instants a transition can start from: max(0, kv_lo) .. min(nT - 2, kv_hi)
+    int slab32_stride;      // cells between fp32 slabs: nlat * nlon rounded up to even, so every slab is 16-byte
+                            // aligned (TMA bulk copies into shared memory need that)
 };
 
 // Boat.* / module constants (pmcts_set_params), plus values derived once on the host.

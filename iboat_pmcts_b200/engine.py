@@ -125,6 +125,9 @@ class Engine:
     def synchronize(self):
         N.check(self._lib.pmcts_synchronize(self._h))
 
+    def set_option(self, option, value):
+        N.check(self._lib.pmcts_set_option(self._h, int(option), int(value)))
+
     def join(self, keep_last=0):
         """Orders the ctx stream after the deferred finishers of all but the ``keep_last`` latest launches."""
         N.check(self._lib.pmcts_join(self._h, int(keep_last)))

@@ -97,6 +97,12 @@ int pmcts_set_fast_margins(pmcts_ctx *ctx, double angle, double along, double ne
                            double bin);
 /* Rollouts (or K1 hand-over flag) the last FAST launch left to the fp64 kernel; synchronises the stream. */
 int64_t pmcts_last_redo_count(pmcts_ctx *ctx);
+/* Engine options.  PMCTS_OPT_STAGE_SLABS (default 0): 1 makes K1 in PMCTS_PREC_FAST stage the wind slab of the
+ * current step in shared memory (TMA bulk copy into a two-slot mbarrier ring) for blocks whose boats share
+ * their time index; 0 reads every gather through L1 / L2.  Same results bit for bit; measured slower on a
+ * B200 (the per-step block barrier costs more than the L1 hits it replaces), kept for grids that miss L1. */
+#define PMCTS_OPT_STAGE_SLABS 1
+int pmcts_set_option(pmcts_ctx *ctx, int option, int value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);
 /* While timing is enabled every kernel launch is bracketed by a cudaEvent pair on the ctx stream;

@@ -44,16 +44,18 @@ void *fm_create(const double *wtime, int nt, const double *wlat, int nlat, const
     m->tc = time_cells(wtime, nt, sim_times, nT);
     m->times.assign(sim_times, sim_times + nT);
     const size_t plane = (size_t)nlat * nlon;
-    m->slab32.resize(plane * nT);
+    const size_t stride = (plane + 1) & ~(size_t)1;
+    m->slab32.resize(stride * nT);
     for (int k = 0; k < nT; ++k)
         for (size_t p = 0; p < plane; ++p) {
             const size_t lo = (size_t)m->tc.it[k] * plane + p, hi = lo + plane;
             const double w = m->tc.wt[k];
-            m->slab32[k * plane + p].x = (float)(u[lo] * (1.0 - w) + u[hi] * w);
-            m->slab32[k * plane + p].y = (float)(v[lo] * (1.0 - w) + v[hi] * w);
+            m->slab32[k * stride + p].x = (float)(u[lo] * (1.0 - w) + u[hi] * w);
+            m->slab32[k * stride + p].y = (float)(v[lo] * (1.0 - w) + v[hi] * w);
         }
     ScenarioView &s = m->sc;
     s.slab32 = m->slab32.data();
+    s.slab32_stride = (int)stride;
     s.times = m->times.data();
     s.dt_sec = m->tc.dt.data();
     s.dt_sec32 = m->tc.dt32.data();

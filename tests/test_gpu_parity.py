@@ -444,6 +444,44 @@ def test_other_hemisphere_and_grid(eng, mode):
     eng.set_precision(N.PREC_F64)
 
 
+def test_staged_slabs_give_the_same_boats(eng):
+    """K1 with the step's wind slab staged in shared memory (TMA bulk copy, blocks whose boats share the time
+    index) == K1 reading every gather through L1 / L2, bit for bit; blocks with mixed time indices, frozen
+    boats and boats that run off the time axis take the same answers either way."""
+    eng.set_precision(N.PREC_FAST)
+    nsteps, n = 60, 5000
+    times = np.linspace(0, 5, 101)
+    upload(eng, 3, 1, times=times)
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=12)
+    head = synth.octagon_headings(h0, nsteps, seg_len=7)
+    res = {}
+    for mixed in (False, True):
+        for stage in (1, 0):
+            eng.set_option(N.OPT_STAGE_SLABS, stage)
+            k = np.zeros(n, np.int32)
+            st = np.zeros(n, np.uint8)
+            if mixed:
+                k[:] = np.random.default_rng(1).integers(0, 60, n)   # most blocks: no common index; some boats hit the end
+                k[:256] = 17                                          # two blocks with a common index ...
+                st[100:140] = N.ST_OUT_OF_BOX                         # ... part of whose boats are frozen
+                k[100:140] = 3
+            lat, lon = lat0.copy(), lon0.copy()
+            eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=7, status=st, seed=21, stream=2)
+            res[(mixed, stage)] = (k, lat, lon, st)
+        for a, b in zip(res[(mixed, 1)], res[(mixed, 0)]):
+            assert np.array_equal(a, b)
+    eng.set_option(N.OPT_STAGE_SLABS, 0)
+    k, lat, lon, st = res[(False, 1)]
+    assert (k == nsteps).all() and (st == 0).all()
+    o = H.oracle_sim(1, times=times)
+    want = o.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=7, seed=21, stream=2, nthreads=8)
+    assert relerr(lat, want["lat"]) < RTOL and relerr(lon, want["lon"]) < RTOL
+    k, lat, lon, st = res[(True, 1)]
+    assert (st[100:140] == N.ST_OUT_OF_BOX).all() and (k[100:140] == 3).all()
+    assert (st == N.ST_PAST_HORIZON).sum() > 0 and (k[st == N.ST_PAST_HORIZON] == 100).all()
+    eng.set_precision(N.PREC_F64)
+
+
 def test_edge_cases(eng):
     eng.set_precision(N.PREC_F64)
     times = upload(eng, 0, 2)
