@@ -399,7 +399,7 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
 // decisions fell inside the error margins writes nothing: its id goes to a.redo_list and the literal
 // kernel above finishes it (same stream, next launch).  kNoise fixes the noise source at compile time;
 // kLean is the throughput form: per-leaf histograms and statistics only, no per-rollout outputs.
-template <int kNoise, bool kLean>
+template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
 __global__ void __launch_bounds__(kBlock)
 rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
     const int64_t n = a.n_leaf * a.replicas;
@@ -411,8 +411,10 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
     fast::RollOut o;
     o.st = PMCTS_ST_OK; o.nstep = 0; o.bin = 0; o.why = 0; o.ta = NAN;
     bool counted = false;
+    // n < 2^28 (the work-list entries hold the rollout id in 28 bits): a 32-bit division, done once
+    const int64_t leaf = (int64_t)((uint32_t)r / (uint32_t)a.replicas);
     if (live) {
-        fast::rollout_one<kNoise, kLean>(sc, bp, nz, a, n, r, o);
+        fast::rollout_one<kNoise, kLean, kDefBoat, kTurbo>(sc, bp, nz, a, n, r, leaf, o);
         if (o.why) {
             a.redo_list[atomicAdd(a.redo_count, 1u)] = ((uint32_t)scen << kRedoShift) | (uint32_t)r;
         } else {
@@ -429,7 +431,7 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
             }
         }
     }
-    reduce_rollouts<true>(a, warp_mask, counted, scen, r / a.replicas, o.bin, o.st, o.nstep, o.ta);
+    reduce_rollouts<true>(a, warp_mask, counted, scen, leaf, o.bin, o.st, o.nstep, o.ta);
 }
 
 // K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
@@ -437,9 +439,9 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
 // than fast::kMaxStepAngle) stops with the internal status kStNeedsLiteral and its step index in
 // j_resume; step_batch_kernel then finishes it.  kLean: no trajectory / previous-state output and no
 // stop-before-terminal mode -- the raw sweep of BASELINE config 3.
-constexpr int kRefreshTrig = 16;  // steps between re-evaluations of sin / cos(lat) from the fp64 latitude
+using fast::kRefreshTrig;
 
-template <int kNoise, bool kLean>
+template <int kNoise, bool kLean, bool kDefBoat = false>
 __global__ void __launch_bounds__(kBlock)
 step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t *__restrict__ k_io,
                  double *__restrict__ lat_io, double *__restrict__ lon_io, double *__restrict__ prev_lat,
@@ -487,7 +489,7 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
         const float z = ns.draw<kNoise>(nz, n, i, j);
         const double la0 = lat, lo0 = lon;
         fast::Move m;
-        st = fast::fast_step(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
+        st = fast::fast_step<false, kDefBoat>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
         if (st == fast::kStNeedsLiteral) { j_resume[i] = j; break; }
         if (st == PMCTS_ST_OK) {
             s = m.s_new;
@@ -1258,6 +1260,7 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
     vw.fo_c0 = -vw.lon0 * inv_dlon;
     vw.ks_lo = std::max(0, tc.kv_lo);
     vw.ks_hi = std::min(nT - 2, tc.kv_hi);
+    finish_fast_view(vw, tc, box);
     vw.fast_ok = (nT > 0 && tc.contiguous && vw.max_abs_lat <= 90.0f && stride32 * nT < ((size_t)1 << 31)) ? 1 : 0;
     {
         uint64_t h = 1469598103934665603ull;
@@ -1361,14 +1364,15 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
             const bool lean = !prev_lat && !prev_lon && !traj_lat && !traj_lon && !(flags & PMCTS_STEP_STOP_BEFORE_TERMINAL);
-#define PMCTS_LAUNCH_STEP(NOISE, LEAN)                                                                      \
-            step_fast_kernel<NOISE, LEAN><<<grid_for(n), kBlock, 0, ctx->stream>>>(                         \
+#define PMCTS_LAUNCH_STEP(NOISE, LEAN, ...)                                                                 \
+            step_fast_kernel<NOISE, LEAN, ##__VA_ARGS__><<<grid_for(n), kBlock, 0, ctx->stream>>>(          \
                 sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz,    \
                 status_dev, traj_lat, traj_lon, flags, j_resume, any_resume)
             // two slabs of the fp32 grid in shared memory: worth it when a block runs several steps and the ring
             // leaves room for >= 8 blocks per SM
             const size_t ring = 2 * (size_t)sc->view.slab32_stride * sizeof(float2);
             const bool stage = lean && ctx->stage_slabs && nsteps >= 4 && ring <= 24 * 1024;
+            const bool defboat = fast::is_default_boat(ctx->params);
 #define PMCTS_LAUNCH_STAGED(NOISE)                                                                          \
             step_fast_staged_kernel<NOISE><<<grid_for(n), kBlock, ring, ctx->stream>>>(                      \
                 sc->view, ctx->params, n, nsteps, k, lat, lon, heading, seg_len, nz, status_dev, j_resume,   \
@@ -1376,6 +1380,9 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
             if (stage && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_PHILOX);
             else if (stage && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_INJECTED);
             else if (stage) PMCTS_LAUNCH_STAGED(PMCTS_NOISE_NONE);
+            else if (lean && defboat && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, true, true);
+            else if (lean && defboat && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, true, true);
+            else if (lean && defboat) PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, true, true);
             else if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_STEP(PMCTS_NOISE_PHILOX, true);
             else if (lean && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_STEP(PMCTS_NOISE_INJECTED, true);
             else if (lean) PMCTS_LAUNCH_STEP(PMCTS_NOISE_NONE, true);
@@ -1529,20 +1536,28 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     const dim3 grid_all(grid_for(n), n_scen);
     cudaStream_t tail_stream = ctx->stream;  // where the fp64 finisher and the statistics fold run
     if (fast) {
-        a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
-        a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
+        fast::prepare_rollout(vw, a);
         a.redo_count = (uint32_t *)work;
         a.redo_list = (uint32_t *)(work + 256 + part_bytes);
         CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
-        a.rw_t0 = vw.tmax * 1.001;
-        a.rw_inv = (float)(1.0 / (vw.tmax * 1.001 - tmin));
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
             const bool lean = !reward && !t_arr && !steps && !status && !bin && !frac && !final_lat && !final_lon &&
                               !traj_lat && !traj_lon;
-#define PMCTS_LAUNCH_ROLL(NOISE, LEAN) \
-            rollout_fast_kernel<NOISE, LEAN><<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs)
-            if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true);
+            // the reference's own boat: its 29 constants as immediates (fast::defboat)
+            const bool defboat = fast::is_default_boat(ctx->params);
+#define PMCTS_LAUNCH_ROLL(NOISE, LEAN, ...) \
+            rollout_fast_kernel<NOISE, LEAN, ##__VA_ARGS__><<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs)
+            // turbo: tree mode from a root that can start a step, on a scenario whose terminal box implies every
+            // range check of the loop (fast::turbo_ok)
+            const bool turbo = defboat && fast::turbo_ok(vw, a);
+            if (lean && turbo && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true);
+            else if (lean && turbo && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true, true);
+            else if (lean && turbo) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true, true);
+            else if (lean && defboat && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true);
+            else if (lean && defboat && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true);
+            else if (lean && defboat) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true);
+            else if (lean && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true);
             else if (lean && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true);
             else if (lean) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true);
             else if (nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, false);

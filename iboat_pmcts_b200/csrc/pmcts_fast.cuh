@@ -145,9 +145,11 @@ PMCTS_HD void box_muller(uint32_t x0, uint32_t x1, float &z0, float &z1) {
 }
 
 struct Noise {
-    float cache[4];
+    // The four normals of a Philox block sit in a shift register: consecutive steps (the only way the kernels
+    // draw) take c0 and move the rest down, so the common path has no indexed selection.
+    float c0, c1, c2, c3;
     int cached_block;
-    PMCTS_HD Noise() : cached_block(-1) {}
+    PMCTS_HD Noise() : c0(0.0f), c1(0.0f), c2(0.0f), c3(0.0f), cached_block(-1) {}
     // kMode: PMCTS_NOISE_* known at compile time, or -1 to read nz.mode
     template <int kMode>
     PMCTS_HD float draw(const NoiseView &nz, int64_t n, int64_t i, int step) {
@@ -160,12 +162,16 @@ struct Noise {
             uint32_t x[4];
             philox4x32_10((uint32_t)boat, (uint32_t)(boat >> 32), (uint32_t)block, (uint32_t)nz.stream,
                           (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), x);
-            box_muller(x[0], x[1], cache[0], cache[1]);
-            box_muller(x[2], x[3], cache[2], cache[3]);
+            box_muller(x[0], x[1], c0, c1);
+            box_muller(x[2], x[3], c2, c3);
             cached_block = block;
+            for (int q = step & 3; q > 0; --q) {  // a sequence that starts inside a block (never, in the kernels)
+                c0 = c1; c1 = c2; c2 = c3;
+            }
         }
-        const int q = step & 3;
-        return q == 0 ? cache[0] : q == 1 ? cache[1] : q == 2 ? cache[2] : cache[3];
+        const float z = c0;
+        c0 = c1; c1 = c2; c2 = c3;
+        return z;
     }
 };
 
@@ -180,9 +186,12 @@ struct GridPos {
     bool inside;   // SciPy bounds_error=True
 };
 
+// kInside = false: the caller holds the position against the terminal box of a roll_safe scenario (box
+// inside the grid), which implies the bounds test.
+template <bool kInside = true>
 PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
     GridPos g;
-    g.inside = lat >= sc.lat0 && lat <= sc.lat_last && lon >= sc.lon0 && lon <= sc.lon_last;
+    g.inside = !kInside || (lat >= sc.lat0 && lat <= sc.lat_last && lon >= sc.lon0 && lon <= sc.lon_last);
     // (lat - lat0) / dlat as one fma; inside the grid it is >= -1e-13, so truncation needs no lower clamp
     const double fa = fma(lat, sc.inv_dlat, sc.fa_c0), fo = fma(lon, sc.inv_dlon, sc.fo_c0);
     g.ia = imin((int)fa, sc.nlat - 2);
@@ -199,8 +208,11 @@ PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
 template <bool kShared = false>
 PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u, float &v,
                       const float2 *slab = nullptr) {
-    const float2 *row0 = (kShared ? slab : sc.slab32 + k * sc.slab32_stride) + (g.ia * sc.nlon + g.io);
-    const float2 *row1 = row0 + sc.nlon;
+    // one 32-bit cell index (< 2^31 cells, checked at upload), then one widening multiply-add per row
+    const int cell = (kShared ? 0 : k * sc.slab32_stride) + (g.ia * sc.nlon + g.io);
+    const float2 *base = kShared ? slab : sc.slab32;
+    const float2 *row0 = base + cell;
+    const float2 *row1 = base + (cell + sc.nlon);
 #if defined(__CUDA_ARCH__)
     float2 c00, c01, c10, c11;
     if (kShared) {
@@ -218,23 +230,56 @@ PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u,
 }
 
 // ---- Boat.getDeterDyn (simulatorTLKT.py:473-502) ----------------------------------------------------
+// The reference's own boat (Boat.FIT_VELOCITY and the module constants, simulatorTLKT.py:454-471) as
+// compile-time constants: derive_fast_params' output for pmcts_create's defaults.  sm_100 takes constants
+// from uniform registers, not from the constant bank, and the rollout loop needs more of them than there are;
+// with kDefBoat these 29 become instruction immediates.  Kernels are instantiated both ways and the host
+// picks the specialised one when is_default_boat(params) (tests/test_abi.py pins the table to
+// derive_fast_params).
+namespace defboat {
+// (scalars: device code may use a constexpr scalar, not an element of a constexpr array)
+constexpr float pc0 = 1.373763084e+00f, pc1 = 1.079237461e-01f, pc2 = -6.408512592e-01f, pc3 = 1.135649323e+00f, pc4 = -3.408502787e-02f, pc5 = -5.383408070e-01f;
+constexpr float pc6 = 7.206667066e-01f, pc7 = 8.731120229e-01f, pc8 = 2.533754408e-01f, pc9 = -2.119406760e-01f, pc10 = -3.206158578e-01f, pc11 = 0.0f;
+constexpr float pc12 = 5.637606978e-02f, pc13 = 2.704189122e-01f, pc14 = 1.337060332e-01f, pc15 = -7.381652296e-02f, pc16 = 0.0f, pc17 = 0.0f;
+constexpr float pc18 = -3.346018121e-02f, pc19 = 3.288391531e-01f, pc20 = 2.619542181e-01f, pc21 = 0.0f, pc22 = 0.0f, pc23 = 0.0f;
+constexpr float pc24 = -2.172237635e-01f, pc25 = -2.437742054e-01f, pc26 = 0.0f, pc27 = 0.0f, pc28 = 0.0f, pc29 = 0.0f;
+constexpr float pc30 = 6.050717458e-02f, pc31 = 0.0f, pc32 = 0.0f, pc33 = 0.0f, pc34 = 0.0f, pc35 = 0.0f;
+constexpr float pc[36] = {pc0, pc1, pc2, pc3, pc4, pc5, pc6, pc7, pc8, pc9, pc10, pc11, pc12, pc13, pc14, pc15, pc16, pc17, pc18, pc19, pc20, pc21, pc22, pc23, pc24, pc25, pc26, pc27, pc28, pc29, pc30, pc31, pc32, pc33, pc34, pc35};  // host side (is_default_boat)
+constexpr float p_mid = 9.75e+01f, p_ihalf = 1.600000076e-02f, w_ihalf = 1.047120392e-01f;
+constexpr float wind_max = 1.910000038e+01f, pmin = 35.0f, pmax = 160.0f;
+constexpr float cos_pmin = 8.191520572e-01f, cos_pmax = -9.396926165e-01f;
+}  // namespace defboat
+
+inline bool is_default_boat(const BoatParams &bp) {
+    for (int i = 0; i < 36; ++i)
+        if (bp.pc[i] != defboat::pc[i]) return false;
+    return bp.polar_tri == 1 && bp.p_mid == defboat::p_mid && bp.p_ihalf == defboat::p_ihalf &&
+           bp.w_ihalf == defboat::w_ihalf && bp.wind_max_f == defboat::wind_max && bp.pmin_f == defboat::pmin &&
+           bp.pmax_f == defboat::pmax && bp.cos_pmin_f == defboat::cos_pmin && bp.cos_pmax_f == defboat::cos_pmax;
+}
+
+template <bool kDefBoat = false>
 PMCTS_HD float polar_centred(const BoatParams &bp, float x, float y) {
-    const float *c = bp.pc;
-    if (bp.polar_tri) {
+#define PMCTS_PC(i) (kDefBoat ? defboat::pc##i : bp.pc[i])
+    if (kDefBoat || bp.polar_tri) {
         // column j (power of y) has degree 5 - j in x
-        float c0 = c[30];
-        c0 = fma_(c0, x, c[24]); c0 = fma_(c0, x, c[18]); c0 = fma_(c0, x, c[12]); c0 = fma_(c0, x, c[6]); c0 = fma_(c0, x, c[0]);
-        float c1 = c[25];
-        c1 = fma_(c1, x, c[19]); c1 = fma_(c1, x, c[13]); c1 = fma_(c1, x, c[7]); c1 = fma_(c1, x, c[1]);
-        float c2 = c[20];
-        c2 = fma_(c2, x, c[14]); c2 = fma_(c2, x, c[8]); c2 = fma_(c2, x, c[2]);
-        float c3 = c[15];
-        c3 = fma_(c3, x, c[9]); c3 = fma_(c3, x, c[3]);
-        float c4 = fma_(c[10], x, c[4]);
-        float acc = c[5];
+        float c0 = PMCTS_PC(30);
+        c0 = fma_(c0, x, PMCTS_PC(24)); c0 = fma_(c0, x, PMCTS_PC(18)); c0 = fma_(c0, x, PMCTS_PC(12));
+        c0 = fma_(c0, x, PMCTS_PC(6)); c0 = fma_(c0, x, PMCTS_PC(0));
+        float c1 = PMCTS_PC(25);
+        c1 = fma_(c1, x, PMCTS_PC(19)); c1 = fma_(c1, x, PMCTS_PC(13)); c1 = fma_(c1, x, PMCTS_PC(7));
+        c1 = fma_(c1, x, PMCTS_PC(1));
+        float c2 = PMCTS_PC(20);
+        c2 = fma_(c2, x, PMCTS_PC(14)); c2 = fma_(c2, x, PMCTS_PC(8)); c2 = fma_(c2, x, PMCTS_PC(2));
+        float c3 = PMCTS_PC(15);
+        c3 = fma_(c3, x, PMCTS_PC(9)); c3 = fma_(c3, x, PMCTS_PC(3));
+        float c4 = fma_(PMCTS_PC(10), x, PMCTS_PC(4));
+        float acc = PMCTS_PC(5);
         acc = fma_(acc, y, c4); acc = fma_(acc, y, c3); acc = fma_(acc, y, c2); acc = fma_(acc, y, c1);
         return fma_(acc, y, c0);
     }
+#undef PMCTS_PC
+    const float *c = bp.pc;
     float acc = 0.0f;
 #pragma unroll
     for (int j = 5; j >= 0; --j) {
@@ -251,7 +296,14 @@ PMCTS_HD float polar_centred(const BoatParams &bp, float x, float y) {
 // Boat.getDeterDyn.  The wind blows *to* (u, v); the point of sail is the angle between the heading
 // and the direction the wind comes *from*, folded to [0, 180] -- i.e. the plain angle between the
 // two unit vectors (the reference's abs / 360 - p fold is that angle for headings in [0, 360)).
+template <bool kDefBoat = false>
 PMCTS_HD float boat_speed(const BoatParams &bp, float u, float v, float sh, float ch) {
+    const float wind_max = kDefBoat ? defboat::wind_max : bp.wind_max_f;
+    const float pmin = kDefBoat ? defboat::pmin : bp.pmin_f, pmax = kDefBoat ? defboat::pmax : bp.pmax_f;
+    const float p_mid = kDefBoat ? defboat::p_mid : bp.p_mid, p_ihalf = kDefBoat ? defboat::p_ihalf : bp.p_ihalf;
+    const float w_ihalf = kDefBoat ? defboat::w_ihalf : bp.w_ihalf;
+    const float cos_pmin = kDefBoat ? defboat::cos_pmin : bp.cos_pmin_f;
+    const float cos_pmax = kDefBoat ? defboat::cos_pmax : bp.cos_pmax_f;
     const float m2 = fma_(u, u, v * v);
     float du = 0.0f, dv = 1.0f, mag = 0.0f;  // atan2(0, 0) = 0: a calm wind "blows north"
     if (m2 > 0.0f) {
@@ -263,11 +315,11 @@ PMCTS_HD float boat_speed(const BoatParams &bp, float u, float v, float sh, floa
     const float cosp = -fma_(du, sh, dv * ch);
     const float sinp = fabsf(fma_(du, ch, -dv * sh));
     const float p = atan2_pos(sinp, cosp) * 57.2957795131f;
-    const float w = fminf(mag, bp.wind_max_f);
-    const float pe = fminf(fmaxf(p, bp.pmin_f), bp.pmax_f);
-    float sp = polar_centred(bp, (pe - bp.p_mid) * bp.p_ihalf, fma_(w, bp.w_ihalf, -1.0f));
-    if (p < bp.pmin_f) sp *= bp.cos_pmin_f * rcp_approx(cosp);
-    else if (p > bp.pmax_f) sp *= bp.cos_pmax_f * rcp_approx(cosp);
+    const float w = fminf(mag, wind_max);
+    const float pe = fminf(fmaxf(p, pmin), pmax);
+    float sp = polar_centred<kDefBoat>(bp, (pe - p_mid) * p_ihalf, fma_(w, w_ihalf, -1.0f));
+    if (p < pmin) sp *= cos_pmin * rcp_approx(cosp);
+    else if (p > pmax) sp *= cos_pmax * rcp_approx(cosp);
     return sp;
 }
 
@@ -414,12 +466,16 @@ constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout co
 // Simulator.doStep (simulatorTLKT.py:181-216).  g = grid position of (lat, lon); (sh, ch) heading;
 // (s, c) = sin/cos(lat); z standard normal.  On PMCTS_ST_OK the state is advanced and m holds the
 // increments; otherwise nothing changes.
-template <bool kShared = false>
+// kTurbo: the caller guarantees that k can start a step and that the position is on the grid (a roll_safe
+// scenario whose state passed the terminal test, or the host-checked root), and that all steps have the same
+// length sc.dt_uniform32: no range checks, no load of the step length.
+template <bool kShared = false, bool kDefBoat = false, bool kTurbo = false>
 PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
                        const GridPos &g, float sh, float ch, float s, float c, float z, Move &m,
                        const float2 *slab = nullptr) {
     // instants a step can start from: inside the weather time axis and not the last one
-    if ((unsigned)(k - sc.ks_lo) > (unsigned)(sc.ks_hi - sc.ks_lo) || sc.ks_hi < sc.ks_lo || !g.inside) {
+    if (!kTurbo &&
+        ((unsigned)(k - sc.ks_lo) > (unsigned)(sc.ks_hi - sc.ks_lo) || sc.ks_hi < sc.ks_lo || !g.inside)) {
         // which error the reference raises: IndexError before anything for a bad index, ValueError from the
         // wind query (simulatorTLKT.py:176-177), IndexError from times[k + 1] (:208)
         if (k < 0 || k >= sc.nT) return PMCTS_ST_PAST_HORIZON;
@@ -428,12 +484,12 @@ PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, dou
     }
     float u, v;
     wind_at<kShared>(sc, k, g, u, v, slab);
-    float speed = boat_speed(bp, u, v, sh, ch);
+    float speed = boat_speed<kDefBoat>(bp, u, v, sh, ch);
     speed = fma_(z, speed * bp.sigma_f, speed);  // Boat.addUncertainty (:504-517)
 #if defined(__CUDA_ARCH__)
-    const float dt = __ldg(sc.dt_sec32 + k);
+    const float dt = kTurbo ? sc.dt_uniform32 : __ldg(sc.dt_sec32 + k);
 #else
-    const float dt = sc.dt_sec32[k];
+    const float dt = kTurbo ? sc.dt_uniform32 : sc.dt_sec32[k];
 #endif
     const float d = speed * dt * bp.inv_radius_f;
     if (!(fabsf(d) <= kMaxStepAngle)) return kStNeedsLiteral;
@@ -480,7 +536,7 @@ PMCTS_HD int hist_bin_checked(const BoatParams &bp, double r, int &why) {
 // Tree.is_state_terminal (worker.py:417-436) on the fp32 grid coordinates of the position.
 PMCTS_HD bool fast_terminal(const ScenarioView &sc, const BoatParams &bp, int k, const GridPos &g, int &why) {
     if (k >= sc.nT - 1) return true;
-    const float m = bp.margin_box * (1.0f + fmaxf(fabsf(g.fa), fabsf(g.fo)) * 0.01f);
+    const float m = bp.margin_box * sc.box_margin_scale;  // 1 + 0.01 * (largest grid index): fp32 spacing of fa / fo
     const float da0 = g.fa - sc.box_fa_lo, da1 = sc.box_fa_hi - g.fa;
     const float do0 = g.fo - sc.box_fo_lo, do1 = sc.box_fo_hi - g.fo;
     const float lo = fminf(fminf(da0, da1), fminf(do0, do1));
@@ -495,15 +551,51 @@ struct RollOut {
     double ta, rw, frac, lat, lon;
 };
 
+// Fills the members of RolloutArgs every rollout of a launch would otherwise derive for itself: destination
+// trigonometry, reward constants, and the root state seen through sincos_lat / dest_rel / grid_pos (the
+// device's own fp32 formulas, evaluated once on the host -- they contain no hardware approximation, so the
+// host and the device agree bit for bit).
+inline void prepare_rollout(const ScenarioView &sc, RolloutArgs &a) {
+    a.sin_dest_lat = (float)sin(a.dest_lat * kDegToRad);
+    a.cos_dest_lat = (float)cos(a.dest_lat * kDegToRad);
+    a.rw_t0 = sc.tmax * 1.001;
+    a.rw_inv = (float)(1.0 / (sc.tmax * 1.001 - a.tmin));
+    RootPre &p = a.root_pre;
+    sincos_lat(a.root_lat, p.s, p.c);
+    const DestRel rd = dest_rel(a.root_lat, a.root_lon, a.dest_lat, a.dest_lon);
+    p.sin_dlat = rd.sin_dlat; p.sin_dlon = rd.sin_dlon; p.h_dlon = rd.h_dlon; p.x_dlat = rd.x_dlat;
+    const GridPos g = grid_pos(sc, a.root_lat, a.root_lon);
+    p.wa = g.wa; p.wo = g.wo; p.fa = g.fa; p.fo = g.fo;
+    p.ia = g.ia; p.io = g.io; p.inside = g.inside ? 1 : 0;
+}
+
+// Whether a launch may use the kTurbo variant (see rollout_one).  Call after prepare_rollout.
+inline bool turbo_ok(const ScenarioView &sc, const RolloutArgs &a);
+
+// Steps between re-evaluations of sin / cos(lat) from the fp64 latitude; in between they are carried by the
+// step's own identities (s' = s cos d + c a, c' = H).  They only scale increments, and their drift over 16
+// steps stays below 2e-6 relative (tests/test_fastmodel.py).
+constexpr int kRefreshTrig = 16;
+
+inline bool turbo_ok(const ScenarioView &sc, const RolloutArgs &a) {
+    const int k0 = (int)a.root_k;
+    return sc.roll_safe && sc.dt_uniform32 > 0.0f && sc.nT - 1 <= kRefreshTrig && !(a.flags & PMCTS_ROLL_PLAN_EVAL) &&
+           (double)k0 == a.root_k && k0 >= 0 && k0 <= sc.nT - 2 && a.root_pre.inside;
+}
+
 // Tree.get_sim_to_estimate_state + Tree.default_policy (worker.py:255-300), estimate_perfomance_plan's
 // inner loop (isochrones.py:498-530).  One loop serves every mode:
 //   step j uses heading prefix[j] while j < n_fixed, the bearing to the destination afterwards;
 //   the arrival / terminal tests run after step j once j + 1 >= n_unchecked.
-// kNoise: PMCTS_NOISE_* or -1 (runtime); kLean: no trajectory output.
-template <int kNoise, bool kLean>
+// kNoise: PMCTS_NOISE_* or -1 (runtime); kLean: no trajectory output; kDefBoat: the reference's boat as
+// immediates.  leaf = r / a.replicas.
+// kTurbo (turbo_ok below, decided on the host): tree mode on a roll_safe scenario with equal steps, at most
+// kRefreshTrig of them, and a root that can start a step -- every state the loop steps from has passed the
+// terminal test (or is the root), so the step's range checks, the bounds test of the grid position, the load
+// of the step length and the sin / cos refresh are compiled out.
+template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
 PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const NoiseView &nz, const RolloutArgs &a,
-                          int64_t n, int64_t r, RollOut &o) {
-    const int64_t leaf = r / a.replicas;
+                          int64_t n, int64_t r, int64_t leaf, RollOut &o) {
     int k = (int)a.root_k;
     double lat = a.root_lat, lon = a.root_lon;
     const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
@@ -527,10 +619,13 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
         o.why = kWhyDegenerate;  // ya == 0 in worker.py:396: left to the literal kernel
     } else {
         Noise ns;
-        float sA, cA;
-        sincos_lat(lat, sA, cA);
-        DestRel rd = dest_rel(lat, lon, a.dest_lat, a.dest_lon);
-        GridPos g = grid_pos(sc, lat, lon);
+        const RootPre &rp = a.root_pre;
+        float sA = rp.s, cA = rp.c;
+        DestRel rd;
+        rd.sin_dlat = rp.sin_dlat; rd.sin_dlon = rp.sin_dlon; rd.h_dlon = rp.h_dlon; rd.x_dlat = rp.x_dlat;
+        GridPos g;
+        g.ia = rp.ia; g.io = rp.io; g.wa = rp.wa; g.wo = rp.wo; g.fa = rp.fa; g.fo = rp.fo; g.inside = rp.inside != 0;
+        int trig_left = kRefreshTrig;
         for (;;) {
             float sh, ch;
             if (o.nstep < n_fixed) {
@@ -544,7 +639,7 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             }
             const float z = ns.draw<kNoise>(nz, n, r, o.nstep);
             Move m;
-            o.st = fast_step(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
+            o.st = fast_step<false, kDefBoat, kTurbo>(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
             if (o.st == kStNeedsLiteral) {
                 o.st = PMCTS_ST_OK;
                 o.why |= kWhyStep;
@@ -556,10 +651,13 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
                 if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = lon;
             }
             ++o.nstep;
-            float sB, cB;
-            sincos_lat(lat, sB, cB);
-            g = grid_pos(sc, lat, lon);
-            if (o.nstep >= n_unchecked) {
+            float sB = m.s_new, cB = m.c_new;
+            if (!kTurbo && --trig_left == 0) {  // (a turbo rollout has at most kRefreshTrig steps)
+                trig_left = kRefreshTrig;
+                sincos_lat(lat, sB, cB);
+            }
+            g = grid_pos<!kTurbo>(sc, lat, lon);
+            if (kTurbo || o.nstep >= n_unchecked) {  // (turbo: tree mode, every step is checked)
                 at = fast_at_dest(bp, rd, m, sA, cA, sB, sD, frac, o.why);
                 if (at || o.why) break;
                 if (fast_terminal(sc, bp, k, g, o.why)) break;

@@ -106,4 +106,16 @@ inline TimeCells time_cells(const double *wtime, int nt, const double *sim_times
     return c;
 }
 
+// Members of the mixed-precision view that follow from the time cells and the terminal box (after ks_lo / ks_hi,
+// the axes and nT have been set).
+inline void finish_fast_view(ScenarioView &vw, const TimeCells &tc, const double box[4]) {
+    const int nT = vw.nT;
+    vw.roll_safe = (vw.ks_lo == 0 && vw.ks_hi == nT - 2 && box && box[0] >= vw.lat0 && box[1] <= vw.lat_last &&
+                    box[2] >= vw.lon0 && box[3] <= vw.lon_last) ? 1 : 0;
+    vw.dt_uniform32 = nT > 1 ? tc.dt32[0] : 0.0f;
+    for (int k = 1; k + 1 < nT; ++k)
+        if (tc.dt32[k] != tc.dt32[0]) vw.dt_uniform32 = 0.0f;
+    vw.box_margin_scale = 1.0f + 0.01f * (float)(vw.nlat > vw.nlon ? vw.nlat : vw.nlon);
+}
+
 }  // namespace pmcts

@@ -43,6 +43,11 @@ struct ScenarioView {
     int ks_lo, ks_hi;       // instants a transition can start from: max(0, kv_lo) .. min(nT - 2, kv_hi)
     int slab32_stride;      // cells between fp32 slabs: nlat * nlon rounded up to even, so every slab is 16-byte
                             // aligned (TMA bulk copies into shared memory need that)
+    float dt_uniform32;     // dt_sec32[k] when it is the same for every k, else 0
+    float box_margin_scale; // 1 + 0.01 * max(nlat, nlon): scales BoatParams::margin_box to the fp32 spacing of the
+                            // largest fractional grid index
+    int roll_safe;          // 1: every instant 0 .. nT - 2 can start a step and the terminal box lies inside the
+                            // grid, so a position that passed Tree.is_state_terminal needs no further range check
 };
 
 // Boat.* / module constants (pmcts_set_params), plus values derived once on the host.
@@ -77,6 +82,16 @@ struct NoiseView {
     uint64_t seed, stream, id0;
 };
 
+// What every rollout of a launch derives from the root state and the destination (fast::prepare_root, on
+// the host with the device's own formulas): sin / cos(root lat), the destination seen from the root
+// (fast::DestRel) and the root's place on the wind grid (fast::GridPos).
+struct RootPre {
+    float s, c;
+    float sin_dlat, sin_dlon, h_dlon, x_dlat;
+    float wa, wo, fa, fo;
+    int ia, io, inside;
+};
+
 // Arguments of one rollout launch (pmcts_rollout_batch).
 struct RolloutArgs {
     int64_t n_leaf;
@@ -99,6 +114,7 @@ struct RolloutArgs {
     float sin_dest_lat, cos_dest_lat;
     double rw_t0;  // 1.001 * TimeMax
     float rw_inv;  // 1 / (1.001 * TimeMax - TimeMin)
+    RootPre root_pre;
     uint32_t *redo_list;
     uint32_t *redo_count;
     const uint32_t *work_list;   // literal kernel: rollout ids to run (NULL = all)

@@ -54,6 +54,14 @@ class FastModel:
             lib().fm_destroy(self.h)
             self.h = None
 
+    def force_generic(self, on=True):
+        """Run the generic variant of rollout_one even where rollout_impl would pick a specialised one."""
+        lib().fm_force_generic(self.h, 1 if on else 0)
+
+    def last_variant(self):
+        """0 generic, 1 default boat (constants as immediates), 2 turbo -- of the last rollout_batch."""
+        return int(lib().fm_last_variant(self.h))
+
     def set_margins(self, angle=4e-3, along=2e-4, near_miss2=1e-5, box=3e-5, bin=2e-5):
         lib().fm_set_margins(self.h, C.c_float(angle), C.c_float(along), C.c_float(near_miss2), C.c_float(box),
                              C.c_double(bin))

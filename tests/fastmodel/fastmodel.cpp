@@ -31,6 +31,8 @@ struct Model {
     std::vector<float2> slab32;
     std::vector<double> times;
     TimeCells tc;
+    bool force_generic = false;  // fm_force_generic: run the generic variant even for the default boat
+    int last_variant = 0;        // 0 generic, 1 default boat, 2 turbo
 };
 
 }  // namespace
@@ -80,6 +82,7 @@ void *fm_create(const double *wtime, int nt, const double *wlat, int nlat, const
     s.fo_c0 = -s.lon0 * s.inv_dlon;
     s.ks_lo = m->tc.kv_lo > 0 ? m->tc.kv_lo : 0;
     s.ks_hi = m->tc.kv_hi < nT - 2 ? m->tc.kv_hi : nT - 2;
+    finish_fast_view(s, m->tc, box);
     s.tmax = sim_times[nT - 1];
     BoatParams &p = m->bp;
     std::memcpy(p.polar, kFit, sizeof kFit);
@@ -93,6 +96,9 @@ void *fm_create(const double *wtime, int nt, const double *wlat, int nlat, const
 }
 
 void fm_destroy(void *h) { delete (Model *)h; }
+
+void fm_force_generic(void *h, int on) { ((Model *)h)->force_generic = on != 0; }
+int fm_last_variant(void *h) { return ((Model *)h)->last_variant; }
 
 void fm_set_margins(void *h, float angle, float along, float near_miss2, float box, double bin) {
     BoatParams &p = ((Model *)h)->bp;
@@ -120,16 +126,19 @@ void fm_rollout_batch(void *h, int64_t n_leaf, int replicas, const double root[3
     a.prefix = prefix; a.prefix_len = prefix_len; a.prefix_stride = prefix_stride;
     a.traj_lat = traj_lat; a.traj_lon = traj_lon; a.traj_stride = traj_stride;
     a.flags = flags;
-    a.sin_dest_lat = (float)std::sin(dest[0] * kDegToRad);
-    a.cos_dest_lat = (float)std::cos(dest[0] * kDegToRad);
-    a.rw_t0 = m->sc.tmax * 1.001;
-    a.rw_inv = (float)(1.0 / (m->sc.tmax * 1.001 - tmin));
+    fast::prepare_rollout(m->sc, a);
     NoiseView nz{};
     nz.mode = noise_mode; nz.z = z; nz.seed = seed; nz.stream = stream; nz.id0 = id0;
     const int64_t n = n_leaf * replicas;
+    const bool defboat = fast::is_default_boat(m->bp) && !m->force_generic;
+    const bool turbo = defboat && fast::turbo_ok(m->sc, a);
+    m->last_variant = turbo ? 2 : defboat ? 1 : 0;
     for (int64_t r = 0; r < n; ++r) {
         fast::RollOut o;
-        fast::rollout_one<-1, false>(m->sc, m->bp, nz, a, n, r, o);
+        // the same variant selection as rollout_impl (pmcts_b200.cu)
+        if (turbo) fast::rollout_one<-1, false, true, true>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
+        else if (defboat) fast::rollout_one<-1, false, true, false>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
+        else fast::rollout_one<-1, false>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
         if (reward) reward[r] = o.rw;
         if (t_arr) t_arr[r] = o.ta;
         if (steps) steps[r] = o.nstep;

@@ -126,6 +126,34 @@ def test_rollout_decisions_outside_margins_agree(scen, flags):
     assert bad[raw["uncertain"] == 0].sum() <= 2
 
 
+def test_specialised_variants_equal_the_generic_one():
+    """rollout_one's compile-time variants (the reference's boat as immediates; "turbo": range checks, bounds
+    test, step-length load and sin / cos refresh compiled out where the host proved them redundant) decide and
+    move exactly like the generic code: same steps, status, bin, hand-overs, bit-identical positions."""
+    f = model(2)
+    rng = np.random.default_rng(77)
+    n_leaf, rep = 128, 64
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 4))
+    plen = rng.integers(1, 5, n_leaf).astype(np.int32)
+    z = rng.standard_normal((13, n_leaf * rep))
+    for flags, want_variant in ((0, 2), (2, 2), (4, 1)):   # tree, full-prefix replay: turbo; plan evaluation: default boat
+        f.force_generic(False)
+        a = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
+        assert f.last_variant() == want_variant
+        f.force_generic(True)
+        b = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
+        assert f.last_variant() == 0
+        for key in ("steps", "status", "bin", "uncertain", "final_lat", "final_lon"):
+            assert np.array_equal(a[key], b[key], equal_nan=key.startswith("final")), (flags, key)
+        assert np.array_equal(a["reward"], b["reward"])
+    # a root that cannot start a step, or sits outside the grid, is not turbo: the generic code reports it
+    f.force_generic(False)
+    r = f.rollout_batch(4, 2, (12, 44.0, 355.0), DEST, TMIN, prefix=prefix[:4], prefix_len=plen[:4], z=z[:, :8])
+    assert f.last_variant() == 1 and (r["status"] == 6).all()      # PMCTS_ST_PAST_HORIZON
+    r = f.rollout_batch(4, 2, (0, 39.0, 355.0), DEST, TMIN, prefix=prefix[:4], prefix_len=plen[:4], z=z[:, :8])
+    assert f.last_variant() == 1 and (r["status"] == 4).all()      # PMCTS_ST_OUT_OF_GRID
+
+
 def test_plan_evaluation_mode_and_golden_rollouts(golden_dir):
     g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
     pe = np.load(os.path.join(golden_dir, "plan_eval_c5.npz"))
