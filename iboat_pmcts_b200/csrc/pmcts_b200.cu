@@ -400,7 +400,7 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
 // kernel above finishes it (same stream, next launch).  kNoise fixes the noise source at compile time;
 // kLean is the throughput form: per-leaf histograms and statistics only, no per-rollout outputs.
 template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, kLean ? 8 : 6)  // lean: 64 registers, 8 blocks per SM
 rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
     const int64_t n = a.n_leaf * a.replicas;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,7 +489,7 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
         const float z = ns.draw<kNoise>(nz, n, i, j);
         const double la0 = lat, lo0 = lon;
         fast::Move m;
-        st = fast::fast_step<false, kDefBoat>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
+        st = fast::fast_step<false, kDefBoat, false, kDefBoat>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
         if (st == fast::kStNeedsLiteral) { j_resume[i] = j; break; }
         if (st == PMCTS_ST_OK) {
             s = m.s_new;
@@ -764,6 +764,7 @@ struct pmcts_ctx {
     } defer[2];
     uint64_t defer_seq = 0;
     int64_t launches = 0;
+    int last_variant = PMCTS_VARIANT_LITERAL;  // of the last K1 / K2 launch (pmcts_last_kernel_variant)
     bool timing = false;
     struct Timed { cudaEvent_t a, b; int kind; };
     std::vector<Timed> timed;
@@ -1023,6 +1024,8 @@ int pmcts_set_precision(pmcts_ctx *ctx, int mode) {
 }
 
 int64_t pmcts_launch_count(pmcts_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pmcts_last_kernel_variant(pmcts_ctx *ctx) { return ctx ? ctx->last_variant : PMCTS_ERR_ARG; }
 
 int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
@@ -1372,7 +1375,10 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
             // leaves room for >= 8 blocks per SM
             const size_t ring = 2 * (size_t)sc->view.slab32_stride * sizeof(float2);
             const bool stage = lean && ctx->stage_slabs && nsteps >= 4 && ring <= 24 * 1024;
-            const bool defboat = fast::is_default_boat(ctx->params);
+            // (K1's specialised variant also takes the step length as a constant)
+            const bool defboat = fast::is_default_boat(ctx->params) && sc->view.dt_uniform32 > 0.0f;
+            ctx->last_variant = !lean ? PMCTS_VARIANT_FULL_OUTPUT : stage ? PMCTS_VARIANT_STAGED
+                                : defboat ? PMCTS_VARIANT_DEFAULT_BOAT : PMCTS_VARIANT_GENERIC;
 #define PMCTS_LAUNCH_STAGED(NOISE)                                                                          \
             step_fast_staged_kernel<NOISE><<<grid_for(n), kBlock, ring, ctx->stream>>>(                      \
                 sc->view, ctx->params, n, nsteps, k, lat, lon, heading, seg_len, nz, status_dev, j_resume,   \
@@ -1400,6 +1406,7 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
                 status_dev, traj_lat, traj_lon, flags, j_resume, any_resume);
         }
     } else {
+        ctx->last_variant = PMCTS_VARIANT_LITERAL;
         LaunchTimer lt(ctx, PMCTS_KERNEL_STEP);
         step_batch_kernel<<<grid_for(n), kBlock, 0, ctx->stream>>>(
             sc->view, ctx->params, n, nsteps, k, lat, lon, prev_lat, prev_lon, heading, seg_len, nz, status,
@@ -1551,6 +1558,8 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             // turbo: tree mode from a root that can start a step, on a scenario whose terminal box implies every
             // range check of the loop (fast::turbo_ok)
             const bool turbo = defboat && fast::turbo_ok(vw, a);
+            ctx->last_variant = !lean ? PMCTS_VARIANT_FULL_OUTPUT : turbo ? PMCTS_VARIANT_TURBO
+                                : defboat ? PMCTS_VARIANT_DEFAULT_BOAT : PMCTS_VARIANT_GENERIC;
             if (lean && turbo && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true);
             else if (lean && turbo && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true, true);
             else if (lean && turbo) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true, true);
@@ -1579,6 +1588,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             rollout_batch_kernel<<<grid, kBlock, 0, tail_stream>>>(vw, ctx->params, nz, a, fs);
         }
     } else {
+        ctx->last_variant = PMCTS_VARIANT_LITERAL;
         LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
         rollout_batch_kernel<<<grid_all, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
     }

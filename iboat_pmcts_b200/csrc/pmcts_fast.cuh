@@ -145,8 +145,9 @@ PMCTS_HD void box_muller(uint32_t x0, uint32_t x1, float &z0, float &z1) {
 }
 
 struct Noise {
-    // The four normals of a Philox block sit in a shift register: consecutive steps (the only way the kernels
-    // draw) take c0 and move the rest down, so the common path has no indexed selection.
+    // The four normals of a Philox block sit in a shift register: consecutive steps starting at a multiple of
+    // four (step 0 in every kernel; the only way they draw) take c0 and move the rest down, so the common path
+    // has no indexed selection.
     float c0, c1, c2, c3;
     int cached_block;
     PMCTS_HD Noise() : c0(0.0f), c1(0.0f), c2(0.0f), c3(0.0f), cached_block(-1) {}
@@ -165,9 +166,6 @@ struct Noise {
             box_muller(x[0], x[1], c0, c1);
             box_muller(x[2], x[3], c2, c3);
             cached_block = block;
-            for (int q = step & 3; q > 0; --q) {  // a sequence that starts inside a block (never, in the kernels)
-                c0 = c1; c1 = c2; c2 = c3;
-            }
         }
         const float z = c0;
         c0 = c1; c1 = c2; c2 = c3;
@@ -233,7 +231,8 @@ PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u,
 // The reference's own boat (Boat.FIT_VELOCITY and the module constants, simulatorTLKT.py:454-471) as
 // compile-time constants: derive_fast_params' output for pmcts_create's defaults.  sm_100 takes constants
 // from uniform registers, not from the constant bank, and the rollout loop needs more of them than there are;
-// with kDefBoat these 29 become instruction immediates.  Kernels are instantiated both ways and the host
+// with kDefBoat these 29 -- and the six tunables below -- become instruction immediates (the noise coefficient stays
+// a run-time value: Tutorial.py sets it).  Kernels are instantiated both ways and the host
 // picks the specialised one when is_default_boat(params) (tests/test_abi.py pins the table to
 // derive_fast_params).
 namespace defboat {
@@ -248,6 +247,11 @@ constexpr float pc[36] = {pc0, pc1, pc2, pc3, pc4, pc5, pc6, pc7, pc8, pc9, pc10
 constexpr float p_mid = 9.75e+01f, p_ihalf = 1.600000076e-02f, w_ihalf = 1.047120392e-01f;
 constexpr float wind_max = 1.910000038e+01f, pmin = 35.0f, pmax = 160.0f;
 constexpr float cos_pmin = 8.191520572e-01f, cos_pmax = -9.396926165e-01f;
+// DESTINATION_ANGLE (worker.py:20) and EARTH_RADIUS (simulatorTLKT.py:26) of the reference, and the default
+// decision margins (pmcts_host.h: default_fast_margins takes them from here)
+constexpr float sin2_dest_angle = 7.615435393e-09f, inv_radius = 1.569612351e-07f;
+constexpr float margin_angle = 2e-4f, margin_along = 2e-5f, near_miss2 = 1e-5f, margin_box = 3e-5f;
+constexpr double margin_bin = 1e-4;  // the fp32 reward is good to ~1e-5 in these units
 }  // namespace defboat
 
 inline bool is_default_boat(const BoatParams &bp) {
@@ -255,7 +259,10 @@ inline bool is_default_boat(const BoatParams &bp) {
         if (bp.pc[i] != defboat::pc[i]) return false;
     return bp.polar_tri == 1 && bp.p_mid == defboat::p_mid && bp.p_ihalf == defboat::p_ihalf &&
            bp.w_ihalf == defboat::w_ihalf && bp.wind_max_f == defboat::wind_max && bp.pmin_f == defboat::pmin &&
-           bp.pmax_f == defboat::pmax && bp.cos_pmin_f == defboat::cos_pmin && bp.cos_pmax_f == defboat::cos_pmax;
+           bp.pmax_f == defboat::pmax && bp.cos_pmin_f == defboat::cos_pmin && bp.cos_pmax_f == defboat::cos_pmax &&
+           bp.sin2_dest_angle == defboat::sin2_dest_angle && bp.inv_radius_f == defboat::inv_radius &&
+           bp.margin_angle == defboat::margin_angle && bp.margin_along == defboat::margin_along &&
+           bp.near_miss2 == defboat::near_miss2 && bp.margin_box == defboat::margin_box;
 }
 
 template <bool kDefBoat = false>
@@ -422,20 +429,25 @@ enum : int { kWhyAngle = 1, kWhyAlong = 2, kWhyBox = 4, kWhyBin = 8, kWhyDegener
 
 // The margins live in BoatParams (margin_*; defaults in pmcts_host.h, pmcts_set_fast_margins overrides).
 
+template <bool kDefBoat = false>
 PMCTS_HD int fast_at_dest(const BoatParams &bp, const DestRel &rd, const Move &m, float sA, float cA, float sB,
                           float sD, float &frac, int &why) {
+    const float sin2_dest_angle = kDefBoat ? defboat::sin2_dest_angle : bp.sin2_dest_angle;
+    const float margin_angle = kDefBoat ? defboat::margin_angle : bp.margin_angle;
+    const float margin_along = kDefBoat ? defboat::margin_along : bp.margin_along;
+    const float near_miss2 = kDefBoat ? defboat::near_miss2 : bp.near_miss2;
     const float dBy = sB * m.sin_dlon;
     const float q = fma_(-cA * sB, m.h_dlon, m.sin_dlat);
     const float r = fma_(cA * sD, rd.h_dlon, -rd.sin_dlat);
     const float dDy = sD * rd.sin_dlon;
     const float T = fma_(dBy, r, dDy * q);
     const float N2 = fma_(dBy, dBy, q * q);
-    const float lhs = T * T, rhs = bp.sin2_dest_angle * N2;
+    const float lhs = T * T, rhs = sin2_dest_angle * N2;
     if (!(N2 > 0.0f)) {  // A == B
         why |= kWhyDegenerate;
         return 0;
     }
-    if (fabsf(lhs - rhs) <= bp.margin_angle * rhs) why |= kWhyAngle;
+    if (fabsf(lhs - rhs) <= margin_angle * rhs) why |= kWhyAngle;
     if (lhs > rhs) return 0;
     const float dBx = fma_(sA, m.cm1_dlat, fma_(cA, m.sin_dlat, -sB * m.h_dlon));
     const float dBz = fma_(cA, m.cm1_dlat, -sA * m.sin_dlat);
@@ -446,11 +458,11 @@ PMCTS_HD int fast_at_dest(const BoatParams &bp, const DestRel &rd, const Move &m
     const float dd = fma_(dDx, dDx, fma_(dDy, dDy, dDz * dDz));
     const float bb = fma_(dBx, dBx, fma_(dBy, dBy, dBz * dBz));
     const float p = ab - dd;  // (D - A).(B - D)
-    if (fabsf(p) <= bp.margin_along * bb) why |= kWhyAlong;
+    if (fabsf(p) <= margin_along * bb) why |= kWhyAlong;
     if (p < 0.0f) {
         // B stopped short of D by less than kNearMiss of a step: the next bearing is taken almost on top
         // of the destination and amplifies the (tiny) position error by step / distance
-        if (dd - 2.0f * ab + bb < bp.near_miss2 * bb) why |= kWhyNearMiss;
+        if (dd - 2.0f * ab + bb < near_miss2 * bb) why |= kWhyNearMiss;
         return 0;
     }
     frac = ab * rcp_approx(bb);
@@ -468,8 +480,8 @@ constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout co
 // increments; otherwise nothing changes.
 // kTurbo: the caller guarantees that k can start a step and that the position is on the grid (a roll_safe
 // scenario whose state passed the terminal test, or the host-checked root), and that all steps have the same
-// length sc.dt_uniform32: no range checks, no load of the step length.
-template <bool kShared = false, bool kDefBoat = false, bool kTurbo = false>
+// length sc.dt_uniform32: no range checks, no load of the step length (kUniformDt alone: only the latter).
+template <bool kShared = false, bool kDefBoat = false, bool kTurbo = false, bool kUniformDt = kTurbo>
 PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
                        const GridPos &g, float sh, float ch, float s, float c, float z, Move &m,
                        const float2 *slab = nullptr) {
@@ -487,11 +499,11 @@ PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, dou
     float speed = boat_speed<kDefBoat>(bp, u, v, sh, ch);
     speed = fma_(z, speed * bp.sigma_f, speed);  // Boat.addUncertainty (:504-517)
 #if defined(__CUDA_ARCH__)
-    const float dt = kTurbo ? sc.dt_uniform32 : __ldg(sc.dt_sec32 + k);
+    const float dt = kUniformDt ? sc.dt_uniform32 : __ldg(sc.dt_sec32 + k);
 #else
-    const float dt = kTurbo ? sc.dt_uniform32 : sc.dt_sec32[k];
+    const float dt = kUniformDt ? sc.dt_uniform32 : sc.dt_sec32[k];
 #endif
-    const float d = speed * dt * bp.inv_radius_f;
+    const float d = speed * dt * (kDefBoat ? defboat::inv_radius : bp.inv_radius_f);
     if (!(fabsf(d) <= kMaxStepAngle)) return kStNeedsLiteral;
     m = move_increments(d, sh, ch, s, c);
     if (!(fabsf(m.sin_dlon) <= kMaxStepAngle)) return kStNeedsLiteral;  // high latitude: dlon = b / cos(lat)
@@ -534,9 +546,10 @@ PMCTS_HD int hist_bin_checked(const BoatParams &bp, double r, int &why) {
 
 
 // Tree.is_state_terminal (worker.py:417-436) on the fp32 grid coordinates of the position.
+template <bool kDefBoat = false>
 PMCTS_HD bool fast_terminal(const ScenarioView &sc, const BoatParams &bp, int k, const GridPos &g, int &why) {
     if (k >= sc.nT - 1) return true;
-    const float m = bp.margin_box * sc.box_margin_scale;  // 1 + 0.01 * (largest grid index): fp32 spacing of fa / fo
+    const float m = (kDefBoat ? defboat::margin_box : bp.margin_box) * sc.box_margin_scale;  // 1 + 0.01 * (largest grid index): fp32 spacing of fa / fo
     const float da0 = g.fa - sc.box_fa_lo, da1 = sc.box_fa_hi - g.fa;
     const float do0 = g.fo - sc.box_fo_lo, do1 = sc.box_fo_hi - g.fo;
     const float lo = fminf(fminf(da0, da1), fminf(do0, do1));
@@ -658,9 +671,9 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             }
             g = grid_pos<!kTurbo>(sc, lat, lon);
             if (kTurbo || o.nstep >= n_unchecked) {  // (turbo: tree mode, every step is checked)
-                at = fast_at_dest(bp, rd, m, sA, cA, sB, sD, frac, o.why);
+                at = fast_at_dest<kDefBoat>(bp, rd, m, sA, cA, sB, sD, frac, o.why);
                 if (at || o.why) break;
-                if (fast_terminal(sc, bp, k, g, o.why)) break;
+                if (fast_terminal<kDefBoat>(sc, bp, k, g, o.why)) break;
                 if (o.why) break;
             }
             sA = sB;
@@ -689,4 +702,14 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
 }
 
 }  // namespace fast
+
+// Default decision margins (calibrated in tests/test_fastmodel.py: >= 30x the largest error seen).
+inline void default_fast_margins(BoatParams &p) {
+    p.margin_angle = fast::defboat::margin_angle;
+    p.margin_along = fast::defboat::margin_along;
+    p.near_miss2 = fast::defboat::near_miss2;
+    p.margin_box = fast::defboat::margin_box;
+    p.margin_bin = fast::defboat::margin_bin;
+}
+
 }  // namespace pmcts

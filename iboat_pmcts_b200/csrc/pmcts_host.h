@@ -49,13 +49,7 @@ inline void derive_fast_params(BoatParams &p) {
 }
 
 // Default decision margins (calibrated in tests/test_fastmodel.py: >= 30x the largest error seen).
-inline void default_fast_margins(BoatParams &p) {
-    p.margin_angle = 2e-4f;
-    p.margin_along = 2e-5f;
-    p.near_miss2 = 1e-5f;
-    p.margin_box = 3e-5f;
-    p.margin_bin = 1e-4;  // the fp32 reward is good to ~1e-5 in these units
-}
+inline void default_fast_margins(BoatParams &p);  // (defined in pmcts_fast.cuh's terms below)
 
 // Time cell / weight of every simulator instant on the weather time axis (SciPy find_indices
 // semantics: i = clip(searchsorted_right(t) - 1, 0, nt - 2)), and the validity range of k.

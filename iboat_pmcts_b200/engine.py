@@ -125,6 +125,10 @@ class Engine:
     def synchronize(self):
         N.check(self._lib.pmcts_synchronize(self._h))
 
+    def last_kernel_variant(self):
+        """N.VARIANT_* of the last step / rollout launch."""
+        return int(self._lib.pmcts_last_kernel_variant(self._h))
+
     def set_option(self, option, value):
         N.check(self._lib.pmcts_set_option(self._h, int(option), int(value)))
 

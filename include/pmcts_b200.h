@@ -103,6 +103,23 @@ int64_t pmcts_last_redo_count(pmcts_ctx *ctx);
  * B200 (the per-step block barrier costs more than the L1 hits it replaces), kept for grids that miss L1. */
 #define PMCTS_OPT_STAGE_SLABS 1
 int pmcts_set_option(pmcts_ctx *ctx, int option, int value);
+/* Which compile-time variant of the K1 / K2 kernel the last pmcts_step_batch / pmcts_rollout_* call launched.
+ * All variants give the same results (tests/test_fastmodel.py, tests/test_gpu_parity.py); the specialised ones
+ * only drop work the host proved redundant:
+ *   LITERAL       PMCTS_PREC_F64, or a scenario / launch the mixed-precision path does not cover
+ *   FULL_OUTPUT   mixed precision with per-rollout / per-step outputs requested
+ *   GENERIC       mixed precision, histogram / statistics outputs only, any pmcts_set_params values
+ *   DEFAULT_BOAT  + the reference's boat, geometry constants and default margins as instruction immediates
+ *   TURBO         + (K2, tree mode) equal steps, at most 16 of them, terminal box inside the grid, root able to
+ *                 start a step: range checks, bounds test, step-length load, sin / cos refresh compiled out
+ *   STAGED        K1 with PMCTS_OPT_STAGE_SLABS */
+#define PMCTS_VARIANT_LITERAL 0
+#define PMCTS_VARIANT_FULL_OUTPUT 1
+#define PMCTS_VARIANT_GENERIC 2
+#define PMCTS_VARIANT_DEFAULT_BOAT 3
+#define PMCTS_VARIANT_TURBO 4
+#define PMCTS_VARIANT_STAGED 5
+int pmcts_last_kernel_variant(pmcts_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);
 /* While timing is enabled every kernel launch is bracketed by a cudaEvent pair on the ctx stream;

@@ -283,6 +283,60 @@ def test_fast_mode_large_batch_decisions_and_redo(eng):
     eng.set_precision(N.PREC_F64)
 
 
+def test_kernel_variants_agree_with_each_other_and_the_oracle(eng):
+    """The throughput launches (histogram / statistics outputs only) pick a compile-time variant of K2:
+    TURBO for tree-mode launches on the reference's boat, DEFAULT_BOAT for plan evaluation, GENERIC for any
+    other pmcts_set_params, FULL_OUTPUT when per-rollout arrays are requested.  Same leaf histograms and
+    statistics from all of them, injected and Philox noise, equal to the oracle's bins."""
+    upload(eng, 0, 5)
+    o = H.oracle_sim(5)
+    dest, tmin = [46.77751005, 355.0], 2.0223605
+    n_leaf, rep = 256, 96
+    n = n_leaf * rep
+    rng = np.random.default_rng(33)
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 3))
+    plen = rng.integers(1, 4, n_leaf).astype(np.int32)
+    z = rng.standard_normal((13, n))
+    eng.set_precision(N.PREC_FAST)
+    lean = ("leaf_bins", "stats")
+    try:
+        for flags, fast_variant in ((0, N.VARIANT_TURBO), (N.ROLL_REPLAY_FULL_PREFIX, N.VARIANT_TURBO),
+                                    (N.ROLL_PLAN_EVAL, N.VARIANT_DEFAULT_BOAT)):
+            want = o.rollout_batch(n, H.STATE0, dest, tmin, prefix=np.repeat(prefix, rep, 0),
+                                   prefix_len=np.repeat(plen, rep), replay_full=bool(flags & N.ROLL_REPLAY_FULL_PREFIX),
+                                   mode=1 if flags & N.ROLL_PLAN_EVAL else 0, z=z, nthreads=8)
+            bins = np.zeros((n_leaf, 12), np.uint32)
+            np.add.at(bins, (np.repeat(np.arange(n_leaf), rep), want["bin"]), 1)
+            res = {}
+            for noise in ("z", "philox"):
+                kw = dict(z=z) if noise == "z" else dict(seed=99, stream=3)
+                a = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen,
+                                           flags=flags, want=lean, **kw)
+                assert eng.last_kernel_variant() == fast_variant
+                b = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen,
+                                           flags=flags, **kw)
+                assert eng.last_kernel_variant() == N.VARIANT_FULL_OUTPUT
+                # any non-default tunable (here a slightly wider margin): generic kernel
+                eng.set_fast_margins(angle=2.5e-4)
+                c = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen,
+                                           flags=flags, want=lean, **kw)
+                assert eng.last_kernel_variant() == N.VARIANT_GENERIC
+                eng.set_fast_margins()
+                for other in (b, c):
+                    assert np.array_equal(a["leaf_bins"], other["leaf_bins"])
+                    assert np.array_equal(a["stats"][[0, 3, 4, 5]], other["stats"][[0, 3, 4, 5]])
+                    assert np.allclose(a["stats"][1:3], other["stats"][1:3], rtol=1e-7, equal_nan=True)  # arrival times: 1e-6 each
+                res[noise] = a
+            assert np.array_equal(res["z"]["leaf_bins"], bins)
+            assert res["z"]["stats"][4] == want["steps"].sum() and res["z"]["stats"][3] == (want["status"] == 1).sum()
+        eng.set_precision(N.PREC_F64)
+        eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen, z=z, want=lean)
+        assert eng.last_kernel_variant() == N.VARIANT_LITERAL
+    finally:
+        eng.set_fast_margins()
+        eng.set_precision(N.PREC_F64)
+
+
 def test_fast_mode_hands_over_what_it_does_not_cover(eng):
     """K1 in the mixed-precision mode: headings outside [0, 360) and steps longer than its series allow
     are finished by the fp64 kernel from the step they stopped at -- same result as the literal mode."""
