@@ -330,6 +330,30 @@ def main():
         transitions, rollouts = counters
     value = transitions / (dev_ms * 1e-3)
 
+    # ---- cross-check: the same K steps back to back, no L2 flush, one event pair around all of them.  The
+    # side-stream work of a step (fp64 finisher, all-gather, back-up) can only hide under the next step here,
+    # not in a flush gap between timed windows; `value` must not exceed this by more than the warm-L2 effect.
+    b2b = None
+    if args.workload == "c4":
+        run["reset_counters"]()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            run["device_step"](warm + args.steps + i, last=(i == args.steps - 1))
+        e1.record()
+        barrier()
+        c2 = run["read_counters"]()
+        b2b_stat = torch.tensor([e0.elapsed_time(e1), c2[0]], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = b2b_stat.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = b2b_stat.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            b2b_stat = torch.stack([mx[0], sm[1]])
+        b2b = dict(value=float(b2b_stat[1]) / (float(b2b_stat[0]) * 1e-3), ms_per_step=float(b2b_stat[0]) / args.steps,
+                   note="same steps back to back without L2 flush, one CUDA-event pair around all of them")
+
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     run["e2e_step"](0)
@@ -376,6 +400,8 @@ def main():
                              steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST")),
                     gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, finisher_kernel_ms=fin_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
                     roofline=roofline)
+        if b2b:
+            line["back_to_back"] = b2b
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
@@ -409,32 +435,53 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     plen_h = np.full(N_LEAF, 4, np.int32)
 
     scen_slots = np.arange(S_local, dtype=np.int32)
-    # Two histogram buffers: the fp64 finisher of step i (side stream, PMCTS_ROLL_DEFER_REDO) overlaps the
-    # main kernel of step i + 1, so step i's histograms are complete -- and gathered / backed up -- one
-    # launch later.  The last step of a run drains the pipeline inside its own timed window.
-    bins_ring = [bins_local, torch.zeros_like(bins_local)]
+    # Pipeline of a step (what a batched search does with the previous wave while the next one runs):
+    #   main stream   : zero histograms | K2 main kernel of step i
+    #   side stream   : fp64 finisher + statistics fold of step i      (PMCTS_ROLL_DEFER_REDO, inside the library)
+    #   comm stream   : all-gather of step i - 1's histograms (NCCL over NVLink) + K3 back-up into the replicated
+    #                   master table, ordered after the finisher of step i - 1 (pmcts_join)
+    # Three histogram buffers rotate; a buffer is zeroed again only after the comm stream has read it.  The last
+    # step of a run drains the pipeline inside its own timed window (the main stream waits for the comm stream).
+    main = torch.cuda.current_stream(dev)
+    comm = torch.cuda.Stream(device=dev, priority=-1)
+    overlap = not os.environ.get("PMCTS_BENCH_NO_OVERLAP")
+    bins_ring = [bins_local, torch.zeros_like(bins_local), torch.zeros_like(bins_local)]
+    consumed = [torch.cuda.Event() for _ in bins_ring]
     pending = []
 
     def complete(keep_last):
-        eng.join(keep_last)
-        while len(pending) > keep_last:
-            buf = pending.pop(0)
-            src = buf
-            if world > 1:
-                if not os.environ.get("PMCTS_BENCH_NO_AG"):
-                    dist.all_gather_into_tensor(bins_all, buf)
-                src = bins_all
-            if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
-                eng.backup(master, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S_total)
+        if len(pending) <= keep_last:
+            return
+        with torch.cuda.stream(comm if overlap else main):
+            eng.use_torch_stream()
+            eng.join(keep_last)  # this stream now waits for the finishers of the steps it is about to consume
+            while len(pending) > keep_last:
+                slot = pending.pop(0)
+                src = bins_ring[slot]
+                if world > 1:
+                    if not os.environ.get("PMCTS_BENCH_NO_AG"):
+                        dist.all_gather_into_tensor(bins_all, src)
+                    src = bins_all
+                if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
+                    eng.backup(master, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S_total)
+                consumed[slot].record()
+        eng.use_torch_stream()  # back on the main stream
+        if keep_last == 0 and overlap:
+            main.wait_stream(comm)
+
+    step_no = [0]
 
     def device_step(i, last=True):
         for w in range(WAVES):
-            buf = bins_ring[(i * WAVES + w) % 2]
+            slot = step_no[0] % len(bins_ring)
+            step_no[0] += 1
+            buf = bins_ring[slot]
+            main.wait_event(consumed[slot])  # (a never-recorded event does not block)
             buf.zero_()
             eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, prefix_shared=True,
                                seed=SEED, stream=rank * S_local, id0=(i * WAVES + w) * n,
                                out=dict(leaf_bins=buf, stats=stats), flags=N.ROLL_ACCUMULATE | N.ROLL_DEFER_REDO)
-            pending.append(buf)
+            pending.append(slot)
             complete(0 if (last and w == WAVES - 1) else 1)
 
     def reset_counters():

@@ -759,7 +759,8 @@ struct pmcts_ctx {
         char *work = nullptr;
         size_t cap = 0;
         cudaEvent_t main_done = nullptr, redo_done = nullptr;
-        bool pending = false;
+        bool pending = false;  // not yet joined by the caller (pmcts_join)
+        bool used = false;     // redo_done has been recorded at least once
         uint64_t seq = 0;
     } defer[2];
     uint64_t defer_seq = 0;
@@ -1518,8 +1519,9 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&slot->redo_done, cudaEventDisableTiming));
         }
-        // the launch that used this work area two calls ago must have finished with it
-        if (slot->pending) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
+        // the launch that used this work area two calls ago must have finished with it (the caller may have
+        // joined it on another stream -- pmcts_set_stream between calls -- so this does not look at `pending`)
+        if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
         if (256 + work_bytes > slot->cap) {
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
@@ -1601,6 +1603,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     if (defer) {
         CUDA_TRY(cudaEventRecord(slot->redo_done, ctx->side_stream));
         slot->pending = true;
+        slot->used = true;
         slot->seq = ctx->defer_seq++;
     }
     return st.finish();
