@@ -227,6 +227,8 @@ def workload_config(workload, n_gpus):
                 replicas=REPLICAS, waves=WAVES, rollouts_per_scenario_per_step=N_LEAF * REPLICAS * WAVES,
                 sim_axis="6-hourly over 3 days (13 instants)", grid="41x21x31 (t, lat, lon), 0.5 deg, 3-hourly",
                 sharding="scenario s on GPU s // 8; master table replicated; one all-gather per step",
+                pipeline="step i's fp64 finisher (side stream) and step i-1's all-gather + K3 back-up (communication "
+                         "stream) run under step i / i+1's rollout kernel; the last timed step drains the pipeline",
                 l2="L2 flushed (256 MiB write) between timed steps", noise="philox4x32-10 seed 42")
 
 
@@ -443,11 +445,12 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     # Three histogram buffers rotate; a buffer is zeroed again only after the comm stream has read it.  The last
     # step of a run drains the pipeline inside its own timed window (the main stream waits for the comm stream).
     main = torch.cuda.current_stream(dev)
-    comm = torch.cuda.Stream(device=dev, priority=-1)
+    comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMCTS_BENCH_COMM_PRIO", "0")))
     overlap = not os.environ.get("PMCTS_BENCH_NO_OVERLAP")
     bins_ring = [bins_local, torch.zeros_like(bins_local), torch.zeros_like(bins_local)]
     consumed = [torch.cuda.Event() for _ in bins_ring]
     pending = []
+    debug_ev = [] if os.environ.get("PMCTS_BENCH_DEBUG") else None  # (all-gather, back-up) durations on the comm stream
 
     def complete(keep_last):
         if len(pending) <= keep_last:
@@ -458,13 +461,21 @@ def setup_c4(eng, torch, dist, dev, rank, world):
             while len(pending) > keep_last:
                 slot = pending.pop(0)
                 src = bins_ring[slot]
+                dbg = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if debug_ev is not None else None
+                if dbg:
+                    dbg[0].record()
                 if world > 1:
                     if not os.environ.get("PMCTS_BENCH_NO_AG"):
                         dist.all_gather_into_tensor(bins_all, src)
                     src = bins_all
+                if dbg:
+                    dbg[1].record()
                 if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
                     eng.backup(master, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S_total)
                 consumed[slot].record()
+                if dbg:
+                    dbg[2].record()
+                    debug_ev.append(dbg)
         eng.use_torch_stream()  # back on the main stream
         if keep_last == 0 and overlap:
             main.wait_stream(comm)
@@ -487,6 +498,14 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     def reset_counters():
         stats.zero_()
         master.zero_()
+        if debug_ev:
+            torch.cuda.synchronize()
+            ag = [a.elapsed_time(b) for a, b, _ in debug_ev]
+            k3 = [b.elapsed_time(c) for _, b, c in debug_ev]
+            print("rank %d comm stream: all-gather ms %s | back-up ms %s" % (rank, [round(x, 3) for x in ag[-10:]],
+                                                                          [round(x, 3) for x in k3[-10:]]),
+                  file=sys.stderr, flush=True)
+            debug_ev.clear()
 
     def read_counters():
         s = stats.cpu().numpy().reshape(S_local, 8).sum(0)

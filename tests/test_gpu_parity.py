@@ -605,6 +605,15 @@ def test_device_pointer_path_and_backup(eng):
     got = table.cpu().numpy().reshape(n_nodes, 8, 12)
     assert np.array_equal(got, want)
     assert got[0].sum() == n
+    # two scenarios at once, histograms at an address that is not 16-byte aligned (scalar-load variant of K3)
+    big = torch.zeros(1 + 2 * n_leaf * 12, dtype=torch.int32, device=dev)
+    big[1:1 + n_leaf * 12] = out["leaf_bins"]
+    big[1 + n_leaf * 12:] = 2 * out["leaf_bins"]
+    table2 = torch.zeros(2 * n_nodes * 96, dtype=torch.int32, device=dev)
+    eng.backup(table2, n_nodes, t(parent), t(arm), t(np.tile(leaf_node, 2)), t(np.tile(slot, 2)), big[1:], n_scen=2)
+    torch.cuda.synchronize()
+    got2 = table2.cpu().numpy().reshape(2, n_nodes, 8, 12)
+    assert np.array_equal(got2[0], want) and np.array_equal(got2[1], 2 * want)
     mean = torch.empty(n_nodes * 8, dtype=torch.float64, device=dev)
     visits = torch.empty(n_nodes, dtype=torch.int32, device=dev)
     eng.hist_stats(table, n_nodes, mean, visits)
