@@ -178,7 +178,8 @@ def cpu_baseline(workload, budget_s=12.0):
     tr, n, dt = cpu_rollout_sample(4096 * cores, cores)                # calibration
     nr = int(max(4096 * cores, min(8 * N_LEAF * REPLICAS * WAVES, 4096 * cores * budget_s / max(dt, 1e-3))))
     tr, n, dt = cpu_rollout_sample(nr, cores)
-    sample = "%d default-policy rollouts of scenario 0 (same leaves, Philox noise)" % nr
+    sample = "%d default-policy rollouts of scenario 0 (same leaves, Philox noise)%s" % (
+        nr, " = one full step of this workload" if nr == 8 * N_LEAF * REPLICAS * WAVES else "")
     return dict(value=tr / dt, unit="transitions/s", cores=cores, kind="port", sample=sample,
                 rollouts_per_s=n / dt, seconds=dt)
 
@@ -188,7 +189,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 4096 * cores if args.workload != "c3" else 1024 * cores
+    per_step = 65536 * cores if args.workload != "c3" else 8192 * cores  # ~0.5 s / ~1 s of CPU work per step
     times_, tr_tot, n_tot = [], 0, 0
     for i in range(args.warmup + args.steps):
         if args.workload == "c3":
@@ -377,6 +378,7 @@ def main():
         e2e_s, e2e_tr = float(mx[0]), float(sm[1])
 
     if rank == 0:
+        fp32_peak = eng.probe_fp32_peak() or FP32_PEAK_TFLOPS
         per_launch_units = run["dominant"]["units_per_launch"]
         n_dom = run["dominant"]["launches_per_step"] * args.steps
         dom_ms = (dom_kernel_ms + fin_kernel_ms) / n_dom  # main kernel + its fp64 finisher: all the transitions
@@ -384,11 +386,14 @@ def main():
         # units per launch are transitions: measured, averaged over the timed launches of this rank
         units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
         achieved = units * f_alg / (dom_ms * 1e-3) / 1e12
-        roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=FP32_PEAK_TFLOPS,
-                        unit="TFLOP/s", frac=achieved / FP32_PEAK_TFLOPS, traffic=run["dominant"].get("traffic"),
+        roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=fp32_peak,
+                        unit="TFLOP/s", frac=achieved / fp32_peak, peak_nominal=FP32_PEAK_TFLOPS,
+                        frac_of_nominal=achieved / FP32_PEAK_TFLOPS, traffic=run["dominant"].get("traffic"),
                         traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture under profiles/ (round 1)",
-                        peak_source="nominal fp32 FMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has "
-                                    "HBM and bf16-tensor entries only; the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
+                        peak_source="FP32 FMA throughput measured in this run by pmcts_probe_fp32_peak (16 independent FFMA "
+                                    "chains per thread, CUDA events, best of 4); peak_nominal = 148 SM x 128 lanes x 2 x "
+                                    "1.965 GHz.  MEASURED_PEAKS.json has HBM and bf16-tensor entries only and the path is "
+                                    "neither HBM- nor tensor-bound (SURVEY.md 8d)",
                         main_kernel_ms_per_launch=dom_kernel_ms / n_dom, finisher_ms_per_launch=fin_kernel_ms / n_dom,
                         algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
                         hbm_bytes_per_launch=run["dominant"]["hbm_bytes_per_launch"],

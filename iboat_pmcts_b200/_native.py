@@ -27,7 +27,7 @@ ERR_NO_DEVICE = -3
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
-    "pmcts_synchronize", "pmcts_join", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_enable_timing",
+    "pmcts_synchronize", "pmcts_join", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
     "pmcts_forest_create", "pmcts_forest_destroy", "pmcts_forest_last_error", "pmcts_forest_set_coefficients",
@@ -76,6 +76,7 @@ def lib():
     L.pmcts_set_fast_margins.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]
     L.pmcts_last_redo_count.argtypes = [vp]
     L.pmcts_last_kernel_variant.argtypes = [vp]
+    L.pmcts_probe_fp32_peak.argtypes = [vp, vp]
     L.pmcts_last_redo_count.restype = i64
     L.pmcts_launch_count.argtypes = [vp]
     L.pmcts_launch_count.restype = i64

@@ -645,6 +645,22 @@ step_fast_staged_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, i
     status_io[i] = (uint8_t)st;
 }
 
+// Roofline denominator: what the FP32 FMA pipes of this chip sustain (pmcts_probe_fp32_peak).  16 independent
+// FFMA chains per thread, nothing else in the loop.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) x[q] = (float)(threadIdx.x + q);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = fmaf(x[q], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += x[q];
+    if (s == 123.456f) out[0] = s;  // keeps the chains alive; never true for the a, b the host passes
+}
+
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
 // blockIdx.y = scenario.
 __global__ void backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes,
@@ -1035,6 +1051,36 @@ int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
         return PMCTS_OK;
     }
     return fail(PMCTS_ERR_ARG, "unknown option %d", option);
+}
+
+int pmcts_probe_fp32_peak(pmcts_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return fail(PMCTS_ERR_ARG, "NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    float *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 8192;
+    const double flop = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {  // the first launch warms up
+        CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+        fp32_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999f, 0.001f);
+        CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    CUDA_TRY(cudaGetLastError());
+    *tflops = best;
+    return PMCTS_OK;
 }
 
 int pmcts_enable_timing(pmcts_ctx *ctx, int on) {

@@ -125,6 +125,12 @@ class Engine:
     def synchronize(self):
         N.check(self._lib.pmcts_synchronize(self._h))
 
+    def probe_fp32_peak(self):
+        """Measured FP32 FMA throughput of this device, TFLOP/s."""
+        v = C.c_double(0.0)
+        N.check(self._lib.pmcts_probe_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
     def last_kernel_variant(self):
         """N.VARIANT_* of the last step / rollout launch."""
         return int(self._lib.pmcts_last_kernel_variant(self._h))

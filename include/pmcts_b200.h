@@ -122,6 +122,9 @@ int pmcts_set_option(pmcts_ctx *ctx, int option, int value);
 int pmcts_last_kernel_variant(pmcts_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);
+/* Measures what the FP32 FMA pipes of the ctx's device sustain (16 independent FFMA chains per thread, best of
+ * four timed launches, CUDA events): the denominator of bench.py's roofline next to the nominal figure. */
+int pmcts_probe_fp32_peak(pmcts_ctx *ctx, double *tflops);
 /* While timing is enabled every kernel launch is bracketed by a cudaEvent pair on the ctx stream;
  * pmcts_kernel_ms* synchronise the stream and return the accumulated device milliseconds (all
  * kernels, or one PMCTS_KERNEL_* kind). */
