@@ -486,7 +486,7 @@ step_fast_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, int32_t 
         }
         --trig_left;
         const fast::GridPos g = fast::grid_pos(sc, lat, lon);
-        const float z = ns.draw<kNoise>(nz, n, i, j);
+        const float z = ns.draw<kNoise, true>(nz, n, i, j);
         const double la0 = lat, lo0 = lon;
         fast::Move m;
         st = fast::fast_step<false, kDefBoat, false, kDefBoat>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);
@@ -596,7 +596,7 @@ step_fast_staged_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, i
         }
         --trig_left;
         const fast::GridPos g = fast::grid_pos(sc, lat, lon);
-        const float z = ns.draw<kNoise>(nz, n, i, j);
+        const float z = ns.draw<kNoise, true>(nz, n, i, j);
         fast::Move m;
         st = slab ? fast::fast_step<true>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m, slab)
                   : fast::fast_step<false>(sc, bp, k, lat, lon, g, sh, ch, s, c, z, m);

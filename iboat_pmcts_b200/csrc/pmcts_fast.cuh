@@ -114,10 +114,10 @@ PMCTS_HD float atan2_pos(float s, float c) {
 
 // ---- noise: Philox4x32-10 + Box-Muller in fp32 (same counter layout as oracle/pmcts_oracle.c) ------
 PMCTS_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                            uint32_t out[4]) {
+                            uint32_t out[4], uint32_t m0 = 0xD2511F53u, uint32_t m1 = 0xCD9E8D57u) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint64_t p0 = (uint64_t)m0 * c0, p1 = (uint64_t)m1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u;
@@ -152,7 +152,9 @@ struct Noise {
     int cached_block;
     PMCTS_HD Noise() : c0(0.0f), c1(0.0f), c2(0.0f), c3(0.0f), cached_block(-1) {}
     // kMode: PMCTS_NOISE_* known at compile time, or -1 to read nz.mode
-    template <int kMode>
+    // kParamMul: take Philox's multipliers from nz (see NoiseView) -- measured faster in K1 (1.21e11 ->
+    // 1.24e11 transitions/s) and slower in K2 (1.119 -> 1.137 ms), so each kernel picks its own
+    template <int kMode, bool kParamMul = false>
     PMCTS_HD float draw(const NoiseView &nz, int64_t n, int64_t i, int step) {
         const int mode = kMode >= 0 ? kMode : nz.mode;
         if (mode == PMCTS_NOISE_INJECTED) return (float)nz.z[(size_t)step * n + i];
@@ -162,7 +164,8 @@ struct Noise {
             const uint64_t boat = nz.id0 + (uint64_t)i;
             uint32_t x[4];
             philox4x32_10((uint32_t)boat, (uint32_t)(boat >> 32), (uint32_t)block, (uint32_t)nz.stream,
-                          (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), x);
+                          (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), x, kParamMul ? nz.m0 : 0xD2511F53u,
+                          kParamMul ? nz.m1 : 0xCD9E8D57u);
             box_muller(x[0], x[1], c0, c1);
             box_muller(x[2], x[3], c2, c3);
             cached_block = block;
