@@ -332,6 +332,68 @@ int64_t pmcts_forest_tree_size(pmcts_forest *f, int local_index) {
 
 int64_t pmcts_forest_master_size(pmcts_forest *f) { return f ? f->master.size() : -1; }
 
+// `count` consecutive random.shuffle(list(range(n_items))) of CPython's random.Random(seed) -- what Node.__init__
+// does with the tree's generator (worker.py:50-51) -- so that the native search pops the same untried actions as
+// the Python classes without a hundred thousand interpreter-level shuffles.  CPython: Random(int) seeds MT19937
+// with init_by_array over the 32-bit limbs of |seed| (Modules/_randommodule.c), shuffle swaps x[i] with
+// x[_randbelow(i + 1)] for i = n - 1 .. 1, and _randbelow(n) draws getrandbits(n.bit_length()) until < n
+// (Lib/random.py); getrandbits(k <= 32) is the top k bits of one 32-bit output.
+int pmcts_python_shuffles(uint64_t seed, int64_t count, int n_items, uint8_t *out) {
+    if (!out || count < 0 || n_items < 1 || n_items > 255) return fail(PMCTS_ERR_ARG, "bad arguments");
+    uint32_t mt[624];
+    int mti = 624;
+    auto init_genrand = [&](uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    };
+    {
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        const int klen = key[1] ? 2 : 1;
+        init_genrand(19650218u);
+        int i = 1, j = 0;
+        for (int k = 624 > klen ? 624 : klen; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+            if (++j >= klen) j = 0;
+        }
+        for (int k = 623; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            if (++i >= 624) { mt[0] = mt[623]; i = 1; }
+        }
+        mt[0] = 0x80000000u;
+    }
+    auto next32 = [&]() -> uint32_t {
+        if (mti >= 624) {
+            for (int kk = 0; kk < 624; ++kk) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % 624] & 0x7fffffffu);
+                mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            mti = 0;
+        }
+        uint32_t y = mt[mti++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    };
+    for (int64_t c = 0; c < count; ++c) {
+        uint8_t *x = out + (size_t)c * n_items;
+        for (int i = 0; i < n_items; ++i) x[i] = (uint8_t)i;
+        for (int i = n_items - 1; i >= 1; --i) {
+            const uint32_t n = (uint32_t)i + 1u;
+            int bits = 0;
+            for (uint32_t v = n; v; v >>= 1) ++bits;
+            uint32_t r;
+            do r = next32() >> (32 - bits); while (r >= n);
+            const uint8_t tmp = x[i];
+            x[i] = x[r];
+            x[r] = tmp;
+        }
+    }
+    return PMCTS_OK;
+}
+
 int pmcts_forest_export_tree(pmcts_forest *f, int local_index, int32_t *parent, int8_t *arm, int64_t *table,
                              uint8_t *n_untried, uint8_t *untried) {
     if (!f || local_index < 0 || local_index >= f->n_local) return fail(PMCTS_ERR_ARG, "bad tree index");

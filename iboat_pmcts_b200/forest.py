@@ -148,13 +148,18 @@ class Forest:
         # (what Node.__init__ does, worker.py:50-51)
         max_nodes = budget + 2
         perms = np.empty((S_loc, max_nodes, len(ACTIONS)), np.uint8)
-        base = list(range(len(ACTIONS)))
         for ti, t in enumerate(trees):
-            rng = rand.Random(1000003 * seed + t.id)
-            for j in range(max_nodes):
-                order = list(base)
-                rng.shuffle(order)
-                perms[ti, j] = order
+            # = rng = random.Random(1000003 * seed + t.id); rng.shuffle(list(range(8))) per node, generated natively
+            # (tests/test_host_forest.py holds the two together)
+            tree_seed = 1000003 * seed + t.id
+            if 0 <= tree_seed < 2 ** 64:
+                N.check_forest(lib.pmcts_python_shuffles(tree_seed, max_nodes, len(ACTIONS), perms[ti].ctypes.data))
+            else:  # (seeds beyond 64 bits: the interpreter's own generator)
+                rng = rand.Random(tree_seed)
+                for j in range(max_nodes):
+                    order = list(range(len(ACTIONS)))
+                    rng.shuffle(order)
+                    perms[ti, j] = order
         ids = np.asarray(local_ids, np.int32)
         prob = np.ascontiguousarray(trees[0].probability, np.float64)
         handle = C.c_void_p()
@@ -201,7 +206,7 @@ class Forest:
                 done += b
                 wave += 1
             for ti, t in enumerate(trees):
-                _import_tree(lib, handle, ti, t, root_state, done)
+                _export_tree(lib, handle, ti, t, root_state, done)
             return _import_master(lib, handle, S)
         finally:
             lib.pmcts_forest_destroy(handle)
@@ -217,8 +222,9 @@ def _dist_env(group):
     return None, 0, 1
 
 
-def _import_tree(lib, handle, ti, tree, root_state, iterations):
-    """Rebuilds ``tree.Nodes`` (``worker.Node`` objects over one table) from the native arrays."""
+def _export_tree(lib, handle, ti, tree, root_state, iterations):
+    """Copies a native worker tree into NumPy arrays; ``tree.Nodes`` / ``rootNode`` / ``depth`` (``worker.Node``
+    objects over one table) are rebuilt from them the first time they are read (``Tree.__getattr__``)."""
     n = int(lib.pmcts_forest_tree_size(handle, ti))
     parent = np.empty(n, np.int32)
     arm = np.empty(n, np.int8)
@@ -228,13 +234,20 @@ def _import_tree(lib, handle, ti, tree, root_state, iterations):
     N.check_forest(lib.pmcts_forest_export_tree(handle, ti, parent.ctypes.data, arm.ctypes.data, table.ctypes.data,
                                                 n_untried.ctypes.data, untried.ctypes.data))
     tree.table, tree._cap = table.astype(int, copy=False), n
-    tree.Nodes = []
     tree.ite = iterations
+    for name in ("Nodes", "rootNode", "depth"):
+        tree.__dict__.pop(name, None)
+    tree._lazy_nodes = (parent, arm, n_untried, untried, tuple(root_state))
+
+
+def materialize_tree(tree):
+    """Builds ``tree.Nodes`` from the arrays ``_export_tree`` left (called by ``Tree.__getattr__``)."""
+    parent, arm, n_untried, untried, root_state = tree.__dict__.pop("_lazy_nodes")
     nodes = []
-    for i in range(n):
+    for i in range(parent.size):
         node = mt.Node.__new__(mt.Node)
         p = nodes[parent[i]] if parent[i] >= 0 else None
-        node.state = tuple(root_state) if p is None else None
+        node.state = root_state if p is None else None
         node.parent = p
         node.origins = [] if p is None else p.origins + [ACTIONS[arm[i]]]
         node.children = []

@@ -142,6 +142,15 @@ class Tree:
         self._cap = 0
         self.table = np.zeros((0, len(SimC.ACTIONS), Hist.N_BINS), dtype=int)
 
+    def __getattr__(self, name):
+        # Only reached when the attribute is missing: after a native batched search (forest._export_tree) the node
+        # objects are built on first use -- a 10^4-node tree costs 50 ms of interpreter time nobody may ask for.
+        if name in ("Nodes", "rootNode", "depth") and "_lazy_nodes" in self.__dict__:
+            from .forest import materialize_tree
+            materialize_tree(self)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
     # ---- storage ---------------------------------------------------------------------------------
     def _new_row(self):
         """Row of the tree's table for the next node; the table grows by doubling (views of earlier rows are

@@ -126,3 +126,21 @@ def test_native_forest_errors():
             N.check_forest(lib.pmcts_forest_select(h, 1, 4, leaf.ctypes.data, plen.ctypes.data, path.ctypes.data))
     finally:
         lib.pmcts_forest_destroy(h)
+
+
+def test_native_shuffles_are_cpythons():
+    """pmcts_python_shuffles == random.Random(seed).shuffle(list(range(n))) repeated, for seeds of one and two
+    32-bit limbs: the native search pops the same untried actions as worker.Node.__init__ (worker.py:50-51)."""
+    import random
+    from iboat_pmcts_b200 import _native as N
+    L = N.lib()
+    for seed, n_items in ((0, 8), (5, 8), (1000003 * 3 + 7, 8), (2 ** 32 + 17, 8), (2 ** 63 + 5, 8), (99, 13)):
+        out = np.empty((500, n_items), np.uint8)
+        N.check_forest(L.pmcts_python_shuffles(seed, 500, n_items, out.ctypes.data))
+        rng = random.Random(seed)
+        ref = []
+        for _ in range(500):
+            order = list(range(n_items))
+            rng.shuffle(order)
+            ref.append(order)
+        assert np.array_equal(out, np.array(ref, np.uint8)), seed
