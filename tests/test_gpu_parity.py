@@ -14,6 +14,7 @@ import pytest
 import pmcts_helpers as H
 from iboat_pmcts_b200 import _native as N
 from iboat_pmcts_b200 import synth
+from oracle import cport
 
 pytestmark = pytest.mark.gpu
 
@@ -533,6 +534,34 @@ def test_staged_slabs_give_the_same_boats(eng):
     k, lat, lon, st = res[(True, 1)]
     assert (st[100:140] == N.ST_OUT_OF_BOX).all() and (k[100:140] == 3).all()
     assert (st == N.ST_PAST_HORIZON).sum() > 0 and (k[st == N.ST_PAST_HORIZON] == 100).all()
+    eng.set_precision(N.PREC_F64)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_large_grid_scattered_boats(eng, mode):
+    """A near-global 1-degree grid (151 x 360 nodes, odd row length, slabs far larger than L1) with boats spread
+    over all of it and both hemispheres: K1 against the oracle, same statuses and instants, positions to 1e-6."""
+    t, la, lo, u, v = synth.wind_fields(3, lat=(-75.0, 75.0, 1.0), lon=(0.0, 359.0, 1.0))
+    nsteps, n = 40, 20000
+    times = np.linspace(0, 1.5, nsteps + 1)
+    eng.upload_scenario(5, t, la, lo, u.astype(np.float32), v.astype(np.float32), times, [la[0], la[-1], lo[0], lo[-1]])
+    eng.set_precision(mode)
+    rng = np.random.default_rng(8)
+    lat0, lon0 = rng.uniform(-74.0, 74.0, n), rng.uniform(0.5, 358.5, n)   # some start next to the edges and leave
+    head = 360.0 * rng.random((2, n))
+    k = np.zeros(n, np.int32)
+    st = np.zeros(n, np.uint8)
+    lat, lon = lat0.copy(), lon0.copy()
+    eng.step_batch(5, k, lat, lon, head, nsteps=nsteps, seg_len=20, status=st, seed=17, stream=4)
+    o = cport.OracleSim(t, la, lo, u, v, times, la, lo)
+    want = o.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=20, seed=17, stream=4, nthreads=8)
+    assert np.array_equal(st, want["status"]) and np.array_equal(k, want["k"])
+    assert (st == N.ST_OUT_OF_GRID).sum() > 0 and (st == 0).sum() > n // 2
+    tol = rtol_for(mode)
+    # (coordinates pass through zero on this grid: relative to max(|x|, 1 degree))
+    assert np.max(np.abs(lat - want["lat"]) / np.maximum(np.abs(want["lat"]), 1.0)) < tol
+    assert np.max(np.abs(lon - want["lon"]) / np.maximum(np.abs(want["lon"]), 1.0)) < tol
+    eng.free_scenario(5)
     eng.set_precision(N.PREC_F64)
 
 
