@@ -19,10 +19,13 @@
 //     fp64 whatever the summation order;
 //   * a leaf's wave histogram goes to a random action slot of the leaf (worker.py:62-63,
 //     master_node.py:42-44) and to the slot of the action taken at every ancestor.
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/pmcts_b200.h"
@@ -38,6 +41,32 @@ thread_local std::string g_err;
 int fail(int code, const char *msg) {
     g_err = msg;
     return code;
+}
+
+// The reference runs one process per worker tree (forest.py:69-75).  Here the trees of a wave are walked by a few
+// host threads: selection and back-up touch only their own tree (the master is read-only while leaves are
+// selected, apart from its per-wave memo, which is written with release / acquire ordering and holds the same
+// value whoever computes it), and the master update of a wave is split by scenario slice.  Small waves stay on
+// the calling thread: a thread start costs more than a few hundred tree walks.
+constexpr int64_t kMinParallelWork = 1024;
+
+template <typename F>
+void parallel_for(int n, int64_t work, F &&fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::min<unsigned>((unsigned)n, std::min<unsigned>(hw ? hw : 1u, 16u));
+    if (nt <= 1 || work < kMinParallelWork) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    auto body = [&]() {
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+    };
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back(body);
+    body();
+    for (auto &x : th) x.join();
 }
 
 // (visit count, max over actions of the binned mean) of one node's 8 x 12 counters
@@ -98,7 +127,13 @@ struct Master {
     int n_scen = 0;
     std::vector<int32_t> parent, child;  // child [node][kA] by action index
     std::vector<int8_t> arm;
-    std::vector<uint32_t> table;         // [node][n_scen][kA][kB]
+    // [node][n_scen][kA][kB], in chunks of kChunk nodes: the table is hundreds of megabytes at the end of a search,
+    // and growing one contiguous vector would copy all of it every time it doubles
+    static constexpr int kChunk = 256;
+    std::vector<std::vector<uint32_t>> table;
+    uint32_t *row_of(int32_t node, int s) {
+        return table[node / kChunk].data() + ((size_t)(node % kChunk) * n_scen + s) * kRow;
+    }
     std::vector<int64_t> visits;         // [node][n_scen] cached
     std::vector<double> best;            // [node][n_scen] cached
     std::vector<double> memo;            // master UCT per node, valid when stamp == wave
@@ -111,7 +146,7 @@ struct Master {
         parent.push_back(par);
         arm.push_back((int8_t)a);
         child.insert(child.end(), kA, -1);
-        table.insert(table.end(), (size_t)n_scen * kRow, 0u);
+        if (idx % kChunk == 0) table.emplace_back((size_t)kChunk * n_scen * kRow, 0u);
         visits.insert(visits.end(), n_scen, 0);
         best.insert(best.end(), n_scen, 0.0);
         memo.push_back(0.0);
@@ -132,7 +167,7 @@ struct Master {
     }
 
     void add(int32_t node, int s, int slot, const uint32_t *bins) {
-        uint32_t *row = table.data() + ((size_t)node * n_scen + s) * kRow;
+        uint32_t *row = row_of(node, s);
         for (int b = 0; b < kB; ++b) row[slot * kB + b] += bins[b];
         node_value(row, visits[(size_t)node * n_scen + s], best[(size_t)node * n_scen + s]);
     }
@@ -150,7 +185,7 @@ struct pmcts_forest {
 
     double master_uct(int32_t m) {
         if (m < 0) return 0.0;
-        if (master.stamp[m] == wave) return master.memo[m];
+        if (__atomic_load_n(&master.stamp[m], __ATOMIC_ACQUIRE) == wave) return master.memo[m];
         const int32_t p = master.parent[m];
         double acc = 0.0;
         bool any = false;
@@ -164,9 +199,10 @@ struct pmcts_forest {
                 any = true;
             }
         }
-        master.stamp[m] = wave;
-        master.memo[m] = any ? acc : 0.0;
-        return master.memo[m];
+        const double value = any ? acc : 0.0;
+        master.memo[m] = value;  // (threads that race here store the same value)
+        __atomic_store_n(&master.stamp[m], wave, __ATOMIC_RELEASE);
+        return value;
     }
 
     // master node of a worker node (by its action path), or -1 when the master does not know it yet
@@ -258,12 +294,16 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
                         int32_t *prefix_len, int8_t *prefix_act) {
     if (!f || !leaf_node || !prefix_len || !prefix_act) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n_leaves < 1 || prefix_stride < f->max_depth) return fail(PMCTS_ERR_ARG, "prefix_stride must hold max_depth actions");
-    for (int i = 0; i < f->n_local; ++i) {
+    std::atomic<int> exhausted{0};
+    parallel_for(f->n_local, (int64_t)f->n_local * n_leaves, [&](int i) {
         Tree &t = f->trees[i];
         t.wave_leaves.clear();
         for (int l = 0; l < n_leaves; ++l) {
             const int32_t leaf = f->tree_policy(t);
-            if (leaf < 0) return fail(PMCTS_ERR_ARG, "tree capacity (max_nodes) exhausted");
+            if (leaf < 0) {
+                exhausted.store(1);
+                return;
+            }
             for (int32_t x = leaf; x >= 0; x = t.parent[x]) t.pending[x] += 1;
             t.wave_leaves.push_back(leaf);
             const size_t o = (size_t)i * n_leaves + l;
@@ -275,15 +315,18 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
             int d = len;
             for (int32_t x = leaf; t.parent[x] >= 0; x = t.parent[x]) p[--d] = t.arm[x];
         }
-    }
+    });
+    if (exhausted.load()) return fail(PMCTS_ERR_ARG, "tree capacity (max_nodes) exhausted");
     return PMCTS_OK;
 }
 
 int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) {
     if (!f || !leaf_bins || !slots) return fail(PMCTS_ERR_ARG, "NULL argument");
-    for (int i = 0; i < f->n_local; ++i) {
+    for (int i = 0; i < f->n_local; ++i)
+        if ((int)f->trees[i].wave_leaves.size() != n_leaves)
+            return fail(PMCTS_ERR_ARG, "back-up does not match the last selection");
+    parallel_for(f->n_local, (int64_t)f->n_local * n_leaves, [&](int i) {
         Tree &t = f->trees[i];
-        if ((int)t.wave_leaves.size() != n_leaves) return fail(PMCTS_ERR_ARG, "back-up does not match the last selection");
         for (int l = 0; l < n_leaves; ++l) {
             const int32_t leaf = t.wave_leaves[l];
             const uint32_t *bins = leaf_bins + ((size_t)i * n_leaves + l) * kB;
@@ -297,7 +340,7 @@ int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins
             }
         }
         t.wave_leaves.clear();
-    }
+    });
     return PMCTS_OK;
 }
 
@@ -306,21 +349,35 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
                               const int8_t *slots, const uint32_t *leaf_bins) {
     if (!f || !scen_ids || !prefix_len || !prefix_act || !slots || !leaf_bins) return fail(PMCTS_ERR_ARG, "NULL argument");
     Master &m = f->master;
+    std::vector<uint8_t> seen(f->n_scen, 0);
+    bool distinct = true;
     for (int i = 0; i < n_blocks_scen; ++i) {
         const int s = scen_ids[i];
         if (s < 0 || s >= f->n_scen) return fail(PMCTS_ERR_ARG, "scenario id out of range");
+        if (seen[s]) distinct = false;
+        seen[s] = 1;
+    }
+    // 1. the nodes of every path, created in block / leaf order (the order the serial walk creates them in)
+    std::vector<int32_t> leaf_master((size_t)n_blocks_scen * n_leaves);
+    for (size_t o = 0; o < leaf_master.size(); ++o)
+        leaf_master[o] = m.descend(prefix_act + o * prefix_stride, prefix_len[o]);
+    // 2. the counters: block i only touches the slice of its own scenario, so distinct scenarios run side by side
+    auto apply_block = [&](int i) {
+        const int s = scen_ids[i];
         for (int l = 0; l < n_leaves; ++l) {
             const size_t o = (size_t)i * n_leaves + l;
-            const int8_t *path = prefix_act + o * prefix_stride;
             const uint32_t *bins = leaf_bins + o * kB;
-            int32_t node = m.descend(path, prefix_len[o]);
+            int32_t node = leaf_master[o];
             m.add(node, s, slots[o], bins);
             while (m.parent[node] >= 0) {
                 m.add(m.parent[node], s, m.arm[node], bins);
                 node = m.parent[node];
             }
         }
-    }
+    };
+    if (distinct) parallel_for(n_blocks_scen, (int64_t)n_blocks_scen * n_leaves, apply_block);
+    else
+        for (int i = 0; i < n_blocks_scen; ++i) apply_block(i);
     f->wave += 1;  // the master changed: its UCT values are recomputed on next use
     return PMCTS_OK;
 }
@@ -413,7 +470,12 @@ int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, ui
     const size_t n = m.parent.size();
     if (parent) std::memcpy(parent, m.parent.data(), n * sizeof(int32_t));
     if (arm) std::memcpy(arm, m.arm.data(), n);
-    if (table) std::memcpy(table, m.table.data(), n * (size_t)m.n_scen * kRow * sizeof(uint32_t));
+    if (table)
+        for (size_t c = 0; c * Master::kChunk < n; ++c) {
+            const size_t nodes = std::min<size_t>(Master::kChunk, n - c * Master::kChunk);
+            std::memcpy(table + c * Master::kChunk * m.n_scen * kRow, m.table[c].data(),
+                        nodes * (size_t)m.n_scen * kRow * sizeof(uint32_t));
+        }
     return PMCTS_OK;
 }
 

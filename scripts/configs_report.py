@@ -71,7 +71,7 @@ def main():
               flush=True)
     # ---- config 5: plan evaluation, 10^5 draws per scenario, 10 scenarios ---------------------------------
     plan = [0, 0, 315, 0, 45, 0]
-    iso.estimate_perfomance_plan(sims, 1000, STATE0, dest, plan=plan, verbose=False, seed=5)  # warm-up
+    iso.estimate_perfomance_plan(sims, 100000, STATE0, dest, plan=plan, verbose=False, seed=4)  # warm-up at full size (scratch allocation)
     t0 = time.perf_counter()
     mean, var = iso.estimate_perfomance_plan(sims, 100000, STATE0, dest, plan=plan, verbose=False, seed=5)
     dt = time.perf_counter() - t0
