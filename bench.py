@@ -381,20 +381,26 @@ def main():
         fp32_peak = eng.probe_fp32_peak() or FP32_PEAK_TFLOPS
         per_launch_units = run["dominant"]["units_per_launch"]
         n_dom = run["dominant"]["launches_per_step"] * args.steps
-        dom_ms = (dom_kernel_ms + fin_kernel_ms) / n_dom  # main kernel + its fp64 finisher: all the transitions
+        dom_ms = dom_kernel_ms / n_dom  # the dominant kernel's own average launch duration (CUDA events)
+        both_ms = (dom_kernel_ms + fin_kernel_ms) / n_dom  # ... plus its fp64 finisher, which runs on a side stream
         f_alg = run["dominant"]["flop_per_unit"]
         # units per launch are transitions: measured, averaged over the timed launches of this rank
         units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
         achieved = units * f_alg / (dom_ms * 1e-3) / 1e12
+        achieved_both = units * f_alg / (both_ms * 1e-3) / 1e12
         roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=fp32_peak,
                         unit="TFLOP/s", frac=achieved / fp32_peak, peak_nominal=FP32_PEAK_TFLOPS,
                         frac_of_nominal=achieved / FP32_PEAK_TFLOPS, traffic=run["dominant"].get("traffic"),
-                        traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture under profiles/ (round 1)",
+                        traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                                       + run["dominant"].get("traffic_source", "under profiles/"),
                         peak_source="FP32 FMA throughput measured in this run by pmcts_probe_fp32_peak (16 independent FFMA "
                                     "chains per thread, CUDA events, best of 4); peak_nominal = 148 SM x 128 lanes x 2 x "
                                     "1.965 GHz.  MEASURED_PEAKS.json has HBM and bf16-tensor entries only and the path is "
                                     "neither HBM- nor tensor-bound (SURVEY.md 8d)",
                         main_kernel_ms_per_launch=dom_kernel_ms / n_dom, finisher_ms_per_launch=fin_kernel_ms / n_dom,
+                        with_finisher=dict(ms_per_launch=both_ms, achieved=achieved_both, frac=achieved_both / fp32_peak,
+                                           note="main kernel + fp64 finisher durations added, although the finisher "
+                                                "overlaps the next launch on a side stream"),
                         algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
                         hbm_bytes_per_launch=run["dominant"]["hbm_bytes_per_launch"],
                         hbm_gbs=run["dominant"]["hbm_bytes_per_launch"] / (dom_ms * 1e-3) / 1e9)
@@ -542,11 +548,12 @@ def setup_c4(eng, torch, dist, dev, rank, world):
 
     return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
                 e2e_step=e2e_step,
-                dominant=dict(kernel="rollout_fast_kernel (+ rollout_batch_kernel on its work list)",
+                dominant=dict(kernel="rollout_fast_kernel",
                               launches_per_step=WAVES, units_per_launch=None,
                               flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
                               api="pmcts_rollout_forest with PMCTS_MEM_HOST (host prefix in, host leaf_bins / stats out)",
-                              traffic=1801984 + 1559808,  # profiles/r01_c4_forest_full.txt: main kernel + fp64 finisher
+                              traffic=1798400,  # profiles/r01_c4_forest_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
+                              traffic_source="profiles/r01_c4_forest_final_full.txt",
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))
 
 
@@ -601,7 +608,8 @@ def setup_c3(eng, torch, dev, rank, world):
                 dominant=dict(kernel="step_fast_kernel", launches_per_step=1, units_per_launch=None,
                               flop_per_unit=F_ALG_RAW, kind=0,
                               api="pmcts_step_batch with PMCTS_MEM_HOST (host state / headings in, host state out)",
-                              traffic=182030848 + 15603456,  # profiles/r01_c3_step_fast_full.txt
+                              traffic=181827072 + 16585984,  # profiles/r01_c3_step_final_full.txt
+                              traffic_source="profiles/r01_c3_step_final_full.txt",
                               hbm_bytes_per_launch=n * (21 + 21) + head_h.nbytes))
 
 
