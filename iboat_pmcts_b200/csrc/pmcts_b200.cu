@@ -645,6 +645,14 @@ step_fast_staged_kernel(ScenarioView sc, BoatParams bp, int64_t n, int nsteps, i
     status_io[i] = (uint8_t)st;
 }
 
+// PMCTS_STEP_HEADING_ACTIONS: headings handed over as indices into the reference's ACTIONS (simulatorTLKT.py:29,
+// 0 .. 7 -> 0, 45, ... 315 degrees; any uint8 a means 45 a degrees) -- an eighth of the bytes a host caller has to
+// send -- are expanded to the fp64 degrees the step kernels read.
+__global__ void expand_actions_kernel(const uint8_t *__restrict__ a, double *__restrict__ h, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) h[i] = 45.0 * (double)a[i];
+}
+
 // Roofline denominator: what the FP32 FMA pipes of this chip sustain (pmcts_probe_fp32_peak).  16 independent
 // FFMA chains per thread, nothing else in the loop.
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out, int iters, float a, float b) {
@@ -765,6 +773,8 @@ struct pmcts_ctx {
     // then the rollout ids (uint32) or per-boat resume steps (int32) and a status byte per boat
     char *work = nullptr;
     size_t work_cap = 0;
+    double *head_buf = nullptr;  // PMCTS_STEP_HEADING_ACTIONS: the action indices expanded to degrees
+    size_t head_cap = 0;
     bool margins_set = false;
     bool stage_slabs = false;  // K1: stage the step's wind slab in shared memory (pmcts_set_option); measured
                                // 21 % slower than the L1 / L2 gathers on config 3 (profiles/README.md), so off
@@ -1000,6 +1010,7 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work) cudaFree(ctx->work);
+    if (ctx->head_buf) cudaFree(ctx->head_buf);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     for (auto &d : ctx->defer) {
         if (d.work) cudaFree(d.work);
@@ -1388,17 +1399,34 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
     NoiseView nz = noise_view(noise);
     if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
     const size_t nseg = ((size_t)nsteps + seg_len - 1) / seg_len;
+    const bool actions = (flags & PMCTS_STEP_HEADING_ACTIONS) != 0;
+    const uint8_t *heading8 = actions ? reinterpret_cast<const uint8_t *>(heading) : nullptr;
     Stager st(ctx, flags & PMCTS_MEM_HOST);
-    rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(nseg * n * 8) + al(n) +
+    rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(nseg * n * (actions ? 1 : 8)) + al(n) +
                     (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)nsteps * n * 8) : 0) +
                     (traj_lat ? al((size_t)nsteps * n * 8) : 0) + (traj_lon ? al((size_t)nsteps * n * 8) : 0));
     if (rc) return rc;
     if ((rc = st.in(k, n, true)) || (rc = st.in(lat, n, true)) || (rc = st.in(lon, n, true)) ||
         (rc = st.in(prev_lat, n, true)) || (rc = st.in(prev_lon, n, true)) ||
-        (rc = st.in(heading, nseg * n)) || (rc = st.in(status, n, true)) ||
+        (rc = actions ? st.in(heading8, nseg * n) : st.in(heading, nseg * n)) || (rc = st.in(status, n, true)) ||
         (rc = st.out(traj_lat, (size_t)nsteps * n, 0xFF)) || (rc = st.out(traj_lon, (size_t)nsteps * n, 0xFF)))
         return rc;
     if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)nsteps * n))) return rc;
+    if (actions) {
+        const size_t count = nseg * (size_t)n;
+        if (count > ctx->head_cap) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (ctx->head_buf) CUDA_TRY(cudaFree(ctx->head_buf));
+            ctx->head_buf = nullptr;
+            ctx->head_cap = 0;
+            CUDA_TRY(cudaMalloc((void **)&ctx->head_buf, (count + count / 4) * sizeof(double)));
+            ctx->head_cap = count + count / 4;
+        }
+        LaunchTimer lt(ctx);
+        expand_actions_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(heading8, ctx->head_buf, count);
+        CUDA_TRY(cudaGetLastError());
+        heading = ctx->head_buf;
+    }
     if (fast_eligible(ctx, sc)) {
         // work area: counter | j_resume[n] | status[n] (when the caller passes no status array)
         const size_t o_status = al(n * sizeof(int32_t));

@@ -213,14 +213,19 @@ class Engine:
     # ---- K1 ---------------------------------------------------------------------------------------
     def step_batch(self, scen, k, lat, lon, heading, nsteps=1, seg_len=1, prev_lat=None, prev_lon=None,
                    status=None, z=None, seed=None, stream=0, id0=0, traj_lat=None, traj_lon=None, flags=0):
-        """In-place batched Simulator.doStep.  k/lat/lon/(prev_*)/(status) are updated in place."""
+        """In-place batched Simulator.doStep.  k/lat/lon/(prev_*)/(status) are updated in place.  ``heading`` is
+        [nseg][n] degrees (float64), or -- dtype uint8 -- indices into the reference's ACTIONS (45 degrees each)."""
         a = _Args()
         n = lat.numel() if _is_tensor(lat) else lat.size
         nseg = (nsteps + seg_len - 1) // seg_len
         pk = a.ptr(k, "i32", n, True)
         plat, plon = a.ptr(lat, "f64", n, True), a.ptr(lon, "f64", n, True)
         ppl, ppo = a.ptr(prev_lat, "f64", n, True), a.ptr(prev_lon, "f64", n, True)
-        ph = a.ptr(heading, "f64", nseg * n)
+        if getattr(heading, "dtype", None) == (torch.uint8 if _is_tensor(heading) else np.uint8):
+            ph = a.ptr(heading, "u8", nseg * n)
+            flags = int(flags) | N.STEP_HEADING_ACTIONS
+        else:
+            ph = a.ptr(heading, "f64", nseg * n)
         pst = a.ptr(status, "u8", n, True)
         ptl, pto = a.ptr(traj_lat, "f64", nsteps * n, True), a.ptr(traj_lon, "f64", nsteps * n, True)
         nz = make_noise(a, z, seed, stream, id0, nsteps * n)

@@ -48,6 +48,9 @@ typedef struct pmcts_ctx pmcts_ctx;
 
 /* flags */
 #define PMCTS_STEP_STOP_BEFORE_TERMINAL 0x1 /* step_batch: fixed-heading sweep of initialize_simulators (forest.py:239) */
+#define PMCTS_STEP_HEADING_ACTIONS 0x2      /* step_batch: `heading` points to uint8_t[nseg][n] action indices instead of
+                                               fp64 degrees: heading = 45 a degrees, the reference's ACTIONS
+                                               (simulatorTLKT.py:29) -- an eighth of the bytes for a host caller */
 #define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
 #define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
 #define PMCTS_ROLL_ACCUMULATE 0x8           /* rollout_batch, device arrays only: add to leaf_bins / stats instead of zeroing them first */

@@ -338,6 +338,37 @@ def test_kernel_variants_agree_with_each_other_and_the_oracle(eng):
         eng.set_precision(N.PREC_F64)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_action_index_headings(eng, mode):
+    """PMCTS_STEP_HEADING_ACTIONS: headings given as uint8 indices into the reference's ACTIONS (45 degrees each)
+    move the boats exactly like the same headings in fp64 degrees -- host arrays and device tensors."""
+    import torch
+    eng.set_precision(mode)
+    times = np.linspace(0, 5, 101)
+    upload(eng, 3, 1, times=times)
+    n, nsteps = 3000, 60
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=3)
+    acts = ((h0[None, :] + np.arange(6)[:, None]) % 8).astype(np.uint8)       # [nseg][n]
+    res = []
+    for head in (45.0 * acts.astype(np.float64), acts):
+        k, st, lat, lon = np.zeros(n, np.int32), np.zeros(n, np.uint8), lat0.copy(), lon0.copy()
+        eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=10, status=st, seed=9, stream=1)
+        res.append((k, st, lat, lon))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    dev = torch.device("cuda:0")
+    eng.use_torch_stream()
+    k, st = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    lat, lon = torch.tensor(lat0, device=dev), torch.tensor(lon0, device=dev)
+    eng.step_batch(3, k, lat, lon, torch.tensor(acts, device=dev).reshape(-1), nsteps=nsteps, seg_len=10, status=st,
+                   seed=9, stream=1)
+    torch.cuda.synchronize()
+    eng.use_own_stream()
+    assert np.array_equal(lat.cpu().numpy(), res[0][2]) and np.array_equal(lon.cpu().numpy(), res[0][3])
+    assert (res[0][0] == nsteps).all()
+    eng.set_precision(N.PREC_F64)
+
+
 def test_fast_mode_hands_over_what_it_does_not_cover(eng):
     """K1 in the mixed-precision mode: headings outside [0, 360) and steps longer than its series allow
     are finished by the fp64 kernel from the step they stopped at -- same result as the literal mode."""
