@@ -483,6 +483,7 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                     dbg[1].record()
                 if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
                     eng.backup(master, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S_total)
+                bins_ring[slot].zero_()  # ready for its next step: the clear stays off the rollout stream
                 consumed[slot].record()
                 if dbg:
                     dbg[2].record()
@@ -498,8 +499,7 @@ def setup_c4(eng, torch, dist, dev, rank, world):
             slot = step_no[0] % len(bins_ring)
             step_no[0] += 1
             buf = bins_ring[slot]
-            main.wait_event(consumed[slot])  # (a never-recorded event does not block)
-            buf.zero_()
+            main.wait_event(consumed[slot])  # consumed and cleared (a never-recorded event does not block)
             eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix, plen, 4, prefix_shared=True,
                                seed=SEED, stream=rank * S_local, id0=(i * WAVES + w) * n,
                                out=dict(leaf_bins=buf, stats=stats), flags=N.ROLL_ACCUMULATE | N.ROLL_DEFER_REDO)

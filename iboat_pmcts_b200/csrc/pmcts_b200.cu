@@ -1612,9 +1612,12 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         work = ctx->work;
     }
     double *stats_part = (double *)(work + 256);
+    // (counter and partial sums are neighbours in the work area: one memset clears both for a mixed-precision launch)
+    const size_t stats_part_bytes = S * kStatsCopies * 8 * sizeof(double);
     if (stats) {
         a.stats = stats_part;
-        CUDA_TRY(cudaMemsetAsync(stats_part, 0, S * kStatsCopies * 8 * sizeof(double), ctx->stream));
+        if (fast) CUDA_TRY(cudaMemsetAsync(work, 0, 256 + stats_part_bytes, ctx->stream));
+        else CUDA_TRY(cudaMemsetAsync(stats_part, 0, stats_part_bytes, ctx->stream));
     }
     const dim3 grid_all(grid_for(n), n_scen);
     cudaStream_t tail_stream = ctx->stream;  // where the fp64 finisher and the statistics fold run
@@ -1622,7 +1625,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         fast::prepare_rollout(vw, a);
         a.redo_count = (uint32_t *)work;
         a.redo_list = (uint32_t *)(work + 256 + part_bytes);
-        CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
+        if (!stats) CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
             const bool lean = !reward && !t_arr && !steps && !status && !bin && !frac && !final_lat && !final_lon &&
