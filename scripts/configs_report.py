@@ -1,7 +1,7 @@
 """Runs BASELINE.json configs 1, 2 and 5 through the reference-API mirror on one GPU and prints one JSON
-line per config (configs 3 and 4 are bench.py --workload c3 / c4).  The CPU column is the oracle port on the
-host cores for the same rollouts (the Python reference itself cannot travel to the GPU box; its measured
-numbers are in BASELINE.md)."""
+line per config (configs 3 and 4 are bench.py --workload c3 / c4).  CPU figures: bench.py's cpu_baseline and
+--impl reference (the Python reference itself cannot travel to the GPU box; its measured numbers are in
+BASELINE.md)."""
 import json
 import os
 import random
@@ -75,19 +75,10 @@ def main():
     t0 = time.perf_counter()
     mean, var = iso.estimate_perfomance_plan(sims, 100000, STATE0, dest, plan=plan, verbose=False, seed=5)
     dt = time.perf_counter() - t0
-    from oracle import cport
-    import pmcts_helpers as H
-    o = H.oracle_sim(0)
-    n_cpu = 20000 * cores
-    t0 = time.perf_counter()
-    r = o.rollout_batch(n_cpu, STATE0, dest, 0.0, prefix=np.tile(np.array(plan, np.float64), (n_cpu, 1)), mode=1, seed=5,
-                        nthreads=cores)
-    dt_cpu = time.perf_counter() - t0
     print(json.dumps(dict(config="c5 policy evaluation: plan %s, 10^5 draws x 10 scenarios" % plan, seconds=dt,
                           rollouts_per_s=1e6 / dt, global_mean_days=float(mean[0]), global_var=float(var[0]),
-                          cpu_port=dict(rollouts_per_s=n_cpu / dt_cpu, cores=cores, sample="%d rollouts, scenario 0" % n_cpu,
-                                        mean_days=float(r["t_arr"].mean())))), flush=True)
-
+                          cpu="bench.py's cpu_baseline / --impl reference time the CPU restatement of the same rollouts")),
+          flush=True)
 
 if __name__ == "__main__":
     main()
