@@ -358,8 +358,10 @@ def main():
                    note="same steps back to back without L2 flush, one CUDA-event pair around all of them")
 
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 3)) if args.workload == "c3" else max(1, args.steps)
+    drain = run.get("e2e_drain", lambda: 0)
     run["e2e_step"](0)
+    drain()
     barrier()
     t0 = time.perf_counter()
     e2e_tr, h2d, d2h = 0, 0, 0
@@ -367,6 +369,7 @@ def main():
         tr, bi, bo = run["e2e_step"](1 + i)
         e2e_tr += tr
         h2d, d2h = bi, bo
+    e2e_tr += drain()
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_stat = torch.tensor([e2e_s, float(e2e_tr)], dtype=torch.float64, device=dev)
@@ -533,25 +536,44 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     prefix_p[:] = prefix_h.reshape(-1)
     plen_p = pinned(N_LEAF, torch.int32)
     plen_p[:] = plen_h
-    e2e_out = dict(leaf_bins=pinned(S_local * N_LEAF * 12, torch.int32).view(np.uint32),
-                   stats=pinned(S_local * 8, torch.float64))
+    # Host arrays in, host arrays out, one call in flight while the previous one's fp64 finisher and copies back
+    # complete on the library's side stream (PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO, pmcts_wait): a step's results
+    # are read one call later, the last ones after e2e_drain -- all inside the timed region.
+    e2e_outs = [dict(leaf_bins=pinned(S_local * N_LEAF * 12, torch.int32).view(np.uint32),
+                     stats=pinned(S_local * 8, torch.float64)) for _ in range(3)]
+    inflight, e2e_calls = [], [0]
+
+    def e2e_read(out):
+        return int(out["stats"].reshape(S_local, 8)[:, 4].sum()) + 0 * int(out["leaf_bins"][0])
 
     def e2e_step(i):
         tr = 0
         for w in range(WAVES):
-            out = e2e_out
+            out = e2e_outs[e2e_calls[0] % len(e2e_outs)]
+            e2e_calls[0] += 1
             eng.rollout_forest(scen_slots, N_LEAF, REPLICAS, STATE0, DEST, TMIN, prefix_p, plen_p, 4,
                                prefix_shared=True, seed=SEED, stream=rank * S_local, id0=(1000 + i * WAVES + w) * n,
-                               out=out)
-            tr += int(out["stats"].reshape(S_local, 8)[:, 4].sum())
+                               out=out, flags=N.ROLL_DEFER_REDO)
+            inflight.append(out)
+            if len(inflight) > 1:
+                eng.wait(1)
+                tr += e2e_read(inflight.pop(0))
         return tr, WAVES * (prefix_h.nbytes + plen_h.nbytes), WAVES * (S_local * N_LEAF * 12 * 4 + S_local * 64)
 
+    def e2e_drain():
+        eng.wait(0)
+        tr = 0
+        while inflight:
+            tr += e2e_read(inflight.pop(0))
+        return tr
+
     return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
-                e2e_step=e2e_step,
+                e2e_step=e2e_step, e2e_drain=e2e_drain,
                 dominant=dict(kernel="rollout_fast_kernel",
                               launches_per_step=WAVES, units_per_launch=None,
                               flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
-                              api="pmcts_rollout_forest with PMCTS_MEM_HOST (host prefix in, host leaf_bins / stats out)",
+                              api="pmcts_rollout_forest with PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO + pmcts_wait (host prefix in, host "
+                                  "leaf_bins / stats out; one call in flight while the previous one's finisher and copies complete)",
                               traffic=1798400,  # profiles/r01_c4_forest_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
                               traffic_source="profiles/r01_c4_forest_final_full.txt",
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))

@@ -28,7 +28,7 @@ ERR_NO_DEVICE = -3
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
-    "pmcts_synchronize", "pmcts_join", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
+    "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
     "pmcts_forest_create", "pmcts_forest_destroy", "pmcts_forest_last_error", "pmcts_forest_set_coefficients",
@@ -72,6 +72,7 @@ def lib():
     L.pmcts_reset_stream.argtypes = [vp]
     L.pmcts_synchronize.argtypes = [vp]
     L.pmcts_join.argtypes = [vp, i32]
+    L.pmcts_wait.argtypes = [vp, i32]
     L.pmcts_set_option.argtypes = [vp, i32, i32]
     L.pmcts_set_precision.argtypes = [vp, i32]
     L.pmcts_set_fast_margins.argtypes = [vp, dbl, dbl, dbl, dbl, dbl]

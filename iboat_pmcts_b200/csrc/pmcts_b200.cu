@@ -766,9 +766,11 @@ struct pmcts_ctx {
     int precision = PMCTS_PREC_F64;
     BoatParams params{};
     std::map<int, Scenario> scenarios;
-    // grow-only device scratch for PMCTS_MEM_HOST calls
-    char *scratch = nullptr;
-    size_t scratch_cap = 0, scratch_used = 0;
+    // grow-only device scratch for PMCTS_MEM_HOST calls (deferred launches stage in their slot's own buffer)
+    struct StageBuf {
+        char *p = nullptr;
+        size_t cap = 0, used = 0;
+    } stage;
     // grow-only device work area of the mixed-precision kernels: [0] redo / resume counter,
     // then the rollout ids (uint32) or per-boat resume steps (int32) and a status byte per boat
     char *work = nullptr;
@@ -784,6 +786,7 @@ struct pmcts_ctx {
     struct Deferred {
         char *work = nullptr;
         size_t cap = 0;
+        StageBuf stage;  // PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO: device copies of this launch's host arrays
         cudaEvent_t main_done = nullptr, redo_done = nullptr;
         bool pending = false;  // not yet joined by the caller (pmcts_join)
         bool used = false;     // redo_done has been recorded at least once
@@ -827,32 +830,34 @@ struct DeviceGuard {
 struct Stager {
     pmcts_ctx *ctx;
     bool host;
+    pmcts_ctx::StageBuf *buf;
     struct Out { void *host_ptr; void *dev_ptr; size_t bytes; };
     std::vector<Out> outs;
 
-    Stager(pmcts_ctx *c, bool h) : ctx(c), host(h) {}
+    Stager(pmcts_ctx *c, bool h, pmcts_ctx::StageBuf *b = nullptr) : ctx(c), host(h), buf(b ? b : &c->stage) {}
 
     static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
 
     int reserve(size_t total) {
         if (!host) return PMCTS_OK;
         total += 4096;
-        if (total > ctx->scratch_cap) {
+        if (total > buf->cap) {
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            if (ctx->scratch) CUDA_TRY(cudaFree(ctx->scratch));
-            ctx->scratch = nullptr;
-            ctx->scratch_cap = 0;
+            if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
+            if (buf->p) CUDA_TRY(cudaFree(buf->p));
+            buf->p = nullptr;
+            buf->cap = 0;
             size_t cap = total + total / 4;
-            CUDA_TRY(cudaMalloc((void **)&ctx->scratch, cap));
-            ctx->scratch_cap = cap;
+            CUDA_TRY(cudaMalloc((void **)&buf->p, cap));
+            buf->cap = cap;
         }
-        ctx->scratch_used = 0;
+        buf->used = 0;
         return PMCTS_OK;
     }
 
     void *carve(size_t bytes) {
-        void *p = ctx->scratch + ctx->scratch_used;
-        ctx->scratch_used += align(bytes);
+        void *p = buf->p + buf->used;
+        buf->used += align(bytes);
         return p;
     }
 
@@ -880,10 +885,17 @@ struct Stager {
         if (fill >= 0) CUDA_TRY(cudaMemsetAsync(ptr, fill, bytes, ctx->stream));
         return PMCTS_OK;
     }
-    int finish() {
+    // results back to the caller's arrays on `stream` (no host synchronisation)
+    int copy_back(cudaStream_t stream) {
         if (!host) return PMCTS_OK;
         for (auto &o : outs)
-            CUDA_TRY(cudaMemcpyAsync(o.host_ptr, o.dev_ptr, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(o.host_ptr, o.dev_ptr, o.bytes, cudaMemcpyDeviceToHost, stream));
+        return PMCTS_OK;
+    }
+    int finish() {
+        if (!host) return PMCTS_OK;
+        int rc = copy_back(ctx->stream);
+        if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PMCTS_OK;
     }
@@ -1008,10 +1020,12 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
-    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
+    if (ctx->stage.p) cudaFree(ctx->stage.p);
+    for (auto &d : ctx->defer)
+        if (d.stage.p) cudaFree(d.stage.p);
     if (ctx->work) cudaFree(ctx->work);
     if (ctx->head_buf) cudaFree(ctx->head_buf);
-    if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     for (auto &d : ctx->defer) {
         if (d.work) cudaFree(d.work);
         if (d.main_done) cudaEventDestroy(d.main_done);
@@ -1530,7 +1544,33 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     const int max_steps = sc->view.nT;
     if (nz.mode == PMCTS_NOISE_INJECTED && !nz.z) return fail(PMCTS_ERR_ARG, "injected noise needs z");
     const bool acc = (flags & PMCTS_ROLL_ACCUMULATE) && !(flags & PMCTS_MEM_HOST);
-    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    // the fp32 kernels also need the destination within 90 degrees of every grid point (their
+    // sin / cos kernels cover [-pi/2, pi/2] for latD - lat and lonD - lon)
+    const ScenarioView &vw = sc->view;
+    const bool dest_ok = std::fabs(dest[0]) <= 90.0 && std::fabs(dest[0] - vw.lat0) <= 89.0 &&
+                         std::fabs(dest[0] - vw.lat_last) <= 89.0 && std::fabs(dest[1] - vw.lon0) <= 89.0 &&
+                         std::fabs(dest[1] - vw.lon_last) <= 89.0;
+    const bool fast = fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift);
+    // PMCTS_ROLL_DEFER_REDO: finisher, fold and -- with host arrays -- the copies back to the caller run on the side
+    // stream under the caller's next launch; two slots (work area, staging buffer, events) alternate
+    const bool defer = fast && (flags & PMCTS_ROLL_DEFER_REDO);
+    pmcts_ctx::Deferred *slot = nullptr;
+    if (defer) {
+        slot = &ctx->defer[ctx->defer_seq & 1];
+        if (!ctx->side_stream) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        }
+        if (!slot->main_done) {
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->redo_done, cudaEventDisableTiming));
+        }
+        // the launch that used this slot two calls ago must have finished with it (the caller may have
+        // joined it on another stream -- pmcts_set_stream between calls -- so this does not look at `pending`)
+        if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
+    }
+    Stager st(ctx, flags & PMCTS_MEM_HOST, slot ? &slot->stage : nullptr);
     const size_t traj_bytes = al(S * traj_stride * n * 8);
     rc = st.reserve(al(P * n_leaf * prefix_stride * 8) + al(P * n_leaf * 4) + 6 * al(S * n * 8) + 2 * al(S * n * 4) +
                     al(S * n) + (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(S * n_leaf * 48) +
@@ -1569,33 +1609,11 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     a.traj_stride = traj_stride;
     a.leaf_bins = leaf_bins;
     a.flags = flags;
-    // the fp32 kernels also need the destination within 90 degrees of every grid point (their
-    // sin / cos kernels cover [-pi/2, pi/2] for latD - lat and lonD - lon)
-    const ScenarioView &vw = sc->view;
-    const bool dest_ok = std::fabs(dest[0]) <= 90.0 && std::fabs(dest[0] - vw.lat0) <= 89.0 &&
-                         std::fabs(dest[0] - vw.lat_last) <= 89.0 && std::fabs(dest[1] - vw.lon0) <= 89.0 &&
-                         std::fabs(dest[1] - vw.lon_last) <= 89.0;
-    const bool fast = fast_eligible(ctx, sc) && all_fast && dest_ok && n < ((int64_t)1 << kRedoShift);
-    const bool defer = fast && (flags & PMCTS_ROLL_DEFER_REDO) && !(flags & PMCTS_MEM_HOST);
     // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list
     const size_t part_bytes = al(S * kStatsCopies * 8 * sizeof(double));
     const size_t work_bytes = part_bytes + S * n * sizeof(uint32_t);
     char *work = nullptr;
-    pmcts_ctx::Deferred *slot = nullptr;
     if (defer) {
-        slot = &ctx->defer[ctx->defer_seq & 1];
-        if (!ctx->side_stream) {
-            int lo = 0, hi = 0;
-            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
-        }
-        if (!slot->main_done) {
-            CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&slot->redo_done, cudaEventDisableTiming));
-        }
-        // the launch that used this work area two calls ago must have finished with it (the caller may have
-        // joined it on another stream -- pmcts_set_stream between calls -- so this does not look at `pending`)
-        if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
         if (256 + work_bytes > slot->cap) {
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
@@ -1678,12 +1696,29 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         CUDA_TRY(cudaGetLastError());
     }
     if (defer) {
+        // host arrays: the copies back follow the finisher and the fold on the side stream; the call returns without
+        // waiting for them (pmcts_wait)
+        if ((rc = st.copy_back(ctx->side_stream))) return rc;
         CUDA_TRY(cudaEventRecord(slot->redo_done, ctx->side_stream));
         slot->pending = true;
         slot->used = true;
         slot->seq = ctx->defer_seq++;
+        return PMCTS_OK;
     }
     return st.finish();
+}
+
+int pmcts_wait(pmcts_ctx *ctx, int keep_last) {
+    if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    if (keep_last < 0) keep_last = 0;
+    DeviceGuard g(ctx->device);
+    for (auto &d : ctx->defer) {
+        if (d.pending && d.seq + (uint64_t)keep_last < ctx->defer_seq) {
+            CUDA_TRY(cudaEventSynchronize(d.redo_done));
+            d.pending = false;
+        }
+    }
+    return PMCTS_OK;
 }
 
 int pmcts_join(pmcts_ctx *ctx, int keep_last) {

@@ -142,6 +142,11 @@ class Engine:
         """Orders the ctx stream after the deferred finishers of all but the ``keep_last`` latest launches."""
         N.check(self._lib.pmcts_join(self._h, int(keep_last)))
 
+    def wait(self, keep_last=0):
+        """Blocks until the deferred launches of all but the ``keep_last`` latest calls are complete (host arrays
+        filled)."""
+        N.check(self._lib.pmcts_wait(self._h, int(keep_last)))
+
     def launch_count(self):
         return int(self._lib.pmcts_launch_count(self._h))
 

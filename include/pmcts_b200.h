@@ -54,10 +54,13 @@ typedef struct pmcts_ctx pmcts_ctx;
 #define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
 #define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
 #define PMCTS_ROLL_ACCUMULATE 0x8           /* rollout_batch, device arrays only: add to leaf_bins / stats instead of zeroing them first */
-#define PMCTS_ROLL_DEFER_REDO 0x10          /* rollout_batch / rollout_forest, device arrays, PMCTS_PREC_FAST: the fp64
-                                               finisher (and the statistics fold) run on a side stream, so they
-                                               overlap the NEXT launch on this ctx; the outputs of this call are
-                                               complete only after pmcts_join (or pmcts_synchronize) */
+#define PMCTS_ROLL_DEFER_REDO 0x10          /* rollout_batch / rollout_forest, PMCTS_PREC_FAST: the fp64 finisher, the
+                                               statistics fold and -- with PMCTS_MEM_HOST -- the copies back into the
+                                               caller's arrays run on a side stream, so they overlap the NEXT launch on
+                                               this ctx.  The outputs of this call are complete only after pmcts_join
+                                               (device arrays: orders the stream), pmcts_wait (blocks the host: what a
+                                               caller with host arrays needs) or pmcts_synchronize; host arrays must
+                                               stay alive until then.  Two launches may be in flight. */
 #define PMCTS_MEM_HOST 0x100                /* array arguments are host memory */
 
 /* arithmetic mode */
@@ -90,6 +93,9 @@ int pmcts_synchronize(pmcts_ctx *ctx);
 /* Makes the ctx stream wait for the deferred finishers (PMCTS_ROLL_DEFER_REDO) of all but the `keep_last`
  * most recent launches: work enqueued on the stream afterwards sees their complete outputs. */
 int pmcts_join(pmcts_ctx *ctx, int keep_last);
+/* Blocks the calling thread until the deferred launches (PMCTS_ROLL_DEFER_REDO) of all but the `keep_last` most
+ * recent calls are complete, copies into host arrays included. */
+int pmcts_wait(pmcts_ctx *ctx, int keep_last);
 int pmcts_set_precision(pmcts_ctx *ctx, int mode);
 /* Decision margins of PMCTS_PREC_FAST (a negative value keeps the current one; all negative restores
  * the defaults): relative margin on sin^2 of the arrival angle vs sin^2(DESTINATION_ANGLE); margin on the

@@ -489,6 +489,55 @@ def test_deferred_finisher_gives_the_same_results(eng):
         eng.set_precision(N.PREC_F64)
 
 
+def test_deferred_host_arrays_and_wait(eng):
+    """PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO: the call returns while its finisher and the copies back to the caller's
+    (pinned) arrays still run on the side stream; after pmcts_wait the arrays hold what the synchronous call returns,
+    with two calls in flight and the slots reused."""
+    import torch
+    eng.set_precision(N.PREC_FAST)
+    for slot, sid in enumerate((1, 4)):
+        upload(eng, 20 + slot, sid)
+    try:
+        dest, tmin = [46.77751005, 355.0], 2.0223605
+        n_leaf, rep, S = 256, 128, 2
+        prefix = 45.0 * (np.arange(n_leaf) % 8).astype(np.float64)
+        plen = np.ones(n_leaf, np.int32)
+
+        def pinned(n, dt):
+            return torch.empty(n, dtype=dt, pin_memory=True).numpy()
+
+        def call(seed, flags, out):
+            eng.rollout_forest([20, 21], n_leaf, rep, H.STATE0, dest, tmin, prefix, plen, 1, prefix_shared=True,
+                               seed=seed, out=out, flags=flags)
+
+        want = []
+        for seed in range(5):
+            out = dict(leaf_bins=np.empty(S * n_leaf * 12, np.uint32), stats=np.empty(S * 8))
+            call(seed, 0, out)
+            want.append(out)
+        outs = [dict(leaf_bins=pinned(S * n_leaf * 12, torch.int32).view(np.uint32), stats=pinned(S * 8, torch.float64))
+                for _ in range(5)]
+        for seed in range(5):
+            outs[seed]["leaf_bins"][:] = 0xFFFFFFFF
+            call(seed, N.ROLL_DEFER_REDO, outs[seed])
+            eng.wait(keep_last=1)
+            if seed:  # the previous call is complete, this one may still be running
+                assert np.array_equal(outs[seed - 1]["leaf_bins"], want[seed - 1]["leaf_bins"])
+        eng.wait()
+        for got, w in zip(outs, want):
+            assert np.array_equal(got["leaf_bins"], w["leaf_bins"]) and int(got["leaf_bins"].sum()) == S * n_leaf * rep
+            assert np.array_equal(got["stats"][[0, 3, 4, 5, 8, 11, 12, 13]], w["stats"][[0, 3, 4, 5, 8, 11, 12, 13]])
+            assert np.allclose(got["stats"], w["stats"], rtol=1e-12)
+        # a synchronous host call right after deferred ones still works (its own staging buffer)
+        out = dict(leaf_bins=np.empty(S * n_leaf * 12, np.uint32), stats=np.empty(S * 8))
+        call(2, N.ROLL_DEFER_REDO, outs[0])
+        call(3, 0, out)
+        eng.wait()
+        assert np.array_equal(out["leaf_bins"], want[3]["leaf_bins"]) and np.array_equal(outs[0]["leaf_bins"], want[2]["leaf_bins"])
+    finally:
+        eng.set_precision(N.PREC_F64)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_other_hemisphere_and_grid(eng, mode):
     """Southern hemisphere, negative longitudes, 0.25-degree grid, hourly weather, 2-hour steps, arbitrary
