@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpmcts_b200.so")
 ST_OK, ST_ARRIVED, ST_HORIZON, ST_OUT_OF_BOX, ST_OUT_OF_GRID, ST_DEGENERATE, ST_PAST_HORIZON = range(7)
 STEP_STOP_BEFORE_TERMINAL = 0x1
 STEP_HEADING_ACTIONS = 0x2
+STEP_DEFER = 0x4
 ROLL_REPLAY_FULL_PREFIX = 0x2
 ROLL_PLAN_EVAL = 0x4
 ROLL_ACCUMULATE = 0x8

@@ -793,6 +793,16 @@ struct pmcts_ctx {
         uint64_t seq = 0;
     } defer[2];
     uint64_t defer_seq = 0;
+    // PMCTS_STEP_DEFER (host arrays): copies in on their own stream, kernel on the ctx stream, copies out on the side
+    // stream -- the three stages of consecutive calls overlap; two staging buffers alternate
+    cudaStream_t in_stream = nullptr;
+    struct StepDeferred {
+        StageBuf stage;
+        cudaEvent_t in_done = nullptr, main_done = nullptr, out_done = nullptr;
+        bool pending = false, used = false;
+        uint64_t seq = 0;
+    } step_defer[2];
+    uint64_t step_seq = 0;
     int64_t launches = 0;
     int last_variant = PMCTS_VARIANT_LITERAL;  // of the last K1 / K2 launch (pmcts_last_kernel_variant)
     bool timing = false;
@@ -834,7 +844,10 @@ struct Stager {
     struct Out { void *host_ptr; void *dev_ptr; size_t bytes; };
     std::vector<Out> outs;
 
-    Stager(pmcts_ctx *c, bool h, pmcts_ctx::StageBuf *b = nullptr) : ctx(c), host(h), buf(b ? b : &c->stage) {}
+    cudaStream_t in_stream;  // where the copies in are enqueued (the ctx stream unless the caller pipelines them)
+
+    Stager(pmcts_ctx *c, bool h, pmcts_ctx::StageBuf *b = nullptr, cudaStream_t ins = nullptr)
+        : ctx(c), host(h), buf(b ? b : &c->stage), in_stream(ins ? ins : c->stream) {}
 
     static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -844,6 +857,7 @@ struct Stager {
         if (total > buf->cap) {
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
+            if (ctx->in_stream) CUDA_TRY(cudaStreamSynchronize(ctx->in_stream));
             if (buf->p) CUDA_TRY(cudaFree(buf->p));
             buf->p = nullptr;
             buf->cap = 0;
@@ -867,7 +881,7 @@ struct Stager {
         if (!host || ptr == nullptr) return PMCTS_OK;
         const size_t bytes = count * sizeof(T);
         void *d = carve(bytes);
-        CUDA_TRY(cudaMemcpyAsync(d, (const void *)ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d, (const void *)ptr, bytes, cudaMemcpyHostToDevice, in_stream));
         if (also_out) outs.push_back({(void *)ptr, d, bytes});
         ptr = (T *)d;
         return PMCTS_OK;
@@ -1024,6 +1038,14 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     if (ctx->stage.p) cudaFree(ctx->stage.p);
     for (auto &d : ctx->defer)
         if (d.stage.p) cudaFree(d.stage.p);
+    if (ctx->in_stream) cudaStreamSynchronize(ctx->in_stream);
+    for (auto &d : ctx->step_defer) {
+        if (d.stage.p) cudaFree(d.stage.p);
+        if (d.in_done) cudaEventDestroy(d.in_done);
+        if (d.main_done) cudaEventDestroy(d.main_done);
+        if (d.out_done) cudaEventDestroy(d.out_done);
+    }
+    if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);
     if (ctx->work) cudaFree(ctx->work);
     if (ctx->head_buf) cudaFree(ctx->head_buf);
     for (auto &d : ctx->defer) {
@@ -1053,6 +1075,7 @@ int pmcts_reset_stream(pmcts_ctx *ctx) {
 int pmcts_synchronize(pmcts_ctx *ctx) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
     DeviceGuard g(ctx->device);
+    if (ctx->in_stream) CUDA_TRY(cudaStreamSynchronize(ctx->in_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
     return PMCTS_OK;
@@ -1415,7 +1438,26 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
     const size_t nseg = ((size_t)nsteps + seg_len - 1) / seg_len;
     const bool actions = (flags & PMCTS_STEP_HEADING_ACTIONS) != 0;
     const uint8_t *heading8 = actions ? reinterpret_cast<const uint8_t *>(heading) : nullptr;
-    Stager st(ctx, flags & PMCTS_MEM_HOST);
+    // PMCTS_STEP_DEFER with host arrays: three-stage pipeline over consecutive calls (see pmcts_ctx::StepDeferred)
+    const bool defer = (flags & PMCTS_STEP_DEFER) && (flags & PMCTS_MEM_HOST);
+    pmcts_ctx::StepDeferred *slot = nullptr;
+    if (defer) {
+        slot = &ctx->step_defer[ctx->step_seq & 1];
+        if (!ctx->in_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
+        if (!ctx->side_stream) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        }
+        if (!slot->in_done) {
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->in_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&slot->out_done, cudaEventDisableTiming));
+        }
+        // the call that staged in this buffer two calls ago must have copied its results out
+        if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->in_stream, slot->out_done, 0));
+    }
+    Stager st(ctx, flags & PMCTS_MEM_HOST, slot ? &slot->stage : nullptr, slot ? ctx->in_stream : nullptr);
     rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(nseg * n * (actions ? 1 : 8)) + al(n) +
                     (nz.mode == PMCTS_NOISE_INJECTED ? al((size_t)nsteps * n * 8) : 0) +
                     (traj_lat ? al((size_t)nsteps * n * 8) : 0) + (traj_lon ? al((size_t)nsteps * n * 8) : 0));
@@ -1426,6 +1468,10 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         (rc = st.out(traj_lat, (size_t)nsteps * n, 0xFF)) || (rc = st.out(traj_lon, (size_t)nsteps * n, 0xFF)))
         return rc;
     if (nz.mode == PMCTS_NOISE_INJECTED && (rc = st.in(nz.z, (size_t)nsteps * n))) return rc;
+    if (defer) {
+        CUDA_TRY(cudaEventRecord(slot->in_done, ctx->in_stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->in_done, 0));
+    }
     if (actions) {
         const size_t count = nseg * (size_t)n;
         if (count > ctx->head_cap) {
@@ -1502,6 +1548,16 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
             traj_lat, traj_lon, flags, nullptr, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
+    if (defer) {
+        CUDA_TRY(cudaEventRecord(slot->main_done, ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->side_stream, slot->main_done, 0));
+        if ((rc = st.copy_back(ctx->side_stream))) return rc;
+        CUDA_TRY(cudaEventRecord(slot->out_done, ctx->side_stream));
+        slot->pending = true;
+        slot->used = true;
+        slot->seq = ctx->step_seq++;
+        return PMCTS_OK;
+    }
     return st.finish();
 }
 
@@ -1715,6 +1771,12 @@ int pmcts_wait(pmcts_ctx *ctx, int keep_last) {
     for (auto &d : ctx->defer) {
         if (d.pending && d.seq + (uint64_t)keep_last < ctx->defer_seq) {
             CUDA_TRY(cudaEventSynchronize(d.redo_done));
+            d.pending = false;
+        }
+    }
+    for (auto &d : ctx->step_defer) {
+        if (d.pending && d.seq + (uint64_t)keep_last < ctx->step_seq) {
+            CUDA_TRY(cudaEventSynchronize(d.out_done));
             d.pending = false;
         }
     }

@@ -51,6 +51,11 @@ typedef struct pmcts_ctx pmcts_ctx;
 #define PMCTS_STEP_HEADING_ACTIONS 0x2      /* step_batch: `heading` points to uint8_t[nseg][n] action indices instead of
                                                fp64 degrees: heading = 45 a degrees, the reference's ACTIONS
                                                (simulatorTLKT.py:29) -- an eighth of the bytes for a host caller */
+#define PMCTS_STEP_DEFER 0x4                /* step_batch with PMCTS_MEM_HOST: the call returns once its work is enqueued;
+                                               copies in, kernel and copies out run on three streams, so the stages of
+                                               consecutive calls overlap.  Results are in the caller's arrays after
+                                               pmcts_wait (or pmcts_synchronize); the arrays must stay alive until
+                                               then.  Two calls may be in flight. */
 #define PMCTS_ROLL_REPLAY_FULL_PREFIX 0x2   /* rollout_batch: replay the whole prefix (fixes quirk Q1, worker.py:297) */
 #define PMCTS_ROLL_PLAN_EVAL 0x4            /* rollout_batch: estimate_perfomance_plan semantics (isochrones.py:498-530) */
 #define PMCTS_ROLL_ACCUMULATE 0x8           /* rollout_batch, device arrays only: add to leaf_bins / stats instead of zeroing them first */
@@ -94,7 +99,8 @@ int pmcts_synchronize(pmcts_ctx *ctx);
  * most recent launches: work enqueued on the stream afterwards sees their complete outputs. */
 int pmcts_join(pmcts_ctx *ctx, int keep_last);
 /* Blocks the calling thread until the deferred launches (PMCTS_ROLL_DEFER_REDO) of all but the `keep_last` most
- * recent calls are complete, copies into host arrays included. */
+ * recent calls are complete, copies into host arrays included (rollout and PMCTS_STEP_DEFER step calls are counted
+ * separately). */
 int pmcts_wait(pmcts_ctx *ctx, int keep_last);
 int pmcts_set_precision(pmcts_ctx *ctx, int mode);
 /* Decision margins of PMCTS_PREC_FAST (a negative value keeps the current one; all negative restores

@@ -538,6 +538,49 @@ def test_deferred_host_arrays_and_wait(eng):
         eng.set_precision(N.PREC_F64)
 
 
+def test_deferred_step_batch_pipeline(eng):
+    """PMCTS_STEP_DEFER: copies in, kernel and copies out of consecutive host-array calls overlap; after pmcts_wait
+    every call's arrays hold what the synchronous call returns (five calls, two in flight, both staging buffers
+    reused), for fp64 and action-index headings."""
+    import torch
+    eng.set_precision(N.PREC_FAST)
+    times = np.linspace(0, 5, 101)
+    upload(eng, 3, 1, times=times)
+    n, nsteps = 20000, 80
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=5)
+    acts = ((h0[None, :] + np.arange(4)[:, None]) % 8).astype(np.uint8)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True).numpy()
+        t[...] = a
+        return t
+
+    try:
+        for head in (45.0 * acts.astype(np.float64), acts):
+            want = []
+            for c in range(5):
+                k, st, lat, lon = np.zeros(n, np.int32), np.zeros(n, np.uint8), lat0 + 0.01 * c, lon0.copy()
+                eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=20, status=st, seed=9, stream=c)
+                want.append((k, st, lat, lon))
+            got, hp = [], pinned(head)
+            for c in range(5):
+                arrs = (pinned(np.zeros(n, np.int32)), pinned(np.zeros(n, np.uint8)), pinned(lat0 + 0.01 * c), pinned(lon0))
+                eng.step_batch(3, arrs[0], arrs[2], arrs[3], hp, nsteps=nsteps, seg_len=20, status=arrs[1], seed=9,
+                               stream=c, flags=N.STEP_DEFER)
+                got.append(arrs)
+                eng.wait(keep_last=1)
+                if c:
+                    for a, b in zip(got[c - 1], want[c - 1]):
+                        assert np.array_equal(a, b)
+            eng.wait()
+            for g, w in zip(got, want):
+                for a, b in zip(g, w):
+                    assert np.array_equal(a, b)
+            assert (want[0][0] == nsteps).all()
+    finally:
+        eng.set_precision(N.PREC_F64)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_other_hemisphere_and_grid(eng, mode):
     """Southern hemisphere, negative longitudes, 0.25-degree grid, hourly weather, 2-hour steps, arbitrary
