@@ -13,7 +13,8 @@
  *  - array arguments are DEVICE pointers and the call returns without synchronising, unless
  *    PMCTS_MEM_HOST is set in `flags`: then every array argument is HOST memory (pinned or
  *    pageable), the library stages it through device scratch and the call returns after the
- *    results are back in the caller's arrays;
+ *    results are back in the caller's arrays (or, with PMCTS_ROLL_DEFER_REDO / PMCTS_STEP_DEFER, as
+ *    soon as its work is enqueued: see pmcts_wait);
  *  - optional outputs may be NULL;
  *  - there is no CPU fallback: without a CUDA device pmcts_create fails.
  */
