@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <algorithm>
@@ -59,14 +60,20 @@ void parallel_for(int n, int64_t work, F &&fn) {
         return;
     }
     std::atomic<int> next{0};
+    std::atomic<bool> failed{false};
     auto body = [&]() {
-        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        try {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        } catch (...) {  // (allocation failure while a tree grows): reported by the caller, never thrown across a thread
+            failed.store(true);
+        }
     };
     std::vector<std::thread> th;
     th.reserve(nt - 1);
     for (int t = 1; t < nt; ++t) th.emplace_back(body);
     body();
     for (auto &x : th) x.join();
+    if (failed.load()) throw std::bad_alloc();
 }
 
 // (visit count, max over actions of the binned mean) of one node's 8 x 12 counters
@@ -291,7 +298,7 @@ int pmcts_forest_set_coefficients(pmcts_forest *f, double uct_coeff, double rho)
 }
 
 int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_t *leaf_node,
-                        int32_t *prefix_len, int8_t *prefix_act) {
+                        int32_t *prefix_len, int8_t *prefix_act) try {
     if (!f || !leaf_node || !prefix_len || !prefix_act) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n_leaves < 1 || prefix_stride < f->max_depth) return fail(PMCTS_ERR_ARG, "prefix_stride must hold max_depth actions");
     std::atomic<int> exhausted{0};
@@ -318,6 +325,8 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
     });
     if (exhausted.load()) return fail(PMCTS_ERR_ARG, "tree capacity (max_nodes) exhausted");
     return PMCTS_OK;
+} catch (const std::bad_alloc &) {
+    return fail(PMCTS_ERR_ARG, "out of host memory");
 }
 
 int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) {
