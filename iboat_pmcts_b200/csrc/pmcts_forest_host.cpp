@@ -329,7 +329,7 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
     return fail(PMCTS_ERR_ARG, "out of host memory");
 }
 
-int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) {
+int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) try {
     if (!f || !leaf_bins || !slots) return fail(PMCTS_ERR_ARG, "NULL argument");
     for (int i = 0; i < f->n_local; ++i)
         if ((int)f->trees[i].wave_leaves.size() != n_leaves)
@@ -351,11 +351,13 @@ int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins
         t.wave_leaves.clear();
     });
     return PMCTS_OK;
+} catch (const std::bad_alloc &) {
+    return fail(PMCTS_ERR_ARG, "out of host memory");
 }
 
 int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t *scen_ids, int n_leaves,
                               int prefix_stride, const int32_t *prefix_len, const int8_t *prefix_act,
-                              const int8_t *slots, const uint32_t *leaf_bins) {
+                              const int8_t *slots, const uint32_t *leaf_bins) try {
     if (!f || !scen_ids || !prefix_len || !prefix_act || !slots || !leaf_bins) return fail(PMCTS_ERR_ARG, "NULL argument");
     Master &m = f->master;
     std::vector<uint8_t> seen(f->n_scen, 0);
@@ -389,6 +391,8 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
         for (int i = 0; i < n_blocks_scen; ++i) apply_block(i);
     f->wave += 1;  // the master changed: its UCT values are recomputed on next use
     return PMCTS_OK;
+} catch (const std::bad_alloc &) {
+    return fail(PMCTS_ERR_ARG, "out of host memory");
 }
 
 int64_t pmcts_forest_tree_size(pmcts_forest *f, int local_index) {
