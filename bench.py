@@ -420,7 +420,7 @@ def main():
                     roofline=roofline)
         if b2b:
             line["back_to_back"] = b2b
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # (the CPU leg is timed at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
     if world > 1:
