@@ -415,7 +415,9 @@ def main():
                     rollouts_per_s=rollouts / (dev_ms * 1e-3) if rollouts else None,
                     config=workload_config(args.workload, world), precision_mode="f64" if prec == N.PREC_F64 else "fast",
                     e2e=dict(value=e2e_tr / e2e_s, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST")),
+                             steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST"),
+                             note="every rank times its own host-array calls (no L2 flush, no all-gather / back-up in "
+                                  "this leg); max time over ranks, transitions summed"),
                     gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, finisher_kernel_ms=fin_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
                     roofline=roofline)
         if b2b:
