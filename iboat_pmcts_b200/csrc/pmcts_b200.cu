@@ -400,7 +400,8 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
 // kernel above finishes it (same stream, next launch).  kNoise fixes the noise source at compile time;
 // kLean is the throughput form: per-leaf histograms and statistics only, no per-rollout outputs.
 template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
-__global__ void __launch_bounds__(kBlock, kLean ? 8 : 6)  // lean: 64 registers, 8 blocks per SM
+// (turbo: a cap of 73 registers lets ptxas keep the pinned constants below; it uses 64, so 8 blocks per SM stay resident)
+__global__ void __launch_bounds__(kBlock, kLean ? (kTurbo ? 7 : 8) : 6)  // lean: 64 registers, 8 blocks per SM
 rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
     const int64_t n = a.n_leaf * a.replicas;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,6 +414,18 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
     bool counted = false;
     // n < 2^28 (the work-list entries hold the rollout id in 28 bits): a 32-bit division, done once
     const int64_t leaf = (int64_t)((uint32_t)r / (uint32_t)a.replicas);
+    if (kTurbo) {
+        // The loop's scalar constants as opaque register values: ptxas otherwise re-loads them from the constant bank
+        // at every step (17 of the 316 instructions of a step).  Twelve registers; the kernel still fits 64.
+#define PIN_I(x) asm volatile("" : "+r"(x))
+#define PIN_F(x) asm volatile("" : "+f"(x))
+        PIN_I(sc.nlon); PIN_I(sc.slab32_stride); PIN_I(sc.nT);
+        PIN_F(sc.dt_uniform32); PIN_F(sc.box_margin_scale);
+        PIN_F(sc.box_fa_lo); PIN_F(sc.box_fa_hi); PIN_F(sc.box_fo_lo); PIN_F(sc.box_fo_hi);
+        PIN_F(bp.sigma_f); PIN_F(a.sin_dest_lat); PIN_F(a.cos_dest_lat);
+#undef PIN_I
+#undef PIN_F
+    }
     if (live) {
         fast::rollout_one<kNoise, kLean, kDefBoat, kTurbo>(sc, bp, nz, a, n, r, leaf, o);
         if (o.why) {
