@@ -220,9 +220,12 @@ constexpr int kRedoShift = 28;
 // MATCH; the lowest lane of each group adds the group's size to leaf_bins[leaf][bin].
 // `a` is the lane's own (scenario-offset) argument block; with kUniform every lane of the warp belongs
 // to the same scenario (the stats of a warp go to one place), otherwise lanes add their own.
+// Every lane of the warp calls this (converged) -- lanes without a rollout pass counted = false -- so the warp
+// primitives run with the full mask, as PTX requires of every lane that executes them.
 template <bool kUniform>
-__device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned warp_mask, bool counted, int scen,
+__device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, bool counted, int scen,
                                                 int64_t leaf, int bin, int st, int nstep, double ta) {
+    constexpr unsigned warp_mask = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     if (a.leaf_bins) {
         const unsigned long long key =
@@ -255,7 +258,7 @@ __device__ __forceinline__ void reduce_rollouts(const RolloutArgs &a, unsigned w
             s1 += __shfl_xor_sync(warp_mask, s1, off);
             s2 += __shfl_xor_sync(warp_mask, s2, off);
         }
-        if (lane == __ffs(warp_mask) - 1) {
+        if (lane == 0) {
             if (c_t) {
                 atomicAdd(&stats[0], (double)c_t);
                 atomicAdd(&stats[1], s1);
@@ -304,7 +307,6 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
     NoiseView nz = nz0;
     RolloutArgs a = a0;
     select_scenario(scen, n, fs, sc, nz, a);
-    const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     int bin = 0, st = PMCTS_ST_OK, nstep_out = 0;
     int64_t leaf = 0;
     double ta = NAN, rw = 0.0;
@@ -390,8 +392,8 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
         if (a.final_lat) a.final_lat[r] = blat;
         if (a.final_lon) a.final_lon[r] = blon;
     }
-    if (a0.work_list) reduce_rollouts<false>(a, warp_mask, live, scen, leaf, bin, st, nstep_out, ta);
-    else reduce_rollouts<true>(a, warp_mask, live, scen, leaf, bin, st, nstep_out, ta);
+    if (a0.work_list) reduce_rollouts<false>(a, live, scen, leaf, bin, st, nstep_out, ta);
+    else reduce_rollouts<true>(a, live, scen, leaf, bin, st, nstep_out, ta);
     }
 }
 
@@ -408,7 +410,6 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
     const int scen = blockIdx.y;
     select_scenario<kLean>(scen, n, fs, sc, nz, a);
     const bool live = r < n;
-    const unsigned warp_mask = __ballot_sync(0xffffffffu, live);
     fast::RollOut o;
     o.st = PMCTS_ST_OK; o.nstep = 0; o.bin = 0; o.why = 0; o.ta = NAN;
     bool counted = false;
@@ -444,7 +445,7 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
             }
         }
     }
-    reduce_rollouts<true>(a, warp_mask, counted, scen, leaf, o.bin, o.st, o.nstep, o.ta);
+    reduce_rollouts<true>(a, counted, scen, leaf, o.bin, o.st, o.nstep, o.ta);
 }
 
 // K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
@@ -823,7 +824,10 @@ struct pmcts_ctx {
     std::vector<Timed> timed;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
     double timed_ms[5] = {0, 0, 0, 0, 0};  // per PMCTS_KERNEL_* kind
-    std::mutex mu;
+    // Every entry point that takes a ctx holds this lock for its duration: calls on one ctx from several host
+    // threads are serialised (they are stream-ordered anyway); recursive because upload frees the slot it replaces.
+    std::recursive_mutex mu;
+    Deferred *last_fast = nullptr;  // work area of the last mixed-precision rollout launch when it was a deferred one
 };
 
 namespace {
@@ -838,6 +842,8 @@ const double kFitVelocity[36] = {
 
 struct DeviceGuard {
     int prev = -1;
+    std::unique_lock<std::recursive_mutex> lock;
+    explicit DeviceGuard(pmcts_ctx *ctx) : DeviceGuard(ctx->device) { lock = std::unique_lock<std::recursive_mutex>(ctx->mu); }
     explicit DeviceGuard(int dev) {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
@@ -1044,7 +1050,7 @@ int pmcts_create(int device, pmcts_ctx **out) {
 
 void pmcts_destroy(pmcts_ctx *ctx) {
     if (!ctx) return;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx->device);  // (no lock: the caller must not use a ctx it is destroying)
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
@@ -1075,19 +1081,21 @@ void pmcts_destroy(pmcts_ctx *ctx) {
 
 int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ctx->stream = (cudaStream_t)cuda_stream;
     return PMCTS_OK;
 }
 
 int pmcts_reset_stream(pmcts_ctx *ctx) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ctx->stream = ctx->own_stream;
     return PMCTS_OK;
 }
 
 int pmcts_synchronize(pmcts_ctx *ctx) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     if (ctx->in_stream) CUDA_TRY(cudaStreamSynchronize(ctx->in_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
@@ -1096,6 +1104,7 @@ int pmcts_synchronize(pmcts_ctx *ctx) {
 
 int pmcts_set_precision(pmcts_ctx *ctx, int mode) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (mode != PMCTS_PREC_F64 && mode != PMCTS_PREC_FAST) return fail(PMCTS_ERR_ARG, "unknown precision mode %d", mode);
     ctx->precision = mode;
     return PMCTS_OK;
@@ -1107,6 +1116,7 @@ int pmcts_last_kernel_variant(pmcts_ctx *ctx) { return ctx ? ctx->last_variant :
 
 int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (option == PMCTS_OPT_STAGE_SLABS) {
         ctx->stage_slabs = value != 0;
         return PMCTS_OK;
@@ -1116,7 +1126,7 @@ int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
 
 int pmcts_probe_fp32_peak(pmcts_ctx *ctx, double *tflops) {
     if (!ctx || !tflops) return fail(PMCTS_ERR_ARG, "NULL argument");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
     float *out = nullptr;
@@ -1146,6 +1156,7 @@ int pmcts_probe_fp32_peak(pmcts_ctx *ctx, double *tflops) {
 
 int pmcts_enable_timing(pmcts_ctx *ctx, int on) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     ctx->timing = on != 0;
     return PMCTS_OK;
 }
@@ -1163,7 +1174,7 @@ static void drain_timers(pmcts_ctx *ctx) {
 
 double pmcts_kernel_ms(pmcts_ctx *ctx, int kind, int reset) {
     if (!ctx || kind < 0 || kind > 4) return -1.0;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     drain_timers(ctx);
     const double r = ctx->timed_ms[kind];
     if (reset) ctx->timed_ms[kind] = 0.0;
@@ -1180,6 +1191,7 @@ double pmcts_kernel_ms_total(pmcts_ctx *ctx, int reset) {
 int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, double pofsail_min,
                      double pofsail_max, double sigma_coeff, double dest_angle, double earth_radius) {
     if (!ctx || !polar) return fail(PMCTS_ERR_ARG, "NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     BoatParams &p = ctx->params;
     for (int i = 0; i < 36; ++i) p.polar[i] = polar[i];
     p.wind_max = wind_max;
@@ -1197,6 +1209,7 @@ int pmcts_set_params(pmcts_ctx *ctx, const double polar[36], double wind_max, do
 
 int pmcts_set_fast_margins(pmcts_ctx *ctx, double angle, double along, double near_miss2, double box, double bin) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     BoatParams &p = ctx->params;
     if (angle < 0 && along < 0 && near_miss2 < 0 && box < 0 && bin < 0) {
         default_fast_margins(p);
@@ -1213,20 +1226,26 @@ int pmcts_set_fast_margins(pmcts_ctx *ctx, double angle, double along, double ne
 }
 
 int64_t pmcts_last_redo_count(pmcts_ctx *ctx) {
-    if (!ctx || !ctx->work) return 0;
-    DeviceGuard g(ctx->device);
+    if (!ctx) return 0;
+    DeviceGuard g(ctx);
+    const char *work = ctx->last_fast ? ctx->last_fast->work : ctx->work;  // a deferred launch counts in its slot
+    if (!work) return 0;
     uint32_t c = 0;
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-    if (cudaMemcpy(&c, ctx->work, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (ctx->side_stream && cudaStreamSynchronize(ctx->side_stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&c, work, sizeof c, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int64_t)c;
 }
 
 int pmcts_scenario_free(pmcts_ctx *ctx, int scen) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     auto it = ctx->scenarios.find(scen);
     if (it == ctx->scenarios.end()) return PMCTS_OK;
+    // deferred finishers (side stream) and pipelined copies (in stream) may still read the slabs
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->side_stream) CUDA_TRY(cudaStreamSynchronize(ctx->side_stream));
+    if (ctx->in_stream) CUDA_TRY(cudaStreamSynchronize(ctx->in_stream));
     CUDA_TRY(cudaFree(it->second.blob));
     ctx->scenarios.erase(it);
     return PMCTS_OK;
@@ -1246,7 +1265,7 @@ int pmcts_scenario_upload(pmcts_ctx *ctx, int scen, const double *wtime, int nt,
         return fail(PMCTS_ERR_AXIS, "latitude / longitude axes must be ascending and uniformly spaced");
     for (int i = 1; i < nt; ++i)
         if (!(wtime[i] > wtime[i - 1])) return fail(PMCTS_ERR_AXIS, "weather time axis must be strictly ascending");
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     int rc = pmcts_scenario_free(ctx, scen);
     if (rc) return rc;
 
@@ -1387,7 +1406,7 @@ int pmcts_get_wind(pmcts_ctx *ctx, int scen, int64_t n, const int32_t *k, const 
                    const double *lon, double *u, double *v, uint8_t *status, int flags) {
     if (!ctx || !k || !lat || !lon || !u || !v) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n <= 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     Scenario *sc;
     int rc = find_scenario(ctx, scen, &sc);
     if (rc) return rc;
@@ -1409,7 +1428,7 @@ int pmcts_interp_wind(pmcts_ctx *ctx, int scen, int64_t n, const double *t, cons
                       double *u, double *v, uint8_t *status, int flags) {
     if (!ctx || !t || !lat || !lon || !u || !v) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n <= 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     Scenario *sc;
     int rc = find_scenario(ctx, scen, &sc, false);
     if (rc) return rc;
@@ -1442,7 +1461,7 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
     if (!ctx || !k || !lat || !lon || !heading) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n < 0 || nsteps < 0 || seg_len < 1) return fail(PMCTS_ERR_ARG, "bad sizes");
     if (n == 0 || nsteps == 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     Scenario *sc;
     int rc = find_scenario(ctx, scen, &sc);
     if (rc) return rc;
@@ -1467,8 +1486,13 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
             CUDA_TRY(cudaEventCreateWithFlags(&slot->main_done, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&slot->out_done, cudaEventDisableTiming));
         }
-        // the call that staged in this buffer two calls ago must have copied its results out
-        if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->in_stream, slot->out_done, 0));
+        // the call that staged in this buffer two calls ago must have copied its results out before anything of this
+        // call touches the buffer: the copies in (in_stream) and the fills of the trajectory outputs, which the
+        // Stager enqueues on the ctx stream
+        if (slot->used) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->in_stream, slot->out_done, 0));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->out_done, 0));
+        }
     }
     Stager st(ctx, flags & PMCTS_MEM_HOST, slot ? &slot->stage : nullptr, slot ? ctx->in_stream : nullptr);
     rc = st.reserve(al(n * 4) + 4 * al(n * 8) + al(nseg * n * (actions ? 1 : 8)) + al(n) +
@@ -1506,6 +1530,7 @@ int pmcts_step_batch(pmcts_ctx *ctx, int scen, int64_t n, int nsteps, int32_t *k
         if ((rc = ensure_work(ctx, o_status + al(n)))) return rc;
         uint32_t *any_resume = (uint32_t *)ctx->work;
         int32_t *j_resume = (int32_t *)(ctx->work + 256);
+        ctx->last_fast = nullptr;
         uint8_t *status_dev = status;
         CUDA_TRY(cudaMemsetAsync(any_resume, 0, sizeof(uint32_t), ctx->stream));
         if (!status_dev) {
@@ -1585,7 +1610,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     if (n_leaf < 0 || replicas < 1 || prefix_stride < 0 || traj_stride < 0) return fail(PMCTS_ERR_ARG, "bad sizes");
     if ((prefix == nullptr) != (prefix_len == nullptr)) return fail(PMCTS_ERR_ARG, "prefix and prefix_len go together");
     if (n_leaf == 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     Scenario *sc;
     int rc = find_scenario(ctx, scens[0], &sc);
     if (rc) return rc;
@@ -1712,6 +1737,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         fast::prepare_rollout(vw, a);
         a.redo_count = (uint32_t *)work;
         a.redo_list = (uint32_t *)(work + 256 + part_bytes);
+        ctx->last_fast = slot;  // (NULL for a launch that counts in ctx->work)
         if (!stats) CUDA_TRY(cudaMemsetAsync(a.redo_count, 0, sizeof(uint32_t), ctx->stream));
         {
             LaunchTimer lt(ctx, PMCTS_KERNEL_ROLLOUT);
@@ -1780,7 +1806,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
 int pmcts_wait(pmcts_ctx *ctx, int keep_last) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
     if (keep_last < 0) keep_last = 0;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     for (auto &d : ctx->defer) {
         if (d.pending && d.seq + (uint64_t)keep_last < ctx->defer_seq) {
             CUDA_TRY(cudaEventSynchronize(d.redo_done));
@@ -1799,7 +1825,7 @@ int pmcts_wait(pmcts_ctx *ctx, int keep_last) {
 int pmcts_join(pmcts_ctx *ctx, int keep_last) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
     if (keep_last < 0) keep_last = 0;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     for (auto &d : ctx->defer) {
         if (d.pending && d.seq + (uint64_t)keep_last < ctx->defer_seq) {
             CUDA_TRY(cudaStreamWaitEvent(ctx->stream, d.redo_done, 0));
@@ -1840,7 +1866,7 @@ int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, c
     if (flags & PMCTS_MEM_HOST) return fail(PMCTS_ERR_ARG, "pmcts_backup works on a device-resident table");
     if (n_scen < 1 || n_scen > 65535 || n_nodes < 1) return fail(PMCTS_ERR_ARG, "bad sizes");
     if (n_leaf <= 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     {
         LaunchTimer lt(ctx, PMCTS_KERNEL_BACKUP);
         dim3 grid(grid_for(n_leaf * 12), n_scen);
@@ -1855,7 +1881,7 @@ int pmcts_hist_stats(pmcts_ctx *ctx, const uint32_t *table, int64_t n_nodes, dou
                      uint32_t *visits, int flags) {
     if (!ctx || !table) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n_nodes <= 0) return PMCTS_OK;
-    DeviceGuard g(ctx->device);
+    DeviceGuard g(ctx);
     Stager st(ctx, flags & PMCTS_MEM_HOST);
     int rc = st.reserve(al(n_nodes * 96 * 4) + al(n_nodes * 8 * 8) + al(n_nodes * 4));
     if (rc) return rc;

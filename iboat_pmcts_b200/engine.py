@@ -87,6 +87,7 @@ class Engine:
         N.check(self._lib.pmcts_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._nT = {}  # simulator instants per scenario slot (size of an injected-noise array)
         self.set_precision(precision)
 
     def close(self):
@@ -182,6 +183,7 @@ class Engine:
                 self._h, int(scen), wtime.ctypes.data, wtime.size, wlat.ctypes.data, wlat.size,
                 wlon.ctypes.data, wlon.size, u.ctypes.data, v.ctypes.data, 1 if dt == np.float32 else 0,
                 None, 0, None))
+            self._nT[int(scen)] = 0
             return
         sim_times = np.ascontiguousarray(sim_times, np.float64)
         box = np.ascontiguousarray(box, np.float64).reshape(4)
@@ -189,9 +191,16 @@ class Engine:
             self._h, int(scen), wtime.ctypes.data, wtime.size, wlat.ctypes.data, wlat.size,
             wlon.ctypes.data, wlon.size, u.ctypes.data, v.ctypes.data, 1 if dt == np.float32 else 0,
             sim_times.ctypes.data, sim_times.size, box.ctypes.data))
+        self._nT[int(scen)] = int(sim_times.size)
 
     def free_scenario(self, scen):
         N.check(self._lib.pmcts_scenario_free(self._h, int(scen)))
+        self._nT.pop(int(scen), None)
+
+    def _z_size(self, scen, n_scen, n):
+        """Elements the library reads from an injected-noise array: z[n_scen][nT][n] (one row per simulator
+        instant, not per step made)."""
+        return n_scen * self._nT.get(int(scen), 0) * n
 
     def get_wind(self, scen, k, lat, lon):
         """Simulator.getWind for arrays of query points (host arrays in, host arrays out)."""
@@ -241,7 +250,8 @@ class Engine:
     def rollout_batch(self, scen, n_leaf, replicas, root, dest, tmin, prefix=None, prefix_len=None,
                       prefix_stride=0, z=None, seed=None, stream=0, id0=0, out=None, traj_stride=0, flags=0):
         """Batched default-policy rollouts.  ``out`` maps output names (reward, t_arr, steps, status,
-        bin, frac, final_lat, final_lon, traj_lat, traj_lon, leaf_bins, stats) to preallocated arrays."""
+        bin, frac, final_lat, final_lon, traj_lat, traj_lon, leaf_bins, stats) to preallocated arrays.
+        Injected noise ``z`` has shape [len(times)][n] (a row per simulator instant; ValueError if shorter)."""
         out = out or {}
         a = _Args()
         n = int(n_leaf) * int(replicas)
@@ -255,7 +265,7 @@ class Engine:
                 g("traj_lat", "f64", traj_stride * n), g("traj_lon", "f64", traj_stride * n)]
         plb = g("leaf_bins", "u32", n_leaf * 12)
         pstats = g("stats", "f64", 8)
-        nz = make_noise(a, z, seed, stream, id0)
+        nz = make_noise(a, z, seed, stream, id0, self._z_size(scen, 1, n))
         N.check(self._lib.pmcts_rollout_batch(self._h, int(scen), int(n_leaf), int(replicas), root.ctypes.data,
                                               dest.ctypes.data, float(tmin), ppre, plen, int(prefix_stride),
                                               C.byref(nz), *ptrs, int(traj_stride), plb, pstats,
@@ -280,7 +290,7 @@ class Engine:
         ptrs = [g("reward", "f64", S * n), g("t_arr", "f64", S * n), g("steps", "i32", S * n),
                 g("status", "u8", S * n), g("bin", "i32", S * n), g("leaf_bins", "u32", S * n_leaf * 12),
                 g("stats", "f64", S * 8)]
-        nz = make_noise(a, z, seed, stream, id0)
+        nz = make_noise(a, z, seed, stream, id0, self._z_size(scens[0], S, n) if S else 0)
         N.check(self._lib.pmcts_rollout_forest(self._h, S, scens.ctypes.data, int(n_leaf), int(replicas),
                                                root.ctypes.data, dest.ctypes.data, float(tmin), ppre, plen,
                                                int(prefix_stride), int(bool(prefix_shared)), C.byref(nz), *ptrs,

@@ -76,8 +76,16 @@ class Weather:
         return d
 
     def _fingerprint(self):
+        """Key of the device copy: identity and shape of the fields, the time axis ends, and a checksum of a
+        strided sample of u / v (at most 4096 values each), so that an in-place edit of the fields is seen
+        without hashing a global grid on every call."""
+        u, v = np.asarray(self.u), np.asarray(self.v)
+        su, sv = u.reshape(-1), v.reshape(-1)
+        step = max(1, su.size // 4096)
+        check = (float(np.ma.filled(su[::step], 0.0).sum(dtype=np.float64)),
+                 float(np.ma.filled(sv[::step], 0.0).sum(dtype=np.float64)))
         return (id(self.u), id(self.v), float(np.asarray(self.time)[0]), float(np.asarray(self.time)[-1]),
-                np.shape(self.u))
+                np.shape(self.u), check)
 
     def _weather_slot(self):
         key = self._fingerprint()

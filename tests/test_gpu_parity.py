@@ -581,6 +581,57 @@ def test_deferred_step_batch_pipeline(eng):
         eng.set_precision(N.PREC_F64)
 
 
+def test_deferred_step_batch_with_trajectories(eng):
+    """PMCTS_STEP_DEFER with trajectory outputs over six pipelined calls: the NaN fill of call i + 2 must not land in
+    a staging buffer whose copy back for call i is still running (each call's trajectories equal the synchronous
+    call's, NaN pattern included)."""
+    import torch
+    eng.set_precision(N.PREC_FAST)
+    times = np.linspace(0, 5, 101)
+    upload(eng, 3, 1, times=times)
+    n, nsteps = 60000, 40
+    lat0, lon0, h0 = synth.octagon_fleet(n, seed=6)
+    head = 45.0 * ((h0[None, :] + np.arange(2)[:, None]) % 8).astype(np.float64)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True).numpy()
+        t[...] = a
+        return t
+
+    try:
+        want = []
+        for c in range(6):
+            k, st, lat, lon = np.full(n, 70, np.int32), np.zeros(n, np.uint8), lat0 + 0.01 * c, lon0.copy()
+            tl, to = np.empty((nsteps, n)), np.empty((nsteps, n))
+            eng.step_batch(3, k, lat, lon, head, nsteps=nsteps, seg_len=20, status=st, seed=9, stream=c,
+                           traj_lat=tl, traj_lon=to)
+            want.append((k, st, lat, lon, tl, to))
+        assert np.isnan(want[0][4][-1]).all() and not np.isnan(want[0][4][0]).any()  # boats stop at the horizon (k = 100)
+        got, hp = [], pinned(head)
+        for c in range(6):
+            arrs = (pinned(np.full(n, 70, np.int32)), pinned(np.zeros(n, np.uint8)), pinned(lat0 + 0.01 * c),
+                    pinned(lon0), pinned(np.zeros((nsteps, n))), pinned(np.zeros((nsteps, n))))
+            eng.step_batch(3, arrs[0], arrs[2], arrs[3], hp, nsteps=nsteps, seg_len=20, status=arrs[1], seed=9,
+                           stream=c, traj_lat=arrs[4], traj_lon=arrs[5], flags=N.STEP_DEFER)
+            got.append(arrs)
+        eng.wait()
+        for g, w in zip(got, want):
+            for a, b in zip(g, w):
+                assert np.array_equal(a, b, equal_nan=True)
+    finally:
+        eng.set_precision(N.PREC_F64)
+
+
+def test_injected_noise_must_cover_every_instant(eng):
+    """z is [len(times)][n]: a shorter array (sized to the steps made, say) is refused instead of being read past
+    its end."""
+    upload(eng, 0, 0)
+    nT = len(H.sim_axes(*synth.wind_fields(0)[1:3])[0])
+    z = np.zeros((nT - 1, 8))
+    with pytest.raises(ValueError):
+        eng.rollout_batch_host(0, 8, 1, H.STATE0, [46.7, 355.0], 2.0, prefix=np.zeros((8, 1)), z=z)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_other_hemisphere_and_grid(eng, mode):
     """Southern hemisphere, negative longitudes, 0.25-degree grid, hourly weather, 2-hour steps, arbitrary
