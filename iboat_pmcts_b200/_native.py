@@ -19,6 +19,7 @@ ROLL_REPLAY_FULL_PREFIX = 0x2
 ROLL_PLAN_EVAL = 0x4
 ROLL_ACCUMULATE = 0x8
 ROLL_DEFER_REDO = 0x10
+ROLL_PREFIX_ACTIONS = 0x20
 OPT_STAGE_SLABS = 1
 VARIANT_LITERAL, VARIANT_FULL_OUTPUT, VARIANT_GENERIC, VARIANT_DEFAULT_BOAT, VARIANT_TURBO, VARIANT_STAGED = range(6)
 MEM_HOST = 0x100
@@ -29,18 +30,47 @@ ERR_NO_DEVICE = -3
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
+    "pmcts_get_stream", "pmcts_get_device", "pmcts_comm_unique_id", "pmcts_comm_create", "pmcts_comm_destroy",
+    "pmcts_allgather_updates", "pmcts_forest_search",
     "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
     "pmcts_forest_create", "pmcts_forest_destroy", "pmcts_forest_last_error", "pmcts_forest_set_coefficients",
     "pmcts_forest_select", "pmcts_forest_backup", "pmcts_forest_master_apply", "pmcts_forest_tree_size",
     "pmcts_forest_master_size", "pmcts_forest_export_tree", "pmcts_forest_export_master", "pmcts_python_shuffles",
+    "pmcts_forest_master_rows", "pmcts_forest_export_master_rows",
 ]
 
 
 class Noise(C.Structure):
     _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("z", C.c_void_p),
                 ("seed", C.c_uint64), ("stream", C.c_uint64), ("id0", C.c_uint64)]
+
+
+#: int exchange(void *user, const void *send, size_t bytes, void *recv) -- all-gather over host buffers
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+#: int hook(void *user, int wave, int n_local, const int32_t *scen_ids, int n_leaves, int stride,
+#:          const int32_t *prefix_len, const int8_t *prefix_act, uint32_t *leaf_bins) -- test stand-in for the GPU launch
+ROLLOUT_HOOK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                              C.c_void_p, C.c_void_p)
+
+
+class SearchParams(C.Structure):
+    """pmcts_search_params (include/pmcts_b200.h)."""
+    _fields_ = [("n_leaves", C.c_int32), ("replicas", C.c_int32), ("budget", C.c_int64), ("seed", C.c_uint64),
+                ("roll_flags", C.c_int32), ("pipeline", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
+                ("slots_w", C.c_void_p), ("slots_m", C.c_void_p), ("comm", C.c_void_p),
+                ("exchange", EXCHANGE_FN), ("exchange_user", C.c_void_p),
+                ("rollout_hook", ROLLOUT_HOOK_FN), ("hook_user", C.c_void_p)]
+
+
+class SearchReport(C.Structure):
+    """pmcts_search_report."""
+    _fields_ = [(k, C.c_int64) for k in ("waves", "leaves", "rollouts", "transitions", "arrived", "launches")] + \
+               [(k, C.c_double) for k in ("ms_total", "ms_select", "ms_wait", "ms_backup", "ms_master", "ms_exchange")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class PmctsError(RuntimeError):
@@ -71,6 +101,15 @@ def lib():
     L.pmcts_version.restype = C.c_char_p
     L.pmcts_set_stream.argtypes = [vp, vp]
     L.pmcts_reset_stream.argtypes = [vp]
+    L.pmcts_get_stream.argtypes = [vp]
+    L.pmcts_get_stream.restype = vp
+    L.pmcts_get_device.argtypes = [vp]
+    L.pmcts_comm_unique_id.argtypes = [vp]
+    L.pmcts_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.pmcts_comm_destroy.argtypes = [vp]
+    L.pmcts_comm_destroy.restype = None
+    L.pmcts_allgather_updates.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.pmcts_forest_search.argtypes = [vp, vp, vp, vp, vp, dbl, C.POINTER(SearchParams), C.POINTER(SearchReport)]
     L.pmcts_synchronize.argtypes = [vp]
     L.pmcts_join.argtypes = [vp, i32]
     L.pmcts_wait.argtypes = [vp, i32]
@@ -116,6 +155,9 @@ def lib():
     L.pmcts_python_shuffles.argtypes = [C.c_uint64, i64, i32, vp]
     L.pmcts_forest_export_tree.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.pmcts_forest_export_master.argtypes = [vp, vp, vp, vp]
+    L.pmcts_forest_master_rows.argtypes = [vp]
+    L.pmcts_forest_master_rows.restype = i64
+    L.pmcts_forest_export_master_rows.argtypes = [vp, vp, vp, vp, vp]
     _lib = L
     return L
 

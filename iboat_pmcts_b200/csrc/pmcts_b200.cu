@@ -667,6 +667,12 @@ __global__ void expand_actions_kernel(const uint8_t *__restrict__ a, double *__r
     if (i < count) h[i] = 45.0 * (double)a[i];
 }
 
+// PMCTS_ROLL_PREFIX_ACTIONS: the leaves' action paths as int8 indices into ACTIONS (-1 = padding, never read).
+__global__ void expand_prefix_kernel(const int8_t *__restrict__ a, double *__restrict__ h, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) h[i] = 45.0 * (double)a[i];
+}
+
 // Roofline denominator: what the FP32 FMA pipes of this chip sustain (pmcts_probe_fp32_peak).  16 independent
 // FFMA chains per thread, nothing else in the loop.
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out, int iters, float a, float b) {
@@ -827,6 +833,8 @@ struct pmcts_ctx {
     // Every entry point that takes a ctx holds this lock for its duration: calls on one ctx from several host
     // threads are serialised (they are stream-ordered anyway); recursive because upload frees the slot it replaces.
     std::recursive_mutex mu;
+    void *attachment = nullptr;  // pmcts::ctx_attachment
+    void (*attachment_free)(void *) = nullptr;
     Deferred *last_fast = nullptr;  // work area of the last mixed-precision rollout launch when it was a deferred one
 };
 
@@ -1021,6 +1029,15 @@ bool uniform_axis(const double *g, int n, double *inv_step) {
 
 }  // namespace
 
+// (for the other translation units of the library -- pmcts_search.cu: they report through pmcts_last_error too)
+namespace pmcts {
+void set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
+void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *)) {
+    ctx->attachment_free = free_fn;
+    return &ctx->attachment;
+}
+}  // namespace pmcts
+
 extern "C" {
 
 const char *pmcts_last_error(void) { return g_last_error.c_str(); }
@@ -1052,6 +1069,8 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);  // (no lock: the caller must not use a ctx it is destroying)
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->attachment && ctx->attachment_free) ctx->attachment_free(ctx->attachment);
+    ctx->attachment = nullptr;
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     if (ctx->stage.p) cudaFree(ctx->stage.p);
@@ -1085,6 +1104,9 @@ int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream) {
     ctx->stream = (cudaStream_t)cuda_stream;
     return PMCTS_OK;
 }
+
+void *pmcts_get_stream(pmcts_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int pmcts_get_device(pmcts_ctx *ctx) { return ctx ? ctx->device : PMCTS_ERR_ARG; }
 
 int pmcts_reset_stream(pmcts_ctx *ctx) {
     if (!ctx) return fail(PMCTS_ERR_ARG, "ctx is NULL");
@@ -1665,12 +1687,15 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
         if (slot->used) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slot->redo_done, 0));
     }
     Stager st(ctx, flags & PMCTS_MEM_HOST, slot ? &slot->stage : nullptr);
+    const bool pre_actions = (flags & PMCTS_ROLL_PREFIX_ACTIONS) && prefix;
+    const int8_t *prefix8 = pre_actions ? reinterpret_cast<const int8_t *>(prefix) : nullptr;
+    const size_t pre_count = P * (size_t)n_leaf * prefix_stride;
     const size_t traj_bytes = al(S * traj_stride * n * 8);
     rc = st.reserve(al(P * n_leaf * prefix_stride * 8) + al(P * n_leaf * 4) + 6 * al(S * n * 8) + 2 * al(S * n * 4) +
                     al(S * n) + (traj_lat ? traj_bytes : 0) + (traj_lon ? traj_bytes : 0) + al(S * n_leaf * 48) +
                     al(S * 64) + (nz.mode == PMCTS_NOISE_INJECTED ? al(S * max_steps * n * 8) : 0));
     if (rc) return rc;
-    if ((rc = st.in(prefix, P * n_leaf * prefix_stride)) || (rc = st.in(prefix_len, P * n_leaf)) ||
+    if ((rc = pre_actions ? st.in(prefix8, pre_count) : st.in(prefix, pre_count)) || (rc = st.in(prefix_len, P * n_leaf)) ||
         (rc = st.out(reward, S * n)) || (rc = st.out(t_arr, S * n)) || (rc = st.out(steps, S * n)) ||
         (rc = st.out(status, S * n)) || (rc = st.out(bin, S * n)) || (rc = st.out(frac, S * n)) ||
         (rc = st.out(final_lat, S * n)) || (rc = st.out(final_lon, S * n)) ||
@@ -1703,9 +1728,10 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     a.traj_stride = traj_stride;
     a.leaf_bins = leaf_bins;
     a.flags = flags;
-    // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list
+    // work area: counter | partial statistics [n_scen][kStatsCopies][8] | redo list | action paths expanded to degrees
     const size_t part_bytes = al(S * kStatsCopies * 8 * sizeof(double));
-    const size_t work_bytes = part_bytes + S * n * sizeof(uint32_t);
+    const size_t redo_bytes = al(S * n * sizeof(uint32_t));
+    const size_t work_bytes = part_bytes + redo_bytes + (pre_actions ? al(pre_count * sizeof(double)) : 0);
     char *work = nullptr;
     if (defer) {
         if (256 + work_bytes > slot->cap) {
@@ -1722,6 +1748,15 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
     } else {
         if ((rc = ensure_work(ctx, work_bytes))) return rc;
         work = ctx->work;
+    }
+    if (pre_actions) {
+        // (in the launch's own work area: the deferred fp64 finisher of this launch reads the paths too, after the next
+        // launch has been enqueued)
+        double *expanded = (double *)(work + 256 + part_bytes + redo_bytes);
+        LaunchTimer lt(ctx);
+        expand_prefix_kernel<<<(unsigned)((pre_count + 255) / 256), 256, 0, ctx->stream>>>(prefix8, expanded, pre_count);
+        CUDA_TRY(cudaGetLastError());
+        a.prefix = expanded;
     }
     double *stats_part = (double *)(work + 256);
     // (counter and partial sums are neighbours in the work area: one memset clears both for a mixed-precision launch)

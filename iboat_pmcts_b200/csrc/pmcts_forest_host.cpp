@@ -19,10 +19,16 @@
 //     fp64 whatever the summation order;
 //   * a leaf's wave histogram goes to a random action slot of the leaf (worker.py:62-63,
 //     master_node.py:42-44) and to the slot of the action taken at every ancestor.
+#include <unistd.h>
+
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <new>
 #include <string>
 #include <thread>
@@ -30,6 +36,7 @@
 #include <vector>
 
 #include "../../include/pmcts_b200.h"
+#include "pmcts_internal.h"
 
 namespace {
 
@@ -47,32 +54,90 @@ int fail(int code, const char *msg) {
 // The reference runs one process per worker tree (forest.py:69-75).  Here the trees of a wave are walked by a few
 // host threads: selection and back-up touch only their own tree (the master is read-only while leaves are
 // selected, apart from its per-wave memo, which is written with release / acquire ordering and holds the same
-// value whoever computes it), and the master update of a wave is split by scenario slice.  Small waves stay on
-// the calling thread: a thread start costs more than a few hundred tree walks.
-constexpr int64_t kMinParallelWork = 1024;
+// value whoever computes it), and the master update of a wave is split by scenario slice.  The threads are a
+// process-wide pool that sleeps between waves: a wave of a small search is a few hundred tree walks, less than the
+// cost of starting threads for it.  Tiny waves stay on the calling thread.
+constexpr int64_t kMinParallelWork = 128;
+
+class Pool {
+  public:
+    static Pool &get() {
+        static Pool *pool = nullptr;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pool || pool->pid_ != getpid()) pool = new Pool();  // (a forked child starts its own threads)
+        return *pool;
+    }
+    int size() const { return (int)workers_.size() + 1; }
+
+    // fn(i) for i in [0, n), on the pool's threads and the caller; returns when all are done
+    void run(int n, const std::function<void(int)> &fn) {
+        std::lock_guard<std::mutex> serial(run_mu_);  // one job at a time
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            running_ = (int)workers_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return running_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    Pool() : pid_(getpid()) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+        for (int t = 1; t < nt; ++t) {
+            workers_.emplace_back([this] { loop(); });
+            workers_.back().detach();
+        }
+    }
+    void work() {
+        for (int i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) (*fn_)(i);
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--running_ == 0) done_cv_.notify_one();
+        }
+    }
+    pid_t pid_;
+    std::vector<std::thread> workers_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, running_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t generation_ = 0;
+};
 
 template <typename F>
 void parallel_for(int n, int64_t work, F &&fn) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::min<unsigned>((unsigned)n, std::min<unsigned>(hw ? hw : 1u, 16u));
-    if (nt <= 1 || work < kMinParallelWork) {
+    if (n <= 1 || work < kMinParallelWork || Pool::get().size() <= 1) {
         for (int i = 0; i < n; ++i) fn(i);
         return;
     }
-    std::atomic<int> next{0};
     std::atomic<bool> failed{false};
-    auto body = [&]() {
+    const std::function<void(int)> body = [&](int i) {
         try {
-            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+            fn(i);
         } catch (...) {  // (allocation failure while a tree grows): reported by the caller, never thrown across a thread
             failed.store(true);
         }
     };
-    std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    for (int t = 1; t < nt; ++t) th.emplace_back(body);
-    body();
-    for (auto &x : th) x.join();
+    Pool::get().run(n, body);
     if (failed.load()) throw std::bad_alloc();
 }
 
@@ -108,7 +173,19 @@ struct Tree {
     std::vector<double> best;         // cached
     const uint8_t *perms = nullptr;   // caller-owned [max_nodes][kA]
     int64_t max_nodes = 0;
-    std::vector<int32_t> wave_leaves;
+    // leaves of the waves selected and not yet backed up, oldest first (the pipelined search keeps two in flight)
+    std::deque<std::vector<int32_t>> waves;
+    // A wave files hundreds of histograms through the same ancestors: the cached (visits, best) of a node are
+    // recomputed once per wave, after the last add, from the nodes listed here
+    std::vector<int64_t> touch_stamp;
+    std::vector<int32_t> touched;
+    int64_t backups = 0;
+
+    void reserve(size_t n) {
+        parent.reserve(n); mnode.reserve(n); pending.reserve(n); arm.reserve(n); depth.reserve(n);
+        child.reserve(n * kA); n_child.reserve(n); n_untried.reserve(n); untried.reserve(n * kA);
+        table.reserve(n * kRow); visits.reserve(n); best.reserve(n); touch_stamp.reserve(n);
+    }
 
     int32_t size() const { return (int32_t)parent.size(); }
 
@@ -126,6 +203,7 @@ struct Tree {
         table.insert(table.end(), kRow, 0);
         visits.push_back(0);
         best.push_back(0.0);
+        touch_stamp.push_back(-1);
         return idx;
     }
 };
@@ -134,28 +212,47 @@ struct Master {
     int n_scen = 0;
     std::vector<int32_t> parent, child;  // child [node][kA] by action index
     std::vector<int8_t> arm;
-    // [node][n_scen][kA][kB], in chunks of kChunk nodes: the table is hundreds of megabytes at the end of a search,
-    // and growing one contiguous vector would copy all of it every time it doubles
-    static constexpr int kChunk = 256;
-    std::vector<std::vector<uint32_t>> table;
-    uint32_t *row_of(int32_t node, int s) {
-        return table[node / kChunk].data() + ((size_t)(node % kChunk) * n_scen + s) * kRow;
-    }
-    std::vector<int64_t> visits;         // [node][n_scen] cached
-    std::vector<double> best;            // [node][n_scen] cached
+    // Counters.  A node near the root is visited by every scenario, a deep one by the one tree that grew it: a dense
+    // table[node][scenario][8][12] is nine tenths zeros at 10 scenarios (and was most of the cost of a search:
+    // 384 MB to allocate, clear and page in for 10^5 nodes).  So a (node, scenario) pair gets its 8 x 12 row when
+    // the scenario first files a histogram there: row[node][scenario] indexes the scenario's own pool (-1: none
+    // yet).  One pool per scenario, because the update of a wave runs one thread per scenario slice.
+    static constexpr int kChunk = 256;  // rows per allocation: a pool never moves its rows
+    struct Slice {
+        std::vector<std::vector<uint32_t>> chunks;
+        std::vector<int64_t> visits, touch;  // cached visit total; the update that last added to the row
+        std::vector<double> best;            // cached max over actions of the binned mean
+        std::vector<int32_t> node;           // the row's node
+        int32_t rows = 0;
+        uint32_t *counters(int32_t r) { return chunks[r / kChunk].data() + (size_t)(r % kChunk) * kRow; }
+        const uint32_t *counters(int32_t r) const { return chunks[r / kChunk].data() + (size_t)(r % kChunk) * kRow; }
+        int32_t add_row(int32_t nd) {
+            if (rows % kChunk == 0) chunks.emplace_back((size_t)kChunk * kRow, 0u);
+            visits.push_back(0);
+            touch.push_back(-1);
+            best.push_back(0.0);
+            node.push_back(nd);
+            return rows++;
+        }
+    };
+    std::vector<Slice> slices;           // [n_scen]
+    std::vector<int32_t> row;            // [node][n_scen]
     std::vector<double> memo;            // master UCT per node, valid when stamp == wave
     std::vector<int64_t> stamp;
+    int64_t applies = 0;
 
     int32_t size() const { return (int32_t)parent.size(); }
+    int64_t visits_of(int32_t node, int s) const {
+        const int32_t r = row[(size_t)node * n_scen + s];
+        return r < 0 ? 0 : slices[s].visits[r];
+    }
 
     int32_t add_node(int32_t par, int a) {
         const int32_t idx = size();
         parent.push_back(par);
         arm.push_back((int8_t)a);
         child.insert(child.end(), kA, -1);
-        if (idx % kChunk == 0) table.emplace_back((size_t)kChunk * n_scen * kRow, 0u);
-        visits.insert(visits.end(), n_scen, 0);
-        best.insert(best.end(), n_scen, 0.0);
+        row.insert(row.end(), n_scen, -1);
         memo.push_back(0.0);
         stamp.push_back(-1);
         if (par >= 0) child[(size_t)par * kA + a] = idx;
@@ -173,10 +270,22 @@ struct Master {
         return node;
     }
 
-    void add(int32_t node, int s, int slot, const uint32_t *bins) {
-        uint32_t *row = row_of(node, s);
-        for (int b = 0; b < kB; ++b) row[slot * kB + b] += bins[b];
-        node_value(row, visits[(size_t)node * n_scen + s], best[(size_t)node * n_scen + s]);
+    // adds a histogram; the cached (visits, best) of the row are refreshed by the caller once per update, from
+    // `touched` (rows of scenario s; scenario slices are disjoint, so concurrent callers never share an entry)
+    void add(int32_t node, int s, int slot, const uint32_t *bins, std::vector<int32_t> &touched) {
+        Slice &sl = slices[s];
+        int32_t &r = row[(size_t)node * n_scen + s];
+        if (r < 0) r = sl.add_row(node);
+        uint32_t *c = sl.counters(r);
+        for (int b = 0; b < kB; ++b) c[slot * kB + b] += bins[b];
+        if (sl.touch[r] != applies) {
+            sl.touch[r] = applies;
+            touched.push_back(r);
+        }
+    }
+    void refresh(int s, const std::vector<int32_t> &touched) {
+        Slice &sl = slices[s];
+        for (int32_t r : touched) node_value(sl.counters(r), sl.visits[r], sl.best[r]);
     }
 };
 
@@ -197,10 +306,11 @@ struct pmcts_forest {
         double acc = 0.0;
         bool any = false;
         for (int s = 0; s < n_scen; ++s) {
-            const int64_t n_node = master.visits[(size_t)m * n_scen + s];
-            const int64_t n_par = p >= 0 ? master.visits[(size_t)p * n_scen + s] : 0;
+            const int32_t r = master.row[(size_t)m * n_scen + s];
+            const int64_t n_node = r < 0 ? 0 : master.slices[s].visits[r];
+            const int64_t n_par = p >= 0 ? master.visits_of(p, s) : 0;
             if (n_node != 0 && n_par != 0) {
-                const double uct = master.best[(size_t)m * n_scen + s] +
+                const double uct = master.slices[s].best[r] +
                                    uct_coeff * std::pow(2.0 * std::log((double)n_par) / (double)n_node, 0.5);
                 acc += uct * probability[s];
                 any = true;
@@ -257,6 +367,11 @@ struct pmcts_forest {
     }
 };
 
+namespace pmcts {
+ForestInfo forest_info(const pmcts_forest *f) { return ForestInfo{f->n_scen, f->n_local, f->max_depth}; }
+int forest_local_id(const pmcts_forest *f, int local_index) { return f->trees[local_index].scen; }
+}  // namespace pmcts
+
 extern "C" {
 
 const char *pmcts_forest_last_error(void) { return g_err.c_str(); }
@@ -280,9 +395,11 @@ int pmcts_forest_create(int n_scen, int n_local, const int32_t *local_ids, int m
         t.scen = local_ids[i];
         t.perms = perms + (size_t)i * max_nodes * kA;
         t.max_nodes = max_nodes;
+        t.reserve((size_t)max_nodes);
         t.add_node(-1, 0);
     }
     f->master.n_scen = n_scen;
+    f->master.slices.resize(n_scen);
     f->master.add_node(-1, 0);
     *out = f;
     return PMCTS_OK;
@@ -304,7 +421,9 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
     std::atomic<int> exhausted{0};
     parallel_for(f->n_local, (int64_t)f->n_local * n_leaves, [&](int i) {
         Tree &t = f->trees[i];
-        t.wave_leaves.clear();
+        t.waves.emplace_back();
+        std::vector<int32_t> &wave_leaves = t.waves.back();
+        wave_leaves.reserve(n_leaves);
         for (int l = 0; l < n_leaves; ++l) {
             const int32_t leaf = f->tree_policy(t);
             if (leaf < 0) {
@@ -312,7 +431,7 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
                 return;
             }
             for (int32_t x = leaf; x >= 0; x = t.parent[x]) t.pending[x] += 1;
-            t.wave_leaves.push_back(leaf);
+            wave_leaves.push_back(leaf);
             const size_t o = (size_t)i * n_leaves + l;
             leaf_node[o] = leaf;
             const int len = t.depth[leaf];
@@ -332,23 +451,30 @@ int pmcts_forest_select(pmcts_forest *f, int n_leaves, int prefix_stride, int32_
 int pmcts_forest_backup(pmcts_forest *f, int n_leaves, const uint32_t *leaf_bins, const int8_t *slots) try {
     if (!f || !leaf_bins || !slots) return fail(PMCTS_ERR_ARG, "NULL argument");
     for (int i = 0; i < f->n_local; ++i)
-        if ((int)f->trees[i].wave_leaves.size() != n_leaves)
-            return fail(PMCTS_ERR_ARG, "back-up does not match the last selection");
+        if (f->trees[i].waves.empty() || (int)f->trees[i].waves.front().size() != n_leaves)
+            return fail(PMCTS_ERR_ARG, "back-up does not match the oldest selection not yet backed up");
     parallel_for(f->n_local, (int64_t)f->n_local * n_leaves, [&](int i) {
         Tree &t = f->trees[i];
+        const std::vector<int32_t> &wave_leaves = t.waves.front();
+        const int64_t stamp = ++t.backups;
+        t.touched.clear();
         for (int l = 0; l < n_leaves; ++l) {
-            const int32_t leaf = t.wave_leaves[l];
+            const int32_t leaf = wave_leaves[l];
             const uint32_t *bins = leaf_bins + ((size_t)i * n_leaves + l) * kB;
             int slot = slots[(size_t)i * n_leaves + l];
             for (int32_t x = leaf; x >= 0; x = t.parent[x]) {
                 int64_t *row = t.table.data() + (size_t)x * kRow;
                 for (int b = 0; b < kB; ++b) row[slot * kB + b] += bins[b];
-                node_value(row, t.visits[x], t.best[x]);
+                if (t.touch_stamp[x] != stamp) {
+                    t.touch_stamp[x] = stamp;
+                    t.touched.push_back(x);
+                }
                 t.pending[x] -= 1;
                 slot = t.arm[x];  // the ancestors take the histogram in the slot of the action that led here
             }
         }
-        t.wave_leaves.clear();
+        for (int32_t x : t.touched) node_value(t.table.data() + (size_t)x * kRow, t.visits[x], t.best[x]);
+        t.waves.pop_front();
     });
     return PMCTS_OK;
 } catch (const std::bad_alloc &) {
@@ -373,18 +499,23 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
     for (size_t o = 0; o < leaf_master.size(); ++o)
         leaf_master[o] = m.descend(prefix_act + o * prefix_stride, prefix_len[o]);
     // 2. the counters: block i only touches the slice of its own scenario, so distinct scenarios run side by side
+    m.applies += 1;
     auto apply_block = [&](int i) {
         const int s = scen_ids[i];
+        std::vector<int32_t> touched;
+        touched.reserve((size_t)n_leaves * 2);
         for (int l = 0; l < n_leaves; ++l) {
             const size_t o = (size_t)i * n_leaves + l;
             const uint32_t *bins = leaf_bins + o * kB;
             int32_t node = leaf_master[o];
-            m.add(node, s, slots[o], bins);
+            m.add(node, s, slots[o], bins, touched);
             while (m.parent[node] >= 0) {
-                m.add(m.parent[node], s, m.arm[node], bins);
+                m.add(m.parent[node], s, m.arm[node], bins, touched);
                 node = m.parent[node];
             }
         }
+        m.refresh(s, touched);
+        if (!distinct) m.applies += 1;  // (a scenario listed twice: its second block must refresh again)
     };
     if (distinct) parallel_for(n_blocks_scen, (int64_t)n_blocks_scen * n_leaves, apply_block);
     else
@@ -483,11 +614,46 @@ int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, ui
     const size_t n = m.parent.size();
     if (parent) std::memcpy(parent, m.parent.data(), n * sizeof(int32_t));
     if (arm) std::memcpy(arm, m.arm.data(), n);
-    if (table)
-        for (size_t c = 0; c * Master::kChunk < n; ++c) {
-            const size_t nodes = std::min<size_t>(Master::kChunk, n - c * Master::kChunk);
-            std::memcpy(table + c * Master::kChunk * m.n_scen * kRow, m.table[c].data(),
-                        nodes * (size_t)m.n_scen * kRow * sizeof(uint32_t));
+    if (table) {
+        std::memset(table, 0, n * (size_t)m.n_scen * kRow * sizeof(uint32_t));
+        for (int s = 0; s < m.n_scen; ++s) {
+            const Master::Slice &sl = m.slices[s];
+            for (int32_t r = 0; r < sl.rows; ++r)
+                std::memcpy(table + ((size_t)sl.node[r] * m.n_scen + s) * kRow, sl.counters(r), kRow * sizeof(uint32_t));
+        }
+    }
+    return PMCTS_OK;
+}
+
+int64_t pmcts_forest_master_rows(pmcts_forest *f) {
+    if (!f) return -1;
+    int64_t total = 0;
+    for (const Master::Slice &sl : f->master.slices) total += sl.rows;
+    return total;
+}
+
+int pmcts_forest_export_master_rows(pmcts_forest *f, int32_t *parent, int8_t *arm, int32_t *row_index, uint32_t *rows) {
+    if (!f) return fail(PMCTS_ERR_ARG, "forest is NULL");
+    const Master &m = f->master;
+    const size_t n = m.parent.size();
+    if (parent) std::memcpy(parent, m.parent.data(), n * sizeof(int32_t));
+    if (arm) std::memcpy(arm, m.arm.data(), n);
+    std::vector<int64_t> first(m.n_scen + 1, 0);  // rows are numbered scenario by scenario
+    for (int s = 0; s < m.n_scen; ++s) first[s + 1] = first[s] + m.slices[s].rows;
+    if (row_index)
+        for (size_t i = 0; i < n; ++i)
+            for (int s = 0; s < m.n_scen; ++s) {
+                const int32_t r = m.row[i * m.n_scen + s];
+                row_index[i * m.n_scen + s] = r < 0 ? -1 : (int32_t)(first[s] + r);
+            }
+    if (rows)
+        for (int s = 0; s < m.n_scen; ++s) {
+            const Master::Slice &sl = m.slices[s];
+            for (int32_t c = 0; c * Master::kChunk < sl.rows; ++c) {
+                const size_t cnt = std::min<size_t>(Master::kChunk, sl.rows - (size_t)c * Master::kChunk);
+                std::memcpy(rows + ((size_t)first[s] + (size_t)c * Master::kChunk) * kRow, sl.chunks[c].data(),
+                            cnt * kRow * sizeof(uint32_t));
+            }
         }
     return PMCTS_OK;
 }

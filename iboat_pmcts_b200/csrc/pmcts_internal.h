@@ -1,0 +1,21 @@
+// pmcts_b200 -- what the translation units of the library share beyond the public C ABI.
+#pragma once
+#include "../../include/pmcts_b200.h"
+
+namespace pmcts {
+
+// message returned by pmcts_last_error() on the calling thread (pmcts_b200.cu)
+void set_last_error(const char *msg);
+
+// One object another translation unit keeps with a ctx for the ctx's lifetime (the search driver's staging buffers):
+// returns the slot; pmcts_destroy calls free_fn on what it holds.
+void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *));
+
+// shape of a host forest (pmcts_forest_host.cpp)
+struct ForestInfo {
+    int n_scen, n_local, max_depth;
+};
+ForestInfo forest_info(const pmcts_forest *f);
+int forest_local_id(const pmcts_forest *f, int local_index);
+
+}  // namespace pmcts

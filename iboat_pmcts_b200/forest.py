@@ -18,7 +18,6 @@ from .master_node import MasterNode
 from .simulatorTLKT import A_DICT, ACTIONS, HOURS_TO_DAY, Simulator
 
 ROOT_HASH = hash(tuple([]))
-MAX_DEPTH = 32  # fixed width of a leaf's action path in the all-gathered update block
 
 
 class Forest:
@@ -36,7 +35,7 @@ class Forest:
 
     # ------------------------------------------------------------------------------------------------
     def launch_search(self, root_state, frequency, mode="batched", leaves=64, replicas=32, seed=0,
-                      replay_full_prefix=False, group=None, host="native"):
+                      replay_full_prefix=False, group=None, host="native", pipeline=1):
         """Runs the search and returns the master dictionary ``{hash(tuple(origins)): MasterNode}`` (deep
         copy it with ``master_node.deepcopy_dict`` before use, as with the reference).
 
@@ -50,9 +49,13 @@ class Forest:
         every wave (the role ``frequency`` plays in the reference).  With ``torch.distributed`` initialised
         (``group``; ``False`` = ignore it), rank ``r`` owns workers ``r * S/world .. (r+1) * S/world - 1`` and the waves' update blocks are
         all-gathered; seeded alike, the ranks return the same dictionary as a single process would.
-        ``host="native"`` keeps the trees and the master in the C++ host runtime (``pmcts_forest_*``) during
-        the search and turns them into ``Node`` / ``MasterNode`` objects afterwards; ``host="python"`` runs the
-        same search on the Python classes (same leaves, same counts: tests/test_host_forest.py).
+        ``host="native"`` runs the whole search as one native call (``pmcts_forest_search``): trees and master in
+        the C++ host runtime, one launch per wave, update blocks all-gathered on the device; ``Node`` /
+        ``MasterNode`` objects are built afterwards, when they are first read.  ``host="python"`` runs the same
+        search on the Python classes (same leaves, same counts: tests/test_host_forest.py).
+        ``pipeline=2`` (native host) keeps two waves in flight: wave ``w + 1`` is selected on the host while the
+        GPU rolls out wave ``w``, whose leaves hold virtual visits until they are backed up -- other trees than
+        ``pipeline=1`` (which reproduces the synchronous search), equally reproducible.
         """
         Master_nodes = dict()
         Master_nodes[ROOT_HASH] = MasterNode(len(self.workers), nodehash=ROOT_HASH)
@@ -65,7 +68,7 @@ class Forest:
             raise ValueError("mode must be 'sequential' or 'batched'")
         if host == "native":
             return self._search_native(list(root_state), int(leaves), int(replicas), int(seed),
-                                       bool(replay_full_prefix), group)
+                                       bool(replay_full_prefix), group, int(pipeline))
         return self._search_batched(list(root_state), Master_nodes, int(leaves), int(replicas), int(seed),
                                     bool(replay_full_prefix), group)
 
@@ -94,8 +97,6 @@ class Forest:
             b = min(B, budget - trees[0].ite)
             leaves = [t.select_leaves(b, Master_nodes) for t in trees]
             depth = max(1, max(len(l.origins) for ls in leaves for l in ls))
-            if depth > MAX_DEPTH:
-                raise ValueError("tree deeper than %d" % MAX_DEPTH)
             prefix = np.zeros((S_loc, b, depth), np.float64)
             plen = np.zeros((S_loc, b), np.int32)
             for si, ls in enumerate(leaves):
@@ -115,7 +116,8 @@ class Forest:
             for t, ls, bb, sw in zip(trees, leaves, bins, slot_w):
                 t.back_up_leaves(ls, bb, sw)
             # update block of this rank: action paths, slots and histograms of its leaves
-            paths = np.full((S_loc, b, MAX_DEPTH), -1, np.int32)
+            width = len(trees[0].Simulator.times) - 1  # deepest possible leaf (worker.py:438-445)
+            paths = np.full((S_loc, b, width), -1, np.int32)
             paths[:, :, :depth] = np.where(np.arange(depth)[None, None, :] < plen[:, :, None], prefix, -1).astype(np.int32)
             block = dict(ids=np.asarray(local_ids, np.int32), paths=paths, slots=slot_m.astype(np.int32), bins=bins)
             blocks = _all_gather_blocks(block, dist, group, world)
@@ -129,8 +131,11 @@ class Forest:
 
 
     # ------------------------------------------------------------------------------------------------
-    def _search_native(self, root_state, B, K, seed, replay_full, group):
-        """The batched search with the trees and the master in the C++ host runtime."""
+    def _search_native(self, root_state, B, K, seed, replay_full, group, pipeline=1):
+        """The batched search as ONE native call (``pmcts_forest_search``): the trees and the master live in the
+        C++ host runtime, every wave's rollouts are one launch over this rank's scenarios, and the update blocks
+        (int8 paths + packed per-leaf histograms) are all-gathered on the device when several ranks search
+        together."""
         import ctypes as C
         from . import worker as W
         lib = N.lib()
@@ -143,7 +148,7 @@ class Forest:
         trees = [self.workers[i] for i in local_ids]
         budget = trees[0].budget
         nT = len(trees[0].Simulator.times)
-        max_depth = nT - 1
+        max_depth = nT - 1  # a node at depth len(times) - 1 is terminal (worker.py:438-445): no fixed path width
         # every node's shuffled action list, drawn tree by tree in creation order with the tree's own generator
         # (what Node.__init__ does, worker.py:50-51)
         max_nodes = budget + 2
@@ -162,6 +167,16 @@ class Forest:
                     perms[ti, j] = order
         ids = np.asarray(local_ids, np.int32)
         prob = np.ascontiguousarray(trees[0].probability, np.float64)
+        # random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward (master_node.py:42): drawn
+        # wave by wave for ALL scenarios on every rank (ranks seeded alike draw alike), so the search does not
+        # depend on the number of ranks
+        slot_w, slot_m, done = [], [], 0
+        while done < budget:
+            b = min(B, budget - done)
+            slot_w.append(np.random.randint(len(ACTIONS), size=(S, b)).astype(np.int8).ravel())
+            slot_m.append(np.random.randint(len(ACTIONS), size=(S, b)).astype(np.int8).ravel())
+            done += b
+        slot_w, slot_m = np.concatenate(slot_w), np.concatenate(slot_m)
         handle = C.c_void_p()
         N.check_forest(lib.pmcts_forest_create(S, S_loc, ids.ctypes.data, max_depth, prob.ctypes.data,
                                                float(W.UCT_COEFF), float(W.RHO), perms.ctypes.data, max_nodes,
@@ -171,45 +186,155 @@ class Forest:
             for t in trees:
                 eng, s = t.Simulator.scenario()
                 slots.append(s)
-            eng.set_precision(N.PREC_FAST)
-            flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
-            done, wave = 0, 0
-            while done < budget:
-                b = min(B, budget - done)
-                leaf_node = np.empty((S_loc, b), np.int32)
-                plen = np.empty((S_loc, b), np.int32)
-                path = np.empty((S_loc, b, MAX_DEPTH), np.int8)
-                N.check_forest(lib.pmcts_forest_select(handle, b, MAX_DEPTH, leaf_node.ctypes.data, plen.ctypes.data,
-                                                       path.ctypes.data))
-                depth = max(1, int(plen.max()))
-                prefix = np.where(path[:, :, :depth] >= 0, path[:, :, :depth].astype(np.float64) * 45.0, 0.0)
-                bins = np.zeros((S_loc, b, 12), np.uint32)
-                eng.rollout_forest(slots, b, K, root_state, self.destination, self.timemin,
-                                   np.ascontiguousarray(prefix).reshape(-1), plen.reshape(-1), depth,
-                                   prefix_shared=False, seed=seed, stream=wave * S + rank * S_loc, id0=0,
-                                   out=dict(leaf_bins=bins.reshape(-1)), flags=flags)
-                slot_w = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc].astype(np.int8)
-                slot_m = np.random.randint(len(ACTIONS), size=(S, b))[local_ids[0]:local_ids[0] + S_loc].astype(np.int8)
-                slot_w = np.ascontiguousarray(slot_w)
-                N.check_forest(lib.pmcts_forest_backup(handle, b, bins.ctypes.data, slot_w.ctypes.data))
-                paths32 = np.where(path >= 0, path.astype(np.int32) * 45, -1).astype(np.int32)
-                block = dict(ids=ids, paths=paths32, slots=slot_m.astype(np.int32), bins=bins)
-                for blk in _all_gather_blocks(block, dist, group, world):
-                    bp = np.ascontiguousarray(np.where(blk["paths"] >= 0, blk["paths"] // 45, -1).astype(np.int8))
-                    bl = np.ascontiguousarray((blk["paths"] >= 0).sum(2).astype(np.int32))
-                    bs = np.ascontiguousarray(blk["slots"].astype(np.int8))
-                    bb = np.ascontiguousarray(blk["bins"].astype(np.uint32))
-                    bi = np.ascontiguousarray(blk["ids"].astype(np.int32))
-                    N.check_forest(lib.pmcts_forest_master_apply(handle, bi.size, bi.ctypes.data, b, MAX_DEPTH,
-                                                                 bl.ctypes.data, bp.ctypes.data, bs.ctypes.data,
-                                                                 bb.ctypes.data))
-                done += b
-                wave += 1
-            for ti, t in enumerate(trees):
-                _export_tree(lib, handle, ti, t, root_state, done)
-            return _import_master(lib, handle, S)
-        finally:
+            slots = np.asarray(slots, np.int32)
+            params = N.SearchParams()
+            params.n_leaves, params.replicas, params.budget, params.seed = B, K, budget, seed
+            params.roll_flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
+            params.pipeline, params.world, params.rank = int(pipeline), world, rank
+            params.slots_w, params.slots_m = slot_w.ctypes.data, slot_m.ctypes.data
+            keep = []  # ctypes callbacks must outlive the call
+            native_engine = getattr(eng, "_h", None) is not None
+            if not native_engine:
+                # tests: an engine object without a device context stands in for the launch (tests/test_host_forest.py)
+                hook = _rollout_hook(eng, slots, K, root_state, self.destination, self.timemin, seed, S, rank * S_loc,
+                                     params.roll_flags)
+                keep.append(hook)
+                params.rollout_hook = hook
+            if world > 1:
+                comm = _device_comm(eng, dist, group, rank, world) if native_engine else None
+                if comm is not None:
+                    params.comm = comm
+                else:
+                    cb = _host_exchange(dist, group, world)
+                    keep.append(cb)
+                    params.exchange = cb
+            report = N.SearchReport()
+            root = np.ascontiguousarray(root_state, np.float64)
+            dest = np.ascontiguousarray(self.destination, np.float64)
+            rc = lib.pmcts_forest_search(eng._h if native_engine else None, handle, slots.ctypes.data, root.ctypes.data,
+                                         dest.ctypes.data, float(self.timemin), C.byref(params), C.byref(report))
+            N.check(rc)
+            self.last_search_report = report.as_dict()
+        except BaseException:
             lib.pmcts_forest_destroy(handle)
+            raise
+        # The native forest lives on behind the results: the arrays of a tree / of the master are copied out of it
+        # when they are first read, and it is destroyed with the last object that refers to it.
+        native = _NativeForest(lib, handle, S)
+        for ti, t in enumerate(trees):
+            _export_tree(native, ti, t, root_state, budget)
+        from .master_node import MasterDict
+        return MasterDict(loader=native.master_arrays, size=native.master_size())
+
+
+class _NativeForest:
+    """Owner of a ``pmcts_forest`` handle after a search."""
+
+    def __init__(self, lib, handle, nscen):
+        self.lib, self.handle, self.nscen = lib, handle, nscen
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.pmcts_forest_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def master_size(self):
+        return int(self.lib.pmcts_forest_master_size(self.handle))
+
+    def master_arrays(self):
+        n = self.master_size()
+        parent = np.empty(n, np.int32)
+        arm = np.empty(n, np.int8)
+        table = np.empty((n, self.nscen, len(ACTIONS), 12), np.uint32)
+        N.check_forest(self.lib.pmcts_forest_export_master(self.handle, parent.ctypes.data, arm.ctypes.data,
+                                                           table.ctypes.data))
+        return parent, arm, table
+
+    def tree_arrays(self, ti):
+        n = int(self.lib.pmcts_forest_tree_size(self.handle, ti))
+        parent = np.empty(n, np.int32)
+        arm = np.empty(n, np.int8)
+        table = np.empty((n, len(ACTIONS), 12), np.int64)
+        n_untried = np.empty(n, np.uint8)
+        untried = np.empty((n, len(ACTIONS)), np.uint8)
+        N.check_forest(self.lib.pmcts_forest_export_tree(self.handle, ti, parent.ctypes.data, arm.ctypes.data,
+                                                         table.ctypes.data, n_untried.ctypes.data, untried.ctypes.data))
+        return parent, arm, table.astype(int, copy=False), n_untried, untried
+
+
+def _rollout_hook(eng, slots, K, root_state, destination, timemin, seed, S, first_scenario, flags):
+    """ctypes callback that hands a wave to ``eng.rollout_forest`` (an object without a device context: the stand-in
+    engines of the CPU tests)."""
+    import ctypes as C
+
+    def hook(_user, wave, n_local, _scen_ids, b, stride, plen_p, path_p, bins_p):
+        try:
+            plen = np.ctypeslib.as_array(C.cast(plen_p, C.POINTER(C.c_int32)), shape=(n_local * b,))
+            path = np.ctypeslib.as_array(C.cast(path_p, C.POINTER(C.c_int8)), shape=(n_local, b, stride))
+            bins = np.ctypeslib.as_array(C.cast(bins_p, C.POINTER(C.c_uint32)), shape=(n_local * b * 12,))
+            depth = max(1, int(plen.max()))
+            prefix = np.where(path[:, :, :depth] >= 0, path[:, :, :depth].astype(np.float64) * 45.0, 0.0)
+            eng.rollout_forest(slots, b, K, root_state, destination, timemin, np.ascontiguousarray(prefix).reshape(-1),
+                               plen, depth, prefix_shared=False, seed=seed, stream=wave * S + first_scenario, id0=0,
+                               out=dict(leaf_bins=bins), flags=flags)
+            return 0
+        except Exception:  # an exception must not cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 1
+    return N.ROLLOUT_HOOK_FN(hook)
+
+
+def _host_exchange(dist, group, world):
+    """All-gather of the update blocks over host buffers (gloo in the CPU tests; any backend without a device
+    communicator)."""
+    import ctypes as C
+    import torch
+
+    def exchange(_user, send_p, nbytes, recv_p):
+        try:
+            send = torch.from_numpy(np.ctypeslib.as_array(C.cast(send_p, C.POINTER(C.c_uint8)), shape=(nbytes,)))
+            recv = torch.from_numpy(np.ctypeslib.as_array(C.cast(recv_p, C.POINTER(C.c_uint8)), shape=(nbytes * world,)))
+            if dist.get_backend(group) == "nccl":
+                dev = torch.device("cuda", torch.cuda.current_device())
+                out = torch.empty(nbytes * world, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(out, send.to(dev), group=group)
+                recv.copy_(out.cpu())
+            else:
+                dist.all_gather_into_tensor(recv, send, group=group)
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+    return N.EXCHANGE_FN(exchange)
+
+
+def _device_comm(eng, dist, group, rank, world):
+    """The engine's NCCL communicator for this process group (``pmcts_comm``), created on first use: rank 0's
+    unique id reaches the other ranks through one ``torch.distributed`` broadcast."""
+    import ctypes as C
+    import torch
+    if dist.get_backend(group) != "nccl":
+        return None
+    cache = eng.__dict__.setdefault("_comms", {})
+    key = (id(group), world, rank)
+    if key not in cache:
+        lib = N.lib()
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            N.check(lib.pmcts_comm_unique_id(uid.ctypes.data))
+        t = torch.from_numpy(uid).to(torch.device("cuda", eng.device))
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        uid = t.cpu().numpy()
+        h = C.c_void_p()
+        N.check(lib.pmcts_comm_create(eng._h, world, rank, uid.ctypes.data, C.byref(h)))
+        cache[key] = h
+    return cache[key]
 
 
 def _dist_env(group):
@@ -222,27 +347,20 @@ def _dist_env(group):
     return None, 0, 1
 
 
-def _export_tree(lib, handle, ti, tree, root_state, iterations):
-    """Copies a native worker tree into NumPy arrays; ``tree.Nodes`` / ``rootNode`` / ``depth`` (``worker.Node``
-    objects over one table) are rebuilt from them the first time they are read (``Tree.__getattr__``)."""
-    n = int(lib.pmcts_forest_tree_size(handle, ti))
-    parent = np.empty(n, np.int32)
-    arm = np.empty(n, np.int8)
-    table = np.empty((n, len(ACTIONS), 12), np.int64)
-    n_untried = np.empty(n, np.uint8)
-    untried = np.empty((n, len(ACTIONS)), np.uint8)
-    N.check_forest(lib.pmcts_forest_export_tree(handle, ti, parent.ctypes.data, arm.ctypes.data, table.ctypes.data,
-                                                n_untried.ctypes.data, untried.ctypes.data))
-    tree.table, tree._cap = table.astype(int, copy=False), n
+def _export_tree(native, ti, tree, root_state, iterations):
+    """Points a worker ``Tree`` at its native tree: ``tree.table`` and ``tree.Nodes`` / ``rootNode`` / ``depth``
+    (``worker.Node`` objects over that table) are built the first time they are read (``Tree.__getattr__``)."""
     tree.ite = iterations
-    for name in ("Nodes", "rootNode", "depth"):
+    for name in ("Nodes", "rootNode", "depth", "table", "_cap"):
         tree.__dict__.pop(name, None)
-    tree._lazy_nodes = (parent, arm, n_untried, untried, tuple(root_state))
+    tree._lazy_nodes = (native, ti, tuple(root_state))
 
 
 def materialize_tree(tree):
-    """Builds ``tree.Nodes`` from the arrays ``_export_tree`` left (called by ``Tree.__getattr__``)."""
-    parent, arm, n_untried, untried, root_state = tree.__dict__.pop("_lazy_nodes")
+    """Builds ``tree.table`` and ``tree.Nodes`` from the native tree (called by ``Tree.__getattr__``)."""
+    native, ti, root_state = tree.__dict__.pop("_lazy_nodes")
+    parent, arm, table, n_untried, untried = native.tree_arrays(ti)
+    tree.table, tree._cap = table, parent.size
     nodes = []
     for i in range(parent.size):
         node = mt.Node.__new__(mt.Node)
@@ -262,33 +380,6 @@ def materialize_tree(tree):
     tree.Nodes = nodes
     tree.rootNode = nodes[0]
     tree.depth = max(nd.depth for nd in nodes)
-
-
-def _import_master(lib, handle, nscen):
-    """The master dictionary ``{hash(tuple(origins)): MasterNode}`` from the native master tree."""
-    n = int(lib.pmcts_forest_master_size(handle))
-    parent = np.empty(n, np.int32)
-    arm = np.empty(n, np.int8)
-    table = np.empty((n, nscen, len(ACTIONS), 12), np.uint32)
-    N.check_forest(lib.pmcts_forest_export_master(handle, parent.ctypes.data, arm.ctypes.data, table.ctypes.data))
-    table = table.astype(int)
-    out, nodes, paths = dict(), [], []
-    for i in range(n):
-        p = nodes[parent[i]] if parent[i] >= 0 else None
-        path = [] if p is None else paths[parent[i]] + [int(ACTIONS[arm[i]])]
-        node = MasterNode.__new__(MasterNode)
-        node.hash = hash(tuple(path))
-        node.arm = None if p is None else ACTIONS[arm[i]]
-        node.parentNode = p
-        node.children = []
-        node.depth = None
-        node.guessed_rewards = dict()
-        node._table = table[i]
-        node._rewards = None
-        nodes.append(node)
-        paths.append(path)
-        out[node.hash] = node
-    return out
 
 
 def _master_add(Master_nodes, nscen, scen_id, path, slot, bins):
@@ -331,7 +422,7 @@ def _all_gather_blocks(block, dist, group, world):
     for r in range(world):
         o = 0
         blk = {}
-        for name, shape in (("ids", (s_loc,)), ("paths", (s_loc, b, MAX_DEPTH)), ("slots", (s_loc, b)),
+        for name, shape in (("ids", (s_loc,)), ("paths", (s_loc, b, block["paths"].shape[2])), ("slots", (s_loc, b)),
                             ("bins", (s_loc, b, 12))):
             size = int(np.prod(shape))
             blk[name] = recv[r, o:o + size].reshape(shape)

@@ -30,7 +30,18 @@ class MasterNode:
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_rewards"] = None  # views of _table: rebuilt on first use after unpickling
+        if d.get("_owner") is not None:  # a node of an array-backed dictionary pickles as a plain node
+            d["children"] = self.children
+            d["_owner"] = None
         return d
+
+    def __getattr__(self, name):
+        # Only reached when the attribute is missing: the children of a node of an array-backed dictionary
+        # (MasterDict) are listed the first time they are read.
+        if name == "children" and self.__dict__.get("_owner") is not None:
+            kids = self.__dict__["children"] = self._owner._children_of(self._index)
+            return kids
+        raise AttributeError(name)
 
     @property
     def rewards(self):
@@ -57,9 +68,131 @@ class MasterNode:
         return bool(self._table[idscenario].any())
 
 
+class MasterDict(dict):
+    """The master dictionary ``{hash(tuple(origins)): MasterNode}`` over the arrays of the native master tree
+    (``parent[node]``, ``arm[node]`` = index in ACTIONS, ``table[node][scenario][8][12]``; a node's parent always
+    has a smaller index).  A search of 10^5 nodes would spend longer building 10^5 ``MasterNode`` objects than
+    searching, so they are built when the dictionary is first read -- all of them by the ``dict`` methods, one by
+    one (with its ancestors) by ``node_at``.  ``wired`` dictionaries (what ``deepcopy_dict`` returns) also carry
+    ``children`` and ``depth``.  ``arrays()`` hands the arrays to array consumers (``MasterTree``'s device
+    reductions) as long as the dictionary has not been edited through the ``dict`` interface."""
+
+    def __init__(self, parent=None, arm=None, table=None, wired=False, loader=None, size=None):
+        super().__init__()
+        self._loader = loader  # () -> (parent, arm, table): the arrays are fetched on first need
+        self._parent, self._arm, self._table = parent, arm, table
+        self._wired = bool(wired)
+        n = int(size if loader is not None else parent.size)
+        self._nodes = [None] * n
+        self._filled = n == 0
+        self._dirty = False
+        self._depth = None
+        self._kids = None
+
+    # ---- array side ------------------------------------------------------------------------------------
+    def _load(self):
+        if self._loader is not None:
+            self._parent, self._arm, self._table = self._loader()
+            self._loader = None
+
+    def arrays(self):
+        """(parent, arm, table) or None once nodes have been added / removed through the dict interface."""
+        if self._dirty:
+            return None
+        self._load()
+        return self._parent, self._arm, self._table
+
+    def depths(self):
+        self._load()
+        if self._depth is None:
+            d = np.zeros(self._parent.size, np.int32)
+            for i in range(1, d.size):  # parents come first
+                d[i] = d[self._parent[i]] + 1
+            self._depth = d
+        return self._depth
+
+    def _children_of(self, i):
+        self._load()
+        if self._kids is None:
+            kids = [[] for _ in range(self._parent.size)]
+            for j in range(1, self._parent.size):
+                kids[self._parent[j]].append(j)
+            self._kids = kids
+        return [self.node_at(j) for j in self._kids[i]]
+
+    def node_at(self, i):
+        """The ``MasterNode`` of array index ``i`` (built with its ancestors on first use)."""
+        node = self._nodes[i]
+        if node is not None:
+            return node
+        self._load()
+        p = int(self._parent[i])
+        parent = self.node_at(p) if p >= 0 else None
+        node = MasterNode.__new__(MasterNode)
+        node._path = () if parent is None else parent._path + (int(ACTIONS[self._arm[i]]),)
+        node.hash = hash(node._path)
+        node.arm = None if parent is None else ACTIONS[self._arm[i]]
+        node.parentNode = parent
+        node.guessed_rewards = dict()
+        node._table = self._table[i]
+        node._rewards = None
+        node._index = i
+        if self._wired:
+            node._owner = self  # children are listed on first read (MasterNode.__getattr__)
+            node.depth = 0 if parent is None else parent.depth + 1
+        else:  # as the search leaves them: not linked downwards (master_node.py:21-22)
+            node._owner = None
+            node.children = []
+            node.depth = None
+        self._nodes[i] = node
+        return node
+
+    def _fill(self):
+        if not self._filled:
+            self._filled = True
+            for i in range(len(self._nodes)):
+                dict.__setitem__(self, self.node_at(i).hash, self._nodes[i])
+
+    # ---- dict side: everything reads through _fill -----------------------------------------------------
+    def __len__(self):
+        return dict.__len__(self) if self._filled else len(self._nodes)
+
+    def __reduce__(self):  # pickles as a plain dict of plain nodes (master.py:390-410 tools read it)
+        self._fill()
+        return (dict, (), None, None, iter(dict.items(self)))
+
+
+def _reads(name, edits=False):
+    base = getattr(dict, name)
+
+    def method(self, *a, **k):
+        self._fill()
+        if edits:
+            self._dirty = True
+        return base(self, *a, **k)
+    method.__name__ = name
+    return method
+
+
+for _name in ("__getitem__", "__contains__", "__iter__", "get", "keys", "values", "items", "__repr__", "__eq__",
+              "__ne__", "copy", "__reversed__"):
+    setattr(MasterDict, _name, _reads(_name))
+for _name in ("__setitem__", "__delitem__", "pop", "popitem", "setdefault", "update", "clear", "__ior__"):
+    setattr(MasterDict, _name, _reads(_name, edits=True))
+MasterDict.__hash__ = None
+
+
 def deepcopy_dict(nodes):
     """Deep copy of the dictionary the search returns, rewired with ``parentNode``, ``children`` and
     ``depth`` (master_node.py:66-109).  Empties ``nodes`` as the reference does."""
+    if isinstance(nodes, MasterDict) and nodes.arrays() is not None:
+        # array-backed result of the native search: the copy is three array copies
+        parent, arm, table = nodes.arrays()
+        new = MasterDict(parent.copy(), arm.copy(), np.array(table, dtype=int), wired=True)
+        dict.clear(nodes)
+        nodes._parent, nodes._arm, nodes._table = parent[:0], arm[:0], table[:0]
+        nodes._nodes, nodes._filled, nodes._kids, nodes._depth = [], True, None, None
+        return new
     root_key = hash(tuple([]))
     n = nodes[root_key]._table.shape[0]
     new_dict = dict()

@@ -145,7 +145,7 @@ class Tree:
     def __getattr__(self, name):
         # Only reached when the attribute is missing: after a native batched search (forest._export_tree) the node
         # objects are built on first use -- a 10^4-node tree costs 50 ms of interpreter time nobody may ask for.
-        if name in ("Nodes", "rootNode", "depth") and "_lazy_nodes" in self.__dict__:
+        if name in ("Nodes", "rootNode", "depth", "table", "_cap") and "_lazy_nodes" in self.__dict__:
             from .forest import materialize_tree
             materialize_tree(self)
             return self.__dict__[name]

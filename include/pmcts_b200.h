@@ -67,6 +67,9 @@ typedef struct pmcts_ctx pmcts_ctx;
                                                (device arrays: orders the stream), pmcts_wait (blocks the host: what a
                                                caller with host arrays needs) or pmcts_synchronize; host arrays must
                                                stay alive until then.  Two launches may be in flight. */
+#define PMCTS_ROLL_PREFIX_ACTIONS 0x20       /* rollout_batch / rollout_forest: `prefix` points to int8_t[..][prefix_stride] indices into
+                                               the reference's ACTIONS (simulatorTLKT.py:29; heading = 45 a degrees, -1 pads a path)
+                                               instead of fp64 degrees: what the host tree hands over, an eighth of the bytes */
 #define PMCTS_MEM_HOST 0x100                /* array arguments are host memory */
 
 /* arithmetic mode */
@@ -95,6 +98,10 @@ const char *pmcts_version(void);
  * stream, which pmcts_reset_stream restores. */
 int pmcts_set_stream(pmcts_ctx *ctx, void *cuda_stream);
 int pmcts_reset_stream(pmcts_ctx *ctx);
+/* The cudaStream_t the ctx currently runs on, and its device ordinal (for callers that enqueue their own work
+ * -- copies, collectives -- in order with the library's). */
+void *pmcts_get_stream(pmcts_ctx *ctx);
+int pmcts_get_device(pmcts_ctx *ctx);
 int pmcts_synchronize(pmcts_ctx *ctx);
 /* Makes the ctx stream wait for the deferred finishers (PMCTS_ROLL_DEFER_REDO) of all but the `keep_last`
  * most recent launches: work enqueued on the stream afterwards sees their complete outputs. */
@@ -285,6 +292,74 @@ int pmcts_python_shuffles(uint64_t seed, int64_t count, int n_items, uint8_t *ou
 int pmcts_forest_export_tree(pmcts_forest *f, int local_index, int32_t *parent, int8_t *arm, int64_t *table,
                              uint8_t *n_untried, uint8_t *untried);
 int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, uint32_t *table);
+/* The master as the runtime keeps it -- a node near the root is visited by every scenario, a deep one by the tree
+ * that grew it, so a (node, scenario) pair owns an 8 x 12 row only once that scenario has filed a histogram there:
+ * row_index[node][n_scen] (-1: no row) into rows[pmcts_forest_master_rows()][8][12] uint32.  This is the layout
+ * pmcts_master_policy reads. */
+int64_t pmcts_forest_master_rows(pmcts_forest *f);
+int pmcts_forest_export_master_rows(pmcts_forest *f, int32_t *parent, int8_t *arm, int32_t *row_index, uint32_t *rows);
+
+/* ---- multi-GPU exchange: the all-gather of the per-wave update blocks ------------------------------------
+ * Replaces the Manager().dict() proxy through which the reference's worker processes reach the master tree
+ * (forest.py:60-66, worker.py:348-378): every rank contributes the block of its own scenarios and receives
+ * everybody's, in rank order.  One communicator per ctx (= per GPU, one process per GPU); the collective is
+ * NCCL's all-gather over NVLink / NVSwitch (libnccl.so.2, loaded on first use -- the library has no link-time
+ * dependency on it), enqueued on the ctx stream.
+ *   pmcts_comm_unique_id: on rank 0; hand the 128 bytes to every rank by any channel (torch.distributed
+ *     broadcast, MPI, a file) before pmcts_comm_create.
+ *   pmcts_allgather_updates: send [bytes] and recv [world * bytes] are DEVICE buffers; returns without
+ *     synchronising. */
+typedef struct pmcts_comm pmcts_comm;
+int pmcts_comm_unique_id(uint8_t id[128]);
+int pmcts_comm_create(pmcts_ctx *ctx, int world, int rank, const uint8_t id[128], pmcts_comm **out);
+void pmcts_comm_destroy(pmcts_comm *comm);
+int pmcts_allgather_updates(pmcts_ctx *ctx, pmcts_comm *comm, const void *send, size_t bytes, void *recv);
+
+/* ---- the leaf-batched search of Forest.launch_search as ONE native call -------------------------------
+ * (forest.py:45-81 + Tree.uct_search, worker.py:147-186, restated for waves of leaves.)  Per wave:
+ *   host   pmcts_forest_select: n_leaves runs of the tree policy per local tree (virtual visits);
+ *   GPU    the leaves' int8 action paths go up (one copy), K2 rolls out replicas x n_leaves x local scenarios in
+ *          one launch (PMCTS_PREC_FAST + its fp64 finisher on the side stream), the per-leaf histograms are
+ *          packed to uint8 / uint16 counts behind the paths, all-gathered when world > 1 (pmcts_comm), and come
+ *          back in one copy;
+ *   host   pmcts_forest_backup on the local trees, pmcts_forest_master_apply of every rank's block in rank order.
+ * `pipeline` waves are in flight: 1 reproduces the synchronous search (wave w + 1 is selected after wave w has
+ * been backed up); 2 selects wave w + 1 on the host while the GPU rolls out wave w (its leaves hold virtual
+ * visits until they are backed up).  Rank r owns the scenarios r * n_local .. (r + 1) * n_local - 1 (the forest's
+ * local ids) in the ctx slots scen_slots[0 .. n_local).  Scenario s of wave w draws Philox stream w * n_scen + s.
+ * slots_w / slots_m: the random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward
+ * (master_node.py:42), wave after wave, [n_scen][leaves of that wave] each -- drawn by the caller (the
+ * reference uses np.random.randint), for ALL scenarios, identically on every rank.
+ * exchange (optional): an all-gather over HOST buffers used instead of pmcts_comm (gloo, MPI ...).
+ * rollout_hook (test instrumentation; the product passes NULL): stands in for the GPU launch -- fills
+ * leaf_bins[n_local][n_leaves][12] for the given paths -- so that the host logic runs without a device;
+ * then ctx may be NULL. */
+typedef int (*pmcts_exchange_fn)(void *user, const void *send, size_t bytes, void *recv);
+typedef int (*pmcts_rollout_hook_fn)(void *user, int wave, int n_local, const int32_t *scen_ids, int n_leaves,
+                                     int prefix_stride, const int32_t *prefix_len, const int8_t *prefix_act,
+                                     uint32_t *leaf_bins);
+typedef struct {
+    int32_t n_leaves;   /* leaves per tree per wave */
+    int32_t replicas;   /* noise replicas per leaf */
+    int64_t budget;     /* leaves per tree in total */
+    uint64_t seed;      /* Philox key */
+    int32_t roll_flags; /* PMCTS_ROLL_REPLAY_FULL_PREFIX or 0 */
+    int32_t pipeline;   /* waves in flight, 1 or 2 */
+    int32_t world, rank;
+    const int8_t *slots_w, *slots_m;
+    pmcts_comm *comm;   /* world > 1 with device buffers */
+    pmcts_exchange_fn exchange;
+    void *exchange_user;
+    pmcts_rollout_hook_fn rollout_hook;
+    void *hook_user;
+} pmcts_search_params;
+typedef struct {
+    int64_t waves, leaves, rollouts, transitions, arrived, launches;
+    double ms_total, ms_select, ms_wait, ms_backup, ms_master, ms_exchange;
+} pmcts_search_report;
+int pmcts_forest_search(pmcts_ctx *ctx, pmcts_forest *f, const int32_t *scen_slots, const double root[3],
+                        const double dest[2], double tmin, const pmcts_search_params *params,
+                        pmcts_search_report *report);
 
 #ifdef __cplusplus
 }

@@ -24,15 +24,23 @@ def main():
     np.random.seed(2)
     dest, tmin = ft.initialize_simulators(sims, 50, cr.STATE0, 0, seed=2)
     f = ft.Forest(listsimulators=sims, destination=dest, timemin=tmin, budget=budget)
-    f.launch_search(cr.STATE0, 10, mode="batched", leaves=leaves, replicas=replicas, seed=3)  # warm-up
+    pipeline = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    f.launch_search(cr.STATE0, 10, mode="batched", leaves=leaves, replicas=replicas, seed=3, pipeline=pipeline)  # warm-up
+    for _ in range(3):  # plain timings first (the profiler's own overhead is of the order of the search)
+        f = ft.Forest(listsimulators=sims, destination=dest, timemin=tmin, budget=budget)
+        t0 = time.perf_counter()
+        f.launch_search(cr.STATE0, 10, mode="batched", leaves=leaves, replicas=replicas, seed=3, pipeline=pipeline)
+        dt = time.perf_counter() - t0
+        rep = f.last_search_report
+        print("leaves %d replicas %d budget %d pipeline %d: %.2f ms, %.3g rollouts/s | native %s" % (
+            leaves, replicas, budget, pipeline, dt * 1e3, rep["rollouts"] / dt,
+            {k: (round(v, 3) if isinstance(v, float) else v) for k, v in rep.items()}))
     f = ft.Forest(listsimulators=sims, destination=dest, timemin=tmin, budget=budget)
     pr = cProfile.Profile()
-    t0 = time.perf_counter()
     pr.enable()
-    f.launch_search(cr.STATE0, 10, mode="batched", leaves=leaves, replicas=replicas, seed=3)
+    f.launch_search(cr.STATE0, 10, mode="batched", leaves=leaves, replicas=replicas, seed=3, pipeline=pipeline)
     pr.disable()
-    print("leaves %d replicas %d budget %d: %.3f s" % (leaves, replicas, budget, time.perf_counter() - t0))
-    pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(16)
 
 
 if __name__ == "__main__":

@@ -227,6 +227,44 @@ def test_forest_batched_search_decides_like_the_sequential_one(golden_dir):
     assert int(mt2.best_policy[-1][0]) in (0, 45, 315)
 
 
+def _search(sims, destination, timemin, **kw):
+    np.random.seed(5)
+    random.seed(5)
+    forest = ft.Forest(listsimulators=sims, destination=destination, timemin=timemin, budget=kw.pop("budget", 200))
+    master = forest.launch_search(STATE0, 10, mode="batched", seed=9, **kw)
+    return forest, master
+
+
+def test_native_search_driver_grows_the_trees_of_the_python_classes(golden_dir):
+    """pmcts_forest_search (one native call: int8 paths up, K2 over all scenarios, packed histograms back) against
+    the same search on the Python classes with one synchronous host-array launch per wave: same master, node for
+    node and counter for counter, same worker trees -- with 8-bit and with 16-bit counts in the update block.  Two
+    waves in flight: every rollout filed once, reproducible."""
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    destination, timemin = [float(x) for x in g["destination"]], float(g["timemin"])
+    sims = make_sims([0, 1, 2])
+    for replicas in (32, 300):
+        fp, mp = _search(sims, destination, timemin, leaves=48, replicas=replicas, host="python")
+        fn, mn_ = _search(sims, destination, timemin, leaves=48, replicas=replicas, host="native")
+        assert list(mp) == list(mn_) and len(mp) > 200
+        for k in mp:
+            assert np.array_equal(mp[k]._table, mn_[k]._table), k
+        for i in range(3):
+            tp, tn = fp.workers[i], fn.workers[i]
+            assert len(tp.Nodes) == len(tn.Nodes) == 201
+            assert np.array_equal(tp.table[:201], tn.table[:201])
+            assert all([int(x) for x in a.origins] == [int(x) for x in b.origins] for a, b in zip(tp.Nodes, tn.Nodes))
+        rep = fn.last_search_report
+        assert rep["waves"] == 5 and rep["rollouts"] == 3 * 200 * replicas
+        assert rep["transitions"] > 3 * rep["rollouts"] and 0 < rep["arrived"] <= rep["rollouts"]
+        assert int(mn_[ft.ROOT_HASH]._table.sum()) == rep["rollouts"]
+    f2, m2 = _search(sims, destination, timemin, leaves=48, replicas=32, host="native", pipeline=2)
+    f3, m3 = _search(sims, destination, timemin, leaves=48, replicas=32, host="native", pipeline=2)
+    assert list(m2) == list(m3) and all(np.array_equal(m2[k]._table, m3[k]._table) for k in m2)
+    assert [int(m2[ft.ROOT_HASH]._table[s].sum()) for s in range(3)] == [200 * 32] * 3
+    assert all(len(f2.workers[i].Nodes) == 201 for i in range(3))
+
+
 def test_device_backup_equals_host_tree_backup(golden_dir):
     """K3 (pmcts_backup on a device table) adds a wave's histograms exactly where worker.Tree.back_up_leaves
     does on the host table, and pmcts_hist_stats returns Hist.get_mean / visit totals of every node."""

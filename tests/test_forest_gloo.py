@@ -14,7 +14,9 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from iboat_pmcts_b200 import master_node as mn
-from iboat_pmcts_b200.forest import MAX_DEPTH, ROOT_HASH, _all_gather_blocks, _master_add
+from iboat_pmcts_b200.forest import ROOT_HASH, _all_gather_blocks, _master_add
+
+MAX_DEPTH = 12  # width of the path block: len(times) - 1 of the 6-hourly, 3-day axis
 
 S, B, WAVES = 4, 6, 5
 
@@ -102,3 +104,55 @@ def test_single_rank_gather_is_identity():
     blk = _wave_block([0, 1], 0)
     assert _all_gather_blocks(blk, None, None, 1) == [blk]
     assert torch.distributed.is_available()
+
+
+# ---- the native search driver (pmcts_forest_search) at world_size 2 ---------------------------------------
+def _driver_rank_main(rank, world, port, out_dir, pipeline):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import test_host_forest as thf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        forest, master, calls = thf.run("native", n_scen=4, budget=70, leaves=16, replicas=24, group=None,
+                                        pipeline=pipeline)
+        assert all(c[0] == 2 for c in calls)  # every launch covers this rank's two scenarios
+        local = range(rank * 2, rank * 2 + 2)
+        trees = {i: (forest.workers[i].table[:71].copy(), [list(map(int, n.origins)) for n in forest.workers[i].Nodes])
+                 for i in local}
+        with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as f:
+            pickle.dump((_tables(master), trees, forest.last_search_report), f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("pipeline", [1, 2])
+def test_native_driver_two_ranks_equal_one_process(pipeline):
+    """pmcts_forest_search with the scenarios split over two gloo ranks (update blocks exchanged through the host
+    all-gather callback): both ranks end with the master of the single-process search, and each rank's worker
+    trees are the single-process trees of its scenarios -- for the synchronous search and for two waves in flight."""
+    import test_host_forest as thf
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_driver_rank_main, args=(world, _free_port(), d, pipeline), nprocs=world, join=True)
+        got = []
+        for r in range(world):
+            with open(os.path.join(d, "rank%d.pkl" % r), "rb") as f:
+                got.append(pickle.load(f))
+    forest, master, _ = thf.run("native", n_scen=4, budget=70, leaves=16, replicas=24, group=False, pipeline=pipeline)
+    want = _tables(master)
+    for tables, trees, report in got:
+        assert list(tables) == list(want)  # same nodes, created in the same order
+        for k in want:
+            assert np.array_equal(tables[k][0], want[k][0]) and tables[k][1:] == want[k][1:]
+        for i, (table, origins) in trees.items():
+            assert np.array_equal(table, forest.workers[i].table[:71])
+            assert origins == [list(map(int, n.origins)) for n in forest.workers[i].Nodes]
+        assert report["waves"] == 5 and report["leaves"] == 2 * 70 and report["rollouts"] == 2 * 70 * 24
+    root = want[ROOT_HASH][0]
+    assert [int(root[s].sum()) for s in range(4)] == [70 * 24] * 4

@@ -58,14 +58,14 @@ class FakeSim:
         return self
 
 
-def run(host, n_scen=3, budget=150, leaves=16, replicas=24, seed=4):
+def run(host, n_scen=3, budget=150, leaves=16, replicas=24, seed=4, group=False, pipeline=1):
     FakeSim._engine = FakeEngine()
     random.seed(10)
     np.random.seed(10)
     forest = ft.Forest(listsimulators=[FakeSim(i) for i in range(n_scen)], destination=[46.7, 355.0], timemin=2.0,
                        budget=budget)
     master = forest.launch_search([0, 44.0, 355.0], 10, mode="batched", leaves=leaves, replicas=replicas, seed=seed,
-                                  host=host, group=False)
+                                  host=host, group=group, pipeline=pipeline)
     return forest, master, FakeSim._engine.calls
 
 
@@ -97,6 +97,28 @@ def test_native_forest_equals_python_forest():
         mt.get_best_policy(verbose=False)
         pols.append({k: [int(a) for a in v] for k, v in mt.best_policy.items()})
     assert pols[0] == pols[1] and len(pols[0][-1]) >= 1
+
+
+def test_two_waves_in_flight():
+    """pipeline=2: wave w + 1 is selected while wave w is out (its leaves hold virtual visits).  Every rollout is
+    still filed exactly once, the trees have one node per iteration, the search is reproducible, and it is not the
+    synchronous search."""
+    f1, m1, calls1 = run("native", pipeline=1)
+    f2, m2, calls2 = run("native", pipeline=2)
+    f3, m3, _ = run("native", pipeline=2)
+    assert [c[:3] for c in calls1] == [c[:3] for c in calls2] and len(calls2) == 10
+    assert list(m2) == list(m3) and all(np.array_equal(m2[k]._table, m3[k]._table) for k in m2)
+    assert list(m1) != list(m2)
+    root = m2[ft.ROOT_HASH]._table
+    assert [int(root[s].sum()) for s in range(3)] == [150 * 24] * 3
+    for i in range(3):
+        t = f2.workers[i]
+        assert len(t.Nodes) == 151 and int(t.rootNode.visits()) == 150 * 24
+        # a node's counters are the sum of its children's plus what was filed at the node itself (as a leaf)
+        for node in t.Nodes:
+            below = sum(int(c._table.sum()) for c in node.children)
+            assert int(node._table.sum()) >= below
+    assert f2.last_search_report["waves"] == 10
 
 
 def test_native_forest_reads_the_module_coefficients(monkeypatch):
