@@ -342,6 +342,31 @@ class Engine:
                                            a.ptr(visits, "u32", n_nodes, True), a.mem_flag))
 
 
+    def master_policy(self, parent, arm, row_index, rows, probability, uct_coeff, max_depth,
+                      want=("policy", "policy_nodes")):
+        """``pmcts_master_policy`` on host arrays: returns a dict with the outputs named in ``want`` (value,
+        explore, guess, best_child, policy, policy_nodes)."""
+        parent = np.ascontiguousarray(parent, np.int32)
+        arm = np.ascontiguousarray(arm, np.int8)
+        row_index = np.ascontiguousarray(row_index, np.int32)
+        rows = np.ascontiguousarray(rows, np.uint32)
+        prob = np.ascontiguousarray(probability, np.float64)
+        n, S = int(parent.size), int(prob.size)
+        n_rows = int(rows.size // 96)
+        if row_index.size != n * S:
+            raise ValueError("row_index must have shape (nodes, scenarios)")
+        spec = dict(value=((n, S + 1), np.float64), explore=((n, S + 1), np.float64), guess=((n, S), np.float64),
+                    best_child=((n, S + 1), np.int32), policy=((S + 1, max_depth), np.int8),
+                    policy_nodes=((S + 1, max_depth + 1), np.int32))
+        out = {k: np.empty(*spec[k]) for k in want}
+        ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        N.check(self._lib.pmcts_master_policy(self._h, n, S, parent.ctypes.data, arm.ctypes.data, row_index.ctypes.data,
+                                              n_rows, rows.ctypes.data, prob.ctypes.data, float(uct_coeff),
+                                              int(max_depth), ptr("value"), ptr("explore"), ptr("guess"),
+                                              ptr("best_child"), ptr("policy"), ptr("policy_nodes"), N.MEM_HOST))
+        return out
+
+
 _default = {}
 _default_device = None
 

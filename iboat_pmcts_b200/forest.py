@@ -224,7 +224,7 @@ class Forest:
         for ti, t in enumerate(trees):
             _export_tree(native, ti, t, root_state, budget)
         from .master_node import MasterDict
-        return MasterDict(loader=native.master_arrays, size=native.master_size())
+        return MasterDict(loader=native.master_arrays, size=native.master_size(), sparse_loader=native.master_rows)
 
 
 class _NativeForest:
@@ -252,6 +252,16 @@ class _NativeForest:
         N.check_forest(self.lib.pmcts_forest_export_master(self.handle, parent.ctypes.data, arm.ctypes.data,
                                                            table.ctypes.data))
         return parent, arm, table
+
+    def master_rows(self):
+        n = self.master_size()
+        parent = np.empty(n, np.int32)
+        arm = np.empty(n, np.int8)
+        row_index = np.empty((n, self.nscen), np.int32)
+        rows = np.empty((int(self.lib.pmcts_forest_master_rows(self.handle)), 96), np.uint32)
+        N.check_forest(self.lib.pmcts_forest_export_master_rows(self.handle, parent.ctypes.data, arm.ctypes.data,
+                                                                row_index.ctypes.data, rows.ctypes.data))
+        return parent, arm, row_index, rows
 
     def tree_arrays(self, ti):
         n = int(self.lib.pmcts_forest_tree_size(self.handle, ti))

@@ -1,14 +1,18 @@
 """Drop-in mirror of ``code/solver/master.py`` (reference): ``MasterTree`` post-processing of a search --
 best policy per scenario and globally, utilities, reward guesses for unexplored (node, scenario) pairs,
-pickle save / load.  Host code, as in the reference (O(nodes) work after the search; SURVEY.md section 8f
-N1).  Plotting methods are out of scope.
+pickle save / load.  Plotting methods are out of scope.
+
+The reference walks ``MasterNode`` objects and their ``Hist`` arrays in Python loops (master.py:57-185).
+Here the whole tree is reduced at once on the GPU (``pmcts_master_policy``, csrc/pmcts_master.cu): for every
+node, every scenario and the probability-weighted global tree -- the two utility terms, the guessed rewards,
+the best child, and the greedy policies.  The methods of the reference's API read those arrays; node objects
+are only built for what the caller looks at (the nodes along the best policies).
 """
 import pickle
-from math import log
 
 import numpy as np
 
-from .master_node import MasterNode
+from .master_node import MasterDict, MasterNode
 from .simulatorTLKT import ACTIONS
 from .worker import UCT_COEFF  # bound at import, like the reference (master.py:11; quirk Q4)
 
@@ -34,89 +38,130 @@ class MasterTree:
             self.probability = np.array([1 / num_scenarios for _ in range(num_scenarios)])
         else:
             self.probability = np.array(proba)
+        self._solved = None
 
+    # ---- the tree as arrays, reduced on the device -----------------------------------------------------
+    def _arrays(self):
+        """(parent, arm, row_index, rows, node_of_index): the layout ``pmcts_master_policy`` reads.  Straight from
+        the native search when ``nodes`` is its array-backed dictionary; otherwise gathered from the node objects
+        (children ranked in dictionary order, as ``deepcopy_dict`` links them)."""
+        nodes = self.nodes
+        if isinstance(nodes, MasterDict):
+            sparse = nodes.sparse()
+            if sparse is not None:
+                return sparse + (nodes.node_at,)
+        order, index = [], {}
+        for node in nodes.values():  # parents first: a child is created after its parent in every search
+            order.append(node)
+        order.sort(key=lambda nd: _depth_of(nd))  # stable: keeps dictionary order within a depth
+        for i, node in enumerate(order):
+            index[id(node)] = i
+            node._index = i
+        n, S = len(order), self.numScenarios
+        parent = np.array([index[id(nd.parentNode)] if nd.parentNode is not None else -1 for nd in order], np.int32)
+        arm = np.array([list(ACTIONS).index(nd.arm) if nd.parentNode is not None else 0 for nd in order], np.int8)
+        table = np.stack([np.asarray(nd._table) for nd in order]).astype(np.uint32).reshape(n * S, 96)
+        used = table.any(axis=1)
+        row_index = np.where(used, np.cumsum(used) - 1, -1).astype(np.int32).reshape(n, S)
+        return parent, arm, row_index, np.ascontiguousarray(table[used]), order.__getitem__
+
+    def _solve(self, want=("value", "explore", "guess", "best_child", "policy", "policy_nodes")):
+        from .engine import default_engine
+        parent, arm, row_index, rows, node_of = self._arrays()
+        eng = default_engine()
+        max_depth = max(1, len(self.Simulators[0].times) - 1) if len(self.Simulators) else 64
+        out = eng.master_policy(parent, arm, row_index, rows, self.probability, UCT_COEFF, max_depth, want=want)
+        out["node_of"], out["arm"], out["parent"] = node_of, arm, parent
+        return out
+
+    def _full(self):
+        """All per-node arrays (the API calls that look at single nodes read them); computed once."""
+        if self._solved is None or "value" not in self._solved:
+            self._solved = self._solve()
+        return self._solved
+
+    # ---- reference API ---------------------------------------------------------------------------------
     def get_best_policy(self, verbose=True):
-        """Greedy descent from the root for every scenario and for the global tree (master.py:57-84)."""
+        """Greedy descent from the root for every scenario and for the global tree (master.py:57-84): the
+        device follows ``get_best_child`` for all of them at once; only the policies come back."""
+        sol = self._solve(want=("policy", "policy_nodes", "value") if verbose else ("policy", "policy_nodes"))
+        node_of = sol["node_of"]
         for id_scenario in range(-1, len(self.Simulators)):
+            row = id_scenario + 1
+            idx = [int(i) for i in sol["policy_nodes"][row] if i >= 0]
+            policy = [ACTIONS[a] for a in sol["policy"][row] if a >= 0]
             if verbose:
                 print("Global policy" if id_scenario == -1 else "Policy for scenario {}".format(id_scenario))
-            node = self.nodes[ROOT_HASH]
-            nodes_policy, policy = [node], []
-            while node.children:
-                child, action = self.get_best_child(node, idscenario=id_scenario, verbose=verbose)
-                if child is None:
-                    break
-                nodes_policy.append(child)
-                policy.append(action)
-                node = child
+                col = self.numScenarios if id_scenario == -1 else id_scenario
+                for depth, (i, action) in enumerate(zip(idx[1:], policy), 1):
+                    print("Depth {}: best reward = {} for action = {}".format(depth, sol["value"][i, col], action))
             self.best_policy[id_scenario] = policy
-            self.best_nodes_policy[id_scenario] = nodes_policy
+            self.best_nodes_policy[id_scenario] = [node_of(i) for i in idx]
+
+    def _col(self, idscenario):
+        return self.numScenarios if idscenario == -1 else int(idscenario)
+
+    def _index(self, node):
+        self._full()  # (gathering the arrays numbers the nodes of a plain dictionary)
+        return node._index
 
     def get_best_child(self, node, idscenario=-1, verbose=False):
-        """Child with the largest exploitation value (first maximum wins; values must be > 0)."""
-        best_reward, best_action, best_child = 0, None, None
-        if idscenario != -1 and all(not child.is_expanded(idscenario) for child in node.children):
-            return best_child, best_action
-        for child in node.children:
-            value, _ = self.get_utility(child, idscenario)
-            if value > best_reward:
-                best_reward, best_child, best_action = value, child, child.arm
-        if verbose and best_child is not None:
-            print("Depth {}: best reward = {} for action = {}".format(best_child.depth, best_reward, best_action))
-        return best_child, best_action
+        """Child with the largest exploitation value (first maximum wins; values must be > 0); ``(None, None)``
+        when the scenario expanded none of the children (master.py:86-115)."""
+        sol = self._full()
+        c = int(sol["best_child"][self._index(node), self._col(idscenario)])
+        if c < 0:
+            return None, None
+        child = sol["node_of"](c)
+        if verbose:
+            print("Depth {}: best reward = {} for action = {}".format(child.depth, sol["value"][c, self._col(idscenario)],
+                                                                      child.arm))
+        return child, child.arm
 
     def guess_reward(self, node, idscenario):
-        """Reward of a node a scenario never explored: the lowest reward for which its father would have been
-        expanded next (master.py:117-138)."""
-        father = node.parentNode
-        if father.is_expanded(idscenario):
-            _, exploration = self.get_utility(father, idscenario)
-            best_uncle, _ = self.get_best_child(father.parentNode, idscenario)
-            value_grd, expl_grd = self.get_utility(best_uncle, idscenario)
-            return value_grd + expl_grd - exploration
-        return father.guessed_rewards[idscenario]
+        """Reward of a node a scenario never explored: the lowest reward for which its nearest explored ancestor
+        would have been expanded next (master.py:117-138)."""
+        g = float(self._full()["guess"][self._index(node), int(idscenario)])
+        if g != g:
+            raise AttributeError("'NoneType' object has no attribute 'children'")  # what the reference runs into
+        return g
 
     def get_utility(self, node, idscenario):
         """(exploitation, exploration) of a node for one scenario, or probability-weighted over the scenarios
         for ``idscenario == -1`` with guessed rewards where a scenario did not expand the node
         (master.py:140-185)."""
-        if idscenario != -1 and not node.is_expanded(idscenario):
-            return 0, 0
-        num_parent = 0
-        num_node = 0
-        reward_per_action = np.zeros(shape=len(ACTIONS))
-        for j in range(len(ACTIONS)):
-            if idscenario == -1:
-                per_scenario = []
-                for i in range(self.numScenarios):
-                    if node.is_expanded(i):
-                        per_scenario.append(node.rewards[i, j].get_mean())
-                        num_node += sum(node.rewards[i, j].h)
-                        num_parent += sum(node.parentNode.rewards[i, j].h)
-                    else:
-                        guess = self.guess_reward(node, i)
-                        node.guessed_rewards[i] = guess
-                        per_scenario.append(guess)
-                reward_per_action[j] = np.dot(per_scenario, self.probability)
-            else:
-                num_node += sum(node.rewards[idscenario, j].h)
-                if node.parentNode is None:
-                    num_parent = num_node
-                else:
-                    num_parent += sum(node.parentNode.rewards[idscenario, j].h)
-                reward_per_action[j] = node.rewards[idscenario, j].get_mean()
-        value = np.max(reward_per_action)
-        exploration = UCT_COEFF * (2 * log(num_parent) / num_node) ** 0.5
-        return value, exploration
+        sol = self._full()
+        i, col = self._index(node), self._col(idscenario)
+        if idscenario == -1:  # the reference leaves its guesses on the node
+            for s in range(self.numScenarios):
+                g = sol["guess"][i, s]
+                if g == g:
+                    node.guessed_rewards[s] = float(g)
+        return float(sol["value"][i, col]), float(sol["explore"][i, col])
 
     def get_depth(self):
+        if isinstance(self.nodes, MasterDict) and self.nodes.arrays() is not None:
+            return int(self.nodes.depths().max())
         return max(node.depth for node in self.nodes.values())
 
     def save_tree(self, name, directory="../results/"):
         with open(directory + name + '.pickle', 'wb') as f:
             pickle.dump(self, f)
 
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_solved"] = None
+        return d
+
     @classmethod
     def load_tree(cls, name, directory="../results/"):
         with open(directory + name + '.pickle', 'rb') as f:
             return pickle.load(f)
+
+
+def _depth_of(node):
+    d = 0
+    while node.parentNode is not None:
+        node = node.parentNode
+        d += 1
+    return d

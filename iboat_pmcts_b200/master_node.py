@@ -77,9 +77,10 @@ class MasterDict(dict):
     ``children`` and ``depth``.  ``arrays()`` hands the arrays to array consumers (``MasterTree``'s device
     reductions) as long as the dictionary has not been edited through the ``dict`` interface."""
 
-    def __init__(self, parent=None, arm=None, table=None, wired=False, loader=None, size=None):
+    def __init__(self, parent=None, arm=None, table=None, wired=False, loader=None, size=None, sparse_loader=None):
         super().__init__()
         self._loader = loader  # () -> (parent, arm, table): the arrays are fetched on first need
+        self._sparse_loader = sparse_loader  # () -> (parent, arm, row_index, rows): the native runtime's own layout
         self._parent, self._arm, self._table = parent, arm, table
         self._wired = bool(wired)
         n = int(size if loader is not None else parent.size)
@@ -101,6 +102,20 @@ class MasterDict(dict):
             return None
         self._load()
         return self._parent, self._arm, self._table
+
+    def sparse(self):
+        """(parent, arm, row_index[node][scenario], rows[n_rows][96]) -- a (node, scenario) pair has a row only if
+        the scenario visited the node -- or None once the dictionary has been edited."""
+        if self._dirty:
+            return None
+        if self._sparse_loader is not None:
+            return self._sparse_loader()
+        parent, arm, table = self.arrays()
+        n, S = table.shape[0], table.shape[1]
+        flat = np.ascontiguousarray(table, dtype=np.uint32).reshape(n * S, 96)
+        used = flat.any(axis=1)
+        row_index = np.where(used, np.cumsum(used) - 1, -1).astype(np.int32).reshape(n, S)
+        return parent, arm, row_index, np.ascontiguousarray(flat[used])
 
     def depths(self):
         self._load()
@@ -187,10 +202,18 @@ def deepcopy_dict(nodes):
     ``depth`` (master_node.py:66-109).  Empties ``nodes`` as the reference does."""
     if isinstance(nodes, MasterDict) and nodes.arrays() is not None:
         # array-backed result of the native search: the copy is three array copies
-        parent, arm, table = nodes.arrays()
-        new = MasterDict(parent.copy(), arm.copy(), np.array(table, dtype=int), wired=True)
+        if nodes._loader is not None:
+            # not read yet: the copy fetches its own arrays from the (immutable) native forest when it needs them
+            loader = nodes._loader
+            new = MasterDict(wired=True, size=len(nodes), sparse_loader=nodes._sparse_loader,
+                             loader=lambda: tuple(np.array(a, dtype=int if a.ndim == 4 else a.dtype) for a in loader()))
+        else:
+            parent, arm, table = nodes.arrays()
+            new = MasterDict(parent.copy(), arm.copy(), np.array(table, dtype=int), wired=True)
         dict.clear(nodes)
-        nodes._parent, nodes._arm, nodes._table = parent[:0], arm[:0], table[:0]
+        empty = np.zeros(0, np.int32)
+        nodes._loader = nodes._sparse_loader = None
+        nodes._parent, nodes._arm, nodes._table = empty, empty.astype(np.int8), np.zeros((0, 1, 8, 12), np.uint32)
         nodes._nodes, nodes._filled, nodes._kids, nodes._depth = [], True, None, None
         return new
     root_key = hash(tuple([]))

@@ -299,6 +299,24 @@ int pmcts_forest_export_master(pmcts_forest *f, int32_t *parent, int8_t *arm, ui
 int64_t pmcts_forest_master_rows(pmcts_forest *f);
 int pmcts_forest_export_master_rows(pmcts_forest *f, int32_t *parent, int8_t *arm, int32_t *row_index, uint32_t *rows);
 
+/* ---- MasterTree.get_utility / guess_reward / get_best_child / get_best_policy (master.py:57-185) ------------
+ * over the replicated master table, for every node, every scenario and the probability-weighted global tree
+ * (idscenario = -1) at once.  Inputs in the layout of pmcts_forest_export_master_rows: parent[n_nodes] (-1 for the
+ * root; a parent has a smaller index than its children; children are ranked by index, i.e. creation order),
+ * arm[n_nodes], row_index[n_nodes][n_scen], rows[n_rows][8][12], probability[n_scen]; uct_coeff is master.py's
+ * UCT_COEFF (bound at import, master.py:11).  Outputs, any of which may be NULL (column n_scen = the global tree):
+ *   value, explore [n_nodes][n_scen + 1]   the two terms of get_utility (0, 0 where a scenario never expanded the node)
+ *   guess          [n_nodes][n_scen]       guess_reward where the scenario never expanded the node, NaN elsewhere
+ *   best_child     [n_nodes][n_scen + 1]   node index get_best_child returns, -1 for None
+ *   policy         [n_scen + 1][max_depth] int8 action indices of best_policy, -1 padded; row 0 is the global
+ *                                          policy (best_policy[-1]), row 1 + s that of scenario s
+ *   policy_nodes   [n_scen + 1][max_depth + 1] int32 node indices of best_nodes_policy (root first), -1 padded
+ * PMCTS_MEM_HOST: all arrays are host memory and the call returns with the outputs filled. */
+int pmcts_master_policy(pmcts_ctx *ctx, int64_t n_nodes, int n_scen, const int32_t *parent, const int8_t *arm,
+                        const int32_t *row_index, int64_t n_rows, const uint32_t *rows, const double *probability,
+                        double uct_coeff, int max_depth, double *value, double *explore, double *guess,
+                        int32_t *best_child, int8_t *policy, int32_t *policy_nodes, int flags);
+
 /* ---- multi-GPU exchange: the all-gather of the per-wave update blocks ------------------------------------
  * Replaces the Manager().dict() proxy through which the reference's worker processes reach the master tree
  * (forest.py:60-66, worker.py:348-378): every rank contributes the block of its own scenarios and receives

@@ -321,9 +321,80 @@ def isochrone_fixture(R, destination):
                                  for front in solver.isochrone_stock])
 
 
+def master_policy_fixture(R, n_scen=10, budget=120, leaves=16, replicas=24):
+    """The reference's own MasterTree post-processing (master.py:57-185) on a 10-scenario master tree: best policy
+    of every scenario and of the global tree (uniform and skewed scenario probabilities), and along every policy
+    the utilities / guessed rewards the reference computed on the way.  The tree itself comes from this repo's host
+    search runtime driven by a deterministic stand-in for the rollouts (tests/fake_device.py: no GPU here); what is
+    pinned is the reduction of a given table, so any table with shallow nodes shared by all scenarios and deep
+    nodes visited by one will do."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_device
+    mnode, mstr = R.master_node, R.master
+    _, master, _ = fake_device.run("native", n_scen=n_scen, budget=budget, leaves=leaves, replicas=replicas)
+    parent, arm, table = master.arrays()
+    n = parent.size
+    actions = [int(a) for a in R.simulatorTLKT.ACTIONS]
+
+    def build():
+        paths, nodes = [], {}
+        objs = []
+        for i in range(n):
+            path = [] if parent[i] < 0 else paths[parent[i]] + [actions[arm[i]]]
+            paths.append(path)
+            node = mnode.MasterNode(n_scen, nodehash=hash(tuple(path)), parentNode=objs[parent[i]] if parent[i] >= 0 else None,
+                                    action=actions[arm[i]] if parent[i] >= 0 else None)
+            for s in range(n_scen):
+                for a in range(8):
+                    node.rewards[s, a].h = np.array(table[i, s, a], dtype=int)
+            objs.append(node)
+            nodes[node.hash] = node
+
+        class _ProxyLike(dict):  # Manager().dict().items() returns a list copy; deepcopy_dict deletes while iterating
+            def items(self):
+                return list(dict.items(self))
+        return mnode.deepcopy_dict(_ProxyLike(nodes)), paths
+
+    out = dict(parent=parent, arm=arm, table=table.astype(np.uint16), uct_coeff=float(mstr.UCT_COEFF))
+    rng = np.random.default_rng(11)
+    skew = rng.uniform(0.2, 1.0, n_scen)
+    skew[3] = 12.0  # one scenario carries most of the weight: another global policy than the uniform one
+    skew /= skew.sum()
+    for tag, proba in (("uniform", []), ("skewed", list(skew))):
+        nodes, paths = build()
+        index = {hash(tuple(p)): i for i, p in enumerate(paths)}
+        mt = mstr.MasterTree([None] * n_scen, [46.7, 355.0], nodes=nodes, proba=proba)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mt.get_best_policy()
+        pol = np.full((n_scen + 1, 12), -1, np.int32)
+        for sid, acts in mt.best_policy.items():
+            pol[sid + 1, :len(acts)] = acts
+        out["policy_" + tag] = pol
+        out["probability_" + tag] = np.asarray(mt.probability, np.float64)
+        # utilities along the policies, as the reference's own calls return them
+        rec = []
+        for sid, path_nodes in mt.best_nodes_policy.items():
+            for node in path_nodes[1:]:
+                value, expl = mt.get_utility(node, sid)
+                rec.append((index[node.hash], sid, value, expl))
+        out["utility_" + tag] = np.asarray(rec, np.float64)
+        # every guess the global descent left on the nodes (master.py:165-167)
+        gs = [(index[h], s, g) for h, node in nodes.items() for s, g in node.guessed_rewards.items()]
+        out["guess_" + tag] = np.asarray(gs, np.float64)
+    return out
+
+
 def main():
     R = refshim.load_reference()
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-master" in sys.argv:
+        fx = master_policy_fixture(R)
+        np.savez_compressed(os.path.join(GOLD, "master_policy_s10.npz"), **fx)
+        print("master policy: nodes", fx["parent"].size, "global policy", fx["policy_uniform"][0], "skewed",
+              fx["policy_skewed"][0], "guesses", fx["guess_uniform"].shape, "utilities", fx["utility_uniform"].shape)
+        return
     if "--only-isochrone" in sys.argv:
         g = np.load(os.path.join(GOLD, "rollouts_c1.npz"))
         fx = isochrone_fixture(R, g["destination"])
@@ -345,6 +416,7 @@ def main():
         json.dump(tr, f)
     with open(os.path.join(GOLD, "isochrone_c1.json"), "w") as f:
         json.dump(isochrone_fixture(R, g["destination"]), f)
+    np.savez_compressed(os.path.join(GOLD, "master_policy_s10.npz"), **master_policy_fixture(R))
     print("destination", g["destination"], "timemin", g["timemin"])
     print("best_policy", tr["best_policy"], "depth", tr["depth"])
     for fn in sorted(os.listdir(GOLD)):

@@ -2,9 +2,6 @@
 classes it restates (worker.Tree.select_leaves / back_up_leaves, forest._master_add): same leaves, wave after
 wave, same counters in every worker-tree node and every master node, same best policy.  No GPU: the rollout
 launch is replaced by a deterministic stand-in that fills the per-leaf histograms from the leaf's path."""
-import random
-import zlib
-
 import numpy as np
 import pytest
 
@@ -12,61 +9,9 @@ from iboat_pmcts_b200 import _native as N
 from iboat_pmcts_b200 import forest as ft
 from iboat_pmcts_b200 import master_node as mn
 from iboat_pmcts_b200 import worker
-from iboat_pmcts_b200.master import MasterTree
 
 
-class FakeEngine:
-    """Stands in for engine.Engine: rollout_forest files `replicas` rewards per leaf into bins chosen from
-    the leaf's first action, its depth and the scenario (so the trees have something to prefer)."""
-    precision = N.PREC_F64
-
-    def __init__(self):
-        self.calls = []
-
-    def set_precision(self, mode):
-        self.precision = mode
-
-    def rollout_forest(self, scens, n_leaf, replicas, root, dest, tmin, prefix, prefix_len, prefix_stride,
-                       prefix_shared=True, z=None, seed=None, stream=0, id0=0, out=None, flags=0):
-        S = len(scens)
-        pre = np.asarray(prefix, np.float64).reshape(S, n_leaf, prefix_stride)
-        plen = np.asarray(prefix_len).reshape(S, n_leaf)
-        bins = out["leaf_bins"].reshape(S, n_leaf, 12)
-        bins[:] = 0
-        for s in range(S):
-            for l in range(n_leaf):
-                path = tuple(int(a) for a in pre[s, l, :plen[s, l]])
-                h = zlib.crc32(repr((int(scens[s]), path, int(seed), int(stream) + s)).encode())
-                centre = 2 + (path[0] // 45 + 3 * int(scens[s])) % 8
-                rng = np.random.default_rng(h)
-                draws = np.clip(np.rint(rng.normal(centre, 1.2, replicas)), 0, 11).astype(int)
-                bins[s, l] = np.bincount(draws, minlength=12)
-        self.calls.append((S, n_leaf, replicas, int(stream)))
-
-
-class FakeSim:
-    times = np.arange(0, 3 + 6 / 24, 6 * (1 / 24))
-    _engine = None
-
-    def __init__(self, slot):
-        self.slot = slot
-
-    def scenario(self):
-        return FakeSim._engine, self.slot
-
-    def __deepcopy__(self, memo):
-        return self
-
-
-def run(host, n_scen=3, budget=150, leaves=16, replicas=24, seed=4, group=False, pipeline=1):
-    FakeSim._engine = FakeEngine()
-    random.seed(10)
-    np.random.seed(10)
-    forest = ft.Forest(listsimulators=[FakeSim(i) for i in range(n_scen)], destination=[46.7, 355.0], timemin=2.0,
-                       budget=budget)
-    master = forest.launch_search([0, 44.0, 355.0], 10, mode="batched", leaves=leaves, replicas=replicas, seed=seed,
-                                  host=host, group=group, pipeline=pipeline)
-    return forest, master, FakeSim._engine.calls
+from fake_device import FakeEngine, FakeSim, run  # noqa: E402,F401
 
 
 def test_native_forest_equals_python_forest():
@@ -90,13 +35,14 @@ def test_native_forest_equals_python_forest():
             assert len(a.children) == len(b.children) and a.depth == b.depth
         assert int(tn.rootNode.visits()) == 150 * 24
         assert np.array_equal(np.array([h.h for h in tn.Nodes[5].Values]), tn.table[5])
-    # and the decision taken from it
-    pols = []
-    for forest, master in ((fp, mp), (fn, mn_)):
-        mt = MasterTree([w.Simulator for w in forest.workers.values()], [46.7, 355.0], nodes=mn.deepcopy_dict(master))
-        mt.get_best_policy(verbose=False)
-        pols.append({k: [int(a) for a in v] for k, v in mt.best_policy.items()})
-    assert pols[0] == pols[1] and len(pols[0][-1]) >= 1
+    # (the decision taken from it -- MasterTree, reduced on the device -- is compared in tests/test_master_policy_gpu.py)
+    # deepcopy_dict of the array-backed dictionary: same nodes, wired, the source emptied -- without building a
+    # node object until one is read
+    copy = mn.deepcopy_dict(mn_)
+    assert len(mn_) == 0 and len(copy) == len(mp) and not copy._filled
+    root = copy[ft.ROOT_HASH]
+    assert root.depth == 0 and len(root.children) == 8 and all(c.parentNode is root and c.depth == 1 for c in root.children)
+    assert list(copy) == list(mp) and all(np.array_equal(copy[k]._table, mp[k]._table) for k in mp)
 
 
 def test_two_waves_in_flight():
