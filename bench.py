@@ -11,7 +11,14 @@ stream and overlaps the main kernel of step i + 1 (its histograms are gathered a
 later; the last timed step drains the pipeline inside its own window).  Scenarios are the unit of sharding,
 so scaling is weak: per-GPU work is fixed as N grows.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c5|c1] [--impl reference]
+
+The other BASELINE.json configurations run through the reference's own Python API (the mirror classes):
+  c2  Forest.launch_search on 10 scenarios per GPU, 10^4 rollouts per tree (320 leaves x 32 replicas), followed by
+      MasterTree.get_best_policy -- one step = one whole search and its decision;
+  c5  estimate_perfomance_plan: a 6-heading plan replayed on 10^5 noisy draws for each of 10 scenarios per GPU;
+  c1  Tutorial.py's search: 1 scenario, 1 tree, 1000 sequential rollouts in the reference's order;
+  c3  the raw Simulator.doStep sweep (C ABI).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident whole-job transitions/s; `e2e` is the same
 metric through the host-buffer C ABI calls (H2D / D2H inside the timed region).
@@ -27,7 +34,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from iboat_pmcts_b200 import synth  # noqa: E402
 
@@ -44,6 +50,10 @@ F_ALG_ROLLOUT = 480.0  # algorithmic flop per default-policy transition (SURVEY.
 F_ALG_RAW = 328.0      # per raw doStep
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, nominal (no measured fp32 entry in MEASURED_PEAKS.json)
 C3_BOATS, C3_STEPS = 1_000_000, 500
+API_WORKLOADS = ("c1", "c2", "c5")
+C2_SCEN_PER_GPU, C2_LEAVES, C2_REPLICAS, C2_BUDGET = 10, 64, 32, 320   # 320 leaves x 32 replicas ~ 10^4 rollouts per tree
+C5_SCEN_PER_GPU, C5_DRAWS, C5_PLAN = 10, 100_000, (0, 0, 315, 0, 45, 0)
+C1_BUDGET = 1000
 
 
 def sim_axes(wlat, wlon, simtimestep=6, ndaysim=3, d=0.5):
@@ -166,8 +176,27 @@ def cpu_raw_sample(n_boats, nsteps, nthreads):
     return int(r["k"].sum()), n_boats, dt
 
 
+def cpu_plan_sample(n_rollouts, nthreads, scenario=0):
+    """The oracle port on the plan-evaluation workload (c5): the plan replayed unchecked, then the default policy."""
+    from oracle import cport
+    t, la, lo, u, v = synth.wind_fields(scenario)
+    times, lats, lons = sim_axes(la, lo)
+    o = cport.OracleSim(t, la, lo, u, v, times, lats, lons)
+    pre = np.tile(np.asarray(C5_PLAN, np.float64), (n_rollouts, 1))
+    t0 = time.perf_counter()
+    r = o.rollout_batch(n_rollouts, STATE0, DEST, 0.0, prefix=pre, mode=1, seed=SEED, stream=scenario, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return int(r["steps"].sum()), n_rollouts, dt
+
+
 def cpu_baseline(workload, budget_s=12.0):
     cores = os.cpu_count() or 1
+    if workload == "c5":
+        tr, n, dt = cpu_plan_sample(4096 * cores, cores)               # calibration
+        nr = int(max(4096 * cores, min(10 * C5_DRAWS, 4096 * cores * budget_s / max(dt, 1e-3))))
+        tr, n, dt = cpu_plan_sample(nr, cores)
+        return dict(value=tr / dt, unit="transitions/s", cores=cores, kind="port", rollouts_per_s=n / dt, seconds=dt,
+                    sample="%d plan-evaluation rollouts of scenario 0 (same plan, Philox noise)" % nr)
     if workload == "c3":
         tr, n, dt = cpu_raw_sample(2048 * cores, 50, cores)            # calibration
         nb = int(min(C3_BOATS, max(2048 * cores, 2048 * cores * budget_s / max(dt, 1e-3) / 10)))
@@ -194,6 +223,8 @@ def run_reference(args):
     for i in range(args.warmup + args.steps):
         if args.workload == "c3":
             tr, n, dt = cpu_raw_sample(per_step, C3_STEPS, cores)
+        elif args.workload == "c5":
+            tr, n, dt = cpu_plan_sample(per_step, cores, scenario=i % 10)
         else:
             tr, n, dt = cpu_rollout_sample(per_step, cores, scenario=i % SCEN_PER_GPU)
         if i >= args.warmup:
@@ -217,6 +248,8 @@ def run_reference(args):
 
 
 def workload_config(workload, n_gpus):
+    if workload in API_WORKLOADS:
+        return api_config(workload, n_gpus)
     if workload == "c3":
         return dict(workload="c3 raw Simulator.doStep sweep: 10^6 boats x 500 steps per GPU on one 0.5-deg 3-hourly "
                              "5-day grid (BASELINE.json configs[2])",
@@ -234,6 +267,234 @@ def workload_config(workload, n_gpus):
 
 
 # ====================================================================================================
+# B200 arm, BASELINE configs 1 / 2 / 5: through the reference's Python API (the mirror classes)
+# ====================================================================================================
+def api_config(workload, n_gpus):
+    common = dict(sim_axis="6-hourly over 3 days (13 instants)", grid="41x21x31 (t, lat, lon), 0.5 deg, 3-hourly",
+                  l2="L2 flushed (256 MiB write) between timed steps",
+                  timing="one step = one call of the reference API on host objects; `value` from CUDA events around the "
+                         "call, `e2e` from the host clock around separate calls (Python included)")
+    if workload == "c2":
+        return dict(workload="c2 PMCTS forest: %d scenarios per GPU, one worker tree each, %d leaves x %d replicas = 10^4 "
+                             "rollouts per tree, through Forest.launch_search + MasterTree.get_best_policy "
+                             "(BASELINE.json configs[1])" % (C2_SCEN_PER_GPU, C2_BUDGET, C2_REPLICAS),
+                    scenarios_per_gpu=C2_SCEN_PER_GPU, scenarios_total=C2_SCEN_PER_GPU * n_gpus, leaves_per_wave=C2_LEAVES,
+                    replicas=C2_REPLICAS, leaves_per_tree=C2_BUDGET, waves=C2_BUDGET // C2_LEAVES,
+                    sharding="scenario s on GPU s // 10; update blocks all-gathered on the device every wave (pmcts_comm); "
+                             "master replicated", noise="philox4x32-10", **common)
+    if workload == "c5":
+        return dict(workload="c5 policy evaluation: plan %s replayed on 10^5 noisy draws for each of %d scenarios per GPU, "
+                             "through estimate_perfomance_plan (BASELINE.json configs[4])" % (list(C5_PLAN), C5_SCEN_PER_GPU),
+                    scenarios_per_gpu=C5_SCEN_PER_GPU, draws_per_scenario=C5_DRAWS, plan=list(C5_PLAN),
+                    sharding="scenarios split across GPUs, no exchange (replicas only)", noise="philox4x32-10", **common)
+    return dict(workload="c1 Tutorial.py search: 1 scenario, 1 UCT tree, %d sequential rollouts in the reference's order "
+                         "(one rollout per iteration, random.gauss noise), through Forest.launch_search(mode='sequential') "
+                         "(BASELINE.json configs[0])" % C1_BUDGET,
+                scenarios_per_gpu=1, rollouts=C1_BUDGET, sharding="one independent search per GPU (replicas only)",
+                noise="random.gauss stream of the reference", **common)
+
+
+def run_api_workload(args):
+    import contextlib
+    import io
+    import random
+
+    import torch
+    import torch.distributed as dist
+    from iboat_pmcts_b200 import _native as N
+    from iboat_pmcts_b200 import forest as ft, isochrones as iso, master_node as mn, worker
+    from iboat_pmcts_b200.engine import default_engine, set_default_device
+    from iboat_pmcts_b200.master import MasterTree
+    from iboat_pmcts_b200.weatherTLKT import Weather
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(3, args.warmup)
+    args.warmup = warm
+    set_default_device(local)
+    eng = default_engine()
+    wl = args.workload
+    state0, dest = list(STATE0), list(DEST)
+
+    def sims_for(ids):
+        ws = []
+        for s in ids:
+            t, la, lo, u, v = synth.wind_fields(s)
+            ws.append(Weather(la, lo, t, u.astype(np.float32), v.astype(np.float32)))
+        return ft.create_simulators(ws, len(ws), simtimestep=6, stateinit=tuple(state0), ndaysim=3)
+
+    n_total = args.warmup + args.steps + 2 + max(20, args.steps)
+    if wl == "c2":
+        S = C2_SCEN_PER_GPU * world
+        sims = sims_for(range(S))
+        forests = [ft.Forest(listsimulators=sims, destination=dest, timemin=TMIN, budget=C2_BUDGET) for _ in range(n_total)]
+        it = iter(forests)
+
+        def step(i):
+            f = next(it)
+            np.random.seed(100 + i)
+            m = f.launch_search(state0, 10, mode="batched", leaves=C2_LEAVES, replicas=C2_REPLICAS, seed=SEED + i)
+            mt = MasterTree(sims, dest, nodes=mn.deepcopy_dict(m))
+            mt.get_best_policy(verbose=False)
+            rep = f.last_search_report
+            return rep["transitions"], rep["rollouts"], mt.best_policy[-1]
+        waves = (C2_BUDGET + C2_LEAVES - 1) // C2_LEAVES
+        head = C2_SCEN_PER_GPU * C2_LEAVES * (4 + 12)
+        h2d, d2h = waves * head, waves * C2_SCEN_PER_GPU * C2_LEAVES * 12
+        dom = dict(kernel="rollout_fast_kernel", kind=N.KERNEL_ROLLOUT, launches_per_step=waves, flop=F_ALG_ROLLOUT,
+                   api="Forest.launch_search(mode='batched') -> pmcts_forest_search (int8 paths up, packed histograms back, "
+                       "one launch per wave) + MasterTree.get_best_policy -> pmcts_master_policy")
+    elif wl == "c5":
+        sims = sims_for(range(rank * C5_SCEN_PER_GPU, (rank + 1) * C5_SCEN_PER_GPU))
+
+        def step(i):
+            mean, var = iso.estimate_perfomance_plan(sims, C5_DRAWS, state0, dest, plan=list(C5_PLAN), verbose=False,
+                                                     seed=SEED + i)
+            st = iso.estimate_perfomance_plan.last_stats
+            return int(st[:, 4].sum()), int(st[:, 5].sum()), float(mean[0])
+        h2d, d2h = len(C5_PLAN) * 8 + 4, C5_SCEN_PER_GPU * 64
+        dom = dict(kernel="rollout_fast_kernel (plan-evaluation mode)", kind=N.KERNEL_ROLLOUT, launches_per_step=1,
+                   flop=F_ALG_ROLLOUT, api="estimate_perfomance_plan(seed=...) -> pmcts_rollout_forest(PMCTS_ROLL_PLAN_EVAL), "
+                                           "statistics reduced in the kernel")
+    else:
+        sims = sims_for([rank])
+        worker.RHO, worker.UCT_COEFF = 0.5, 1 / 2 ** 0.5  # Tutorial.py:61-62
+        forests = [ft.Forest(listsimulators=sims, destination=dest, timemin=TMIN, budget=C1_BUDGET) for _ in range(n_total)]
+        it = iter(forests)
+
+        def step(i):
+            f = next(it)
+            random.seed(1 + i)
+            np.random.seed(1 + i)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = f.launch_search(state0, 10, mode="sequential")
+            mt = MasterTree(sims, dest, nodes=mn.deepcopy_dict(m))
+            mt.get_best_policy(verbose=False)
+            rep = getattr(f, "last_search_report", None) or {}
+            return rep.get("transitions", 0), C1_BUDGET, mt.best_policy[-1]
+        h2d, d2h = C1_BUDGET * (13 * 8 + 8 + 4), C1_BUDGET * 5 * 8
+        dom = dict(kernel="rollout_batch_kernel / rollout_fast_kernel (one rollout per launch)", kind=N.KERNEL_ROLLOUT,
+                   launches_per_step=C1_BUDGET, flop=F_ALG_ROLLOUT,
+                   api="Forest.launch_search(mode='sequential'): Tree.uct_search in the reference's order")
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warm):
+        step(i)
+    barrier()
+    eng.enable_timing(True)
+    eng.kernel_ms(reset=True)
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    wall0 = time.perf_counter()
+    tr = ro = 0
+    decision = None
+    for i in range(args.steps):
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        ev[i][0].record()
+        a, b, decision = step(warm + i)
+        eng.synchronize()
+        ev[i][1].record()
+        tr += a
+        ro += b
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - launches0
+    dom_ms = eng.kernel_ms(reset=False, kind=dom["kind"])
+    fin_ms = eng.kernel_ms(reset=False, kind=N.KERNEL_FINISHER)
+    kernel_ms = eng.kernel_ms(reset=True)
+    eng.enable_timing(False)
+    dev_ms = sum(x.elapsed_time(y) for x, y in ev)
+    stat = torch.tensor([dev_ms, tr, ro, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx, sm = stat.clone(), stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, kernel_ms = float(mx[0]), float(mx[3])
+        tr_all, ro_all = float(sm[1]), float(sm[2])
+    else:
+        tr_all, ro_all = float(tr), float(ro)
+    # ---- end to end: the same API calls, host clock, no flush, no event bookkeeping ---------------------
+    e2e_steps = max(20, args.steps) if wl != "c1" else args.steps
+    step(warm + args.steps)
+    step(warm + args.steps + 1)
+    barrier()
+    t0 = time.perf_counter()
+    e_tr = e_ro = 0
+    for i in range(e2e_steps):
+        a, b, _ = step(warm + args.steps + 2 + i)
+        e_tr += a
+        e_ro += b
+    eng.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    es = torch.tensor([e2e_s, float(e_tr), float(e_ro)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx, sm = es.clone(), es.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_s, e_tr, e_ro = float(mx[0]), float(sm[1]), float(sm[2])
+    if rank == 0:
+        # c1 counts rollouts (its transitions are not reported by the sequential search): the metric falls back
+        unit_tr = tr_all > 0
+        value = (tr_all if unit_tr else ro_all) / (dev_ms * 1e-3)
+        n_dom = dom["launches_per_step"] * args.steps
+        per_launch_ms = dom_ms / max(n_dom, 1)
+        units = (tr / max(n_dom, 1)) if unit_tr else None
+        fp32_probe = eng.probe_fp32_peak()
+        roof = dict(bound="fp32", kernel=dom["kernel"], unit="TFLOP/s", peak=FP32_PEAK_TFLOPS,
+                    peak_source="nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 entry)",
+                    peak_measured=fp32_probe, ms_per_launch=per_launch_ms, finisher_ms_per_launch=fin_ms / max(n_dom, 1),
+                    algorithmic_flop_per_transition=dom["flop"], transitions_per_launch=units, traffic=None,
+                    note="launches of this workload are far below one wave of the chip (a search wave is %s): the kernel "
+                         "is latency-bound here, see the c4 line for its throughput form" % (
+                             "%d rollouts" % (C2_SCEN_PER_GPU * C2_LEAVES * C2_REPLICAS) if wl == "c2" else
+                             "one rollout" if wl == "c1" else "10^6 rollouts"))
+        if units:
+            roof["achieved"] = units * dom["flop"] / (per_launch_ms * 1e-3) / 1e12
+            roof["frac"] = roof["achieved"] / FP32_PEAK_TFLOPS
+        else:
+            roof["achieved"], roof["frac"] = None, None
+        line = dict(metric="sim transitions/s" if unit_tr else "rollouts/s", value=value,
+                    unit="transitions/s" if unit_tr else "rollouts/s", n_gpus=world, steps=args.steps, warmup=warm,
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32+f64" if wl != "c1" else "f64", data="synthetic", rollouts_per_s=ro_all / (dev_ms * 1e-3),
+                    config=api_config(wl, world),
+                    e2e=dict(value=(e_tr if unit_tr else e_ro) / e2e_s, unit="transitions/s" if unit_tr else "rollouts/s",
+                             rollouts_per_s=e_ro / e2e_s, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
+                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api=dom["api"]),
+                    gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_ms,
+                    finisher_kernel_ms=fin_ms, wall_s_timed_region=wall, clocks=clocks, roofline=roof,
+                    last_decision=[int(a) for a in decision] if isinstance(decision, list) else decision)
+        if wl == "c2":
+            line["search_report_last_step"] = {k: (round(v, 4) if isinstance(v, float) else v)
+                                               for k, v in forests[warm + args.steps - 1].last_search_report.items()}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ====================================================================================================
 # B200 arm
 # ====================================================================================================
 def main():
@@ -242,12 +503,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c3"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c3", "c2", "c5", "c1"])
     ap.add_argument("--precision", default="default", choices=["default", "f64", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in API_WORKLOADS:
+        return run_api_workload(args)
 
     import torch
     import torch.distributed as dist

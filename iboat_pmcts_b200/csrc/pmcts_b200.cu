@@ -1032,6 +1032,7 @@ bool uniform_axis(const double *g, int n, double *inv_step) {
 // (for the other translation units of the library -- pmcts_search.cu: they report through pmcts_last_error too)
 namespace pmcts {
 void set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
+void count_launches(pmcts_ctx *ctx, int n) { ctx->launches += n; }
 void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *)) {
     ctx->attachment_free = free_fn;
     return &ctx->attachment;

@@ -11,6 +11,9 @@ void set_last_error(const char *msg);
 // returns the slot; pmcts_destroy calls free_fn on what it holds.
 void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *));
 
+// kernels launched on behalf of the ctx by another translation unit (pmcts_launch_count)
+void count_launches(pmcts_ctx *ctx, int n);
+
 // shape of a host forest (pmcts_forest_host.cpp)
 struct ForestInfo {
     int n_scen, n_local, max_depth;

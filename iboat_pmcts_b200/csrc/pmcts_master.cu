@@ -321,6 +321,7 @@ extern "C" int pmcts_master_policy(pmcts_ctx *ctx, int64_t n_nodes, int n_scen, 
     best_child_kernel<<<grid(n), kThreads, 0, st>>>(d_child, d_value, n, S, S, 1, d_bc);
     policy_kernel<<<grid(C), kThreads, 0, st>>>(d_bc, d_arm, S, max_depth, d_policy, d_pnodes);
     M_TRY(cudaGetLastError());
+    pmcts::count_launches(ctx, n_rows > 0 ? 8 : 7);
     const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (value) M_TRY(cudaMemcpyAsync(value, d_value, (size_t)n * C * sizeof(double), kind, st));
     if (explore) M_TRY(cudaMemcpyAsync(explore, d_explore, (size_t)n * C * sizeof(double), kind, st));

@@ -404,7 +404,7 @@ struct Driver {
             pack_bins_kernel<uint8_t><<<grid, 256, 0, tail>>>(w.d_bins, (uint8_t *)(w.d_send + lay.o_bins), n_counts);
         else
             pack_bins_kernel<uint16_t><<<grid, 256, 0, tail>>>(w.d_bins, (uint16_t *)(w.d_send + lay.o_bins), n_counts);
-        rep.launches += 1;
+        pmcts::count_launches(ctx, 1);
         cudaError_t ke = cudaGetLastError();
         int rc = PMCTS_OK;
         const size_t tail_bytes = (size_t)S_loc * b * 12 * lay.elem;

@@ -63,6 +63,8 @@ class Forest:
             for worker in self.workers.values():
                 worker.replay_full_prefix = replay_full_prefix
                 worker.uct_search(deepcopy(root_state), frequency, Master_nodes)
+            self.last_search_report = dict(rollouts=sum(w.ite for w in self.workers.values()),
+                                           transitions=sum(getattr(w, "transitions", 0) for w in self.workers.values()))
             return Master_nodes
         if mode != "batched":
             raise ValueError("mode must be 'sequential' or 'batched'")

@@ -103,6 +103,7 @@ def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose):
             r = e.rollout_batch_host(scen, ntra, 1, root, destination, 0.0, prefix=pre, seed=seed, stream=si,
                                      flags=N.ROLL_PLAN_EVAL, want=("status",))
             _raise_unless(r["status"], (N.ST_ARRIVED, N.ST_HORIZON, N.ST_OUT_OF_BOX))
+    estimate_perfomance_plan.last_stats = stats  # per scenario: runs, sum t, sum t^2, arrived, transitions, rollouts
     means = stats[:, 1] / ntra
     variances = np.maximum(stats[:, 2] / ntra - means ** 2, 0.0)
     gmean = stats[:, 1].sum() / (S * ntra)

@@ -81,6 +81,7 @@ class MasterDict(dict):
         super().__init__()
         self._loader = loader  # () -> (parent, arm, table): the arrays are fetched on first need
         self._sparse_loader = sparse_loader  # () -> (parent, arm, row_index, rows): the native runtime's own layout
+        self._sparse = None
         self._parent, self._arm, self._table = parent, arm, table
         self._wired = bool(wired)
         n = int(size if loader is not None else parent.size)
@@ -95,6 +96,11 @@ class MasterDict(dict):
         if self._loader is not None:
             self._parent, self._arm, self._table = self._loader()
             self._loader = None
+            for node in self._nodes:  # nodes built from the sparse rows before now: re-point them at the table
+                if node is not None:
+                    self._table[node._index] = node._table
+                    node._table = self._table[node._index]
+                    node._rewards = None
 
     def arrays(self):
         """(parent, arm, table) or None once nodes have been added / removed through the dict interface."""
@@ -108,8 +114,14 @@ class MasterDict(dict):
         the scenario visited the node -- or None once the dictionary has been edited."""
         if self._dirty:
             return None
+        if self._sparse is not None:
+            return self._sparse
         if self._sparse_loader is not None:
-            return self._sparse_loader()
+            self._sparse = self._sparse_loader()
+            self._sparse_loader = None
+            if self._parent is None:
+                self._parent, self._arm = self._sparse[0], self._sparse[1]
+            return self._sparse
         parent, arm, table = self.arrays()
         n, S = table.shape[0], table.shape[1]
         flat = np.ascontiguousarray(table, dtype=np.uint32).reshape(n * S, 96)
@@ -118,7 +130,8 @@ class MasterDict(dict):
         return parent, arm, row_index, np.ascontiguousarray(flat[used])
 
     def depths(self):
-        self._load()
+        if self._parent is None:
+            self._load()
         if self._depth is None:
             d = np.zeros(self._parent.size, np.int32)
             for i in range(1, d.size):  # parents come first
@@ -127,7 +140,8 @@ class MasterDict(dict):
         return self._depth
 
     def _children_of(self, i):
-        self._load()
+        if self._parent is None:
+            self._load()
         if self._kids is None:
             kids = [[] for _ in range(self._parent.size)]
             for j in range(1, self._parent.size):
@@ -140,7 +154,13 @@ class MasterDict(dict):
         node = self._nodes[i]
         if node is not None:
             return node
-        self._load()
+        # the dense table is only fetched when somebody asks for all of it (arrays / the dict methods): a single node
+        # takes its counters from the sparse rows
+        sparse = self.sparse() if (self._table is None and (self._sparse is not None or self._sparse_loader is not None)) else None
+        if sparse is None:
+            self._load()
+        elif self._parent is None:
+            self._parent, self._arm = sparse[0], sparse[1]
         p = int(self._parent[i])
         parent = self.node_at(p) if p >= 0 else None
         node = MasterNode.__new__(MasterNode)
@@ -149,7 +169,14 @@ class MasterDict(dict):
         node.arm = None if parent is None else ACTIONS[self._arm[i]]
         node.parentNode = parent
         node.guessed_rewards = dict()
-        node._table = self._table[i]
+        if sparse is None:
+            node._table = self._table[i]  # a view: edits through the node show in arrays()
+        else:
+            rows = sparse[2][i]
+            tab = np.zeros((rows.size, len(ACTIONS) * Hist.N_BINS), dtype=int)
+            has = rows >= 0
+            tab[has] = sparse[3][rows[has]]
+            node._table = tab.reshape(rows.size, len(ACTIONS), Hist.N_BINS)
         node._rewards = None
         node._index = i
         if self._wired:
@@ -165,6 +192,7 @@ class MasterDict(dict):
     def _fill(self):
         if not self._filled:
             self._filled = True
+            self._load()  # every node is wanted: they view the dense table
             for i in range(len(self._nodes)):
                 dict.__setitem__(self, self.node_at(i).hash, self._nodes[i])
 
@@ -200,19 +228,20 @@ MasterDict.__hash__ = None
 def deepcopy_dict(nodes):
     """Deep copy of the dictionary the search returns, rewired with ``parentNode``, ``children`` and
     ``depth`` (master_node.py:66-109).  Empties ``nodes`` as the reference does."""
-    if isinstance(nodes, MasterDict) and nodes.arrays() is not None:
+    if isinstance(nodes, MasterDict) and not nodes._dirty:
         # array-backed result of the native search: the copy is three array copies
         if nodes._loader is not None:
             # not read yet: the copy fetches its own arrays from the (immutable) native forest when it needs them
             loader = nodes._loader
             new = MasterDict(wired=True, size=len(nodes), sparse_loader=nodes._sparse_loader,
                              loader=lambda: tuple(np.array(a, dtype=int if a.ndim == 4 else a.dtype) for a in loader()))
+            new._sparse = nodes._sparse
         else:
             parent, arm, table = nodes.arrays()
             new = MasterDict(parent.copy(), arm.copy(), np.array(table, dtype=int), wired=True)
         dict.clear(nodes)
         empty = np.zeros(0, np.int32)
-        nodes._loader = nodes._sparse_loader = None
+        nodes._loader = nodes._sparse_loader = nodes._sparse = None
         nodes._parent, nodes._arm, nodes._table = empty, empty.astype(np.int8), np.zeros((0, 1, 8, 12), np.uint32)
         nodes._nodes, nodes._filled, nodes._kids, nodes._depth = [], True, None, None
         return new

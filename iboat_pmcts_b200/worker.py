@@ -296,6 +296,7 @@ class Tree:
         finally:
             eng.set_precision(prec)
         steps = int(r["steps"][0])
+        self.transitions = getattr(self, "transitions", 0) + steps  # (counted for the search report)
         rand.setstate(state)
         for _ in range(steps):  # leave the generator where the reference's doStep calls would
             rand.gauss(0.0, 1.0)
