@@ -532,6 +532,8 @@ def main():
     eng.use_torch_stream()
     prec = {"default": N.PREC_FAST, "f64": N.PREC_F64, "fast": N.PREC_FAST}[args.precision]
     eng.set_precision(prec)
+    if os.environ.get("PMCTS_PACKED") is not None:  # diagnostic: K2 turbo one rollout per thread (0) / pair variants
+        eng.set_option(N.OPT_PACKED_FP32, int(os.environ["PMCTS_PACKED"]))
     if os.environ.get("PMCTS_NO_STAGE"):  # diagnostic: K1 without the shared-memory slab ring
         eng.set_option(N.OPT_STAGE_SLABS, 0)
 

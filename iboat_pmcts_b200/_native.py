@@ -21,7 +21,9 @@ ROLL_ACCUMULATE = 0x8
 ROLL_DEFER_REDO = 0x10
 ROLL_PREFIX_ACTIONS = 0x20
 OPT_STAGE_SLABS = 1
-VARIANT_LITERAL, VARIANT_FULL_OUTPUT, VARIANT_GENERIC, VARIANT_DEFAULT_BOAT, VARIANT_TURBO, VARIANT_STAGED = range(6)
+OPT_PACKED_FP32 = 2
+(VARIANT_LITERAL, VARIANT_FULL_OUTPUT, VARIANT_GENERIC, VARIANT_DEFAULT_BOAT, VARIANT_TURBO, VARIANT_STAGED,
+ VARIANT_TURBO_PACKED) = range(7)
 MEM_HOST = 0x100
 PREC_F64, PREC_FAST = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2

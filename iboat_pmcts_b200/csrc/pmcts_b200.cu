@@ -16,6 +16,7 @@
 
 #include "pmcts_device.cuh"
 #include "pmcts_fast.cuh"
+#include "pmcts_fast2.cuh"
 #include "pmcts_host.h"
 
 namespace pmcts {
@@ -448,6 +449,55 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
     reduce_rollouts<true>(a, counted, scen, leaf, o.bin, o.st, o.nstep, o.ta);
 }
 
+// K2, turbo variant, two rollouts per thread on the packed FP32 pipe (pmcts_fast2.cuh): thread t carries the
+// rollouts 2 t and 2 t + 1 of its scenario.  Same contract and same results as rollout_fast_kernel<kNoise, true, true,
+// true>: histograms / statistics only, undecided rollouts queued for the fp64 kernel.
+template <int kNoise, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+rollout_fast2_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
+    const int64_t n = a.n_leaf * a.replicas;
+    const int64_t r0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const int scen = blockIdx.y;
+    select_scenario<true>(scen, n, fs, sc, nz, a);
+    const bool live[2] = {r0 < n, r0 + 1 < n};
+    const int64_t leaf[2] = {(int64_t)((uint32_t)r0 / (uint32_t)a.replicas),
+                             (int64_t)((uint32_t)(r0 + 1) / (uint32_t)a.replicas)};
+#define PIN_I(x) asm volatile("" : "+r"(x))
+#define PIN_F(x) asm volatile("" : "+f"(x))
+    PIN_I(sc.nlon); PIN_I(sc.slab32_stride); PIN_I(sc.nT);
+    PIN_F(sc.dt_uniform32); PIN_F(sc.box_margin_scale);
+    PIN_F(sc.box_fa_lo); PIN_F(sc.box_fa_hi); PIN_F(sc.box_fo_lo); PIN_F(sc.box_fo_hi);
+    PIN_F(bp.sigma_f); PIN_F(a.sin_dest_lat); PIN_F(a.cos_dest_lat);
+#undef PIN_I
+#undef PIN_F
+    fast2::Pair o;
+    fast2::rollout_pair<kNoise>(sc, bp, nz, a, n, r0, leaf, live, o);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        // epilogue of fast::rollout_one, per half
+        int st = o.st[h], why = o.why[h];
+        double ta = NAN, rw = 0.0;
+        if (live[h] && st == PMCTS_ST_OK && !why) {
+            const int k = o.k[h];
+            if (o.at[h]) {
+                const double tk = sc.times[k];
+                ta = tk - (1.0 - (double)o.frac[h]) * (tk - sc.times[k - 1]);  // worker.py:274-275
+                rw = (double)((fast::exp_approx((float)(a.rw_t0 - ta) * a.rw_inv) - 1.0f) * 0.58197670686932642f);
+                st = PMCTS_ST_ARRIVED;
+            } else {
+                st = (k >= sc.nT - 1) ? PMCTS_ST_HORIZON : PMCTS_ST_OUT_OF_BOX;
+            }
+        }
+        const int bin = fast::hist_bin_checked(bp, rw, why);
+        bool counted = false;
+        if (live[h]) {
+            if (why) a.redo_list[atomicAdd(a.redo_count, 1u)] = ((uint32_t)scen << kRedoShift) | (uint32_t)(r0 + h);
+            else counted = true;
+        }
+        reduce_rollouts<true>(a, counted, scen, leaf[h], bin, st, o.nstep[h], ta);
+    }
+}
+
 // K1, mixed precision -- Simulator.doStep for n boats, nsteps fused (same contract as
 // step_batch_kernel).  A boat the fp32 formulas do not cover (heading outside [0, 360), a step longer
 // than fast::kMaxStepAngle) stops with the internal status kStNeedsLiteral and its step index in
@@ -798,6 +848,8 @@ struct pmcts_ctx {
     double *head_buf = nullptr;  // PMCTS_STEP_HEADING_ACTIONS: the action indices expanded to degrees
     size_t head_cap = 0;
     bool margins_set = false;
+    int packed_fp32 = 0;       // K2 turbo: two rollouts per thread on FFMA2 / FMUL2 / FADD2 (pmcts_fast2.cuh); measured
+                               // slower than one per thread (4 warps per scheduler instead of 8: profiles/README.md), so off
     bool stage_slabs = false;  // K1: stage the step's wind slab in shared memory (pmcts_set_option); measured
                                // 21 % slower than the L1 / L2 gathers on config 3 (profiles/README.md), so off
     // PMCTS_ROLL_DEFER_REDO: the fp64 finisher of a rollout launch runs on a side stream so that it overlaps
@@ -1142,6 +1194,10 @@ int pmcts_set_option(pmcts_ctx *ctx, int option, int value) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (option == PMCTS_OPT_STAGE_SLABS) {
         ctx->stage_slabs = value != 0;
+        return PMCTS_OK;
+    }
+    if (option == PMCTS_OPT_PACKED_FP32) {
+        ctx->packed_fp32 = value;
         return PMCTS_OK;
     }
     return fail(PMCTS_ERR_ARG, "unknown option %d", option);
@@ -1788,6 +1844,21 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             const bool turbo = defboat && fast::turbo_ok(vw, a);
             ctx->last_variant = !lean ? PMCTS_VARIANT_FULL_OUTPUT : turbo ? PMCTS_VARIANT_TURBO
                                 : defboat ? PMCTS_VARIANT_DEFAULT_BOAT : PMCTS_VARIANT_GENERIC;
+            // turbo launches run two rollouts per thread on the packed FP32 pipe (PMCTS_OPT_PACKED_FP32, default on)
+            const dim3 grid_pair(grid_for((n + 1) / 2), n_scen);
+#define PMCTS_LAUNCH_PAIR(NOISE) rollout_fast2_kernel<NOISE><<<grid_pair, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs)
+            const bool packed = lean && turbo && ctx->packed_fp32;
+            if (packed) ctx->last_variant = PMCTS_VARIANT_TURBO_PACKED;
+            if (packed && nz.mode == PMCTS_NOISE_PHILOX && ctx->packed_fp32 == 5)
+                rollout_fast2_kernel<PMCTS_NOISE_PHILOX, 5><<<grid_pair, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
+            else if (packed && nz.mode == PMCTS_NOISE_PHILOX && ctx->packed_fp32 == 6)
+                rollout_fast2_kernel<PMCTS_NOISE_PHILOX, 6><<<grid_pair, kBlock, 0, ctx->stream>>>(vw, ctx->params, nz, a, fs);
+            else
+            if (packed && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_PAIR(PMCTS_NOISE_PHILOX);
+            else if (packed && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_PAIR(PMCTS_NOISE_INJECTED);
+            else if (packed) PMCTS_LAUNCH_PAIR(PMCTS_NOISE_NONE);
+            else
+#undef PMCTS_LAUNCH_PAIR
             if (lean && turbo && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true);
             else if (lean && turbo && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true, true);
             else if (lean && turbo) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true, true);

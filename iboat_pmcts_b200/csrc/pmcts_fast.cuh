@@ -64,6 +64,43 @@ PMCTS_HD float exp_approx(float x) {
 #endif
 }
 PMCTS_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---- packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2 work on a 64-bit register pair and issue as ONE instruction; an
+// operand may also be one register or an immediate broadcast to both halves).  The mixed-precision kernels are bound
+// by instruction issue, so wherever one rollout evaluates the same expression on two quantities -- the (u, v)
+// components of the wind, the latitude / longitude legs of a polynomial -- the two go through as a pair.  Each half
+// is the same IEEE operation as its scalar form (round to nearest, fused where the scalar form is fused), so results
+// do not change; the host build does them one by one.
+PMCTS_HD float2 pk(float x, float y) {
+    float2 r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+PMCTS_HD float2 pk_fma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return pk(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+PMCTS_HD float2 pk_mul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return pk(a.x * b.x, a.y * b.y);
+#endif
+}
+PMCTS_HD float2 pk_sub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, pk(-b.x, -b.y));
+#else
+    return pk(a.x - b.x, a.y - b.y);
+#endif
+}
+PMCTS_HD float2 pk_fma(float2 a, float2 b, float c) { return pk_fma(a, b, pk(c, c)); }
+PMCTS_HD float2 pk_fma(float2 a, float b, float2 c) { return pk_fma(a, pk(b, b), c); }
+PMCTS_HD float2 pk_mul(float2 a, float b) { return pk_mul(a, pk(b, b)); }
 PMCTS_HD int imin(int a, int b) { return a < b ? a : b; }
 PMCTS_HD int imax(int a, int b) { return a > b ? a : b; }
 
@@ -84,12 +121,22 @@ PMCTS_HD float cosc_poly(float y) {
     p = fma_(p, y, -4.166666179e-02f);
     return fma_(p, y, 0.5f);
 }
+// (sinc_poly of two arguments at once)
+PMCTS_HD float2 sinc_poly2(float2 y) {
+    float2 p = pk_fma(pk(2.605224902e-06f, 2.605224902e-06f), y, -1.980907528e-04f);
+    p = pk_fma(p, y, 8.333051063e-03f);
+    p = pk_fma(p, y, -1.666665799e-01f);
+    return pk_fma(p, y, 1.0f);
+}
 // short forms for a step length |x| <= 0.1 rad (next terms: 2e-10 and 3e-11 relative)
 PMCTS_HD float sinc_small(float y) { return fma_(fma_(8.3333333e-03f, y, -1.6666667e-01f), y, 1.0f); }
 PMCTS_HD float cosc_small(float y) { return fma_(fma_(1.3888889e-03f, y, -4.1666667e-02f), y, 0.5f); }
 // asin(x) = x * asinc_small(x^2), |x| <= 0.12 (next term 3e-10 relative)
 PMCTS_HD float asinc_small(float y) {
     return fma_(fma_(fma_(4.4642857e-02f, y, 7.5e-02f), y, 1.6666667e-01f), y, 1.0f);
+}
+PMCTS_HD float2 asinc_small2(float2 y) {
+    return pk_fma(pk_fma(pk_fma(pk(4.4642857e-02f, 4.4642857e-02f), y, 7.5e-02f), y, 1.6666667e-01f), y, 1.0f);
 }
 // atan2(s, c) for s >= 0, result in [0, pi]
 PMCTS_HD float atan2_pos(float s, float c) {
@@ -224,10 +271,11 @@ PMCTS_HD void wind_at(const ScenarioView &sc, int k, const GridPos &g, float &u,
 #else
     const float2 c00 = row0[0], c01 = row0[1], c10 = row1[0], c11 = row1[1];
 #endif
-    const float u0 = fma_(g.wo, c01.x - c00.x, c00.x), u1 = fma_(g.wo, c11.x - c10.x, c10.x);
-    const float v0 = fma_(g.wo, c01.y - c00.y, c00.y), v1 = fma_(g.wo, c11.y - c10.y, c10.y);
-    u = fma_(g.wa, u1 - u0, u0);
-    v = fma_(g.wa, v1 - v0, v0);
+    // the three blends of (u, v) as pairs: 6 packed operations instead of 12
+    const float2 r0 = pk_fma(pk_sub(c01, c00), g.wo, c00), r1 = pk_fma(pk_sub(c11, c10), g.wo, c10);
+    const float2 uv = pk_fma(pk_sub(r1, r0), g.wa, r0);
+    u = uv.x;
+    v = uv.y;
 }
 
 // ---- Boat.getDeterDyn (simulatorTLKT.py:473-502) ----------------------------------------------------
@@ -363,8 +411,10 @@ PMCTS_HD Move move_increments(float d, float sh, float ch, float s, float c) {
     m.h_dlon = g * rH;
     m.sin_dlat = fma_(-s, g, a);
     m.cm1_dlat = fma_(c, g, -e);
-    m.dlat = m.sin_dlat * asinc_small(m.sin_dlat * m.sin_dlat);
-    m.dlon = m.sin_dlon * asinc_small(m.sin_dlon * m.sin_dlon);
+    const float2 sn = pk(m.sin_dlat, m.sin_dlon);
+    const float2 an = pk_mul(sn, asinc_small2(pk_mul(sn, sn)));
+    m.dlat = an.x;
+    m.dlon = an.y;
     return m;
 }
 
@@ -386,12 +436,13 @@ struct DestRel {
 
 PMCTS_HD DestRel dest_rel(double lat, double lon, double dlat, double dlon) {
     DestRel r;
-    const float xa = (float)((dlat - lat) * kDegToRad), xo = (float)((dlon - lon) * kDegToRad);
-    const float ya = xa * xa, yo = xo * xo;
-    r.sin_dlat = xa * sinc_poly(ya);
-    r.sin_dlon = xo * sinc_poly(yo);
-    r.h_dlon = yo * cosc_poly(yo);
-    r.x_dlat = xa;
+    const float2 x = pk((float)((dlat - lat) * kDegToRad), (float)((dlon - lon) * kDegToRad));
+    const float2 y = pk_mul(x, x);
+    const float2 sn = pk_mul(x, sinc_poly2(y));
+    r.sin_dlat = sn.x;
+    r.sin_dlon = sn.y;
+    r.h_dlon = y.y * cosc_poly(y.y);
+    r.x_dlat = x.x;
     return r;
 }
 
@@ -439,6 +490,15 @@ PMCTS_HD int fast_at_dest(const BoatParams &bp, const DestRel &rd, const Move &m
     const float margin_angle = kDefBoat ? defboat::margin_angle : bp.margin_angle;
     const float margin_along = kDefBoat ? defboat::margin_along : bp.margin_along;
     const float near_miss2 = kDefBoat ? defboat::near_miss2 : bp.near_miss2;
+    // Reach test.  (D - A).(B - D) >= 0 puts D in the ball whose diameter is AB, so D can only be "between" A and B --
+    // or close enough to that for one of the margins below to matter -- when |D - A| <= |B - A| (1 + 1e-2).  In the
+    // reference's coordinates |Q - P|^2 = 2 (1 - cos(latQ - latP)) + 2 sP sQ (1 - cos(lonQ - lonP)), which the step and
+    // the destination hold term by term (all terms >= 0 on one side of the equator: no cancellation);
+    // 2 (1 - cos x) >= sin^2 x bounds |D - A|^2 from below with what is at hand.  A boat still more than a step and a
+    // half from the destination -- every step of a rollout but its last one or two -- is decided here.
+    const float ba2_half = fma_(sA * sB, m.h_dlon, -m.cm1_dlat);
+    const float da2_low = fma_((sA * sD) * rd.h_dlon, 2.0f, rd.sin_dlat * rd.sin_dlat);
+    if (ba2_half > 0.0f && da2_low > 4.0f * ba2_half) return 0;  // |D - A|^2 > 2 |B - A|^2
     const float dBy = sB * m.sin_dlon;
     const float q = fma_(-cA * sB, m.h_dlon, m.sin_dlat);
     const float r = fma_(cA * sD, rd.h_dlon, -rd.sin_dlat);

@@ -125,6 +125,11 @@ int64_t pmcts_last_redo_count(pmcts_ctx *ctx);
  * their time index; 0 reads every gather through L1 / L2.  Same results bit for bit; measured slower on a
  * B200 (the per-step block barrier costs more than the L1 hits it replaces), kept for grids that miss L1. */
 #define PMCTS_OPT_STAGE_SLABS 1
+/* PMCTS_OPT_PACKED_FP32 (default 0): 1 makes K2's turbo variant carry TWO rollouts per thread, all their FP32
+ * arithmetic issued as packed FFMA2 / FMUL2 / FADD2 (csrc/pmcts_fast2.cuh).  Same histograms and statistics; 18 % fewer
+ * instructions, but at 128 registers only 4 warps per scheduler stay resident and the kernel measured 5 % slower on a
+ * B200 than the one-rollout-per-thread form (which packs the pairs a single rollout offers), so it is off. */
+#define PMCTS_OPT_PACKED_FP32 2
 int pmcts_set_option(pmcts_ctx *ctx, int option, int value);
 /* Which compile-time variant of the K1 / K2 kernel the last pmcts_step_batch / pmcts_rollout_* call launched.
  * All variants give the same results (tests/test_fastmodel.py, tests/test_gpu_parity.py); the specialised ones
@@ -135,13 +140,15 @@ int pmcts_set_option(pmcts_ctx *ctx, int option, int value);
  *   DEFAULT_BOAT  + the reference's boat, geometry constants and default margins as instruction immediates
  *   TURBO         + (K2, tree mode) equal steps, at most 16 of them, terminal box inside the grid, root able to
  *                 start a step: range checks, bounds test, step-length load, sin / cos refresh compiled out
- *   STAGED        K1 with PMCTS_OPT_STAGE_SLABS */
+ *   STAGED        K1 with PMCTS_OPT_STAGE_SLABS
+ *   TURBO_PACKED  TURBO with PMCTS_OPT_PACKED_FP32 */
 #define PMCTS_VARIANT_LITERAL 0
 #define PMCTS_VARIANT_FULL_OUTPUT 1
 #define PMCTS_VARIANT_GENERIC 2
 #define PMCTS_VARIANT_DEFAULT_BOAT 3
 #define PMCTS_VARIANT_TURBO 4
 #define PMCTS_VARIANT_STAGED 5
+#define PMCTS_VARIANT_TURBO_PACKED 6 /* TURBO, two rollouts per thread on the packed FP32 pipe */
 int pmcts_last_kernel_variant(pmcts_ctx *ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t pmcts_launch_count(pmcts_ctx *ctx);

@@ -323,7 +323,23 @@ def test_kernel_variants_agree_with_each_other_and_the_oracle(eng):
                                            flags=flags, want=lean, **kw)
                 assert eng.last_kernel_variant() == N.VARIANT_GENERIC
                 eng.set_fast_margins()
-                for other in (b, c):
+                others = [b, c]
+                if fast_variant == N.VARIANT_TURBO:
+                    # two rollouts per thread on the packed FP32 pipe (PMCTS_OPT_PACKED_FP32): odd and even batch sizes
+                    eng.set_option(N.OPT_PACKED_FP32, 1)
+                    try:
+                        d = eng.rollout_batch_host(0, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen,
+                                                   flags=flags, want=lean, **kw)
+                        assert eng.last_kernel_variant() == N.VARIANT_TURBO_PACKED
+                        others.append(d)
+                        if noise == "philox":
+                            odd = [eng.rollout_batch_host(0, 37, 3, H.STATE0, dest, tmin, prefix=prefix[:37],
+                                                          prefix_len=plen[:37], flags=flags, want=lean, **kw)
+                                   for _ in (eng.set_option(N.OPT_PACKED_FP32, 1), eng.set_option(N.OPT_PACKED_FP32, 0))]
+                            assert np.array_equal(odd[0]["leaf_bins"], odd[1]["leaf_bins"]) and odd[0]["stats"][5] == 111
+                    finally:
+                        eng.set_option(N.OPT_PACKED_FP32, 0)
+                for other in others:
                     assert np.array_equal(a["leaf_bins"], other["leaf_bins"])
                     assert np.array_equal(a["stats"][[0, 3, 4, 5]], other["stats"][[0, 3, 4, 5]])
                     assert np.allclose(a["stats"][1:3], other["stats"][1:3], rtol=1e-7, equal_nan=True)  # arrival times: 1e-6 each
