@@ -425,6 +425,8 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
         PIN_F(sc.dt_uniform32); PIN_F(sc.box_margin_scale);
         PIN_F(sc.box_fa_lo); PIN_F(sc.box_fa_hi); PIN_F(sc.box_fo_lo); PIN_F(sc.box_fo_hi);
         PIN_F(bp.sigma_f); PIN_F(a.sin_dest_lat); PIN_F(a.cos_dest_lat);
+        // (the scenario's slab pointer comes out of an indexed constant-bank load: once, not once per step)
+        asm volatile("" : "+l"(sc.slab32));
 #undef PIN_I
 #undef PIN_F
     }

@@ -164,7 +164,15 @@ PMCTS_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
                             uint32_t out[4], uint32_t m0 = 0xD2511F53u, uint32_t m1 = 0xCD9E8D57u) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__)
+        // (one IMAD.WIDE per product: written as a 64-bit C multiply the compiler adds the -- zero -- cross term of the
+        // widened multiplier back in, two more instructions per round)
+        uint64_t p0, p1;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(m0), "r"(c0));
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(m1), "r"(c2));
+#else
         const uint64_t p0 = (uint64_t)m0 * c0, p1 = (uint64_t)m1 * c2;
+#endif
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u;
@@ -179,7 +187,9 @@ PMCTS_HD void box_muller(uint32_t x0, uint32_t x1, float &z0, float &z1) {
     const float u0 = fminf(fma_((float)x0, 2.3283064365386963e-10f, 1.1641532182693481e-10f), 0.99999994f);
     const float th = fma_((float)x1, 1.4629180792671596e-09f, -3.14159265359f + 7.3145904e-10f);
 #if defined(__CUDA_ARCH__)
-    const float t = -1.3862943611198906f * __log2f(u0);  // -2 ln(u0) > 0
+    float l2;  // (u0 >= 2^-33 is a normal number: no denormal scaling around the hardware logarithm)
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u0));
+    const float t = -1.3862943611198906f * l2;  // -2 ln(u0) > 0
     const float r = t * rsqrt_approx(t);
     float s, c;
     __sincosf(th, &s, &c);
@@ -236,14 +246,17 @@ struct GridPos {
 
 // kInside = false: the caller holds the position against the terminal box of a roll_safe scenario (box
 // inside the grid), which implies the bounds test.
-template <bool kInside = true>
+// kRad (with kInside = false only): the position is in radians and known to lie inside the terminal box of a
+// roll_safe scenario, which ends before the last grid node: no clamp either.
+template <bool kInside = true, bool kRad = false>
 PMCTS_HD GridPos grid_pos(const ScenarioView &sc, double lat, double lon) {
     GridPos g;
     g.inside = !kInside || (lat >= sc.lat0 && lat <= sc.lat_last && lon >= sc.lon0 && lon <= sc.lon_last);
     // (lat - lat0) / dlat as one fma; inside the grid it is >= -1e-13, so truncation needs no lower clamp
-    const double fa = fma(lat, sc.inv_dlat, sc.fa_c0), fo = fma(lon, sc.inv_dlon, sc.fo_c0);
-    g.ia = imin((int)fa, sc.nlat - 2);
-    g.io = imin((int)fo, sc.nlon - 2);
+    const double fa = fma(lat, kRad ? sc.inv_dlat_rad : sc.inv_dlat, sc.fa_c0);
+    const double fo = fma(lon, kRad ? sc.inv_dlon_rad : sc.inv_dlon, sc.fo_c0);
+    g.ia = kRad ? (int)fa : imin((int)fa, sc.nlat - 2);
+    g.io = kRad ? (int)fo : imin((int)fo, sc.nlon - 2);
     g.wa = (float)(fa - (double)g.ia);
     g.wo = (float)(fo - (double)g.io);
     g.fa = (float)fa;
@@ -434,9 +447,11 @@ struct DestRel {
     float x_dlat;    // latD - lat, radians (for 1 - cos(latD - lat) in the arrival branch)
 };
 
+template <bool kRad = false>
 PMCTS_HD DestRel dest_rel(double lat, double lon, double dlat, double dlon) {
     DestRel r;
-    const float2 x = pk((float)((dlat - lat) * kDegToRad), (float)((dlon - lon) * kDegToRad));
+    const float2 x = kRad ? pk((float)(dlat - lat), (float)(dlon - lon))
+                          : pk((float)((dlat - lat) * kDegToRad), (float)((dlon - lon) * kDegToRad));
     const float2 y = pk_mul(x, x);
     const float2 sn = pk_mul(x, sinc_poly2(y));
     r.sin_dlat = sn.x;
@@ -544,7 +559,7 @@ constexpr int kStNeedsLiteral = 255;  // internal status: this boat / rollout co
 // kTurbo: the caller guarantees that k can start a step and that the position is on the grid (a roll_safe
 // scenario whose state passed the terminal test, or the host-checked root), and that all steps have the same
 // length sc.dt_uniform32: no range checks, no load of the step length (kUniformDt alone: only the latter).
-template <bool kShared = false, bool kDefBoat = false, bool kTurbo = false, bool kUniformDt = kTurbo>
+template <bool kShared = false, bool kDefBoat = false, bool kTurbo = false, bool kUniformDt = kTurbo, bool kRad = false>
 PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, double &lat, double &lon,
                        const GridPos &g, float sh, float ch, float s, float c, float z, Move &m,
                        const float2 *slab = nullptr) {
@@ -570,8 +585,13 @@ PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, dou
     if (!(fabsf(d) <= kMaxStepAngle)) return kStNeedsLiteral;
     m = move_increments(d, sh, ch, s, c);
     if (!(fabsf(m.sin_dlon) <= kMaxStepAngle)) return kStNeedsLiteral;  // high latitude: dlon = b / cos(lat)
-    lat = fma((double)m.dlat, 180.0 / kPi, lat);
-    lon = fma((double)m.dlon, 180.0 / kPi, lon);
+    if (kRad) {  // (position in radians)
+        lat += (double)m.dlat;
+        lon += (double)m.dlon;
+    } else {
+        lat = fma((double)m.dlat, 180.0 / kPi, lat);
+        lon = fma((double)m.dlon, 180.0 / kPi, lon);
+    }
     k += 1;
     return PMCTS_ST_OK;
 }
@@ -634,6 +654,10 @@ struct RollOut {
 inline void prepare_rollout(const ScenarioView &sc, RolloutArgs &a) {
     a.sin_dest_lat = (float)sin(a.dest_lat * kDegToRad);
     a.cos_dest_lat = (float)cos(a.dest_lat * kDegToRad);
+    a.root_lat_rad = a.root_lat * kDegToRad;
+    a.root_lon_rad = a.root_lon * kDegToRad;
+    a.dest_lat_rad = a.dest_lat * kDegToRad;
+    a.dest_lon_rad = a.dest_lon * kDegToRad;
     a.rw_t0 = sc.tmax * 1.001;
     a.rw_inv = (float)(1.0 / (sc.tmax * 1.001 - a.tmin));
     RootPre &p = a.root_pre;
@@ -672,8 +696,12 @@ inline bool turbo_ok(const ScenarioView &sc, const RolloutArgs &a) {
 template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
 PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const NoiseView &nz, const RolloutArgs &a,
                           int64_t n, int64_t r, int64_t leaf, RollOut &o) {
+    // kTurbo: the position lives in radians inside the loop -- nothing but the histogram leaves a turbo launch, and
+    // the differences to the destination and the grid index need no conversion then
+    constexpr bool kRad = kTurbo;
     int k = (int)a.root_k;
-    double lat = a.root_lat, lon = a.root_lon;
+    double lat = kRad ? a.root_lat_rad : a.root_lat, lon = kRad ? a.root_lon_rad : a.root_lon;
+    const double dest_lat = kRad ? a.dest_lat_rad : a.dest_lat, dest_lon = kRad ? a.dest_lon_rad : a.dest_lon;
     const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
     // both loads are issued back to back: the first heading does not wait for the prefix length
     double fixed_heading = (pre && a.prefix_stride > 0) ? pre[0] : 0.0;
@@ -715,7 +743,7 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             }
             const float z = ns.draw<kNoise>(nz, n, r, o.nstep);
             Move m;
-            o.st = fast_step<false, kDefBoat, kTurbo>(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
+            o.st = fast_step<false, kDefBoat, kTurbo, kTurbo, kRad>(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
             if (o.st == kStNeedsLiteral) {
                 o.st = PMCTS_ST_OK;
                 o.why |= kWhyStep;
@@ -723,8 +751,8 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             }
             if (o.st != PMCTS_ST_OK) break;
             if (!kLean) {
-                if (a.traj_lat && o.nstep < a.traj_stride) a.traj_lat[(size_t)o.nstep * n + r] = lat;
-                if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = lon;
+                if (a.traj_lat && o.nstep < a.traj_stride) a.traj_lat[(size_t)o.nstep * n + r] = kRad ? lat * (180.0 / kPi) : lat;
+                if (a.traj_lon && o.nstep < a.traj_stride) a.traj_lon[(size_t)o.nstep * n + r] = kRad ? lon * (180.0 / kPi) : lon;
             }
             ++o.nstep;
             float sB = m.s_new, cB = m.c_new;
@@ -732,7 +760,7 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
                 trig_left = kRefreshTrig;
                 sincos_lat(lat, sB, cB);
             }
-            g = grid_pos<!kTurbo>(sc, lat, lon);
+            g = grid_pos<!kTurbo, kRad>(sc, lat, lon);
             if (kTurbo || o.nstep >= n_unchecked) {  // (turbo: tree mode, every step is checked)
                 at = fast_at_dest<kDefBoat>(bp, rd, m, sA, cA, sB, sD, frac, o.why);
                 if (at || o.why) break;
@@ -741,7 +769,7 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             }
             sA = sB;
             cA = cB;
-            rd = dest_rel(lat, lon, a.dest_lat, a.dest_lon);
+            rd = dest_rel<kRad>(lat, lon, dest_lat, dest_lon);
         }
     }
     o.ta = NAN;
@@ -760,8 +788,8 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
         }
     }
     o.bin = hist_bin_checked(bp, o.rw, o.why);
-    o.lat = lat;
-    o.lon = lon;
+    o.lat = kRad ? lat * (180.0 / kPi) : lat;
+    o.lon = kRad ? lon * (180.0 / kPi) : lon;
 }
 
 }  // namespace fast

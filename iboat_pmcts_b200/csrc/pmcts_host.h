@@ -104,8 +104,13 @@ inline TimeCells time_cells(const double *wtime, int nt, const double *sim_times
 // the axes and nT have been set).
 inline void finish_fast_view(ScenarioView &vw, const TimeCells &tc, const double box[4]) {
     const int nT = vw.nT;
-    vw.roll_safe = (vw.ks_lo == 0 && vw.ks_hi == nT - 2 && box && box[0] >= vw.lat0 && box[1] <= vw.lat_last &&
-                    box[2] >= vw.lon0 && box[3] <= vw.lon_last) ? 1 : 0;
+    // (the box ends short of the last grid node -- create_simulators' does by a whole cell -- so a position inside it
+    // lies in a cell that has an upper neighbour: no clamp of the cell index)
+    const double eps_lat = 1e-3 / vw.inv_dlat, eps_lon = 1e-3 / vw.inv_dlon;
+    vw.roll_safe = (vw.ks_lo == 0 && vw.ks_hi == nT - 2 && box && box[0] >= vw.lat0 && box[1] <= vw.lat_last - eps_lat &&
+                    box[2] >= vw.lon0 && box[3] <= vw.lon_last - eps_lon) ? 1 : 0;
+    vw.inv_dlat_rad = vw.inv_dlat * (180.0 / kPi);
+    vw.inv_dlon_rad = vw.inv_dlon * (180.0 / kPi);
     vw.dt_uniform32 = nT > 1 ? tc.dt32[0] : 0.0f;
     for (int k = 1; k + 1 < nT; ++k)
         if (tc.dt32[k] != tc.dt32[0]) vw.dt_uniform32 = 0.0f;

@@ -46,6 +46,7 @@ struct ScenarioView {
     float dt_uniform32;     // dt_sec32[k] when it is the same for every k, else 0
     float box_margin_scale; // 1 + 0.01 * max(nlat, nlon): scales BoatParams::margin_box to the fp32 spacing of the
                             // largest fractional grid index
+    double inv_dlat_rad, inv_dlon_rad;  // inv_dlat, inv_dlon per radian (the turbo rollout keeps its position in radians)
     int roll_safe;          // 1: every instant 0 .. nT - 2 can start a step and the terminal box lies inside the
                             // grid, so a position that passed Tree.is_state_terminal needs no further range check
 };
@@ -116,6 +117,7 @@ struct RolloutArgs {
     // mixed-precision path: destination trigonometry (host, fp64 -> fp32) and the work list of
     // rollouts whose decisions fell inside the error margins (re-run by the literal fp64 kernel)
     float sin_dest_lat, cos_dest_lat;
+    double root_lat_rad, root_lon_rad, dest_lat_rad, dest_lon_rad;  // the same positions in radians
     double rw_t0;  // 1.001 * TimeMax
     float rw_inv;  // 1 / (1.001 * TimeMax - TimeMin)
     RootPre root_pre;

@@ -129,7 +129,8 @@ def test_rollout_decisions_outside_margins_agree(scen, flags):
 def test_specialised_variants_equal_the_generic_one():
     """rollout_one's compile-time variants (the reference's boat as immediates; "turbo": range checks, bounds
     test, step-length load and sin / cos refresh compiled out where the host proved them redundant) decide and
-    move exactly like the generic code: same steps, status, bin, hand-overs, bit-identical positions."""
+    move like the generic code: same steps, status, bin, hand-overs; positions bit-identical, except that the turbo
+    variant carries its position in radians inside the loop (1e-13 relative)."""
     f = model(2)
     rng = np.random.default_rng(77)
     n_leaf, rep = 128, 64
