@@ -144,9 +144,14 @@ def test_specialised_variants_equal_the_generic_one():
         f.force_generic(True)
         b = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
         assert f.last_variant() == 0
-        for key in ("steps", "status", "bin", "uncertain", "final_lat", "final_lon"):
-            assert np.array_equal(a[key], b[key], equal_nan=key.startswith("final")), (flags, key)
-        assert np.array_equal(a["reward"], b["reward"])
+        for key in ("steps", "status", "bin", "uncertain"):
+            assert np.array_equal(a[key], b[key]), (flags, key)
+        for key in ("final_lat", "final_lon", "reward"):
+            if want_variant == 2:  # (position in radians inside the loop: the last bits differ)
+                tol = 1e-13 if key != "reward" else 1e-6
+                assert np.allclose(a[key], b[key], rtol=tol, atol=0, equal_nan=True), (flags, key)
+            else:
+                assert np.array_equal(a[key], b[key], equal_nan=True), (flags, key)
     # a root that cannot start a step, or sits outside the grid, is not turbo: the generic code reports it
     f.force_generic(False)
     r = f.rollout_batch(4, 2, (12, 44.0, 355.0), DEST, TMIN, prefix=prefix[:4], prefix_len=plen[:4], z=z[:, :8])
