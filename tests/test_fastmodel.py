@@ -130,7 +130,7 @@ def test_specialised_variants_equal_the_generic_one():
     """rollout_one's compile-time variants (the reference's boat as immediates; "turbo": range checks, bounds
     test, step-length load and sin / cos refresh compiled out where the host proved them redundant) decide and
     move like the generic code: same steps, status, bin, hand-overs; positions bit-identical, except that the turbo
-    variant carries its position in radians inside the loop (1e-13 relative)."""
+    variant carries its position in radians inside the loop (equal to fp32 rounding, 5e-8 relative)."""
     f = model(2)
     rng = np.random.default_rng(77)
     n_leaf, rep = 128, 64
@@ -147,8 +147,8 @@ def test_specialised_variants_equal_the_generic_one():
         for key in ("steps", "status", "bin", "uncertain"):
             assert np.array_equal(a[key], b[key]), (flags, key)
         for key in ("final_lat", "final_lon", "reward"):
-            if want_variant == 2:  # (position in radians inside the loop: the last bits differ)
-                tol = 1e-13 if key != "reward" else 1e-6
+            if want_variant == 2:  # (position in radians inside the loop: its fp32 images round differently now and then)
+                tol = 5e-8 if key != "reward" else 1e-6
                 assert np.allclose(a[key], b[key], rtol=tol, atol=0, equal_nan=True), (flags, key)
             else:
                 assert np.array_equal(a[key], b[key], equal_nan=True), (flags, key)
