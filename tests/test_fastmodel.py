@@ -149,7 +149,7 @@ def test_specialised_variants_equal_the_generic_one():
         for key in ("final_lat", "final_lon", "reward"):
             if want_variant == 2:  # (position in radians inside the loop: its fp32 images round differently now and then)
                 tol = 5e-8 if key != "reward" else 1e-6
-                assert np.allclose(a[key], b[key], rtol=tol, atol=0, equal_nan=True), (flags, key)
+                assert np.allclose(a[key], b[key], rtol=tol, atol=0 if key != "reward" else 3e-6, equal_nan=True), (flags, key)
             else:
                 assert np.array_equal(a[key], b[key], equal_nan=True), (flags, key)
     # a root that cannot start a step, or sits outside the grid, is not turbo: the generic code reports it
