@@ -389,8 +389,7 @@ PMCTS_HD float boat_speed(const BoatParams &bp, float u, float v, float sh, floa
     const float w = fminf(mag, wind_max);
     const float pe = fminf(fmaxf(p, pmin), pmax);
     float sp = polar_centred<kDefBoat>(bp, (pe - p_mid) * p_ihalf, fma_(w, w_ihalf, -1.0f));
-    if (p < pmin) sp *= cos_pmin * rcp_approx(cosp);
-    else if (p > pmax) sp *= cos_pmax * rcp_approx(cosp);
+    if (p != pe) sp *= (p < pmin ? cos_pmin : cos_pmax) * rcp_approx(cosp);  // tacking / gybing (rare): one branch
     return sp;
 }
 
@@ -410,7 +409,8 @@ PMCTS_HD Move move_increments(float d, float sh, float ch, float s, float c) {
     const float d2 = d * d;
     const float sd = d * sinc_small(d2);
     const float e = d2 * cosc_small(d2);  // 1 - cos(d)
-    const float a = sd * ch, b = sd * sh;
+    const float2 ba = pk_mul(pk(sh, ch), sd);
+    const float b = ba.x, a = ba.y;
     const float cd = 1.0f - e;
     const float A = fma_(c, cd, -s * a);
     const float b2 = b * b;
@@ -469,9 +469,9 @@ PMCTS_HD void bearing_unit(const DestRel &r, float s, float sD, float cD, float 
     const float y = fma_(s * cD, r.h_dlon, r.sin_dlat);
     const float n2 = fma_(x, x, y * y);
     if (n2 > 0.0f) {
-        const float rn = rsqrt_approx(n2);
-        sh = x * rn;
-        ch = y * rn;
+        const float2 h = pk_mul(pk(x, y), rsqrt_approx(n2));
+        sh = h.x;
+        ch = h.y;
     } else {  // atan2(0, 0) = 0
         sh = 0.0f;
         ch = 1.0f;
@@ -633,9 +633,9 @@ template <bool kDefBoat = false>
 PMCTS_HD bool fast_terminal(const ScenarioView &sc, const BoatParams &bp, int k, const GridPos &g, int &why) {
     if (k >= sc.nT - 1) return true;
     const float m = (kDefBoat ? defboat::margin_box : bp.margin_box) * sc.box_margin_scale;  // 1 + 0.01 * (largest grid index): fp32 spacing of fa / fo
-    const float da0 = g.fa - sc.box_fa_lo, da1 = sc.box_fa_hi - g.fa;
-    const float do0 = g.fo - sc.box_fo_lo, do1 = sc.box_fo_hi - g.fo;
-    const float lo = fminf(fminf(da0, da1), fminf(do0, do1));
+    const float2 f = pk(g.fa, g.fo);
+    const float2 d0 = pk_sub(f, pk(sc.box_fa_lo, sc.box_fo_lo)), d1 = pk_sub(pk(sc.box_fa_hi, sc.box_fo_hi), f);
+    const float lo = fminf(fminf(d0.x, d1.x), fminf(d0.y, d1.y));
     if (fabsf(lo) <= m) why |= kWhyBox;  // only the binding edge can flip
     return lo < 0.0f;
 }
