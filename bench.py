@@ -506,6 +506,11 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c3", "c2", "c5", "c1"])
     ap.add_argument("--precision", default="default", choices=["default", "f64", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--waves", type=int, default=1,
+                    help="c4: leaf batches per step (the 256 replicas per leaf are split over them; one exchange + "
+                         "back-up per wave)")
+    ap.add_argument("--soak", type=float, default=2.0,
+                    help="c4 / c3: seconds of back-to-back steps after the timed region (sustained clocks); 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -548,6 +553,10 @@ def main():
         torch.cuda.synchronize()
 
     if args.workload == "c4":
+        global WAVES, REPLICAS
+        if args.waves < 1 or 256 % args.waves:
+            raise SystemExit("--waves must divide 256")
+        WAVES, REPLICAS = args.waves, 256 // args.waves
         run = setup_c4(eng, torch, dist, dev, rank, world)
     else:
         run = setup_c3(eng, torch, dev, rank, world)
@@ -622,6 +631,39 @@ def main():
         b2b = dict(value=float(b2b_stat[1]) / (float(b2b_stat[0]) * 1e-3), ms_per_step=float(b2b_stat[0]) / args.steps,
                    note="same steps back to back without L2 flush, one CUDA-event pair around all of them")
 
+    # ---- soak: seconds of back-to-back steps with the clocks sampled (the timed region above lasts milliseconds: the
+    # chip never settles into its sustained clocks there)
+    soak = None
+    if args.soak > 0:
+        est = max(dev_ms / args.steps, 1e-3)
+        n_soak = int(min(20000, max(args.steps, args.soak * 1e3 / est)))
+        run["reset_counters"]()
+        soak_sampler = ClockSampler(local, period_s=0.05) if rank == 0 else None
+        barrier()
+        if soak_sampler:
+            soak_sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_soak):
+            if args.workload == "c4":
+                run["device_step"](warm + 2 * args.steps + i, last=(i == n_soak - 1))
+            else:
+                run["device_step"](warm + 2 * args.steps + i)
+        e1.record()
+        barrier()
+        soak_clocks = soak_sampler.stop() if soak_sampler else None
+        c3_ = run["read_counters"]()
+        sk = torch.tensor([e0.elapsed_time(e1), c3_[0]], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx, sm = sk.clone(), sk.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            sk = torch.stack([mx[0], sm[1]])
+        soak = dict(value=float(sk[1]) / (float(sk[0]) * 1e-3), seconds=float(sk[0]) * 1e-3, steps=n_soak,
+                    ms_per_step=float(sk[0]) / n_soak, clocks=soak_clocks,
+                    note="steps back to back without L2 flush for about --soak seconds, one CUDA-event pair around all of "
+                         "them, NVML clocks sampled every 50 ms")
+
     # ---- end to end through the host-buffer C ABI ------------------------------------------------
     # (host-timed: enough steps that a scheduling hiccup of the host does not decide the figure)
     e2e_steps = 5 if args.workload == "c3" else max(50, args.steps)
@@ -658,17 +700,17 @@ def main():
         units = (counters[0] / n_dom) if per_launch_units is None else per_launch_units
         achieved = units * f_alg / (dom_ms * 1e-3) / 1e12
         achieved_both = units * f_alg / (both_ms * 1e-3) / 1e12
-        roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=fp32_peak,
-                        unit="TFLOP/s", frac=achieved / fp32_peak, peak_nominal=FP32_PEAK_TFLOPS,
-                        frac_of_nominal=achieved / FP32_PEAK_TFLOPS, traffic=run["dominant"].get("traffic"),
+        roofline = dict(bound="fp32", kernel=run["dominant"]["kernel"], achieved=achieved, peak=FP32_PEAK_TFLOPS,
+                        unit="TFLOP/s", frac=achieved / FP32_PEAK_TFLOPS, peak_measured=fp32_peak,
+                        frac_of_measured=achieved / fp32_peak, traffic=run["dominant"].get("traffic"),
                         traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
                                        + run["dominant"].get("traffic_source", "under profiles/"),
-                        peak_source="FP32 FMA throughput measured in this run by pmcts_probe_fp32_peak (16 independent FFMA "
-                                    "chains per thread, CUDA events, best of 4); peak_nominal = 148 SM x 128 lanes x 2 x "
-                                    "1.965 GHz.  MEASURED_PEAKS.json has HBM and bf16-tensor entries only and the path is "
-                                    "neither HBM- nor tensor-bound (SURVEY.md 8d)",
+                        peak_source="nominal FP32: 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has HBM and "
+                                    "bf16-tensor entries only, and the path is neither HBM- nor tensor-bound: SURVEY.md 8d); "
+                                    "peak_measured = FP32 FMA throughput of this run's pmcts_probe_fp32_peak (16 independent "
+                                    "FFMA chains per thread, CUDA events, best of 4)",
                         main_kernel_ms_per_launch=dom_kernel_ms / n_dom, finisher_ms_per_launch=fin_kernel_ms / n_dom,
-                        with_finisher=dict(ms_per_launch=both_ms, achieved=achieved_both, frac=achieved_both / fp32_peak,
+                        with_finisher=dict(ms_per_launch=both_ms, achieved=achieved_both, frac=achieved_both / FP32_PEAK_TFLOPS,
                                            note="main kernel + fp64 finisher durations added, although the finisher "
                                                 "overlaps the next launch on a side stream"),
                         algorithmic_flop_per_transition=f_alg, transitions_per_launch=units, ms_per_launch=dom_ms,
@@ -681,12 +723,16 @@ def main():
                     config=workload_config(args.workload, world), precision_mode="f64" if prec == N.PREC_F64 else "fast",
                     e2e=dict(value=e2e_tr / e2e_s, unit="transitions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              steps=e2e_steps, api=run["dominant"].get("api", "C ABI with PMCTS_MEM_HOST"),
-                             note="every rank times its own host-array calls (no L2 flush, no all-gather / back-up in "
-                                  "this leg); max time over ranks, transitions summed"),
+                             note=run["dominant"].get("e2e_note", "every rank times its own host-array calls (no L2 flush); "
+                                                                  "max time over ranks, transitions summed")),
                     gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_kernel_ms, finisher_kernel_ms=fin_kernel_ms, wall_s_timed_region=wall, clocks=clocks,
                     roofline=roofline)
         if b2b:
             line["back_to_back"] = b2b
+        if soak:
+            line["soak"] = soak
+        if "redo_share" in run:
+            line["fp64_redo_share"] = run["redo_share"]()
         if not args.no_cpu_baseline and world == 1:  # (the CPU leg is timed at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
@@ -715,7 +761,6 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     slots = torch.tensor(np.random.default_rng(3).integers(0, 8, S_total * N_LEAF).astype(np.int8), device=dev)
     master = torch.zeros(S_total * n_nodes * 96, dtype=torch.int32, device=dev)
     bins_local = torch.zeros(S_local * N_LEAF * 12, dtype=torch.int32, device=dev)
-    bins_all = torch.zeros(S_total * N_LEAF * 12, dtype=torch.int32, device=dev) if world > 1 else None
     stats = torch.zeros(S_local * 8, dtype=torch.float64, device=dev)
     plen_h = np.full(N_LEAF, 4, np.int32)
 
@@ -731,6 +776,10 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMCTS_BENCH_COMM_PRIO", "0")))
     overlap = not os.environ.get("PMCTS_BENCH_NO_OVERLAP")
     bins_ring = [bins_local, torch.zeros_like(bins_local), torch.zeros_like(bins_local)]
+    # what travels between GPUs: the wave's counters narrowed to one byte (two when a leaf has more than 255 replicas)
+    pack_dtype = torch.uint8 if REPLICAS <= 255 else torch.int16
+    packed_local = torch.zeros(S_local * N_LEAF * 12, dtype=pack_dtype, device=dev) if world > 1 else None
+    packed_all = torch.zeros(S_total * N_LEAF * 12, dtype=pack_dtype, device=dev) if world > 1 else None
     consumed = [torch.cuda.Event() for _ in bins_ring]
     pending = []
     debug_ev = [] if os.environ.get("PMCTS_BENCH_DEBUG") else None  # (all-gather, back-up) durations on the comm stream
@@ -748,9 +797,10 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                 if dbg:
                     dbg[0].record()
                 if world > 1:
+                    eng.pack_bins(src, packed_local)
                     if not os.environ.get("PMCTS_BENCH_NO_AG"):
-                        dist.all_gather_into_tensor(bins_all, src)
-                    src = bins_all
+                        dist.all_gather_into_tensor(packed_all, packed_local)
+                    src = packed_all
                 if dbg:
                     dbg[1].record()
                 if not os.environ.get("PMCTS_BENCH_NO_BACKUP"):
@@ -836,13 +886,68 @@ def setup_c4(eng, torch, dist, dev, rank, world):
             tr += e2e_read(inflight.pop(0))
         return tr
 
+    # Several ranks: the end-to-end step is the whole sharded pipeline -- this step's inputs come up from pinned host
+    # memory, the wave runs, its histograms are exchanged and backed up into the replicated master, and the step's
+    # result (statistics, and the root's visit totals of the master as the caller's view of the exchange) goes down
+    # to pinned host memory; results are read one step later, the last after e2e_drain.
+    if world > 1:
+        prefix_pt = torch.from_numpy(prefix_p)
+        plen_pt = torch.from_numpy(plen_p)
+        res_pinned = [torch.empty(S_local * 8 + S_total, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+        res_ev = [torch.cuda.Event() for _ in res_pinned]
+        res_dev = torch.zeros(S_local * 8 + S_total, dtype=torch.float64, device=dev)
+        pend = []
+        last_tr = [0.0]
+
+        def e2e_read_multi(slot):
+            res_ev[slot].synchronize()
+            tot = float(res_pinned[slot][:S_local * 8].view(S_local, 8)[:, 4].sum())  # running total of this rank
+            tr, last_tr[0] = tot - last_tr[0], tot
+            return int(tr)
+
+        def e2e_step(i):  # noqa: F811
+            slot = i % len(res_pinned)
+            prefix.copy_(prefix_pt, non_blocking=True)
+            plen.copy_(plen_pt, non_blocking=True)
+            device_step(2000 + i, last=False)
+            res_dev[:S_local * 8].copy_(stats)
+            res_dev[S_local * 8:].copy_(master.view(S_total, n_nodes, 96)[:, 0].sum(1))
+            res_pinned[slot].copy_(res_dev, non_blocking=True)
+            res_ev[slot].record()
+            pend.append(slot)
+            tr = e2e_read_multi(pend.pop(0)) if len(pend) > 1 else 0
+            return tr, WAVES * (prefix_h.nbytes + plen_h.nbytes), (S_local * 8 + S_total) * 8
+
+        def e2e_drain():  # noqa: F811
+            complete(0)
+            torch.cuda.synchronize()
+            tr = 0
+            while pend:
+                tr += e2e_read_multi(pend.pop(0))
+            # the statistics are a running total: what the drain of the device pipeline added after the last copy
+            tot = float(stats.cpu().view(S_local, 8)[:, 4].sum())
+            tr += int(tot - last_tr[0])
+            last_tr[0] = tot
+            return tr
+
+    def redo_share():
+        return dict(share=eng.last_redo_count() / float(S_local * n),
+                    note="rollouts of the last launch the fp32 kernel left to the fp64 finisher (decisions inside a margin)")
+
     return dict(device_step=device_step, reset_counters=reset_counters, read_counters=read_counters,
-                e2e_step=e2e_step, e2e_drain=e2e_drain,
+                e2e_step=e2e_step, e2e_drain=e2e_drain, redo_share=redo_share,
                 dominant=dict(kernel="rollout_fast_kernel",
                               launches_per_step=WAVES, units_per_launch=None,
                               flop_per_unit=F_ALG_ROLLOUT, kind=N.KERNEL_ROLLOUT,
-                              api="pmcts_rollout_forest with PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO + pmcts_wait (host prefix in, host "
-                                  "leaf_bins / stats out; one call in flight while the previous one's finisher and copies complete)",
+                              api=("pmcts_rollout_forest with PMCTS_MEM_HOST | PMCTS_ROLL_DEFER_REDO + pmcts_wait (host prefix in, host "
+                                   "leaf_bins / stats out; one call in flight while the previous one's finisher and copies complete)")
+                              if world == 1 else
+                              ("sharded pipeline per step: pinned host prefix -> device, pmcts_rollout_forest (device arrays, deferred "
+                               "finisher), pmcts_pack_bins + NCCL all-gather + pmcts_backup into the replicated master on the "
+                               "communication stream, statistics and the master's root totals -> pinned host"),
+                              e2e_note=("every rank times its own host-array calls (no L2 flush); max time over ranks, transitions summed"
+                                        if world == 1 else
+                                        "exchange and back-up included; host-timed, max over ranks, transitions summed"),
                               traffic=1798400,  # profiles/r01_c4_forest_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
                               traffic_source="profiles/r01_c4_forest_final_full.txt",
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))

@@ -25,6 +25,7 @@ OPT_PACKED_FP32 = 2
 (VARIANT_LITERAL, VARIANT_FULL_OUTPUT, VARIANT_GENERIC, VARIANT_DEFAULT_BOAT, VARIANT_TURBO, VARIANT_STAGED,
  VARIANT_TURBO_PACKED) = range(7)
 MEM_HOST = 0x100
+BACKUP_BINS_U8, BACKUP_BINS_U16 = 0x1, 0x2
 PREC_F64, PREC_FAST = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
 KERNEL_STEP, KERNEL_ROLLOUT, KERNEL_BACKUP, KERNEL_OTHER, KERNEL_FINISHER = 0, 1, 2, 3, 4
@@ -33,7 +34,8 @@ ERR_NO_DEVICE = -3
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_get_stream", "pmcts_get_device", "pmcts_comm_unique_id", "pmcts_comm_create", "pmcts_comm_destroy",
-    "pmcts_allgather_updates", "pmcts_forest_search", "pmcts_master_policy",
+    "pmcts_allgather_updates", "pmcts_forest_search", "pmcts_master_policy", "pmcts_pack_bins",
+    "pmcts_forest_search_sequential", "pmcts_python_gauss", "pmcts_numpy_randint8",
     "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
@@ -64,6 +66,39 @@ class SearchParams(C.Structure):
                 ("slots_w", C.c_void_p), ("slots_m", C.c_void_p), ("comm", C.c_void_p),
                 ("exchange", EXCHANGE_FN), ("exchange_user", C.c_void_p),
                 ("rollout_hook", ROLLOUT_HOOK_FN), ("hook_user", C.c_void_p)]
+
+
+class MtState(C.Structure):
+    """pmcts_mt_state: a Mersenne Twister as random.getstate() / np.random.get_state() describe it."""
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("gauss_next", C.c_double)]
+
+    @classmethod
+    def from_python(cls, state):
+        version, internal, gauss_next = state
+        st = cls()
+        st.key[:] = internal[:624]
+        st.pos = internal[624]
+        st.has_gauss = 0 if gauss_next is None else 1
+        st.gauss_next = 0.0 if gauss_next is None else float(gauss_next)
+        return st
+
+    def to_python(self):
+        return (3, tuple(int(x) for x in self.key) + (int(self.pos),), float(self.gauss_next) if self.has_gauss else None)
+
+    @classmethod
+    def from_numpy(cls, state):
+        import numpy as np
+        name, key, pos = state[0], state[1], state[2]
+        if name != "MT19937":
+            raise ValueError("np.random must be the legacy MT19937 generator")
+        st = cls()
+        st.key[:] = [int(x) for x in np.asarray(key, dtype=np.uint32)]
+        st.pos = int(pos)
+        return st
+
+    def to_numpy(self, like):
+        import numpy as np
+        return (like[0], np.array(list(self.key), dtype=np.uint32), int(self.pos)) + tuple(like[3:])
 
 
 class SearchReport(C.Structure):
@@ -112,6 +147,10 @@ def lib():
     L.pmcts_comm_destroy.restype = None
     L.pmcts_allgather_updates.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.pmcts_master_policy.argtypes = [vp, i64, i32, vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp, i32]
+    L.pmcts_forest_search_sequential.argtypes = [vp, vp, i32, i32, vp, vp, dbl, i64, i32, i32, C.POINTER(MtState),
+                                                 C.POINTER(MtState), C.POINTER(SearchReport)]
+    L.pmcts_python_gauss.argtypes = [C.POINTER(MtState), i64, vp]
+    L.pmcts_numpy_randint8.argtypes = [C.POINTER(MtState), i64, vp]
     L.pmcts_forest_search.argtypes = [vp, vp, vp, vp, vp, dbl, C.POINTER(SearchParams), C.POINTER(SearchReport)]
     L.pmcts_synchronize.argtypes = [vp]
     L.pmcts_join.argtypes = [vp, i32]
@@ -143,6 +182,7 @@ def lib():
                                        vp, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_backup.argtypes = [vp, vp, i64, i32, vp, vp, i64, vp, vp, vp, i32]
     L.pmcts_hist_stats.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.pmcts_pack_bins.argtypes = [vp, vp, i64, vp, i32]
     L.pmcts_forest_create.argtypes = [i32, i32, vp, i32, vp, dbl, dbl, vp, i64, C.POINTER(vp)]
     L.pmcts_forest_destroy.argtypes = [vp]
     L.pmcts_forest_destroy.restype = None

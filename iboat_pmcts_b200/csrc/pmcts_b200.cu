@@ -725,6 +725,13 @@ __global__ void expand_prefix_kernel(const int8_t *__restrict__ a, double *__res
     if (i < count) h[i] = 45.0 * (double)a[i];
 }
 
+// Narrowing of a wave's histograms for the exchange (pmcts_pack_bins): a count is at most `replicas`.
+template <typename T>
+__global__ void pack_bins_kernel(const uint32_t *__restrict__ bins, T *__restrict__ out, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (T)bins[i];
+}
+
 // Roofline denominator: what the FP32 FMA pipes of this chip sustain (pmcts_probe_fp32_peak).  16 independent
 // FFMA chains per thread, nothing else in the loop.
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out, int iters, float a, float b) {
@@ -743,11 +750,13 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out,
 
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
 // blockIdx.y = scenario.
+// kBin: the width the histograms arrive in (uint32 from K2; uint8 / uint16 from an all-gathered update block).
+template <typename kBin>
 __global__ void backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes,
                               const int32_t *__restrict__ parent, const int8_t *__restrict__ arm,
                               int64_t n_leaf, const int32_t *__restrict__ leaf_node,
                               const int8_t *__restrict__ leaf_slot,
-                              const uint32_t *__restrict__ leaf_bins) {
+                              const kBin *__restrict__ leaf_bins) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_leaf * 12) return;
     const int64_t s = blockIdx.y;
@@ -1979,8 +1988,30 @@ int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, c
     {
         LaunchTimer lt(ctx, PMCTS_KERNEL_BACKUP);
         dim3 grid(grid_for(n_leaf * 12), n_scen);
-        backup_kernel<<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
-                                                       leaf_slot, leaf_bins);
+        if (flags & PMCTS_BACKUP_BINS_U8)
+            backup_kernel<uint8_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
+                                                                    leaf_slot, (const uint8_t *)leaf_bins);
+        else if (flags & PMCTS_BACKUP_BINS_U16)
+            backup_kernel<uint16_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
+                                                                     leaf_slot, (const uint16_t *)leaf_bins);
+        else
+            backup_kernel<uint32_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
+                                                                     leaf_slot, leaf_bins);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PMCTS_OK;
+}
+
+int pmcts_pack_bins(pmcts_ctx *ctx, const uint32_t *bins, int64_t count, void *out, int width) {
+    if (!ctx || !bins || !out) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (width != 1 && width != 2) return fail(PMCTS_ERR_ARG, "width must be 1 or 2 bytes");
+    if (count <= 0) return PMCTS_OK;
+    DeviceGuard g(ctx);
+    {
+        LaunchTimer lt(ctx);
+        const unsigned grid = (unsigned)((count + 255) / 256);
+        if (width == 1) pack_bins_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(bins, (uint8_t *)out, (size_t)count);
+        else pack_bins_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(bins, (uint16_t *)out, (size_t)count);
     }
     CUDA_TRY(cudaGetLastError());
     return PMCTS_OK;

@@ -160,8 +160,70 @@ inline void node_value(const T *row, int64_t &visits, double &best) {
     }
 }
 
+// ---- the reference's random streams ---------------------------------------------------------------------------
+// The sequential search (Tree.uct_search, worker.py:147-186) interleaves three consumers of two generators:
+// random.shuffle at every node creation (worker.py:51) and random.gauss at every transition (simulatorTLKT.py:515)
+// draw from CPython's global Mersenne Twister; np.random.randint picks the action slots of Node.back_up and
+// MasterNode.add_reward (worker.py:62, master_node.py:42) from NumPy's legacy one.  A seeded script must see the same
+// tree here, so both are continued from the caller's state (random.getstate() / np.random.get_state()) and handed
+// back where the reference would have left them.
+struct Mt19937 {
+    uint32_t mt[624];
+    int pos = 624;
+    uint32_t next32() {
+        if (pos >= 624) {
+            for (int kk = 0; kk < 624; ++kk) {
+                const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % 624] & 0x7fffffffu);
+                mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+
+// CPython's random.Random (Lib/random.py, Modules/_randommodule.c)
+struct PyRandom {
+    Mt19937 g;
+    bool has_gauss = false;
+    double gauss_next = 0.0;
+    double random() {  // genrand_res53
+        const uint32_t a = g.next32() >> 5, b = g.next32() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    double gauss() {  // gauss(0.0, 1.0): 0.0 + z * 1.0 == z
+        if (has_gauss) {
+            has_gauss = false;
+            return gauss_next;
+        }
+        const double x2pi = random() * 6.283185307179586476925286766559;  // TWOPI = 2.0 * _pi
+        const double g2rad = std::sqrt(-2.0 * std::log(1.0 - random()));
+        gauss_next = std::sin(x2pi) * g2rad;
+        has_gauss = true;
+        return std::cos(x2pi) * g2rad;
+    }
+    void shuffle(uint8_t *x, int n) {  // x[i], x[_randbelow(i + 1)] swapped for i = n - 1 .. 1
+        for (int i = n - 1; i >= 1; --i) {
+            const uint32_t m = (uint32_t)i + 1u;
+            int bits = 0;
+            for (uint32_t v = m; v; v >>= 1) ++bits;
+            uint32_t r;
+            do r = g.next32() >> (32 - bits); while (r >= m);
+            const uint8_t tmp = x[i];
+            x[i] = x[r];
+            x[r] = tmp;
+        }
+    }
+};
+
 struct Tree {
     int scen = 0;  // global scenario id
+    PyRandom *pyrng = nullptr;  // sequential search: a node's untried actions are shuffled when it is created
     std::vector<int32_t> parent, mnode, pending;
     std::vector<int8_t> arm;
     std::vector<int16_t> depth;
@@ -199,7 +261,14 @@ struct Tree {
         child.insert(child.end(), kA, -1);
         n_child.push_back(0);
         n_untried.push_back(kA);
-        untried.insert(untried.end(), perms + (size_t)idx * kA, perms + (size_t)idx * kA + kA);
+        if (pyrng) {
+            uint8_t order[kA];
+            for (int i = 0; i < kA; ++i) order[i] = (uint8_t)i;
+            pyrng->shuffle(order, kA);
+            untried.insert(untried.end(), order, order + kA);
+        } else {
+            untried.insert(untried.end(), perms + (size_t)idx * kA, perms + (size_t)idx * kA + kA);
+        }
         table.insert(table.end(), kRow, 0);
         visits.push_back(0);
         best.push_back(0.0);
@@ -367,7 +436,108 @@ struct pmcts_forest {
     }
 };
 
+namespace {
+
+void load_state(Mt19937 &g, const pmcts_mt_state &st) {
+    std::memcpy(g.mt, st.key, sizeof g.mt);
+    g.pos = st.pos;
+}
+void store_state(const Mt19937 &g, pmcts_mt_state &st) {
+    std::memcpy(st.key, g.mt, sizeof g.mt);
+    st.pos = g.pos;
+}
+
+}  // namespace
+
 namespace pmcts {
+
+// Tree.uct_search (worker.py:147-186) for one worker tree of the forest, in the reference's order and on the
+// reference's random streams; `rollout` runs Tree.default_policy (worker.py:255-281) for a leaf given the normals its
+// transitions would draw, and reports the reward's histogram bin and the transitions made.
+int forest_sequential(pmcts_forest *f, int local_index, int64_t budget, int frequency, int n_instants,
+                      pmcts_mt_state *py_state, pmcts_mt_state *np_state, const SeqRollout &rollout,
+                      pmcts_search_report *rep) {
+    if (!f || local_index < 0 || local_index >= f->n_local || !py_state || !np_state)
+        return fail(PMCTS_ERR_ARG, "bad arguments");
+    if (budget < 1 || frequency < 1 || n_instants < 2) return fail(PMCTS_ERR_ARG, "bad sizes");
+    Tree &t = f->trees[local_index];
+    if (t.perms) return fail(PMCTS_ERR_ARG, "the forest was created for the batched search (perms given)");
+    PyRandom py;
+    Mt19937 npr;
+    load_state(py.g, *py_state);
+    py.has_gauss = py_state->has_gauss != 0;
+    py.gauss_next = py_state->gauss_next;
+    load_state(npr, *np_state);
+    t.pyrng = &py;
+    t.max_nodes = std::max<int64_t>(t.max_nodes, t.size() + budget + 2);
+    if (t.size() == 0) t.add_node(-1, 0);  // Tree._make_root: the root's actions are shuffled first
+    Master &m = f->master;
+    const int s = t.scen;
+    struct Update { int32_t leaf; int bin; };
+    std::vector<Update> buffer;
+    std::vector<double> z(n_instants);
+    std::vector<int8_t> path(f->max_depth);
+    std::vector<int32_t> touched;
+    uint32_t one_hot[kB];
+    int rc = PMCTS_OK;
+    for (int64_t ite = 1; ite <= budget && !rc; ++ite) {
+        const int32_t leaf = f->tree_policy(t);
+        if (leaf < 0) { rc = fail(PMCTS_ERR_ARG, "tree capacity exhausted"); break; }
+        const int len = t.depth[leaf];
+        {
+            int d = len;
+            for (int32_t x = leaf; t.parent[x] >= 0; x = t.parent[x]) path[--d] = t.arm[x];
+        }
+        // the normals the rollout's transitions draw: taken ahead, then the generator is put back and advanced by
+        // the draws actually made (one per transition, simulatorTLKT.py:515)
+        const PyRandom saved = py;
+        for (int j = 0; j < n_instants; ++j) z[j] = py.gauss();
+        int bin = 0, steps = 0;
+        rc = rollout(s, path.data(), len, z.data(), &bin, &steps);
+        if (rc) break;
+        py = saved;
+        for (int j = 0; j < steps; ++j) py.gauss();
+        if (rep) { rep->rollouts += 1; rep->transitions += steps; rep->leaves += 1; }
+        // Node.back_up (worker.py:55-70)
+        int slot = (int)(npr.next32() & 7u);
+        for (int32_t x = leaf; x >= 0; x = t.parent[x]) {
+            int64_t *row = t.table.data() + (size_t)x * kRow;
+            row[slot * kB + bin] += 1;
+            node_value(row, t.visits[x], t.best[x]);
+            slot = t.arm[x];
+        }
+        buffer.push_back({leaf, bin});
+        // Tree.integrate_buffer (worker.py:348-378) every `frequency` iterations
+        if (ite % frequency == 0) {
+            m.applies += 1;
+            touched.clear();
+            for (const Update &u : buffer) {
+                const int ulen = t.depth[u.leaf];
+                int d = ulen;
+                for (int32_t x = u.leaf; t.parent[x] >= 0; x = t.parent[x]) path[--d] = t.arm[x];
+                int32_t node = m.descend(path.data(), ulen);
+                std::memset(one_hot, 0, sizeof one_hot);
+                one_hot[u.bin] = 1;
+                m.add(node, s, (int)(npr.next32() & 7u), one_hot, touched);  // MasterNode.add_reward: a random slot
+                while (m.parent[node] >= 0) {
+                    m.add(m.parent[node], s, m.arm[node], one_hot, touched);
+                    node = m.parent[node];
+                }
+            }
+            m.refresh(s, touched);
+            f->wave += 1;
+            buffer.clear();
+            if (rep) rep->waves += 1;
+        }
+    }
+    t.pyrng = nullptr;
+    store_state(py.g, *py_state);
+    py_state->has_gauss = py.has_gauss ? 1 : 0;
+    py_state->gauss_next = py.gauss_next;
+    store_state(npr, *np_state);
+    return rc;
+}
+
 ForestInfo forest_info(const pmcts_forest *f) { return ForestInfo{f->n_scen, f->n_local, f->max_depth}; }
 int forest_local_id(const pmcts_forest *f, int local_index) { return f->trees[local_index].scen; }
 }  // namespace pmcts
@@ -379,7 +549,7 @@ const char *pmcts_forest_last_error(void) { return g_err.c_str(); }
 int pmcts_forest_create(int n_scen, int n_local, const int32_t *local_ids, int max_depth,
                         const double *probability, double uct_coeff, double rho, const uint8_t *perms,
                         int64_t max_nodes, pmcts_forest **out) {
-    if (!out || !local_ids || !probability || !perms) return fail(PMCTS_ERR_ARG, "NULL argument");
+    if (!out || !local_ids || !probability) return fail(PMCTS_ERR_ARG, "NULL argument");
     if (n_scen < 1 || n_local < 1 || n_local > n_scen || max_depth < 1 || max_nodes < 1)
         return fail(PMCTS_ERR_ARG, "bad sizes");
     pmcts_forest *f = new pmcts_forest();
@@ -393,10 +563,10 @@ int pmcts_forest_create(int n_scen, int n_local, const int32_t *local_ids, int m
     for (int i = 0; i < n_local; ++i) {
         Tree &t = f->trees[i];
         t.scen = local_ids[i];
-        t.perms = perms + (size_t)i * max_nodes * kA;
+        t.perms = perms ? perms + (size_t)i * max_nodes * kA : nullptr;
         t.max_nodes = max_nodes;
         t.reserve((size_t)max_nodes);
-        t.add_node(-1, 0);
+        if (perms) t.add_node(-1, 0);  // (without perms: pmcts_forest_search_sequential creates the root, shuffled by the caller's generator)
     }
     f->master.n_scen = n_scen;
     f->master.slices.resize(n_scen);
@@ -592,6 +762,28 @@ int pmcts_python_shuffles(uint64_t seed, int64_t count, int n_items, uint8_t *ou
             x[r] = tmp;
         }
     }
+    return PMCTS_OK;
+}
+
+int pmcts_python_gauss(pmcts_mt_state *state, int64_t count, double *out) {
+    if (!state || !out || count < 0) return fail(PMCTS_ERR_ARG, "bad arguments");
+    PyRandom py;
+    load_state(py.g, *state);
+    py.has_gauss = state->has_gauss != 0;
+    py.gauss_next = state->gauss_next;
+    for (int64_t i = 0; i < count; ++i) out[i] = py.gauss();
+    store_state(py.g, *state);
+    state->has_gauss = py.has_gauss ? 1 : 0;
+    state->gauss_next = py.gauss_next;
+    return PMCTS_OK;
+}
+
+int pmcts_numpy_randint8(pmcts_mt_state *state, int64_t count, uint8_t *out) {
+    if (!state || !out || count < 0) return fail(PMCTS_ERR_ARG, "bad arguments");
+    Mt19937 g;
+    load_state(g, *state);
+    for (int64_t i = 0; i < count; ++i) out[i] = (uint8_t)(g.next32() & 7u);
+    store_state(g, *state);
     return PMCTS_OK;
 }
 

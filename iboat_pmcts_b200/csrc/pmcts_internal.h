@@ -1,5 +1,7 @@
 // pmcts_b200 -- what the translation units of the library share beyond the public C ABI.
 #pragma once
+#include <functional>
+
 #include "../../include/pmcts_b200.h"
 
 namespace pmcts {
@@ -20,5 +22,13 @@ struct ForestInfo {
 };
 ForestInfo forest_info(const pmcts_forest *f);
 int forest_local_id(const pmcts_forest *f, int local_index);
+
+// Tree.uct_search for one worker tree (pmcts_forest_host.cpp); `rollout(scenario, path, len, z, &bin, &steps)` runs the
+// default policy of a leaf with the normals z[0 .. n_instants) and returns 0 or a negative PMCTS_ERR_* / the positive
+// status byte of a rollout the reference would have raised on.
+using SeqRollout = std::function<int(int, const int8_t *, int, const double *, int *, int *)>;
+int forest_sequential(pmcts_forest *f, int local_index, int64_t budget, int frequency, int n_instants,
+                      pmcts_mt_state *py_state, pmcts_mt_state *np_state, const SeqRollout &rollout,
+                      pmcts_search_report *rep);
 
 }  // namespace pmcts

@@ -541,3 +541,44 @@ extern "C" int pmcts_forest_search(pmcts_ctx *ctx, pmcts_forest *f, const int32_
 } catch (const std::bad_alloc &) {
     return fail(PMCTS_ERR_ARG, "out of host memory");
 }
+
+// Tree.uct_search natively: the host runtime walks the tree and keeps the reference's random streams
+// (pmcts::forest_sequential); every iteration's rollout is one small launch with host arrays.
+extern "C" int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, int local_index, int scen_slot,
+                                              const double root[3], const double dest[2], double tmin, int64_t budget,
+                                              int frequency, int roll_flags, pmcts_mt_state *py_state,
+                                              pmcts_mt_state *np_state, pmcts_search_report *report) try {
+    if (!ctx) return fail(PMCTS_ERR_NO_DEVICE, "pmcts_forest_search_sequential needs a ctx: the search has no CPU path");
+    if (!f || !root || !dest || !py_state || !np_state) return fail(PMCTS_ERR_ARG, "NULL argument");
+    const pmcts::ForestInfo info = pmcts::forest_info(f);
+    const int n_instants = info.max_depth + 1;
+    pmcts_search_report rep{};
+    const double t0 = now_ms();
+    const int64_t launches0 = pmcts_launch_count(ctx);
+    LIB_TRY(pmcts_set_precision(ctx, PMCTS_PREC_FAST));
+    const int flags = (roll_flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) | PMCTS_ROLL_PREFIX_ACTIONS | PMCTS_MEM_HOST;
+    const pmcts::SeqRollout rollout = [&](int, const int8_t *path, int len, const double *z, int *bin, int *steps) -> int {
+        int32_t plen = len, st_steps = 0, b = 0;
+        uint8_t status = 0;
+        pmcts_noise nz{};
+        nz.mode = PMCTS_NOISE_INJECTED;
+        nz.z = z;
+        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)path, &plen,
+                                           info.max_depth, &nz, nullptr, nullptr, &st_steps, &status, &b, nullptr, nullptr,
+                                           nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags);
+        if (rc) return rc;
+        if (status == PMCTS_ST_OUT_OF_GRID || status == PMCTS_ST_PAST_HORIZON || status == PMCTS_ST_DEGENERATE)
+            return (int)status;  // what the reference raises on
+        *bin = b;
+        *steps = st_steps;
+        return 0;
+    };
+    const int rc = pmcts::forest_sequential(f, local_index, budget, frequency, n_instants, py_state, np_state, rollout, &rep);
+    rep.launches = pmcts_launch_count(ctx) - launches0;
+    rep.ms_total = now_ms() - t0;
+    if (report) *report = rep;
+    if (rc < 0 && std::string(pmcts_last_error()).empty()) fail(rc, "%s", pmcts_forest_last_error());
+    return rc;
+} catch (const std::bad_alloc &) {
+    return fail(PMCTS_ERR_ARG, "out of host memory");
+}

@@ -15,7 +15,7 @@ try:  # torch is plumbing only (device buffers / streams); the host path needs N
 except Exception:  # pragma: no cover
     torch = None
 
-_NP = {"f64": np.float64, "i32": np.int32, "u8": np.uint8, "u32": np.uint32, "i8": np.int8}
+_NP = {"f64": np.float64, "i32": np.int32, "u8": np.uint8, "u32": np.uint32, "i8": np.int8, "i16": np.int16}
 
 
 def _is_tensor(x):
@@ -42,7 +42,7 @@ class _Args:
             if not x.is_cuda:
                 raise TypeError("pmcts_b200: torch tensors must live on a CUDA device")
             want = {"f64": torch.float64, "i32": torch.int32, "u8": torch.uint8, "u32": torch.int32,
-                    "i8": torch.int8}[dtype]
+                    "i8": torch.int8, "i16": torch.int16}[dtype]
             if x.dtype != want or not x.is_contiguous():
                 raise TypeError("pmcts_b200: expected contiguous %s tensor, got %s" % (want, x.dtype))
             if size is not None and x.numel() < size:
@@ -326,14 +326,25 @@ class Engine:
 
     # ---- K3 / statistics --------------------------------------------------------------------------
     def backup(self, table, n_nodes, parent, arm, leaf_node, leaf_slot, leaf_bins, n_scen=1):
-        """table[n_scen][n_nodes][8][12] += per-leaf bins along every ancestor chain (device arrays)."""
+        """table[n_scen][n_nodes][8][12] += per-leaf bins along every ancestor chain (device arrays).  ``leaf_bins``
+        may be the uint32 counters K2 produced or their packed form (uint8 / int16 tensors from ``pack_bins``)."""
         a = _Args()
         n_leaf = leaf_node.numel() // n_scen
+        flag, kind = 0, "u32"
+        if _is_tensor(leaf_bins) and leaf_bins.dtype == torch.uint8:
+            flag, kind = N.BACKUP_BINS_U8, "u8"
+        elif _is_tensor(leaf_bins) and leaf_bins.dtype == torch.int16:
+            flag, kind = N.BACKUP_BINS_U16, "i16"
         N.check(self._lib.pmcts_backup(self._h, a.ptr(table, "u32", n_scen * n_nodes * 96), int(n_nodes),
                                        int(n_scen), a.ptr(parent, "i32", n_nodes), a.ptr(arm, "i8", n_nodes),
                                        n_leaf, a.ptr(leaf_node, "i32", n_scen * n_leaf),
                                        a.ptr(leaf_slot, "i8", n_scen * n_leaf),
-                                       a.ptr(leaf_bins, "u32", n_scen * n_leaf * 12), a.mem_flag))
+                                       a.ptr(leaf_bins, kind, n_scen * n_leaf * 12), a.mem_flag | flag))
+
+    def pack_bins(self, bins, out):
+        """Narrows uint32 histogram counters (int32 tensor) into ``out`` (uint8 or int16 tensor of the same length)."""
+        width = 1 if out.dtype == torch.uint8 else 2
+        N.check(self._lib.pmcts_pack_bins(self._h, bins.data_ptr(), int(bins.numel()), out.data_ptr(), width))
 
     def hist_stats(self, table, n_nodes, mean=None, visits=None):
         a = _Args()

@@ -144,9 +144,16 @@ class MasterTree:
             return int(self.nodes.depths().max())
         return max(node.depth for node in self.nodes.values())
 
-    def save_tree(self, name, directory="../results/"):
+    def save_tree(self, name, directory="../results/", reference_format=False):
+        """``reference_format=True`` writes the file the reference's own ``MasterTree.load_tree`` and plotting tools
+        read (its class names and attribute layout: ``refpickle.dump_reference_tree``); the default is a pickle of
+        this class."""
         with open(directory + name + '.pickle', 'wb') as f:
-            pickle.dump(self, f)
+            if reference_format:
+                from .refpickle import dump_reference_tree
+                dump_reference_tree(self, f)
+            else:
+                pickle.dump(self, f)
 
     def __getstate__(self):
         d = dict(self.__dict__)

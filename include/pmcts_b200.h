@@ -245,10 +245,17 @@ int pmcts_rollout_forest(pmcts_ctx *ctx, int n_scen, const int32_t *scen, int64_
  *   table[s][leaf_node[s][l]][leaf_slot[s][l]] += c        (the random slot of worker.py:62-63)
  *   table[s][parent[x]][arm[x]] += c  for x = leaf, parent(leaf), ... up to the root's child.
  * One launch covers all scenarios; additions are integer atomics, so the result is exact and
- * independent of the order. */
+ * independent of the order.
+ * PMCTS_BACKUP_BINS_U8 / _U16: leaf_bins points to uint8 / uint16 counts (the form histograms travel in between
+ * GPUs: pmcts_pack_bins). */
+#define PMCTS_BACKUP_BINS_U8 0x1
+#define PMCTS_BACKUP_BINS_U16 0x2
 int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, const int32_t *parent,
                  const int8_t *arm, int64_t n_leaf, const int32_t *leaf_node, const int8_t *leaf_slot,
                  const uint32_t *leaf_bins, int flags);
+/* Narrows `count` uint32 histogram counters (device) to `width` = 1 or 2 bytes each (device): what a wave's
+ * histograms are all-gathered as -- a count never exceeds the number of replicas per leaf. */
+int pmcts_pack_bins(pmcts_ctx *ctx, const uint32_t *bins, int64_t count, void *out, int width);
 
 /* Per-(node, action) binned means and visit totals of a histogram table (Hist.get_mean,
  * utils.py:49-59; Node.get_uct's exploitation term, worker.py:91-104):
@@ -267,7 +274,8 @@ int pmcts_hist_stats(pmcts_ctx *ctx, const uint32_t *table, int64_t n_nodes, dou
  * create: n_scen scenarios in total, n_local trees on this rank for the scenarios local_ids[]; a node at depth
  *   max_depth is terminal (Tree.is_node_terminal, worker.py:438-445: len(times) - 1); perms[n_local][max_nodes][8]
  *   gives every node, in creation order, its shuffled list of untried actions (worker.py:50-51; consumed from
- *   the end like list.pop()); the caller keeps perms alive.
+ *   the end like list.pop()); the caller keeps perms alive.  perms = NULL: a forest for
+ *   pmcts_forest_search_sequential, which shuffles with the caller's generator as nodes are created.
  * select: n_leaves runs of the tree policy per local tree, a virtual visit left on each selected path;
  *   outputs [n_local][n_leaves]: the leaf's node index, its depth, its action path (prefix_stride >= max_depth
  *   entries, -1 padded).
@@ -378,6 +386,15 @@ typedef struct {
     pmcts_rollout_hook_fn rollout_hook;
     void *hook_user;
 } pmcts_search_params;
+/* State of a Mersenne Twister as Python and NumPy hand it out: random.getstate() = (3, key[624] + (pos,), gauss_next)
+ * and np.random.get_state() = ('MT19937', key[624], pos, has_gauss, cached_gaussian) -- the latter's Gaussian cache is
+ * not used here. */
+typedef struct {
+    uint32_t key[624];
+    int32_t pos;
+    int32_t has_gauss; /* random.getstate()[2] is not None */
+    double gauss_next;
+} pmcts_mt_state;
 typedef struct {
     int64_t waves, leaves, rollouts, transitions, arrived, launches;
     double ms_total, ms_select, ms_wait, ms_backup, ms_master, ms_exchange;
@@ -385,6 +402,24 @@ typedef struct {
 int pmcts_forest_search(pmcts_ctx *ctx, pmcts_forest *f, const int32_t *scen_slots, const double root[3],
                         const double dest[2], double tmin, const pmcts_search_params *params,
                         pmcts_search_report *report);
+
+/* Tree.uct_search (worker.py:147-186) for the worker tree `local_index` of a forest created WITHOUT perms: the
+ * reference's sequential search -- one rollout per iteration, back-up, updates pushed to the master every `frequency`
+ * iterations -- in the reference's order and on the reference's random streams: node creation shuffles and the
+ * transitions' normals continue Python's generator from *py_state, the random action slots of Node.back_up /
+ * MasterNode.add_reward continue NumPy's from *np_state, and both states come back as the reference would have left
+ * them, so a seeded script grows the reference's tree.  A rollout is one launch of K2 (PMCTS_PREC_FAST with its fp64
+ * re-run: the histogram bin and the number of transitions -- all the tree and the generators depend on -- are exact).
+ * Returns 0, a negative error, or the positive PMCTS_ST_* of a rollout the reference would have raised on.
+ * Call it for the trees one after the other (forest.py's processes, serialised); report->waves counts master updates. */
+int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, int local_index, int scen_slot,
+                                   const double root[3], const double dest[2], double tmin, int64_t budget,
+                                   int frequency, int roll_flags, pmcts_mt_state *py_state, pmcts_mt_state *np_state,
+                                   pmcts_search_report *report);
+/* The two generators above, for checking them against the interpreter: count x random.gauss(0, 1) and count x
+ * np.random.randint(8), continuing the given states. */
+int pmcts_python_gauss(pmcts_mt_state *state, int64_t count, double *out);
+int pmcts_numpy_randint8(pmcts_mt_state *state, int64_t count, uint8_t *out);
 
 #ifdef __cplusplus
 }

@@ -359,3 +359,71 @@ def test_isochrone_solver_matches_the_reference(golden_dir):
     # nodes within 20 km of the arrival is stepped one by one (Isochrone.aller_point_arrivee)
     assert launches < 2000
     assert len(solver.positions_to_states()) == len(positions)
+
+
+def test_gefs_shaped_pickle_ingest(tmp_path):
+    """N3: a Weather pickle as the reference's download writes it (weatherTLKT.py:80-133) -- axes and fields as NumPy
+    MASKED arrays, u / v fp32, a global 0.5-degree grid, time in days since year 1 -- goes through Weather.load / crop
+    (weatherTLKT.py:51-78, 165-218) and create_simulators (time shifted to 0, forest.py:179) onto the device:
+    cropped (fp64, as the reference's crop makes it) and uncropped (fp32 masked, 361 x 720 nodes).  Interpolators equal
+    SciPy's on the same data bit for bit; rollouts and raw steps equal the oracle's."""
+    import pickle
+    import sys
+    from scipy.interpolate import RegularGridInterpolator
+    from iboat_pmcts_b200 import _native as N
+    from iboat_pmcts_b200 import weatherTLKT
+    from oracle import cport
+    rng = np.random.default_rng(12)
+    lat = np.ma.masked_array(np.arange(-90.0, 90.01, 0.5))
+    lon = np.ma.masked_array(np.arange(0.0, 360.0, 0.5))
+    time = np.ma.masked_array(736700.0 + 0.125 * np.arange(24))
+    T, LA, LO = np.meshgrid(np.arange(24) * 0.125, lat.data, lon.data, indexing="ij")
+    u = (8 * np.sin(0.05 * LA + 2 * T) + 4 * np.cos(0.03 * LO) + rng.normal(0, 1, T.shape)).astype(np.float32)
+    v = (7 * np.cos(0.04 * LO - T) - 3 * np.sin(0.06 * LA) + rng.normal(0, 1, T.shape)).astype(np.float32)
+    w = weatherTLKT.Weather(lat, lon, time, np.ma.masked_array(u), np.ma.masked_array(v))
+    sys.modules["weatherTLKT"] = weatherTLKT
+    weatherTLKT.Weather.__module__ = "weatherTLKT"      # what a pickle written by the reference says
+    try:
+        path = tmp_path / "20180108_gep_0100z.obj"
+        path.write_bytes(pickle.dumps(w))
+    finally:
+        weatherTLKT.Weather.__module__ = "iboat_pmcts_b200.weatherTLKT"
+    try:
+        crop = weatherTLKT.Weather.load(str(path), latBound=[38, 52], lonBound=[340, 359.6], timeSteps=[2, 22])
+        glob = weatherTLKT.Weather.load(str(path), timeSteps=[2, 22])
+    finally:
+        del sys.modules["weatherTLKT"]
+    assert crop.u.dtype == np.float64 and crop.u.shape == (20, 27, 39) and crop.time[0] == 736700.25
+    assert isinstance(glob.u, np.ma.MaskedArray) and glob.u.dtype == np.float32 and glob.u.shape == (20, 361, 720)
+    state0 = (0, 44.0, 350.0)
+    for weather, ndays in ((crop, 2), (glob, 2)):
+        t0 = float(weather.time[0])
+        sims = ft.create_simulators([weather], 1, simtimestep=6, stateinit=state0, ndaysim=ndays)
+        sim = sims[0]
+        assert float(weather.time[0]) == 0.0 and abs(float(weather.time[-1]) - 19 * 0.125) < 1e-9 and t0 > 7e5
+        data_u, data_v = np.asarray(weather.u, np.float64), np.asarray(weather.v, np.float64)
+        axes = (np.asarray(weather.time, float), np.asarray(weather.lat, float), np.asarray(weather.lon, float))
+        # interpolators: SciPy on the same (widened) data, bit for bit
+        pts = np.column_stack([rng.uniform(0, 2.3, 300), rng.uniform(axes[1][0], axes[1][-1], 300),
+                               rng.uniform(axes[2][0], axes[2][-1], 300)])
+        assert np.array_equal(sim.uWindAvg(pts), RegularGridInterpolator(axes, data_u)(pts))
+        assert np.array_equal(sim.vWindAvg(pts), RegularGridInterpolator(axes, data_v)(pts))
+        # default-policy rollouts with injected noise: the oracle on the same arrays
+        o = cport.OracleSim(axes[0], axes[1], axes[2], data_u, data_v, np.asarray(sim.times, float),
+                            np.asarray(sim.lats, float), np.asarray(sim.lons, float))
+        n_leaf, rep = 64, 32
+        n = n_leaf * rep
+        prefix = 45.0 * rng.integers(0, 8, (n_leaf, 2))
+        z = rng.standard_normal((len(sim.times), n))
+        dest, tmin = [45.6, 351.4], 0.9
+        eng, scen = sim.scenario()
+        want = o.rollout_batch(n, state0, dest, tmin, prefix=np.repeat(prefix, rep, 0), z=z, nthreads=8)
+        for mode in (N.PREC_F64, N.PREC_FAST):
+            eng.set_precision(mode)
+            got = eng.rollout_batch_host(scen, n_leaf, rep, state0, dest, tmin, prefix=prefix, z=z)
+            for key in ("steps", "status", "bin"):
+                assert np.array_equal(got[key], want[key]), (mode, key)
+            assert np.allclose(got["final_lat"], want["final_lat"], rtol=1e-6, atol=0)
+            assert np.allclose(got["final_lon"], want["final_lon"], rtol=1e-6, atol=0)
+        assert (want["steps"] >= 1).all() and set(np.unique(want["status"])) <= {1, 2, 3}
+        eng.set_precision(N.PREC_F64)

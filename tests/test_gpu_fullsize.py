@@ -2,6 +2,8 @@
 need minutes for them): conservation of counts, determinism, invariance to how a batch is cut into
 launches, and agreement with the oracle on a random subset.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -125,3 +127,43 @@ def test_config4_shard_eight_million_rollouts(eng):
             assert np.abs(bins[s, leaf] - want_bins).sum() <= 2
     finally:
         eng.set_precision(N.PREC_FAST)
+
+
+def test_benchmarked_mode_against_the_oracle_at_scale(eng):
+    """The configuration bench.py times -- mixed precision, in-kernel Philox noise, TURBO variant, histogram outputs only,
+    all 8 scenarios of a config-4 shard in one launch -- against the oracle drawing the same Philox counters
+    (oracle/pmcts_oracle.c: fp64 Box-Muller): 8 x 131 072 rollouts.  The kernel's normals come from the hardware
+    lg2 / rsq / sin / cos (1e-6 relative), so a rollout may land on the other side of a bin edge or an arrival
+    decision now and then: at most 16 of the 10^6 rollouts may change bin, and the arrival / transition totals may
+    differ by as many (measured on a B200: 0 moved, totals equal)."""
+    S, n_leaf, rep = 8, 512, 256
+    n = n_leaf * rep
+    for s in range(S):
+        t, la, lo, u, v = synth.wind_fields(s)
+        times, lats, lons = H.sim_axes(la, lo)
+        eng.upload_scenario(10 + s, t, la, lo, u.astype(np.float32), v.astype(np.float32), times,
+                            [lats[0], lats[-1], lons[0], lons[-1]])
+    dest, tmin = [46.77751005, 355.0], 2.022360548788055
+    rng = np.random.default_rng(8)
+    paths = 45.0 * rng.integers(0, 8, (n_leaf, 4))
+    plen = rng.integers(1, 5, n_leaf).astype(np.int32)
+    eng.set_precision(N.PREC_FAST)
+    bins = np.zeros((S, n_leaf, 12), np.uint32)
+    stats = np.zeros((S, 8))
+    eng.rollout_forest(np.arange(10, 10 + S, dtype=np.int32), n_leaf, rep, H.STATE0, dest, tmin, paths.reshape(-1), plen, 4,
+                       prefix_shared=True, seed=42, stream=100, out=dict(leaf_bins=bins.reshape(-1), stats=stats.reshape(-1)))
+    assert eng.last_kernel_variant() == N.VARIANT_TURBO
+    moved = arrived_gap = steps_gap = 0
+    for s in range(S):
+        o = H.oracle_sim(s)
+        want = o.rollout_batch(n, H.STATE0, dest, tmin, prefix=np.repeat(paths, rep, 0), prefix_len=np.repeat(plen, rep),
+                               seed=42, stream=100 + s, nthreads=os.cpu_count() or 8)
+        wb = np.zeros((n_leaf, 12), np.int64)
+        np.add.at(wb, (np.repeat(np.arange(n_leaf), rep), want["bin"]), 1)
+        moved += int(np.abs(bins[s].astype(np.int64) - wb).sum()) // 2
+        arrived_gap += abs(int(stats[s, 3]) - int((want["status"] == 1).sum()))
+        steps_gap += abs(int(stats[s, 4]) - int(want["steps"].sum()))
+        assert stats[s, 5] == n and (bins[s].sum(1) == rep).all()
+    total = S * n
+    print("moved histogram entries %d of %d, arrival gap %d, transition gap %d" % (moved, total, arrived_gap, steps_gap))
+    assert moved <= 16 and arrived_gap <= 16 and steps_gap <= 16

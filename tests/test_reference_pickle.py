@@ -1,0 +1,79 @@
+"""N4: a search result written by MasterTree.save_tree(reference_format=True) is read by the UNMODIFIED reference's own
+MasterTree.load_tree, whose own post-processing then runs on it (code/solver/master.py:57-185, 390-410).  Live test:
+runs where the reference is mounted (/root/reference: the build container).  No GPU: the tree comes from the native
+search driven by the host-logic stand-in of tests/fake_device.py."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from fake_device import run
+from iboat_pmcts_b200 import master_node as mn
+from iboat_pmcts_b200.master import MasterTree
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference not mounted")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_loads_the_tree_and_decides_on_it(tmp_path):
+    forest, master, _ = run("native", n_scen=4, budget=90)
+    nodes = mn.deepcopy_dict(master)
+    from iboat_pmcts_b200 import synth
+    from iboat_pmcts_b200.forest import create_simulators
+    from iboat_pmcts_b200.weatherTLKT import Weather
+    weathers = [Weather(*[synth.wind_fields(s)[i] for i in (1, 2, 0, 3, 4)]) for s in range(4)]
+    sims = create_simulators(weathers, 4, simtimestep=6, stateinit=(0, 44.0, 355.0), ndaysim=3)  # (no device needed)
+    mt = MasterTree(sims, [46.7, 355.0], nodes=nodes)
+    mt.save_tree("tree", directory=str(tmp_path) + "/", reference_format=True)
+    assert not nodes._filled  # written from the arrays: no node object of the mirror classes was built
+    parent, arm, table = nodes.arrays()
+    np.savez(tmp_path / "want.npz", parent=parent, arm=arm, table=table)
+    script = textwrap.dedent("""
+        import io, contextlib, pickle, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        from oracle import refshim
+        R = refshim.load_reference()
+        with open(%r, "rb") as f:
+            tree = pickle.load(f)                      # what MasterTree.load_tree does (master.py:400-410)
+        assert type(tree) is R.master.MasterTree and type(tree.nodes[hash(())]) is R.master_node.MasterNode
+        want = np.load(%r)
+        # same nodes, same histograms, wired like deepcopy_dict's result
+        paths = {hash(()): ()}
+        root = tree.nodes[hash(())]
+        assert root.depth == 0 and root.parentNode is None
+        seen = 0
+        stack = [(root, 0)]
+        index = {}
+        parent, arm, table = want["parent"], want["arm"], want["table"]
+        kids = {}
+        for i in range(1, parent.size):
+            kids.setdefault(int(parent[i]), []).append(i)
+        while stack:
+            node, i = stack.pop()
+            seen += 1
+            got = np.array([[h.h for h in row] for row in node.rewards])
+            assert np.array_equal(got, table[i]), i
+            assert type(node.rewards[0, 0]) is R.utils.Hist
+            assert [int(c.arm) for c in node.children] == [45 * int(arm[j]) for j in kids.get(i, [])]
+            for c, j in zip(node.children, kids.get(i, [])):
+                assert c.parentNode is node and c.depth == node.depth + 1
+                stack.append((c, j))
+        assert seen == parent.size == len(tree.nodes)
+        sim = tree.Simulators[2]                       # a reference Simulator with working SciPy interpolators
+        assert type(sim) is R.simulatorTLKT.Simulator and len(sim.times) == 13
+        assert np.isfinite(sim.uWindAvg([0.3, 44.2, 355.3])).all()
+        with contextlib.redirect_stdout(io.StringIO()):
+            tree.get_best_policy()                     # the reference's own reductions on the loaded tree
+        print({k: [int(a) for a in v] for k, v in tree.best_policy.items()})
+        """) % (ROOT, str(tmp_path / "tree.pickle"), str(tmp_path / "want.npz"))
+    res = subprocess.run([sys.executable, "-W", "ignore", "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    policy = eval(res.stdout.strip().splitlines()[-1])
+    assert set(policy) == {-1, 0, 1, 2, 3} and all(len(v) >= 1 for v in policy.values())
