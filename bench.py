@@ -397,7 +397,7 @@ def run_api_workload(args):
     eng.kernel_ms(reset=True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, period_s=0.02) if rank == 0 else None  # (a Python-side step: the sampler shares its GIL)
     barrier()
     if sampler:
         sampler.start()
@@ -798,8 +798,8 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                     dbg[0].record()
                 if world > 1:
                     eng.pack_bins(src, packed_local)
-                    if not os.environ.get("PMCTS_BENCH_NO_AG"):
-                        dist.all_gather_into_tensor(packed_all, packed_local)
+                    if not os.environ.get("PMCTS_BENCH_NO_AG"):  # (as bytes: NCCL's process group has no 16-bit integer type)
+                        dist.all_gather_into_tensor(packed_all.view(torch.uint8), packed_local.view(torch.uint8))
                     src = packed_all
                 if dbg:
                     dbg[1].record()

@@ -216,6 +216,8 @@ struct SearchCache {
     double *d_stats = nullptr;
     size_t cap_stats = 0;
     cudaStream_t comm = nullptr;
+    char *seq_host = nullptr;  // the sequential search's per-iteration arrays
+    size_t cap_seq = 0;
 };
 
 void free_search_cache(void *p) {
@@ -230,6 +232,7 @@ void free_search_cache(void *p) {
     }
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->comm) cudaStreamDestroy(c->comm);
+    if (c->seq_host) cudaFreeHost(c->seq_host);
     delete c;
 }
 
@@ -557,20 +560,40 @@ extern "C" int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, i
     const int64_t launches0 = pmcts_launch_count(ctx);
     LIB_TRY(pmcts_set_precision(ctx, PMCTS_PREC_FAST));
     const int flags = (roll_flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) | PMCTS_ROLL_PREFIX_ACTIONS | PMCTS_MEM_HOST;
+    // the launch's host arrays live in page-locked memory (kept with the ctx): six small copies per iteration, which
+    // from pageable memory would each go through the driver's own staging
+    void **slot = pmcts::ctx_attachment(ctx, free_search_cache);
+    if (!*slot) *slot = new SearchCache();
+    SearchCache *cache = (SearchCache *)*slot;
+    const size_t o_path = align16((size_t)n_instants * sizeof(double)), o_plen = o_path + align16(info.max_depth);
+    const size_t o_steps = o_plen + 16, o_bin = o_steps + 16, o_status = o_bin + 16;
+    {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        const int dev = pmcts_get_device(ctx);
+        if (prev != dev) CUDA_TRY(cudaSetDevice(dev));
+        const int rcg = grow_pinned(cache->seq_host, cache->cap_seq, o_status + 16);
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+        if (rcg) return rcg;
+    }
+    char *h = cache->seq_host;
     const pmcts::SeqRollout rollout = [&](int, const int8_t *path, int len, const double *z, int *bin, int *steps) -> int {
-        int32_t plen = len, st_steps = 0, b = 0;
-        uint8_t status = 0;
+        std::memcpy(h, z, (size_t)n_instants * sizeof(double));
+        std::memcpy(h + o_path, path, (size_t)len);
+        *(int32_t *)(h + o_plen) = len;
         pmcts_noise nz{};
         nz.mode = PMCTS_NOISE_INJECTED;
-        nz.z = z;
-        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)path, &plen,
-                                           info.max_depth, &nz, nullptr, nullptr, &st_steps, &status, &b, nullptr, nullptr,
-                                           nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags);
+        nz.z = (const double *)h;
+        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)(h + o_path),
+                                           (const int32_t *)(h + o_plen), info.max_depth, &nz, nullptr, nullptr,
+                                           (int32_t *)(h + o_steps), (uint8_t *)(h + o_status), (int32_t *)(h + o_bin), nullptr,
+                                           nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags);
         if (rc) return rc;
+        const uint8_t status = *(uint8_t *)(h + o_status);
         if (status == PMCTS_ST_OUT_OF_GRID || status == PMCTS_ST_PAST_HORIZON || status == PMCTS_ST_DEGENERATE)
             return (int)status;  // what the reference raises on
-        *bin = b;
-        *steps = st_steps;
+        *bin = *(int32_t *)(h + o_bin);
+        *steps = *(int32_t *)(h + o_steps);
         return 0;
     };
     const int rc = pmcts::forest_sequential(f, local_index, budget, frequency, n_instants, py_state, np_state, rollout, &rep);

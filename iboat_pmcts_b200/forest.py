@@ -42,7 +42,10 @@ class Forest:
         ``mode="sequential"``: every worker runs the reference's ``Tree.uct_search`` (one rollout per
         iteration, ``frequency`` iterations between pushes to the master), one worker after the other --
         what the reference's processes do when they do not interleave; reproducible from
-        ``random.seed`` / ``np.random.seed``.
+        ``random.seed`` / ``np.random.seed``.  With ``host="native"`` (default) the loop runs in the C++ host
+        runtime on the same random streams (``pmcts_forest_search_sequential``); ``host="python"`` runs the Python
+        loop of ``worker.Tree.uct_search`` -- same tree, same master, same generator states afterwards
+        (tests/test_api_gpu.py).
 
         ``mode="batched"`` (default): waves of ``leaves`` leaves per tree, ``replicas`` noise replicas per
         leaf (Philox noise from ``seed``), all local scenarios in one launch; the master is updated after
@@ -59,6 +62,8 @@ class Forest:
         """
         Master_nodes = dict()
         Master_nodes[ROOT_HASH] = MasterNode(len(self.workers), nodehash=ROOT_HASH)
+        if mode == "sequential" and host == "native" and self._native_ok():
+            return self._search_sequential_native(list(root_state), int(frequency), bool(replay_full_prefix))
         if mode == "sequential":
             for worker in self.workers.values():
                 worker.replay_full_prefix = replay_full_prefix
@@ -73,6 +78,63 @@ class Forest:
                                        bool(replay_full_prefix), group, int(pipeline))
         return self._search_batched(list(root_state), Master_nodes, int(leaves), int(replicas), int(seed),
                                     bool(replay_full_prefix), group)
+
+    # ------------------------------------------------------------------------------------------------
+    def _native_ok(self):
+        try:
+            eng, _ = next(iter(self.workers.values())).Simulator.scenario()
+        except Exception:
+            return False
+        return getattr(eng, "_h", None) is not None and np.random.get_state()[0] == "MT19937"
+
+    def _search_sequential_native(self, root_state, frequency, replay_full):
+        """``Tree.uct_search`` of every worker, one after the other (the reference's processes, serialised), as native
+        calls (``pmcts_forest_search_sequential``): the same iterations, in the same order, on the same random streams
+        as the Python loop of ``worker.Tree.uct_search`` -- ``random`` and ``np.random`` are continued from their
+        current states and left where that loop would have left them -- with one small launch per rollout."""
+        import ctypes as C
+        from . import worker as W
+        lib = N.lib()
+        S = len(self.workers)
+        trees = [self.workers[i] for i in range(S)]
+        budget = trees[0].budget
+        max_depth = len(trees[0].Simulator.times) - 1
+        ids = np.arange(S, dtype=np.int32)
+        prob = np.ascontiguousarray(trees[0].probability, np.float64)
+        handle = C.c_void_p()
+        N.check_forest(lib.pmcts_forest_create(S, S, ids.ctypes.data, max_depth, prob.ctypes.data, float(W.UCT_COEFF),
+                                               float(W.RHO), None, budget + 2, C.byref(handle)))
+        np_like = np.random.get_state()
+        py, npst = N.MtState.from_python(rand.getstate()), N.MtState.from_numpy(np_like)
+        root = np.ascontiguousarray(root_state, np.float64)
+        dest = np.ascontiguousarray(self.destination, np.float64)
+        flags = N.ROLL_REPLAY_FULL_PREFIX if replay_full else 0
+        total = dict(rollouts=0, transitions=0, waves=0, launches=0, ms_total=0.0)
+        try:
+            for i, t in enumerate(trees):
+                eng, slot = t.Simulator.scenario()
+                report = N.SearchReport()
+                rc = lib.pmcts_forest_search_sequential(eng._h, handle, i, int(slot), root.ctypes.data, dest.ctypes.data,
+                                                        float(self.timemin), int(t.budget), int(frequency), flags,
+                                                        C.byref(py), C.byref(npst), C.byref(report))
+                # the generators stand where the reference's would, whatever happened
+                rand.setstate(py.to_python())
+                np.random.set_state(npst.to_numpy(np_like))
+                if rc > 0:
+                    from .simulatorTLKT import raise_for_status
+                    raise_for_status(rc)
+                N.check(rc)
+                for k in total:
+                    total[k] += getattr(report, k)
+        except BaseException:
+            lib.pmcts_forest_destroy(handle)
+            raise
+        self.last_search_report = total
+        native = _NativeForest(lib, handle, S)
+        for ti, t in enumerate(trees):
+            _export_tree(native, ti, t, root_state, t.budget)
+        from .master_node import MasterDict
+        return MasterDict(loader=native.master_arrays, size=native.master_size(), sparse_loader=native.master_rows)
 
     # ------------------------------------------------------------------------------------------------
     def _search_batched(self, root_state, Master_nodes, B, K, seed, replay_full, group):

@@ -427,3 +427,61 @@ def test_gefs_shaped_pickle_ingest(tmp_path):
             assert np.allclose(got["final_lon"], want["final_lon"], rtol=1e-6, atol=0)
         assert (want["steps"] >= 1).all() and set(np.unique(want["status"])) <= {1, 2, 3}
         eng.set_precision(N.PREC_F64)
+
+
+def test_native_sequential_search_is_the_python_loop(golden_dir, monkeypatch):
+    """Forest.launch_search(mode="sequential"): the native loop (pmcts_forest_search_sequential -- CPython's and
+    NumPy's generators continued in C++, one mixed-precision launch per rollout) against the Python loop of
+    worker.Tree.uct_search with its literal-fp64 launches: the same master dictionary node for node, the same worker
+    trees, and random / np.random left in the same state -- for Tutorial.py's single tree and for a 3-scenario forest
+    whose workers see each other's statistics through the master."""
+    import contextlib
+    import io
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    destination, timemin = [float(x) for x in g["destination"]], float(g["timemin"])
+    monkeypatch.setattr(worker, "RHO", 0.5)
+    monkeypatch.setattr(worker, "UCT_COEFF", 1 / 2 ** 0.5)
+    for scenarios, budget, frequency in (([0], 300, 10), ([0, 1, 2], 120, 7)):
+        sims = make_sims(scenarios)
+        res = {}
+        for host in ("python", "native"):
+            random.seed(1)
+            np.random.seed(1)
+            forest = ft.Forest(listsimulators=sims, destination=destination, timemin=timemin, budget=budget)
+            with contextlib.redirect_stdout(io.StringIO()):
+                master = forest.launch_search(STATE0, frequency, mode="sequential", host=host)
+            res[host] = (forest, master, random.random(), random.gauss(0, 1), int(np.random.randint(1 << 30)))
+        (fp, mp, *rp), (fn, mn_, *rn) = res["python"], res["native"]
+        assert rp == rn                                   # both generators stand where the reference's would
+        assert list(mp) == list(mn_) and len(mp) > budget // 2
+        for k in mp:
+            assert np.array_equal(mp[k]._table, mn_[k]._table), k
+            assert mp[k].arm == mn_[k].arm
+        for i in range(len(scenarios)):
+            tp, tn = fp.workers[i], fn.workers[i]
+            assert len(tp.Nodes) == len(tn.Nodes) == budget + 1 and tn.ite == budget
+            assert np.array_equal(tp.table[:budget + 1], tn.table[:budget + 1])
+            for a, b in zip(tp.Nodes, tn.Nodes):
+                assert [int(x) for x in a.origins] == [int(x) for x in b.origins]
+                assert [int(x) for x in a.actions] == [int(x) for x in b.actions]
+        assert fn.last_search_report["rollouts"] == budget * len(scenarios)
+        assert fn.last_search_report["transitions"] == fp.last_search_report["transitions"]
+    # the recorded reference run (tests/golden/tree_replay_c1.json) through the native loop
+    with open(os.path.join(golden_dir, "tree_replay_c1.json")) as f:
+        replay = json.load(f)
+    monkeypatch.setattr(worker, "RHO", replay["rho"])
+    monkeypatch.setattr(worker, "UCT_COEFF", replay["uct_coeff"])
+    sims = make_sims([0])
+    random.seed(1)
+    np.random.seed(1)
+    forest = ft.Forest(listsimulators=sims, destination=destination, timemin=timemin, budget=replay["budget"])
+    master = forest.launch_search(STATE0, replay["frequency"], mode="sequential")
+    tree = forest.workers[0]
+    assert [[int(a) for a in n.origins] for n in tree.Nodes] == [n["origins"] for n in replay["nodes"]]
+    for node, want in zip(tree.Nodes, replay["nodes"]):
+        assert np.array_equal(node._table, np.array(want["hist"]))
+    for k, node in master.items():
+        assert np.array_equal(node._table[0], np.array(replay["master_nodes"][str(k)]))
+    mt = MasterTree(sims, destination, nodes=mn.deepcopy_dict(master))
+    mt.get_best_policy(verbose=False)
+    assert {str(k): [int(a) for a in v] for k, v in mt.best_policy.items()} == replay["best_policy"]

@@ -112,3 +112,31 @@ def test_native_shuffles_are_cpythons():
             rng.shuffle(order)
             ref.append(order)
         assert np.array_equal(out, np.array(ref, np.uint8)), seed
+
+
+def test_native_generators_are_the_interpreters():
+    """pmcts_python_gauss / pmcts_numpy_randint8 continue random.getstate() / np.random.get_state() exactly as
+    random.gauss(0, 1) / np.random.randint(8) do -- values bit for bit, states afterwards included (odd counts leave
+    a cached second normal behind) -- which is what lets the native sequential search grow the reference's tree."""
+    import random
+    L = N.lib()
+    for seed, count in ((1, 7), (12345, 1000), (2 ** 40 + 3, 625 * 2 + 1)):
+        random.seed(seed)
+        random.random()
+        if seed == 12345:
+            random.gauss(0.0, 1.0)  # start with a cached normal
+        st = N.MtState.from_python(random.getstate())
+        out = np.empty(count)
+        N.check_forest(L.pmcts_python_gauss(st, count, out.ctypes.data))
+        want = np.array([random.gauss(0.0, 1.0) for _ in range(count)])
+        assert np.array_equal(out, want)
+        assert st.to_python() == random.getstate()
+        np.random.seed(seed % (2 ** 32))
+        np.random.randint(100, size=3)
+        like = np.random.get_state()
+        ns = N.MtState.from_numpy(like)
+        got = np.empty(count, np.uint8)
+        N.check_forest(L.pmcts_numpy_randint8(ns, count, got.ctypes.data))
+        assert np.array_equal(got, np.array([np.random.randint(8) for _ in range(count)], np.uint8))
+        back, now = ns.to_numpy(like), np.random.get_state()
+        assert np.array_equal(back[1], now[1]) and back[2] == now[2]
