@@ -35,7 +35,7 @@ EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_get_stream", "pmcts_get_device", "pmcts_comm_unique_id", "pmcts_comm_create", "pmcts_comm_destroy",
     "pmcts_allgather_updates", "pmcts_forest_search", "pmcts_master_policy", "pmcts_pack_bins",
-    "pmcts_forest_search_sequential", "pmcts_python_gauss", "pmcts_numpy_randint8",
+    "pmcts_forest_search_sequential", "pmcts_python_gauss", "pmcts_numpy_randint8", "pmcts_forest_master_policy",
     "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
@@ -151,6 +151,7 @@ def lib():
                                                  C.POINTER(MtState), C.POINTER(SearchReport)]
     L.pmcts_python_gauss.argtypes = [C.POINTER(MtState), i64, vp]
     L.pmcts_numpy_randint8.argtypes = [C.POINTER(MtState), i64, vp]
+    L.pmcts_forest_master_policy.argtypes = [vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp]
     L.pmcts_forest_search.argtypes = [vp, vp, vp, vp, vp, dbl, C.POINTER(SearchParams), C.POINTER(SearchReport)]
     L.pmcts_synchronize.argtypes = [vp]
     L.pmcts_join.argtypes = [vp, i32]

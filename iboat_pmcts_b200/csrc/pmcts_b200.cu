@@ -896,8 +896,8 @@ struct pmcts_ctx {
     // Every entry point that takes a ctx holds this lock for its duration: calls on one ctx from several host
     // threads are serialised (they are stream-ordered anyway); recursive because upload frees the slot it replaces.
     std::recursive_mutex mu;
-    void *attachment = nullptr;  // pmcts::ctx_attachment
-    void (*attachment_free)(void *) = nullptr;
+    void *attachment[2] = {nullptr, nullptr};  // pmcts::ctx_attachment
+    void (*attachment_free[2])(void *) = {nullptr, nullptr};
     Deferred *last_fast = nullptr;  // work area of the last mixed-precision rollout launch when it was a deferred one
 };
 
@@ -1096,9 +1096,9 @@ bool uniform_axis(const double *g, int n, double *inv_step) {
 namespace pmcts {
 void set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
 void count_launches(pmcts_ctx *ctx, int n) { ctx->launches += n; }
-void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *)) {
-    ctx->attachment_free = free_fn;
-    return &ctx->attachment;
+void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *), int key) {
+    ctx->attachment_free[key] = free_fn;
+    return &ctx->attachment[key];
 }
 }  // namespace pmcts
 
@@ -1133,8 +1133,10 @@ void pmcts_destroy(pmcts_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);  // (no lock: the caller must not use a ctx it is destroying)
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->attachment && ctx->attachment_free) ctx->attachment_free(ctx->attachment);
-    ctx->attachment = nullptr;
+    for (int key = 0; key < 2; ++key) {
+        if (ctx->attachment[key] && ctx->attachment_free[key]) ctx->attachment_free[key](ctx->attachment[key]);
+        ctx->attachment[key] = nullptr;
+    }
     for (auto &kv : ctx->scenarios) cudaFree(kv.second.blob);
     if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
     if (ctx->stage.p) cudaFree(ctx->stage.p);

@@ -9,9 +9,9 @@ namespace pmcts {
 // message returned by pmcts_last_error() on the calling thread (pmcts_b200.cu)
 void set_last_error(const char *msg);
 
-// One object another translation unit keeps with a ctx for the ctx's lifetime (the search driver's staging buffers):
-// returns the slot; pmcts_destroy calls free_fn on what it holds.
-void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *));
+// Objects other translation units keep with a ctx for the ctx's lifetime (staging buffers of the search driver: key 0,
+// of the master reductions: key 1): returns the slot; pmcts_destroy calls free_fn on what it holds.
+void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *), int key = 0);
 
 // kernels launched on behalf of the ctx by another translation unit (pmcts_launch_count)
 void count_launches(pmcts_ctx *ctx, int n);

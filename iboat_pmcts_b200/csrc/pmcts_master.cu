@@ -334,3 +334,60 @@ extern "C" int pmcts_master_policy(pmcts_ctx *ctx, int64_t n_nodes, int n_scen, 
 #undef M_TRY
     return PMCTS_OK;
 }
+
+// ---- the same reductions straight from the host runtime's master (no round trip through the caller's arrays) ------
+namespace {
+
+struct MasterStage {  // page-locked staging of the exported master, kept with the ctx (grow-only)
+    char *p = nullptr;
+    size_t cap = 0;
+};
+void free_master_stage(void *q) {
+    MasterStage *m = (MasterStage *)q;
+    if (m->p) cudaFreeHost(m->p);
+    delete m;
+}
+size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int pmcts_forest_master_policy(pmcts_ctx *ctx, pmcts_forest *f, const double *probability, double uct_coeff,
+                                          int max_depth, double *value, double *explore, double *guess,
+                                          int32_t *best_child, int8_t *policy, int32_t *policy_nodes) {
+    if (!ctx || !f || !probability) return fail(PMCTS_ERR_ARG, "NULL argument");
+    const int64_t n = pmcts_forest_master_size(f), n_rows = pmcts_forest_master_rows(f);
+    const int S = pmcts::forest_info(f).n_scen;
+    if (n < 1) return fail(PMCTS_ERR_ARG, "empty master");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    const int dev = pmcts_get_device(ctx);
+    if (prev != dev) CUDA_TRY(cudaSetDevice(dev));
+    void **slot = pmcts::ctx_attachment(ctx, free_master_stage, 1);
+    if (!*slot) *slot = new MasterStage();
+    MasterStage *st = (MasterStage *)*slot;
+    const size_t o_arm = al256((size_t)n * sizeof(int32_t)), o_idx = o_arm + al256((size_t)n);
+    const size_t o_rows = o_idx + al256((size_t)n * S * sizeof(int32_t));
+    const size_t total = o_rows + al256((size_t)n_rows * kRow * sizeof(uint32_t));
+    int rc = PMCTS_OK;
+    if (total > st->cap) {
+        if (st->p) cudaFreeHost(st->p);
+        st->p = nullptr;
+        st->cap = 0;
+        if (cudaMallocHost((void **)&st->p, total + total / 2) != cudaSuccess)
+            rc = fail(PMCTS_ERR_CUDA, "page-locked staging for the master: %s", cudaGetErrorString(cudaGetLastError()));
+        else
+            st->cap = total + total / 2;
+    }
+    if (!rc) {
+        char *h = st->p;
+        rc = pmcts_forest_export_master_rows(f, (int32_t *)h, (int8_t *)(h + o_arm), (int32_t *)(h + o_idx),
+                                             (uint32_t *)(h + o_rows));
+        if (rc) fail(rc, "%s", pmcts_forest_last_error());
+        else
+            rc = pmcts_master_policy(ctx, n, S, (const int32_t *)h, (const int8_t *)(h + o_arm), (const int32_t *)(h + o_idx),
+                                     n_rows, (const uint32_t *)(h + o_rows), probability, uct_coeff, max_depth, value, explore,
+                                     guess, best_child, policy, policy_nodes, PMCTS_MEM_HOST);
+    }
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    return rc;
+}

@@ -378,6 +378,21 @@ class Engine:
         return out
 
 
+    def forest_master_policy(self, native, probability, uct_coeff, max_depth, want=("policy", "policy_nodes")):
+        """``pmcts_forest_master_policy``: the reductions of ``master_policy`` on the master of a native forest."""
+        prob = np.ascontiguousarray(probability, np.float64)
+        n, S = native.master_size(), int(prob.size)
+        spec = dict(value=((n, S + 1), np.float64), explore=((n, S + 1), np.float64), guess=((n, S), np.float64),
+                    best_child=((n, S + 1), np.int32), policy=((S + 1, max_depth), np.int8),
+                    policy_nodes=((S + 1, max_depth + 1), np.int32))
+        out = {k: np.empty(*spec[k]) for k in want}
+        ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+        N.check(self._lib.pmcts_forest_master_policy(self._h, native.handle, prob.ctypes.data, float(uct_coeff),
+                                                     int(max_depth), ptr("value"), ptr("explore"), ptr("guess"),
+                                                     ptr("best_child"), ptr("policy"), ptr("policy_nodes")))
+        return out
+
+
 _default = {}
 _default_device = None
 

@@ -133,8 +133,7 @@ class Forest:
         native = _NativeForest(lib, handle, S)
         for ti, t in enumerate(trees):
             _export_tree(native, ti, t, root_state, t.budget)
-        from .master_node import MasterDict
-        return MasterDict(loader=native.master_arrays, size=native.master_size(), sparse_loader=native.master_rows)
+        return native.master_dict()
 
     # ------------------------------------------------------------------------------------------------
     def _search_batched(self, root_state, Master_nodes, B, K, seed, replay_full, group):
@@ -288,7 +287,7 @@ class Forest:
         for ti, t in enumerate(trees):
             _export_tree(native, ti, t, root_state, budget)
         from .master_node import MasterDict
-        return MasterDict(loader=native.master_arrays, size=native.master_size(), sparse_loader=native.master_rows)
+        return native.master_dict()
 
 
 class _NativeForest:
@@ -307,6 +306,12 @@ class _NativeForest:
 
     def master_size(self):
         return int(self.lib.pmcts_forest_master_size(self.handle))
+
+    def master_dict(self):
+        from .master_node import MasterDict
+        d = MasterDict(loader=self.master_arrays, size=self.master_size(), sparse_loader=self.master_rows)
+        d.native = self
+        return d
 
     def master_arrays(self):
         n = self.master_size()

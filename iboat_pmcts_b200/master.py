@@ -67,11 +67,18 @@ class MasterTree:
 
     def _solve(self, want=("value", "explore", "guess", "best_child", "policy", "policy_nodes")):
         from .engine import default_engine
-        parent, arm, row_index, rows, node_of = self._arrays()
         eng = default_engine()
         max_depth = max(1, len(self.Simulators[0].times) - 1) if len(self.Simulators) else 64
+        nodes = self.nodes
+        native = getattr(nodes, "native", None) if isinstance(nodes, MasterDict) and not nodes._dirty else None
+        if native is not None and native.handle:
+            # the result of a native search, still in the host runtime: reduced from there, no array leaves it
+            out = eng.forest_master_policy(native, self.probability, UCT_COEFF, max_depth, want=want)
+            out["node_of"] = nodes.node_at
+            return out
+        parent, arm, row_index, rows, node_of = self._arrays()
         out = eng.master_policy(parent, arm, row_index, rows, self.probability, UCT_COEFF, max_depth, want=want)
-        out["node_of"], out["arm"], out["parent"] = node_of, arm, parent
+        out["node_of"] = node_of
         return out
 
     def _full(self):
@@ -96,7 +103,10 @@ class MasterTree:
                 for depth, (i, action) in enumerate(zip(idx[1:], policy), 1):
                     print("Depth {}: best reward = {} for action = {}".format(depth, sol["value"][i, col], action))
             self.best_policy[id_scenario] = policy
-            self.best_nodes_policy[id_scenario] = [node_of(i) for i in idx]
+            if isinstance(self.nodes, MasterDict) and not self.nodes._dirty and not self.nodes._filled:
+                self.best_nodes_policy[id_scenario] = self.nodes.nodes_along(idx, policy)
+            else:
+                self.best_nodes_policy[id_scenario] = [node_of(i) for i in idx]
 
     def _col(self, idscenario):
         return self.numScenarios if idscenario == -1 else int(idscenario)

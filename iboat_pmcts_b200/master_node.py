@@ -33,14 +33,20 @@ class MasterNode:
         if d.get("_owner") is not None:  # a node of an array-backed dictionary pickles as a plain node
             d["children"] = self.children
             d["_owner"] = None
+        if d.get("_source") is not None:
+            d["_table"] = self._table
+            d["_source"] = None
         return d
 
     def __getattr__(self, name):
-        # Only reached when the attribute is missing: the children of a node of an array-backed dictionary
-        # (MasterDict) are listed the first time they are read.
+        # Only reached when the attribute is missing: the children and the counters of a node of an array-backed
+        # dictionary (MasterDict) are fetched the first time they are read.
         if name == "children" and self.__dict__.get("_owner") is not None:
             kids = self.__dict__["children"] = self._owner._children_of(self._index)
             return kids
+        if name == "_table" and self.__dict__.get("_source") is not None:
+            table = self.__dict__["_table"] = self._source._table_of(self._index)
+            return table
         raise AttributeError(name)
 
     @property
@@ -82,6 +88,7 @@ class MasterDict(dict):
         self._loader = loader  # () -> (parent, arm, table): the arrays are fetched on first need
         self._sparse_loader = sparse_loader  # () -> (parent, arm, row_index, rows): the native runtime's own layout
         self._sparse = None
+        self.native = None  # the native forest behind a search result (forest._NativeForest), for consumers of its arrays
         self._parent, self._arm, self._table = parent, arm, table
         self._wired = bool(wired)
         n = int(size if loader is not None else parent.size)
@@ -97,9 +104,11 @@ class MasterDict(dict):
             self._parent, self._arm, self._table = self._loader()
             self._loader = None
             for node in self._nodes:  # nodes built from the sparse rows before now: re-point them at the table
-                if node is not None:
-                    self._table[node._index] = node._table
-                    node._table = self._table[node._index]
+                if node is not None and node.__dict__.get("_source") is not None:
+                    if "_table" in node.__dict__:
+                        self._table[node._index] = node.__dict__["_table"]
+                    node.__dict__["_table"] = self._table[node._index]
+                    node._source = None
                     node._rewards = None
 
     def arrays(self):
@@ -139,6 +148,18 @@ class MasterDict(dict):
             self._depth = d
         return self._depth
 
+    def _table_of(self, i):
+        """[scenario][8][12] counters of node ``i``: a view of the dense table once that is loaded, else gathered from
+        the sparse rows."""
+        if self._table is not None:
+            return self._table[i]
+        sparse = self.sparse()
+        rows = sparse[2][i]
+        tab = np.zeros((rows.size, len(ACTIONS) * Hist.N_BINS), dtype=int)
+        has = rows >= 0
+        tab[has] = sparse[3][rows[has]]
+        return tab.reshape(rows.size, len(ACTIONS), Hist.N_BINS)
+
     def _children_of(self, i):
         if self._parent is None:
             self._load()
@@ -171,12 +192,9 @@ class MasterDict(dict):
         node.guessed_rewards = dict()
         if sparse is None:
             node._table = self._table[i]  # a view: edits through the node show in arrays()
+            node._source = None
         else:
-            rows = sparse[2][i]
-            tab = np.zeros((rows.size, len(ACTIONS) * Hist.N_BINS), dtype=int)
-            has = rows >= 0
-            tab[has] = sparse[3][rows[has]]
-            node._table = tab.reshape(rows.size, len(ACTIONS), Hist.N_BINS)
+            node._source = self  # counters gathered from the sparse rows when first read (MasterNode.__getattr__)
         node._rewards = None
         node._index = i
         if self._wired:
@@ -188,6 +206,38 @@ class MasterDict(dict):
             node.depth = None
         self._nodes[i] = node
         return node
+
+    def nodes_along(self, indices, actions):
+        """The nodes of a root-to-node chain given by array indices (root first) and the actions between them (degrees)
+        -- what a greedy policy is -- built without fetching any array: their counters and children come later, if
+        somebody reads them."""
+        out, parent = [], None
+        for d, i in enumerate(indices):
+            node = self._nodes[i]
+            if node is None:
+                node = MasterNode.__new__(MasterNode)
+                node._path = () if parent is None else parent._path + (int(actions[d - 1]),)
+                node.hash = hash(node._path)
+                node.arm = None if parent is None else actions[d - 1]
+                node.parentNode = parent
+                node.guessed_rewards = dict()
+                node._rewards = None
+                node._index = i
+                if self._table is not None:
+                    node._table, node._source = self._table[i], None
+                else:
+                    node._source = self
+                if self._wired:
+                    node._owner = self
+                    node.depth = d
+                else:
+                    node._owner = None
+                    node.children = []
+                    node.depth = None
+                self._nodes[i] = node
+            out.append(node)
+            parent = node
+        return out
 
     def _fill(self):
         if not self._filled:
@@ -236,6 +286,7 @@ def deepcopy_dict(nodes):
             new = MasterDict(wired=True, size=len(nodes), sparse_loader=nodes._sparse_loader,
                              loader=lambda: tuple(np.array(a, dtype=int if a.ndim == 4 else a.dtype) for a in loader()))
             new._sparse = nodes._sparse
+            new.native = nodes.native
         else:
             parent, arm, table = nodes.arrays()
             new = MasterDict(parent.copy(), arm.copy(), np.array(table, dtype=int), wired=True)

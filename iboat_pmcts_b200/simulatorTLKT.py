@@ -65,7 +65,9 @@ class Simulator:
         self.uWindAvg = WeatherAvg.uInterpolator
         self.vWindAvg = WeatherAvg.vInterpolator
         self._weather = WeatherAvg
-        self._slot = None
+        # the device copy of the scenario, shared with every deep copy of this simulator (Forest.__init__ copies one
+        # per worker before anything has been uploaded): whichever copy needs it first uploads it for all
+        self._dev = {"slot": None, "key": None}
 
     # ---- device scenario ---------------------------------------------------------------------
     def __deepcopy__(self, memo):
@@ -75,7 +77,7 @@ class Simulator:
         new = Simulator.__new__(Simulator)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_slot", "_weather", "uWindAvg", "vWindAvg"):
+            if k in ("_dev", "_weather", "uWindAvg", "vWindAvg"):
                 setattr(new, k, v)
             else:
                 setattr(new, k, copy.deepcopy(v, memo))
@@ -86,17 +88,20 @@ class Simulator:
                 float(self.lons[0]), float(self.lons[-1]), self._weather._fingerprint())
 
     def scenario(self):
-        """(engine, slot id) of this simulator's scenario on the device, uploaded on first use."""
+        """(engine, slot id) of this simulator's scenario on the device, uploaded on first use (and again when the
+        axes or the weather change; the check costs a few strided sums, so a caller that loops over many launches
+        holds on to the pair)."""
         key = self._axis_key()
-        if self._slot is None or self._slot_key != key:
+        dev = self._dev
+        if dev["slot"] is None or dev["key"] != key:
             eng = default_engine()
             slot = Slot(eng)
             w = self._weather
             eng.upload_scenario(slot.id, w.time, w.lat, w.lon, w.u, w.v, self.times,
                                 [self.lats[0], self.lats[-1], self.lons[0], self.lons[-1]])
-            self._slot, self._slot_key = slot, key
-        sync_params(self._slot.engine)
-        return self._slot.engine, self._slot.id
+            dev["slot"], dev["key"] = slot, key
+        sync_params(dev["slot"].engine)
+        return dev["slot"].engine, dev["slot"].id
 
     # ---- reference API -------------------------------------------------------------------------
     def reset(self, stateInit):

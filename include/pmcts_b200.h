@@ -332,6 +332,12 @@ int pmcts_master_policy(pmcts_ctx *ctx, int64_t n_nodes, int n_scen, const int32
                         double uct_coeff, int max_depth, double *value, double *explore, double *guess,
                         int32_t *best_child, int8_t *policy, int32_t *policy_nodes, int flags);
 
+/* The same, straight from the master tree of a host forest (after a search): the runtime's rows go to the device
+ * through page-locked staging kept with the ctx; the outputs are HOST arrays (any may be NULL). */
+int pmcts_forest_master_policy(pmcts_ctx *ctx, pmcts_forest *f, const double *probability, double uct_coeff,
+                               int max_depth, double *value, double *explore, double *guess, int32_t *best_child,
+                               int8_t *policy, int32_t *policy_nodes);
+
 /* ---- multi-GPU exchange: the all-gather of the per-wave update blocks ------------------------------------
  * Replaces the Manager().dict() proxy through which the reference's worker processes reach the master tree
  * (forest.py:60-66, worker.py:348-378): every rank contributes the block of its own scenarios and receives
