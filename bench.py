@@ -948,8 +948,8 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                               e2e_note=("every rank times its own host-array calls (no L2 flush); max time over ranks, transitions summed"
                                         if world == 1 else
                                         "exchange and back-up included; host-timed, max over ranks, transitions summed"),
-                              traffic=1798400,  # profiles/r01_c4_forest_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
-                              traffic_source="profiles/r01_c4_forest_final_full.txt",
+                              traffic=1795840,  # profiles/r02_k2_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
+                              traffic_source="profiles/r02_k2_final_full.txt",
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))
 
 
@@ -1030,8 +1030,8 @@ def setup_c3(eng, torch, dev, rank, world):
                               api="pmcts_step_batch with PMCTS_MEM_HOST | PMCTS_STEP_HEADING_ACTIONS | PMCTS_STEP_DEFER + pmcts_wait "
                                   "(host state and uint8 action-index headings in, host state out; copies and kernel of "
                                   "consecutive calls overlap)",
-                              traffic=181827072 + 16585984,  # profiles/r01_c3_step_final_full.txt
-                              traffic_source="profiles/r01_c3_step_final_full.txt",
+                              traffic=181815552 + 14913024,  # profiles/r02_k1_final_full.txt
+                              traffic_source="profiles/r02_k1_final_full.txt",
                               hbm_bytes_per_launch=n * (21 + 21) + head_h.nbytes))
 
 
