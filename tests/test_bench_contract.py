@@ -47,3 +47,19 @@ def test_b200_arm_line():
     # the per-step windows hide nothing: the same steps back to back, one event pair, within a few percent
     assert abs(d["back_to_back"]["value"] / d["value"] - 1.0) < 0.1
     assert d["clocks"]["sm_mhz"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["c2", "c5", "c3"])
+def test_other_baseline_configs_through_bench(workload):
+    """`--workload c2 | c5 | c3` put BASELINE configs 2, 5 and 3 behind the same JSON contract (c2 and c5 through the
+    reference's Python API, c3 through the C ABI), and the reference arm answers for them too."""
+    d = run_bench("--workload", workload, "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--soak", "0")
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    assert d["metric"] == "sim transitions/s" and d["value"] > 1e7 and d["gpu_launches"] > 0
+    assert workload in d["config"]["workload"][:3]
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    if workload == "c2":
+        assert d["rollouts_per_s"] > 1e6 and len(d["last_decision"]) >= 1
+    r = run_bench("--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0")
+    assert r["impl"] == "reference" and r["config"]["workload"] == d["config"]["workload"] and r["unit"] == d["unit"]
