@@ -397,7 +397,8 @@ def run_api_workload(args):
     eng.kernel_ms(reset=True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local, period_s=0.02) if rank == 0 else None  # (a Python-side step: the sampler shares its GIL)
+    # (NVML queries share the driver with the step's launches -- a thousand synchronous ones per c1 step: sample sparsely)
+    sampler = ClockSampler(local, period_s=0.1 if wl == "c1" else 0.05) if rank == 0 else None
     barrier()
     if sampler:
         sampler.start()

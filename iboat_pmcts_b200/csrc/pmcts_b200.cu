@@ -728,8 +728,9 @@ __global__ void expand_prefix_kernel(const int8_t *__restrict__ a, double *__res
 // Narrowing of a wave's histograms for the exchange (pmcts_pack_bins): a count is at most `replicas`.
 template <typename T>
 __global__ void pack_bins_kernel(const uint32_t *__restrict__ bins, T *__restrict__ out, size_t count) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = (T)bins[i];
+    // (a few blocks striding, for the same reason as backup_kernel)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (T)bins[i];
 }
 
 // Roofline denominator: what the FP32 FMA pipes of this chip sustain (pmcts_probe_fp32_peak).  16 independent
@@ -751,25 +752,30 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out,
 // K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
 // blockIdx.y = scenario.
 // kBin: the width the histograms arrive in (uint32 from K2; uint8 / uint16 from an all-gathered update block).
+// A few fat blocks that stride over all (scenario, leaf, bin) triples rather than one thread each: the back-up of a
+// wave runs on a side stream UNDER the next wave's rollout kernel, whose blocks hold every block slot of the chip; a
+// grid of tens of thousands of tiny blocks then waits for a freed slot tens of thousands of times (0.8 ms of wall time
+// for 40 us of work at 64 scenarios, which put the communication stream on the critical path of an 8-GPU step), a
+// grid of two blocks per SM waits once.
 template <typename kBin>
-__global__ void backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes,
-                              const int32_t *__restrict__ parent, const int8_t *__restrict__ arm,
-                              int64_t n_leaf, const int32_t *__restrict__ leaf_node,
-                              const int8_t *__restrict__ leaf_slot,
-                              const kBin *__restrict__ leaf_bins) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_leaf * 12) return;
-    const int64_t s = blockIdx.y;
-    const int64_t l = t / 12;
-    const int b = (int)(t % 12);
-    const uint32_t c = leaf_bins[s * n_leaf * 12 + t];
-    if (c == 0) return;
-    uint32_t *tab = table + (size_t)s * n_nodes * 96;
-    int node = leaf_node[s * n_leaf + l];
-    atomicAdd(&tab[((size_t)node * 8 + leaf_slot[s * n_leaf + l]) * 12 + b], c);
-    for (int p = parent[node]; p >= 0; p = parent[node]) {
-        atomicAdd(&tab[((size_t)p * 8 + arm[node]) * 12 + b], c);
-        node = p;
+__global__ void __launch_bounds__(256)
+backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes, const int32_t *__restrict__ parent,
+              const int8_t *__restrict__ arm, int64_t n_leaf, int n_scen, const int32_t *__restrict__ leaf_node,
+              const int8_t *__restrict__ leaf_slot, const kBin *__restrict__ leaf_bins) {
+    const int64_t per_scen = n_leaf * 12, total = per_scen * n_scen;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)leaf_bins[i];
+        if (c == 0) continue;
+        const int64_t s = i / per_scen, t = i - s * per_scen;
+        const int64_t l = t / 12;
+        const int b = (int)(t - l * 12);
+        uint32_t *tab = table + (size_t)s * n_nodes * 96;
+        int node = leaf_node[s * n_leaf + l];
+        atomicAdd(&tab[((size_t)node * 8 + leaf_slot[s * n_leaf + l]) * 12 + b], c);
+        for (int p = parent[node]; p >= 0; p = parent[node]) {
+            atomicAdd(&tab[((size_t)p * 8 + arm[node]) * 12 + b], c);
+            node = p;
+        }
     }
 }
 
@@ -842,6 +848,7 @@ using namespace pmcts;
 
 struct pmcts_ctx {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int precision = PMCTS_PREC_F64;
@@ -1124,6 +1131,8 @@ int pmcts_create(int device, pmcts_ctx **out) {
         return fail(PMCTS_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->sm_count < 1) ctx->sm_count = 148;
     pmcts_set_params(ctx, kFitVelocity, 19.1, 35.0, 160.0, 0.2, 0.005 * kDegToRad, 6371e3);
     *out = ctx;
     return PMCTS_OK;
@@ -1989,16 +1998,17 @@ int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, c
     DeviceGuard g(ctx);
     {
         LaunchTimer lt(ctx, PMCTS_KERNEL_BACKUP);
-        dim3 grid(grid_for(n_leaf * 12), n_scen);
+        const int64_t total = n_leaf * 12 * n_scen;
+        const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 2 * ctx->sm_count);
         if (flags & PMCTS_BACKUP_BINS_U8)
-            backup_kernel<uint8_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
-                                                                    leaf_slot, (const uint8_t *)leaf_bins);
+            backup_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
+                                                                 leaf_slot, (const uint8_t *)leaf_bins);
         else if (flags & PMCTS_BACKUP_BINS_U16)
-            backup_kernel<uint16_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
-                                                                     leaf_slot, (const uint16_t *)leaf_bins);
+            backup_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
+                                                                  leaf_slot, (const uint16_t *)leaf_bins);
         else
-            backup_kernel<uint32_t><<<grid, kBlock, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, leaf_node,
-                                                                     leaf_slot, leaf_bins);
+            backup_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
+                                                                  leaf_slot, leaf_bins);
     }
     CUDA_TRY(cudaGetLastError());
     return PMCTS_OK;
@@ -2011,7 +2021,7 @@ int pmcts_pack_bins(pmcts_ctx *ctx, const uint32_t *bins, int64_t count, void *o
     DeviceGuard g(ctx);
     {
         LaunchTimer lt(ctx);
-        const unsigned grid = (unsigned)((count + 255) / 256);
+        const unsigned grid = (unsigned)std::min<int64_t>((count + 255) / 256, 2 * ctx->sm_count);
         if (width == 1) pack_bins_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(bins, (uint8_t *)out, (size_t)count);
         else pack_bins_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(bins, (uint16_t *)out, (size_t)count);
     }

@@ -306,6 +306,10 @@ struct Master {
     };
     std::vector<Slice> slices;           // [n_scen]
     std::vector<int32_t> row;            // [node][n_scen]
+    // the scenarios that own a row of a node, as a list in ascending scenario order (first[node] -> ent_next ...):
+    // the master's value of a node sums over them (worker.py:302-346), and with 80 scenarios on 8 GPUs a walk over all
+    // n_scen slots of every node was most of a wave's selection
+    std::vector<int32_t> first, ent_scen, ent_row, ent_next;
     std::vector<double> memo;            // master UCT per node, valid when stamp == wave
     std::vector<int64_t> stamp;
     int64_t applies = 0;
@@ -322,6 +326,7 @@ struct Master {
         arm.push_back((int8_t)a);
         child.insert(child.end(), kA, -1);
         row.insert(row.end(), n_scen, -1);
+        first.push_back(-1);
         memo.push_back(0.0);
         stamp.push_back(-1);
         if (par >= 0) child[(size_t)par * kA + a] = idx;
@@ -339,12 +344,33 @@ struct Master {
         return node;
     }
 
+    // links (node, s) into the node's scenario list; serial (lists of different scenarios share the node's head)
+    void link(int32_t node, int s) {
+        const int32_t e = (int32_t)ent_scen.size();
+        ent_scen.push_back(s);
+        ent_row.push_back(row[(size_t)node * n_scen + s]);
+        ent_next.push_back(-1);
+        int32_t prev = -1, cur = first[node];
+        while (cur >= 0 && ent_scen[cur] < s) {
+            prev = cur;
+            cur = ent_next[cur];
+        }
+        ent_next[e] = cur;
+        if (prev < 0) first[node] = e;
+        else ent_next[prev] = e;
+    }
+
     // adds a histogram; the cached (visits, best) of the row are refreshed by the caller once per update, from
-    // `touched` (rows of scenario s; scenario slices are disjoint, so concurrent callers never share an entry)
-    void add(int32_t node, int s, int slot, const uint32_t *bins, std::vector<int32_t> &touched) {
+    // `touched` (rows of scenario s; scenario slices are disjoint, so concurrent callers never share an entry); a
+    // node the scenario had no row for yet goes to `created`, for the caller to link() once the slices are done
+    void add(int32_t node, int s, int slot, const uint32_t *bins, std::vector<int32_t> &touched,
+             std::vector<int32_t> &created) {
         Slice &sl = slices[s];
         int32_t &r = row[(size_t)node * n_scen + s];
-        if (r < 0) r = sl.add_row(node);
+        if (r < 0) {
+            r = sl.add_row(node);
+            created.push_back(node);
+        }
         uint32_t *c = sl.counters(r);
         for (int b = 0; b < kB; ++b) c[slot * kB + b] += bins[b];
         if (sl.touch[r] != applies) {
@@ -374,9 +400,10 @@ struct pmcts_forest {
         const int32_t p = master.parent[m];
         double acc = 0.0;
         bool any = false;
-        for (int s = 0; s < n_scen; ++s) {
-            const int32_t r = master.row[(size_t)m * n_scen + s];
-            const int64_t n_node = r < 0 ? 0 : master.slices[s].visits[r];
+        for (int32_t e = master.first[m]; e >= 0; e = master.ent_next[e]) {  // ascending scenario order
+            const int s = master.ent_scen[e];
+            const int32_t r = master.ent_row[e];
+            const int64_t n_node = master.slices[s].visits[r];
             const int64_t n_par = p >= 0 ? master.visits_of(p, s) : 0;
             if (n_node != 0 && n_par != 0) {
                 const double uct = master.slices[s].best[r] +
@@ -477,7 +504,7 @@ int forest_sequential(pmcts_forest *f, int local_index, int64_t budget, int freq
     std::vector<Update> buffer;
     std::vector<double> z(n_instants);
     std::vector<int8_t> path(f->max_depth);
-    std::vector<int32_t> touched;
+    std::vector<int32_t> touched, created;
     uint32_t one_hot[kB];
     int rc = PMCTS_OK;
     for (int64_t ite = 1; ite <= budget && !rc; ++ite) {
@@ -518,13 +545,15 @@ int forest_sequential(pmcts_forest *f, int local_index, int64_t budget, int freq
                 int32_t node = m.descend(path.data(), ulen);
                 std::memset(one_hot, 0, sizeof one_hot);
                 one_hot[u.bin] = 1;
-                m.add(node, s, (int)(npr.next32() & 7u), one_hot, touched);  // MasterNode.add_reward: a random slot
+                m.add(node, s, (int)(npr.next32() & 7u), one_hot, touched, created);  // MasterNode.add_reward: a random slot
                 while (m.parent[node] >= 0) {
-                    m.add(m.parent[node], s, m.arm[node], one_hot, touched);
+                    m.add(m.parent[node], s, m.arm[node], one_hot, touched, created);
                     node = m.parent[node];
                 }
             }
             m.refresh(s, touched);
+            for (int32_t node : created) m.link(node, s);
+            created.clear();
             f->wave += 1;
             buffer.clear();
             if (rep) rep->waves += 1;
@@ -670,6 +699,7 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
         leaf_master[o] = m.descend(prefix_act + o * prefix_stride, prefix_len[o]);
     // 2. the counters: block i only touches the slice of its own scenario, so distinct scenarios run side by side
     m.applies += 1;
+    std::vector<std::vector<int32_t>> created(n_blocks_scen);
     auto apply_block = [&](int i) {
         const int s = scen_ids[i];
         std::vector<int32_t> touched;
@@ -678,9 +708,9 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
             const size_t o = (size_t)i * n_leaves + l;
             const uint32_t *bins = leaf_bins + o * kB;
             int32_t node = leaf_master[o];
-            m.add(node, s, slots[o], bins, touched);
+            m.add(node, s, slots[o], bins, touched, created[i]);
             while (m.parent[node] >= 0) {
-                m.add(m.parent[node], s, m.arm[node], bins, touched);
+                m.add(m.parent[node], s, m.arm[node], bins, touched, created[i]);
                 node = m.parent[node];
             }
         }
@@ -690,6 +720,8 @@ int pmcts_forest_master_apply(pmcts_forest *f, int n_blocks_scen, const int32_t 
     if (distinct) parallel_for(n_blocks_scen, (int64_t)n_blocks_scen * n_leaves, apply_block);
     else
         for (int i = 0; i < n_blocks_scen; ++i) apply_block(i);
+    for (int i = 0; i < n_blocks_scen; ++i)
+        for (int32_t node : created[i]) m.link(node, scen_ids[i]);
     f->wave += 1;  // the master changed: its UCT values are recomputed on next use
     return PMCTS_OK;
 } catch (const std::bad_alloc &) {

@@ -216,8 +216,8 @@ struct SearchCache {
     double *d_stats = nullptr;
     size_t cap_stats = 0;
     cudaStream_t comm = nullptr;
-    char *seq_host = nullptr;  // the sequential search's per-iteration arrays
-    size_t cap_seq = 0;
+    char *seq_host = nullptr, *seq_dev = nullptr;  // the sequential search's per-iteration arrays
+    size_t cap_seq = 0, cap_seq_dev = 0;
 };
 
 void free_search_cache(void *p) {
@@ -233,6 +233,7 @@ void free_search_cache(void *p) {
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->comm) cudaStreamDestroy(c->comm);
     if (c->seq_host) cudaFreeHost(c->seq_host);
+    if (c->seq_dev) cudaFree(c->seq_dev);
     delete c;
 }
 
@@ -559,36 +560,45 @@ extern "C" int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, i
     const double t0 = now_ms();
     const int64_t launches0 = pmcts_launch_count(ctx);
     LIB_TRY(pmcts_set_precision(ctx, PMCTS_PREC_FAST));
-    const int flags = (roll_flags & PMCTS_ROLL_REPLAY_FULL_PREFIX) | PMCTS_ROLL_PREFIX_ACTIONS | PMCTS_MEM_HOST;
-    // the launch's host arrays live in page-locked memory (kept with the ctx): six small copies per iteration, which
-    // from pageable memory would each go through the driver's own staging
+    const int flags = roll_flags & PMCTS_ROLL_REPLAY_FULL_PREFIX;
+    // One block up, one launch on device arrays, one block down per iteration: the rollout's inputs (normals, path in
+    // degrees, its length) and outputs (transitions, bin, status) sit side by side in page-locked host memory and in
+    // a device mirror, both kept with the ctx.
     void **slot = pmcts::ctx_attachment(ctx, free_search_cache);
     if (!*slot) *slot = new SearchCache();
     SearchCache *cache = (SearchCache *)*slot;
-    const size_t o_path = align16((size_t)n_instants * sizeof(double)), o_plen = o_path + align16(info.max_depth);
-    const size_t o_steps = o_plen + 16, o_bin = o_steps + 16, o_status = o_bin + 16;
-    {
-        int prev = -1;
-        cudaGetDevice(&prev);
-        const int dev = pmcts_get_device(ctx);
-        if (prev != dev) CUDA_TRY(cudaSetDevice(dev));
-        const int rcg = grow_pinned(cache->seq_host, cache->cap_seq, o_status + 16);
-        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
-        if (rcg) return rcg;
-    }
-    char *h = cache->seq_host;
+    const size_t o_path = align16((size_t)n_instants * sizeof(double));
+    const size_t o_plen = o_path + align16((size_t)info.max_depth * sizeof(double));
+    const size_t in_bytes = o_plen + 16;
+    const size_t o_steps = in_bytes, o_bin = o_steps + 16, o_status = o_bin + 16, total = o_status + 16;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    const int dev = pmcts_get_device(ctx);
+    if (prev != dev) CUDA_TRY(cudaSetDevice(dev));
+    struct Restore {
+        int prev, dev;
+        ~Restore() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+    } restore{prev, dev};
+    LIB_TRY(grow_pinned(cache->seq_host, cache->cap_seq, total));
+    LIB_TRY(grow_device(cache->seq_dev, cache->cap_seq_dev, total));
+    char *h = cache->seq_host, *d = cache->seq_dev;
+    cudaStream_t st = (cudaStream_t)pmcts_get_stream(ctx);
     const pmcts::SeqRollout rollout = [&](int, const int8_t *path, int len, const double *z, int *bin, int *steps) -> int {
         std::memcpy(h, z, (size_t)n_instants * sizeof(double));
-        std::memcpy(h + o_path, path, (size_t)len);
+        double *deg = (double *)(h + o_path);
+        for (int j = 0; j < len; ++j) deg[j] = 45.0 * (double)path[j];  // ACTIONS[a] (simulatorTLKT.py:29)
         *(int32_t *)(h + o_plen) = len;
+        CUDA_TRY(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
         pmcts_noise nz{};
         nz.mode = PMCTS_NOISE_INJECTED;
-        nz.z = (const double *)h;
-        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)(h + o_path),
-                                           (const int32_t *)(h + o_plen), info.max_depth, &nz, nullptr, nullptr,
-                                           (int32_t *)(h + o_steps), (uint8_t *)(h + o_status), (int32_t *)(h + o_bin), nullptr,
+        nz.z = (const double *)d;
+        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)(d + o_path),
+                                           (const int32_t *)(d + o_plen), info.max_depth, &nz, nullptr, nullptr,
+                                           (int32_t *)(d + o_steps), (uint8_t *)(d + o_status), (int32_t *)(d + o_bin), nullptr,
                                            nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags);
         if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h + o_steps, d + o_steps, total - o_steps, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
         const uint8_t status = *(uint8_t *)(h + o_status);
         if (status == PMCTS_ST_OUT_OF_GRID || status == PMCTS_ST_PAST_HORIZON || status == PMCTS_ST_DEGENERATE)
             return (int)status;  // what the reference raises on

@@ -43,7 +43,8 @@ def test_b200_arm_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.2 < r["frac"] < 1.0
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= 1.05 * d["value"]
+    # (e2e runs 50 steps without the L2 flush between them: it may come out a little above the flushed, 3-step value)
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= 1.15 * d["value"]
     # the per-step windows hide nothing: the same steps back to back, one event pair, within a few percent
     assert abs(d["back_to_back"]["value"] / d["value"] - 1.0) < 0.1
     assert d["clocks"]["sm_mhz"] > 0

@@ -833,6 +833,27 @@ def test_device_pointer_path_and_backup(eng):
     torch.cuda.synchronize()
     got2 = table2.cpu().numpy().reshape(2, n_nodes, 8, 12)
     assert np.array_equal(got2[0], want) and np.array_equal(got2[1], 2 * want)
+    # the form histograms travel in between GPUs: one- and two-byte counts (pmcts_pack_bins), backed up as such, and
+    # the library's own all-gather of them (a communicator of one rank: recv == send)
+    import ctypes as C
+    for dtype in (torch.uint8, torch.int16):
+        packed = torch.zeros(n_leaf * 12, dtype=dtype, device=dev)
+        eng.pack_bins(out["leaf_bins"], packed)
+        assert np.array_equal(packed.cpu().numpy().astype(np.int64), out["leaf_bins"].cpu().numpy())
+        table3 = torch.zeros(n_nodes * 96, dtype=torch.int32, device=dev)
+        eng.backup(table3, n_nodes, t(parent), t(arm), t(leaf_node), t(slot), packed)
+        torch.cuda.synchronize()
+        assert np.array_equal(table3.cpu().numpy().reshape(n_nodes, 8, 12), want)
+    lib = N.lib()
+    uid = np.zeros(128, np.uint8)
+    N.check(lib.pmcts_comm_unique_id(uid.ctypes.data))
+    comm = C.c_void_p()
+    N.check(lib.pmcts_comm_create(eng._h, 1, 0, uid.ctypes.data, C.byref(comm)))
+    recv = torch.zeros_like(packed)
+    N.check(lib.pmcts_allgather_updates(eng._h, comm, packed.data_ptr(), packed.numel() * 2, recv.data_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(recv, packed)
+    lib.pmcts_comm_destroy(comm)
     mean = torch.empty(n_nodes * 8, dtype=torch.float64, device=dev)
     visits = torch.empty(n_nodes, dtype=torch.int32, device=dev)
     eng.hist_stats(table, n_nodes, mean, visits)
