@@ -734,6 +734,8 @@ def main():
             line["soak"] = soak
         if "redo_share" in run:
             line["fp64_redo_share"] = run["redo_share"]()
+        if run["dominant"].get("exchange"):
+            line["exchange"] = run["dominant"]["exchange"]
         if not args.no_cpu_baseline and world == 1:  # (the CPU leg is timed at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
@@ -781,6 +783,17 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     pack_dtype = torch.uint8 if REPLICAS <= 255 else torch.int16
     packed_local = torch.zeros(S_local * N_LEAF * 12, dtype=pack_dtype, device=dev) if world > 1 else None
     packed_all = torch.zeros(S_total * N_LEAF * 12, dtype=pack_dtype, device=dev) if world > 1 else None
+    # The exchange: windows the ranks map from each other, written by the packing kernel itself (pmcts_peer_*); the
+    # library all-gather stays as the fallback when the windows cannot be set up (and for PMCTS_BENCH_EXCHANGE=nccl).
+    peer, exchange = None, "none (one rank)"
+    if world > 1:
+        exchange = "pmcts_pack_bins + ncclAllGather (requested)"
+        if os.environ.get("PMCTS_BENCH_EXCHANGE", "peer") == "peer":
+            from iboat_pmcts_b200.peer import open_exchange
+            peer, why = open_exchange(eng, dist, world, rank, packed_local.numel() * packed_local.element_size())
+            exchange = ("pmcts_peer_put_bins: counters narrowed and stored into every rank's window over NVLink by one "
+                        "kernel, arrival awaited by stream memory operations" if peer is not None else
+                        "pmcts_pack_bins + ncclAllGather (peer windows unavailable: %s)" % why)
     consumed = [torch.cuda.Event() for _ in bins_ring]
     pending = []
     debug_ev = [] if os.environ.get("PMCTS_BENCH_DEBUG") else None  # (all-gather, back-up) durations on the comm stream
@@ -797,7 +810,10 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                 dbg = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if debug_ev is not None else None
                 if dbg:
                     dbg[0].record()
-                if world > 1:
+                if peer is not None:
+                    peer.put_bins(src, packed_local.element_size())
+                    src = peer.wait().view(pack_dtype)
+                elif world > 1:
                     eng.pack_bins(src, packed_local)
                     if not os.environ.get("PMCTS_BENCH_NO_AG"):  # (as bytes: NCCL's process group has no 16-bit integer type)
                         dist.all_gather_into_tensor(packed_all.view(torch.uint8), packed_local.view(torch.uint8))
@@ -944,8 +960,9 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                                    "leaf_bins / stats out; one call in flight while the previous one's finisher and copies complete)")
                               if world == 1 else
                               ("sharded pipeline per step: pinned host prefix -> device, pmcts_rollout_forest (device arrays, deferred "
-                               "finisher), pmcts_pack_bins + NCCL all-gather + pmcts_backup into the replicated master on the "
+                               "finisher), exchange of the narrowed histograms + pmcts_backup into the replicated master on the "
                                "communication stream, statistics and the master's root totals -> pinned host"),
+                              exchange=exchange,
                               e2e_note=("every rank times its own host-array calls (no L2 flush); max time over ranks, transitions summed"
                                         if world == 1 else
                                         "exchange and back-up included; host-timed, max over ranks, transitions summed"),

@@ -30,11 +30,13 @@ PREC_F64, PREC_FAST = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
 KERNEL_STEP, KERNEL_ROLLOUT, KERNEL_BACKUP, KERNEL_OTHER, KERNEL_FINISHER = 0, 1, 2, 3, 4
 ERR_NO_DEVICE = -3
+PEER_HANDLE_BYTES = 64
 
 EXPORTS = [
     "pmcts_create", "pmcts_destroy", "pmcts_last_error", "pmcts_version", "pmcts_set_stream", "pmcts_reset_stream",
     "pmcts_get_stream", "pmcts_get_device", "pmcts_comm_unique_id", "pmcts_comm_create", "pmcts_comm_destroy",
-    "pmcts_allgather_updates", "pmcts_forest_search", "pmcts_master_policy", "pmcts_pack_bins",
+    "pmcts_allgather_updates", "pmcts_peer_create", "pmcts_peer_connect", "pmcts_peer_put_bins", "pmcts_peer_put",
+    "pmcts_peer_wait", "pmcts_peer_poll", "pmcts_peer_destroy", "pmcts_search_block_bytes", "pmcts_forest_search", "pmcts_master_policy", "pmcts_pack_bins",
     "pmcts_forest_search_sequential", "pmcts_python_gauss", "pmcts_numpy_randint8", "pmcts_forest_master_policy",
     "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
@@ -63,7 +65,7 @@ class SearchParams(C.Structure):
     """pmcts_search_params (include/pmcts_b200.h)."""
     _fields_ = [("n_leaves", C.c_int32), ("replicas", C.c_int32), ("budget", C.c_int64), ("seed", C.c_uint64),
                 ("roll_flags", C.c_int32), ("pipeline", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
-                ("slots_w", C.c_void_p), ("slots_m", C.c_void_p), ("comm", C.c_void_p),
+                ("slots_w", C.c_void_p), ("slots_m", C.c_void_p), ("comm", C.c_void_p), ("peer", C.c_void_p),
                 ("exchange", EXCHANGE_FN), ("exchange_user", C.c_void_p),
                 ("rollout_hook", ROLLOUT_HOOK_FN), ("hook_user", C.c_void_p)]
 
@@ -146,6 +148,16 @@ def lib():
     L.pmcts_comm_destroy.argtypes = [vp]
     L.pmcts_comm_destroy.restype = None
     L.pmcts_allgather_updates.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.pmcts_peer_create.argtypes = [vp, i32, i32, C.c_size_t, C.POINTER(vp), vp]
+    L.pmcts_peer_connect.argtypes = [vp, vp]
+    L.pmcts_peer_put_bins.argtypes = [vp, vp, vp, i64, i32]
+    L.pmcts_peer_put.argtypes = [vp, vp, vp, C.c_size_t]
+    L.pmcts_peer_wait.argtypes = [vp, vp, C.POINTER(vp)]
+    L.pmcts_peer_poll.argtypes = [vp, vp, C.POINTER(i32)]
+    L.pmcts_peer_destroy.argtypes = [vp]
+    L.pmcts_peer_destroy.restype = None
+    L.pmcts_search_block_bytes.argtypes = [i32, i32, i32, i32]
+    L.pmcts_search_block_bytes.restype = C.c_size_t
     L.pmcts_master_policy.argtypes = [vp, i64, i32, vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_forest_search_sequential.argtypes = [vp, vp, i32, i32, vp, vp, dbl, i64, i32, i32, C.POINTER(MtState),
                                                  C.POINTER(MtState), C.POINTER(SearchReport)]

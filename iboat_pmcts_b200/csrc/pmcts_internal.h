@@ -16,6 +16,9 @@ void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *), int key = 0);
 // kernels launched on behalf of the ctx by another translation unit (pmcts_launch_count)
 void count_launches(pmcts_ctx *ctx, int n);
 
+// size of the blocks a peer exchange was created for (pmcts_peer.cu)
+size_t peer_block_bytes(const pmcts_peer *peer);
+
 // shape of a host forest (pmcts_forest_host.cpp)
 struct ForestInfo {
     int n_scen, n_local, max_depth;

@@ -123,6 +123,12 @@ struct pmcts_comm {
 
 extern "C" {
 
+size_t pmcts_search_block_bytes(int n_local, int n_leaves, int max_depth, int replicas) {
+    if (n_local < 1 || n_leaves < 1 || max_depth < 1 || replicas < 1) return 0;
+    const size_t n = (size_t)n_local * n_leaves;
+    return align16(n * sizeof(int32_t)) + align16(n * max_depth) + align16(n * 12 * (replicas <= 255 ? 1 : 2));
+}
+
 int pmcts_comm_unique_id(uint8_t id[128]) {
     if (!id) return fail(PMCTS_ERR_ARG, "id is NULL");
     NcclApi *api = nccl_api();
@@ -302,8 +308,8 @@ struct Driver {
         if (S != S_loc * world) return fail(PMCTS_ERR_ARG, "%d scenarios do not split into %d ranks of %d", S, world, S_loc);
         if (rank < 0 || rank >= world) return fail(PMCTS_ERR_ARG, "rank %d outside the world of %d", rank, world);
         if (!p->slots_w || !p->slots_m) return fail(PMCTS_ERR_ARG, "slots_w / slots_m are NULL");
-        if (world > 1 && !p->exchange && !(device && p->comm))
-            return fail(PMCTS_ERR_ARG, "world > 1 needs a pmcts_comm (device) or an exchange callback (host)");
+        if (world > 1 && !p->exchange && !(device && (p->comm || p->peer)))
+            return fail(PMCTS_ERR_ARG, "world > 1 needs a pmcts_peer / pmcts_comm (device) or an exchange callback (host)");
         if (device && !scen_slots) return fail(PMCTS_ERR_ARG, "scen_slots is NULL");
         local_ids.resize(S_loc);
         for (int i = 0; i < S_loc; ++i) {
@@ -312,10 +318,14 @@ struct Driver {
                 return fail(PMCTS_ERR_ARG, "rank %d must own the scenarios %d .. %d in order", rank, rank * S_loc, (rank + 1) * S_loc - 1);
         }
         lay.set(S_loc, B, D, p->replicas <= 255 ? 1 : 2);
+        if (lay.bytes != pmcts_search_block_bytes(S_loc, B, D, p->replicas)) return fail(PMCTS_ERR_ARG, "update block layout out of step");
         leaf_node_scratch.resize((size_t)S_loc * B);
         ids_scratch.resize(S_loc);
         bins32.resize((size_t)S_loc * B * 12);
         dev_gather = device && world > 1 && !p->exchange;
+        if (dev_gather && p->peer && pmcts::peer_block_bytes(p->peer) < lay.bytes)
+            return fail(PMCTS_ERR_ARG, "the peer windows hold blocks of %zu bytes, this search sends %zu (pmcts_search_block_bytes)",
+                        pmcts::peer_block_bytes(p->peer), lay.bytes);
         if (device) {
             main = (cudaStream_t)pmcts_get_stream(ctx);
             void **slot = pmcts::ctx_attachment(ctx, free_search_cache);
@@ -337,7 +347,7 @@ struct Driver {
                     LIB_TRY(grow_device(p, w.cap_bins, (size_t)S_loc * B * 12 * sizeof(uint32_t)));
                     w.d_bins = (uint32_t *)p;
                 }
-                if (dev_gather) LIB_TRY(grow_device(w.d_recv, w.cap_drecv, lay.bytes * world));
+                if (dev_gather && !p->peer) LIB_TRY(grow_device(w.d_recv, w.cap_drecv, lay.bytes * world));
                 if (!w.done) CUDA_TRY(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
                 w.index = -1;
                 std::memset(w.h_send, 0, lay.bytes);
@@ -414,6 +424,14 @@ struct Driver {
         const size_t tail_bytes = (size_t)S_loc * b * 12 * lay.elem;
         if (ke != cudaSuccess) {
             rc = fail(PMCTS_ERR_CUDA, "pack_bins_kernel failed: %s", cudaGetErrorString(ke));
+        } else if (dev_gather && p->peer) {
+            // the block goes into every rank's window; this stream waits for the other ranks' and copies them down in place
+            const void *gathered = nullptr;
+            rc = pmcts_peer_put(ctx, p->peer, w.d_send, lay.bytes);
+            if (!rc) rc = pmcts_peer_wait(ctx, p->peer, &gathered);
+            if (!rc && cudaMemcpy2DAsync(w.h_recv, lay.bytes, gathered, pmcts::peer_block_bytes(p->peer), lay.bytes, world,
+                                         cudaMemcpyDeviceToHost, tail) != cudaSuccess)
+                rc = fail(PMCTS_ERR_CUDA, "copy of the gathered blocks failed");
         } else if (dev_gather) {
             rc = pmcts_allgather_updates(ctx, p->comm, w.d_send, lay.bytes, w.d_recv);
             if (!rc && cudaMemcpyAsync(w.h_recv, w.d_recv, lay.bytes * world, cudaMemcpyDeviceToHost, tail) != cudaSuccess)

@@ -264,8 +264,14 @@ class Forest:
                 keep.append(hook)
                 params.rollout_hook = hook
             if world > 1:
-                comm = _device_comm(eng, dist, group, rank, world) if native_engine else None
-                if comm is not None:
+                # between GPUs: the ranks' windows (NVLink stores, pmcts_peer) when they can be set up, else the
+                # library all-gather (pmcts_comm); over a CPU process group the blocks go through the host
+                block = int(lib.pmcts_search_block_bytes(S_loc, B, max_depth, K))
+                peer = _device_peer(eng, dist, group, rank, world, block) if native_engine else None
+                comm = _device_comm(eng, dist, group, rank, world) if native_engine and peer is None else None
+                if peer is not None:
+                    params.peer = peer._h
+                elif comm is not None:
                     params.comm = comm
                 else:
                     cb = _host_exchange(dist, group, world)
@@ -390,6 +396,26 @@ def _host_exchange(dist, group, world):
             traceback.print_exc()
             return 1
     return N.EXCHANGE_FN(exchange)
+
+
+def _device_peer(eng, dist, group, rank, world, block_bytes):
+    """The engine's peer windows for this process group (``pmcts_peer``), opened on first use and reopened when a
+    search needs larger blocks; ``None`` (on every rank) when they cannot be set up."""
+    if dist.get_backend(group) != "nccl":
+        return None
+    from .peer import open_exchange
+    cache = eng.__dict__.setdefault("_peers", {})
+    key = (id(group), world, rank)
+    have = cache.get(key)
+    if have is not None and have[0] is not None and have[0].block_bytes < block_bytes:
+        eng.synchronize()
+        dist.barrier(group=group)
+        have[0].close()
+        have = None
+    if have is None:
+        px, _why = open_exchange(eng, dist, world, rank, (block_bytes * 2 + 15) // 16 * 16, group=group)
+        have = cache[key] = (px, block_bytes)
+    return have[0]
 
 
 def _device_comm(eng, dist, group, rank, world):

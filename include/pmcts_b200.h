@@ -354,6 +354,33 @@ int pmcts_comm_create(pmcts_ctx *ctx, int world, int rank, const uint8_t id[128]
 void pmcts_comm_destroy(pmcts_comm *comm);
 int pmcts_allgather_updates(pmcts_ctx *ctx, pmcts_comm *comm, const void *send, size_t bytes, void *recv);
 
+/* ---- the same exchange over peer memory: NVLink stores into windows the ranks map from each other ----------
+ * (code/solver/worker.py:348-378 again -- every worker hands its buffer of results to all the others.)  One process per
+ * GPU on one node.  Every rank owns a window [2][world][block_bytes] in device memory; a put narrows / copies the rank's
+ * block and stores it into ALL the windows in one small kernel (the packing pass is the all-gather; nothing of a
+ * library runs, no large block has to find room under a resident rollout kernel), then raises the rank's sequence
+ * number in every window; pmcts_peer_wait makes ctx's stream wait for the sequence numbers of all ranks in its own
+ * window (stream memory operations -- no kernel waits on another GPU) and hands out the gathered blocks in place,
+ * laid out like pmcts_allgather_updates' recv.  Two parities alternate: a rank can be one put ahead of the slowest
+ * reader, never two, provided every rank orders put k + 1 after its own reading of put k on the same stream.
+ *   pmcts_peer_create: allocates the window, returns the 64-byte handle the OTHER processes open it with; hand the
+ *     handles of all ranks (rank order, [world][64]) to pmcts_peer_connect by any channel.  world == 1 needs no connect.
+ *   pmcts_peer_put_bins: count uint32 counters, narrowed to width 1 or 2 bytes (as pmcts_pack_bins);
+ *   pmcts_peer_put: bytes as they are (an update block of pmcts_forest_search).  Sources are 16-byte aligned.
+ *   pmcts_peer_poll: host-side check (synchronous, its own stream): how many ranks' blocks of the last put have
+ *     arrived in this window -- for bring-up checks with a deadline before anything is made to wait on a stream.
+ *   All ranks must make the same sequence of puts.  Destroy only after every rank is done with the windows. */
+#define PMCTS_PEER_HANDLE_BYTES 64
+typedef struct pmcts_peer pmcts_peer;
+int pmcts_peer_create(pmcts_ctx *ctx, int world, int rank, size_t block_bytes, pmcts_peer **out,
+                      uint8_t handle[PMCTS_PEER_HANDLE_BYTES]);
+int pmcts_peer_connect(pmcts_peer *peer, const uint8_t *handles);
+int pmcts_peer_put_bins(pmcts_ctx *ctx, pmcts_peer *peer, const uint32_t *bins, int64_t count, int width);
+int pmcts_peer_put(pmcts_ctx *ctx, pmcts_peer *peer, const void *send, size_t bytes);
+int pmcts_peer_wait(pmcts_ctx *ctx, pmcts_peer *peer, const void **gathered);
+int pmcts_peer_poll(pmcts_ctx *ctx, pmcts_peer *peer, int *arrived);
+void pmcts_peer_destroy(pmcts_peer *peer);
+
 /* ---- the leaf-batched search of Forest.launch_search as ONE native call -------------------------------
  * (forest.py:45-81 + Tree.uct_search, worker.py:147-186, restated for waves of leaves.)  Per wave:
  *   host   pmcts_forest_select: n_leaves runs of the tree policy per local tree (virtual visits);
@@ -369,7 +396,7 @@ int pmcts_allgather_updates(pmcts_ctx *ctx, pmcts_comm *comm, const void *send, 
  * slots_w / slots_m: the random action slots of Node.back_up (worker.py:62) and MasterNode.add_reward
  * (master_node.py:42), wave after wave, [n_scen][leaves of that wave] each -- drawn by the caller (the
  * reference uses np.random.randint), for ALL scenarios, identically on every rank.
- * exchange (optional): an all-gather over HOST buffers used instead of pmcts_comm (gloo, MPI ...).
+ * exchange (optional): an all-gather over HOST buffers used instead of pmcts_comm / pmcts_peer (gloo, MPI ...).
  * rollout_hook (test instrumentation; the product passes NULL): stands in for the GPU launch -- fills
  * leaf_bins[n_local][n_leaves][12] for the given paths -- so that the host logic runs without a device;
  * then ctx may be NULL. */
@@ -377,6 +404,9 @@ typedef int (*pmcts_exchange_fn)(void *user, const void *send, size_t bytes, voi
 typedef int (*pmcts_rollout_hook_fn)(void *user, int wave, int n_local, const int32_t *scen_ids, int n_leaves,
                                      int prefix_stride, const int32_t *prefix_len, const int8_t *prefix_act,
                                      uint32_t *leaf_bins);
+/* bytes of one rank's update block (lengths + int8 paths + narrowed counts), the block_bytes of a pmcts_peer that
+ * serves such a search */
+size_t pmcts_search_block_bytes(int n_local, int n_leaves, int max_depth, int replicas);
 typedef struct {
     int32_t n_leaves;   /* leaves per tree per wave */
     int32_t replicas;   /* noise replicas per leaf */
@@ -386,7 +416,8 @@ typedef struct {
     int32_t pipeline;   /* waves in flight, 1 or 2 */
     int32_t world, rank;
     const int8_t *slots_w, *slots_m;
-    pmcts_comm *comm;   /* world > 1 with device buffers */
+    pmcts_comm *comm;   /* world > 1 with device buffers: library all-gather ... */
+    pmcts_peer *peer;   /* ... or, preferred when set, peer windows of at least pmcts_search_block_bytes() per block */
     pmcts_exchange_fn exchange;
     void *exchange_user;
     pmcts_rollout_hook_fn rollout_hook;
