@@ -597,11 +597,18 @@ def main():
         print("rank %d per-step ms: %s" % (rank, [round(a.elapsed_time(b), 3) for a, b in ev]), file=sys.stderr, flush=True)
     counters = run["read_counters"]()  # transitions, rollouts of this rank over the K timed steps
     stat = torch.tensor([dev_ms, counters[0], counters[1], kernel_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         mx = stat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stat.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        every = [torch.zeros_like(stat) for _ in range(world)]
+        dist.all_gather(every, stat)
+        # what each rank did in its own timed windows: the scenarios differ from rank to rank, so does the work of a step
+        per_rank = dict(ms=[round(float(t[0]), 4) for t in every], transitions=[int(t[1]) for t in every],
+                        note="the job's time is the slowest rank's; efficiency against one GPU cannot exceed mean / max of "
+                             "the ranks' work when their scenarios roll out unequally long")
         dev_ms, kernel_ms = float(mx[0]), float(mx[3])
         transitions, rollouts = float(sm[1]), float(sm[2])
     else:
@@ -736,6 +743,8 @@ def main():
             line["fp64_redo_share"] = run["redo_share"]()
         if run["dominant"].get("exchange"):
             line["exchange"] = run["dominant"]["exchange"]
+        if per_rank:
+            line["ranks"] = per_rank
         if not args.no_cpu_baseline and world == 1:  # (the CPU leg is timed at N = 1 only)
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
@@ -776,7 +785,10 @@ def setup_c4(eng, torch, dist, dev, rank, world):
     # Three histogram buffers rotate; a buffer is zeroed again only after the comm stream has read it.  The last
     # step of a run drains the pipeline inside its own timed window (the main stream waits for the comm stream).
     main = torch.cuda.current_stream(dev)
-    comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMCTS_BENCH_COMM_PRIO", "0")))
+    # (high priority: the exchange and the back-up are a few dozen microseconds of work, but at equal priority their
+    #  blocks are handed block slots only when the resident rollout kernel runs out of blocks of its own -- measured at
+    #  8 GPUs: K3 0.9 ms after launch instead of 0.03 -- and the chain put -> wait -> K3 then sets the step time)
+    comm = torch.cuda.Stream(device=dev, priority=int(os.environ.get("PMCTS_BENCH_COMM_PRIO", "-1")))
     overlap = not os.environ.get("PMCTS_BENCH_NO_OVERLAP")
     bins_ring = [bins_local, torch.zeros_like(bins_local), torch.zeros_like(bins_local)]
     # what travels between GPUs: the wave's counters narrowed to one byte (two when a leaf has more than 255 replicas)

@@ -749,32 +749,92 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *__restrict__ out,
     if (s == 123.456f) out[0] = s;  // keeps the chains alive; never true for the a, b the host passes
 }
 
-// K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (leaf, bin),
-// blockIdx.y = scenario.
-// kBin: the width the histograms arrive in (uint32 from K2; uint8 / uint16 from an all-gathered update block).
-// A few fat blocks that stride over all (scenario, leaf, bin) triples rather than one thread each: the back-up of a
-// wave runs on a side stream UNDER the next wave's rollout kernel, whose blocks hold every block slot of the chip; a
-// grid of tens of thousands of tiny blocks then waits for a freed slot tens of thousands of times (0.8 ms of wall time
-// for 40 us of work at 64 scenarios, which put the communication stream on the critical path of an 8-GPU step), a
-// grid of two blocks per SM waits once.
+// K3 -- Node.back_up (worker.py:55-70) for n_scen tables at once: one thread per (scenario, leaf).
+// kBin: the width the histograms arrive in (uint32 from K2; uint8 / uint16 from an exchanged update block).
+// The thread reads its leaf's 12 counts in three vector loads (a warp reads 32 leaves' worth of consecutive bytes),
+// walks the chain of ancestors ONCE and adds the non-empty bins (usually two to four of the twelve) to every row on
+// the way with fire-and-forget reductions -- the first version walked the chain once per (leaf, bin), twelve times the
+// dependent parent / arm loads, and was bound by their latency (long scoreboard 34 cycles per issue).
+// A few fat blocks striding over the leaves rather than one thread each: the back-up of a wave runs on a side stream
+// UNDER the next wave's rollout kernel, whose blocks hold every block slot of the chip; a grid of thousands of tiny
+// blocks then waits for a freed slot thousands of times, a grid of two blocks per SM waits once.
+template <typename kBin>
+__device__ __forceinline__ void load_counts(const kBin *__restrict__ p, bool vector, uint32_t (&c)[12]) {
+    if (!vector) {
+#pragma unroll
+        for (int b = 0; b < 12; ++b) c[b] = (uint32_t)p[b];
+    } else if (sizeof(kBin) == 4) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+        c[0] = q0.x, c[1] = q0.y, c[2] = q0.z, c[3] = q0.w, c[4] = q1.x, c[5] = q1.y, c[6] = q1.z, c[7] = q1.w;
+        c[8] = q2.x, c[9] = q2.y, c[10] = q2.z, c[11] = q2.w;
+    } else if (sizeof(kBin) == 2) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint2 v = q[k];
+            c[4 * k] = v.x & 65535u, c[4 * k + 1] = v.x >> 16, c[4 * k + 2] = v.y & 65535u, c[4 * k + 3] = v.y >> 16;
+        }
+    } else {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t v = q[k];
+            c[4 * k] = v & 255u, c[4 * k + 1] = (v >> 8) & 255u, c[4 * k + 2] = (v >> 16) & 255u, c[4 * k + 3] = v >> 24;
+        }
+    }
+}
+
 template <typename kBin>
 __global__ void __launch_bounds__(256)
 backup_kernel(uint32_t *__restrict__ table, int64_t n_nodes, const int32_t *__restrict__ parent,
               const int8_t *__restrict__ arm, int64_t n_leaf, int n_scen, const int32_t *__restrict__ leaf_node,
-              const int8_t *__restrict__ leaf_slot, const kBin *__restrict__ leaf_bins) {
-    const int64_t per_scen = n_leaf * 12, total = per_scen * n_scen;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = (uint32_t)leaf_bins[i];
-        if (c == 0) continue;
-        const int64_t s = i / per_scen, t = i - s * per_scen;
-        const int64_t l = t / 12;
-        const int b = (int)(t - l * 12);
-        uint32_t *tab = table + (size_t)s * n_nodes * 96;
-        int node = leaf_node[s * n_leaf + l];
-        atomicAdd(&tab[((size_t)node * 8 + leaf_slot[s * n_leaf + l]) * 12 + b], c);
-        for (int p = parent[node]; p >= 0; p = parent[node]) {
-            atomicAdd(&tab[((size_t)p * 8 + arm[node]) * 12 + b], c);
-            node = p;
+              const int8_t *__restrict__ leaf_slot, const kBin *__restrict__ leaf_bins, bool vector) {
+    const int64_t total = n_leaf * n_scen;
+    const int lane = threadIdx.x & 31;
+    // (the trip count is the warp's: every lane stays in the loop, `walking` says whether it still carries counts)
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        uint32_t c[12];
+        uint32_t live = 0;
+        uint32_t *tab = nullptr;
+        int node = 0, slot = 0;
+        if (i < total) {
+            load_counts<kBin>(leaf_bins + i * 12, vector, c);
+#pragma unroll
+            for (int b = 0; b < 12; ++b) live |= (c[b] != 0u) << b;
+            tab = table + (size_t)(i / n_leaf) * n_nodes * 96;
+            node = leaf_node[i];
+            slot = leaf_slot[i];
+        }
+        bool walking = live != 0;
+        // Up the chain.  Leaves of a wave share their upper ancestors (all of them the root): lanes that have reached
+        // the same row add their counts together, one of them files the sum and carries it on, the others are done --
+        // a warp of 32 sibling leaves ends with one reduction per bin at the root instead of 32 on one address.
+        while (true) {
+            const unsigned mask = __ballot_sync(0xffffffffu, walking);
+            if (!mask) break;
+            if (walking) {
+                uint32_t *row = tab + ((size_t)node * 8 + slot) * 12;
+                const unsigned peers = __match_any_sync(mask, (unsigned long long)(uintptr_t)row);
+                if (peers != (1u << lane)) {
+                    live = __reduce_or_sync(peers, live);
+#pragma unroll
+                    for (int b = 0; b < 12; ++b)
+                        if (live >> b & 1u) c[b] = __reduce_add_sync(peers, c[b]);
+                    walking = (int)__ffs(peers) - 1 == lane;
+                }
+                if (walking) {
+#pragma unroll
+                    for (int b = 0; b < 12; ++b)
+                        if (live >> b & 1u) atomicAdd(row + b, c[b]);
+                    const int p = parent[node];
+                    if (p < 0) walking = false;
+                    slot = arm[node];
+                    node = p;
+                }
+            }
         }
     }
 }
@@ -1998,17 +2058,20 @@ int pmcts_backup(pmcts_ctx *ctx, uint32_t *table, int64_t n_nodes, int n_scen, c
     DeviceGuard g(ctx);
     {
         LaunchTimer lt(ctx, PMCTS_KERNEL_BACKUP);
-        const int64_t total = n_leaf * 12 * n_scen;
+        const int64_t total = n_leaf * n_scen;
         const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 2 * ctx->sm_count);
+        // (a leaf's counts in three vector loads when the array starts on a 16-byte boundary -- whatever the width,
+        //  12 counts then start on a multiple of their vector)
+        const bool vector = (uintptr_t)leaf_bins % 16 == 0;
         if (flags & PMCTS_BACKUP_BINS_U8)
             backup_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
-                                                                 leaf_slot, (const uint8_t *)leaf_bins);
+                                                                 leaf_slot, (const uint8_t *)leaf_bins, vector);
         else if (flags & PMCTS_BACKUP_BINS_U16)
             backup_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
-                                                                  leaf_slot, (const uint16_t *)leaf_bins);
+                                                                  leaf_slot, (const uint16_t *)leaf_bins, vector);
         else
             backup_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(table, n_nodes, parent, arm, n_leaf, n_scen, leaf_node,
-                                                                  leaf_slot, leaf_bins);
+                                                                  leaf_slot, leaf_bins, vector);
     }
     CUDA_TRY(cudaGetLastError());
     return PMCTS_OK;

@@ -332,7 +332,13 @@ struct Driver {
             if (!*slot) *slot = new SearchCache();
             SearchCache *cache = (SearchCache *)*slot;
             ring = cache->ring;
-            if (depth > 1 && !cache->comm) CUDA_TRY(cudaStreamCreateWithFlags(&cache->comm, cudaStreamNonBlocking));
+            if (depth > 1 && !cache->comm) {
+                // (above the rollout stream: the tail of a wave is little work, but at equal priority its blocks wait for
+                //  block slots until the next wave's rollout kernel has none of its own left to place)
+                int least = 0, greatest = 0;
+                CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                CUDA_TRY(cudaStreamCreateWithPriority(&cache->comm, cudaStreamNonBlocking, greatest));
+            }
             comm = cache->comm;
             LIB_TRY(grow_device(cache->d_stats, cache->cap_stats, (size_t)S_loc * 8 * sizeof(double)));
             d_stats = cache->d_stats;

@@ -10,6 +10,8 @@ rank applies the same updates, in the same order, to its replica of the master d
 import random as rand
 from copy import deepcopy
 
+import os
+
 import numpy as np
 
 from . import _native as N
@@ -401,7 +403,7 @@ def _host_exchange(dist, group, world):
 def _device_peer(eng, dist, group, rank, world, block_bytes):
     """The engine's peer windows for this process group (``pmcts_peer``), opened on first use and reopened when a
     search needs larger blocks; ``None`` (on every rank) when they cannot be set up."""
-    if dist.get_backend(group) != "nccl":
+    if dist.get_backend(group) != "nccl" or os.environ.get("PMCTS_EXCHANGE") == "nccl":
         return None
     from .peer import open_exchange
     cache = eng.__dict__.setdefault("_peers", {})

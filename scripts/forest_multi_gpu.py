@@ -66,8 +66,11 @@ def main():
     if rank == 0:
         mt = MasterTree(sims, DEST, nodes=mn.deepcopy_dict(master))
         mt.get_best_policy(verbose=False)
-        print("world %d: %d scenarios x %d leaves x 64 replicas in %.2f s; master digest %s; global policy %s"
-              % (world, n_scen, budget, dt, d[:16], [int(a) for a in mt.best_policy[-1]]), flush=True)
+        from iboat_pmcts_b200.engine import default_engine
+        peers = [v[0] for v in default_engine().__dict__.get("_peers", {}).values()]
+        how = "one rank" if world == 1 else ("peer windows" if any(p is not None for p in peers) else "library all-gather")
+        print("world %d (%s): %d scenarios x %d leaves x 64 replicas in %.2f s; master digest %s; global policy %s"
+              % (world, how, n_scen, budget, dt, d[:16], [int(a) for a in mt.best_policy[-1]]), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

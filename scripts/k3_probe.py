@@ -29,18 +29,22 @@ def main():
         slots = torch.tensor(rng.integers(0, 8, S * n_leaf).astype(np.int8), device=dev)
         table = torch.zeros(S * n_nodes * 96, dtype=torch.int32, device=dev)
         b = torch.tensor(bins.view(np.int32).reshape(-1), device=dev)
-        ms = []
-        for it in range(6):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            eng.backup(table, n_nodes, parent, arm, leaf_node, slots, b, n_scen=S)
-            e1.record()
-            torch.cuda.synchronize()
-            ms.append(e0.elapsed_time(e1))
-        root = int(table.view(S, n_nodes, 96)[:, 0].sum().item())
-        assert root == 6 * int(bins.sum()), (root, bins.sum())
-        print("K3 %2d scenarios x %d leaves: %.1f us (min of %s)" % (S, n_leaf, min(ms) * 1e3, [round(m * 1e3, 1) for m in ms]))
+        packed = torch.zeros(b.numel(), dtype=torch.uint8, device=dev)
+        eng.pack_bins(b, packed)
+        for name, src in (("uint32", b), ("uint8", packed)):
+          ms = []
+          table.zero_()
+          for it in range(6):
+              e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+              torch.cuda.synchronize()
+              e0.record()
+              eng.backup(table, n_nodes, parent, arm, leaf_node, slots, src, n_scen=S)
+              e1.record()
+              torch.cuda.synchronize()
+              ms.append(e0.elapsed_time(e1))
+          root = int(table.view(S, n_nodes, 96)[:, 0].sum().item())
+          assert root == 6 * int(bins.sum()), (root, bins.sum())
+          print("K3 %s %2d scenarios x %d leaves: %.1f us (min of %s)" % (name, S, n_leaf, min(ms) * 1e3, [round(m * 1e3, 1) for m in ms]))
 
 
 if __name__ == "__main__":
