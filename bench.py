@@ -84,10 +84,14 @@ class ClockSampler:
     timed region runs (the timed region of this path is tens of milliseconds, below nvidia-smi's -lms floor)."""
 
     def __init__(self, index, period_s=0.004):
+        """``period_s=None``: no background thread -- the caller takes the samples itself (``sample()``), between the
+        timed windows of a host-bound workload whose thousands of small launches an NVML query from another thread
+        stalls (measured: single search steps of 46 ms stretched to 80 and 530 ms)."""
         import threading
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
+        self._period = period_s
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -100,41 +104,48 @@ class ClockSampler:
         except Exception:
             self._nv = None
             return
-        self._period = period_s
-        self._thread = threading.Thread(target=self._run, daemon=True)
+        if period_s is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
 
     def start(self):
         if self._thread is not None:
             self._thread.start()
 
-    def _run(self):
+    def sample(self):
         nv = self._nv
-        names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
-                 ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
-                 ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        if nv is None:
+            return
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for name, bit in names:
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample()
             self._stop.wait(self._period)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
-        if self._thread is None or not self._thread.is_alive():
-            return out
-        self._stop.set()
-        self._thread.join(timeout=2)
+        if self._thread is not None:
+            if not self._thread.is_alive():
+                return out
+            self._stop.set()
+            self._thread.join(timeout=2)
         if self.samples:
             out["sm_mhz"] = statistics.median(self.samples)
             out["samples"] = len(self.samples)
         out["reasons"] = sorted(self.reasons)
-        out["source"] = "NVML, polled every %d ms during the timed region" % round(self._period * 1e3)
+        out["source"] = ("NVML, polled every %d ms during the timed region" % round(self._period * 1e3)
+                         if self._period is not None else
+                         "NVML, one sample after every timed step (the GPU still under that step's load), from the timing thread")
         return out
 
 
@@ -397,8 +408,9 @@ def run_api_workload(args):
     eng.kernel_ms(reset=True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    # (NVML queries share the driver with the step's launches -- a thousand synchronous ones per c1 step: sample sparsely)
-    sampler = ClockSampler(local, period_s=0.1 if wl == "c1" else 0.05) if rank == 0 else None
+    # (NVML queries from a second thread stall the step's launches -- a thousand synchronous ones per c1 step: the
+    #  samples are taken by this thread, right behind each step's closing event)
+    sampler = ClockSampler(local, period_s=None) if rank == 0 else None
     barrier()
     if sampler:
         sampler.start()
@@ -412,6 +424,8 @@ def run_api_workload(args):
         a, b, decision = step(warm + i)
         eng.synchronize()
         ev[i][1].record()
+        if sampler:
+            sampler.sample()
         tr += a
         ro += b
     barrier()
@@ -423,6 +437,10 @@ def run_api_workload(args):
     kernel_ms = eng.kernel_ms(reset=True)
     eng.enable_timing(False)
     dev_ms = sum(x.elapsed_time(y) for x, y in ev)
+    if os.environ.get("PMCTS_BENCH_DEBUG"):
+        import gc
+        print("rank %d per-step ms: %s | gc %s" % (rank, [round(x.elapsed_time(y), 3) for x, y in ev], gc.get_stats()),
+              file=sys.stderr, flush=True)
     stat = torch.tensor([dev_ms, tr, ro, kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         mx, sm = stat.clone(), stat.clone()
