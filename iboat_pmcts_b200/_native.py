@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpmcts_b200.so")
+LIB_PATH = os.environ.get("PMCTS_B200_LIB") or os.path.join(HERE, "libpmcts_b200.so")  # (the override: A/B builds)
 
 # mirrors of the header constants
 ST_OK, ST_ARRIVED, ST_HORIZON, ST_OUT_OF_BOX, ST_OUT_OF_GRID, ST_DEGENERATE, ST_PAST_HORIZON = range(7)

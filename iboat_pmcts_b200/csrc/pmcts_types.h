@@ -118,6 +118,7 @@ struct RolloutArgs {
     // rollouts whose decisions fell inside the error margins (re-run by the literal fp64 kernel)
     float sin_dest_lat, cos_dest_lat;
     double root_lat_rad, root_lon_rad, dest_lat_rad, dest_lon_rad;  // the same positions in radians
+    double fa_c0_rel, fo_c0_rel;  // grid index of the destination: a position held relative to it maps with these offsets
     double rw_t0;  // 1.001 * TimeMax
     float rw_inv;  // 1 / (1.001 * TimeMax - TimeMin)
     RootPre root_pre;

@@ -119,11 +119,26 @@ def test_rollout_decisions_outside_margins_agree(scen, flags):
     arr = ok & (want["status"] == 1)
     assert np.allclose(got["t_arr"][arr], want["t_arr"][arr], rtol=1e-6)
     assert np.allclose(got["reward"][ok], want["reward"][ok], rtol=1e-6, atol=3e-6)
+    # the same launch without the trajectories is the "turbo" variant (position relative to the destination in radians,
+    # cell and weights of the wind grid from the fp32 index): it answers to the oracle directly, not through the
+    # generic code
+    lean = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
+    assert f.last_variant() == 2
+    okl = lean["uncertain"] == 0
+    assert 0.0 < (~okl).mean() < 0.01
+    for key in ("steps", "status", "bin"):
+        assert np.array_equal(lean[key][okl], want[key][okl]), key
+    assert np.allclose(lean["final_lat"][okl], want["final_lat"][okl], rtol=3e-7, atol=0)
+    assert np.allclose(lean["final_lon"][okl], want["final_lon"][okl], rtol=3e-7, atol=0)
+    arr = okl & (want["status"] == 1)
+    assert np.allclose(lean["t_arr"][arr], want["t_arr"][arr], rtol=1e-6)
+    assert np.allclose(lean["reward"][okl], want["reward"][okl], rtol=1e-6, atol=3e-6)
     # with the margins closed the fp32 path would still be right almost always: the margins are slack
     f.set_margins(angle=0.0, along=0.0, near_miss2=0.0, box=0.0, bin=0.0)
-    raw = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
-    bad = (raw["steps"] != want["steps"]) | (raw["status"] != want["status"]) | (raw["bin"] != want["bin"])
-    assert bad[raw["uncertain"] == 0].sum() <= 2
+    for kw in (dict(traj_steps=13), dict()):
+        raw = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags, **kw)
+        bad = (raw["steps"] != want["steps"]) | (raw["status"] != want["status"]) | (raw["bin"] != want["bin"])
+        assert bad[raw["uncertain"] == 0].sum() <= 2
 
 
 def test_specialised_variants_equal_the_generic_one():
@@ -144,12 +159,17 @@ def test_specialised_variants_equal_the_generic_one():
         f.force_generic(True)
         b = f.rollout_batch(n_leaf, rep, H.STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z, flags=flags)
         assert f.last_variant() == 0
-        for key in ("steps", "status", "bin", "uncertain"):
-            assert np.array_equal(a[key], b[key]), (flags, key)
+        # (the turbo variant rounds differently -- radians relative to the destination, fp32 cell split -- so a rollout on
+        #  the edge of a margin may be decided by one variant and left to the literal kernel by the other: decisions are
+        #  compared where both decided, and such rollouts must be rare)
+        both = (a["uncertain"] == 0) & (b["uncertain"] == 0)
+        assert (a["uncertain"] != b["uncertain"]).mean() < (1e-3 if want_variant == 2 else 1e-12)
+        for key in ("steps", "status", "bin"):
+            assert np.array_equal(a[key][both], b[key][both]), (flags, key)
         for key in ("final_lat", "final_lon", "reward"):
-            if want_variant == 2:  # (position in radians inside the loop: its fp32 images round differently now and then)
-                tol = 5e-8 if key != "reward" else 1e-6
-                assert np.allclose(a[key], b[key], rtol=tol, atol=0 if key != "reward" else 3e-6, equal_nan=True), (flags, key)
+            if want_variant == 2:
+                tol = 3e-7 if key != "reward" else 1e-6
+                assert np.allclose(a[key][both], b[key][both], rtol=tol, atol=0 if key != "reward" else 3e-6, equal_nan=True), (flags, key)
             else:
                 assert np.array_equal(a[key], b[key], equal_nan=True), (flags, key)
     # a root that cannot start a step, or sits outside the grid, is not turbo: the generic code reports it
