@@ -404,7 +404,9 @@ def run_api_workload(args):
     for i in range(warm):
         step(i)
     barrier()
-    eng.enable_timing(True)
+    # (per-launch kernel timing is left off for c1: its step is a thousand single-rollout launches, and an event pair
+    #  around each of them was measured to stretch the step from 36 to 50-110 ms depending on the box)
+    eng.enable_timing(wl != "c1")
     eng.kernel_ms(reset=True)
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -480,13 +482,14 @@ def run_api_workload(args):
         fp32_probe = eng.probe_fp32_peak()
         roof = dict(bound="fp32", kernel=dom["kernel"], unit="TFLOP/s", peak=FP32_PEAK_TFLOPS,
                     peak_source="nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 entry)",
-                    peak_measured=fp32_probe, ms_per_launch=per_launch_ms, finisher_ms_per_launch=fin_ms / max(n_dom, 1),
+                    peak_measured=fp32_probe, ms_per_launch=per_launch_ms if wl != "c1" else None,
+                    finisher_ms_per_launch=fin_ms / max(n_dom, 1) if wl != "c1" else None,
                     algorithmic_flop_per_transition=dom["flop"], transitions_per_launch=units, traffic=None,
                     note="launches of this workload are far below one wave of the chip (a search wave is %s): the kernel "
                          "is latency-bound here, see the c4 line for its throughput form" % (
                              "%d rollouts" % (C2_SCEN_PER_GPU * C2_LEAVES * C2_REPLICAS) if wl == "c2" else
                              "one rollout" if wl == "c1" else "10^6 rollouts"))
-        if units:
+        if units and per_launch_ms > 0:
             roof["achieved"] = units * dom["flop"] / (per_launch_ms * 1e-3) / 1e12
             roof["frac"] = roof["achieved"] / FP32_PEAK_TFLOPS
         else:
