@@ -16,6 +16,10 @@ void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *), int key = 0);
 // kernels launched on behalf of the ctx by another translation unit (pmcts_launch_count)
 void count_launches(pmcts_ctx *ctx, int n);
 
+// is per-launch timing on (pmcts_enable_timing)?  Its event pairs bracket single launches, so nothing is replayed
+// from a recorded graph while it is.
+bool ctx_timing(const pmcts_ctx *ctx);
+
 // size of the blocks a peer exchange was created for (pmcts_peer.cu)
 size_t peer_block_bytes(const pmcts_peer *peer);
 

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -262,6 +263,13 @@ int grow_pinned(char *&p, size_t &cap, size_t need) {
     cap = need + need / 2;
     return PMCTS_OK;
 }
+
+// the recorded iteration of the sequential search
+struct SeqGraph {
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+    ~SeqGraph() { if (exec) cudaGraphExecDestroy(exec); }
+};
 
 struct Driver {
     pmcts_ctx *ctx;
@@ -607,27 +615,74 @@ extern "C" int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, i
     LIB_TRY(grow_device(cache->seq_dev, cache->cap_seq_dev, total));
     char *h = cache->seq_host, *d = cache->seq_dev;
     cudaStream_t st = (cudaStream_t)pmcts_get_stream(ctx);
+    // Results: the kernels store the three numbers of the rollout straight into the page-locked block (it is mapped
+    // into the device's address space), so nothing is copied back; if the block cannot be mapped they go to the device
+    // mirror and one copy brings them down.
+    char *out = nullptr;
+    {
+        void *mapped = nullptr;
+        if (cudaHostGetDevicePointer(&mapped, h, 0) == cudaSuccess && mapped) out = (char *)mapped;
+        else cudaGetLastError();
+    }
+    const bool copy_down = out == nullptr;
+    if (copy_down) out = d;
+    // The device work of an iteration is the same every time -- same buffers, same root, the path and its length
+    // travel in the block -- so the second iteration records it as a graph and the rest replay it: one submission per
+    // rollout instead of a copy, a clear and two or three launches.  (Not with per-launch timing on, whose event
+    // pairs belong to single launches, and not when the stream cannot be captured: the plain calls stay.)
+    const char *env = std::getenv("PMCTS_SEQ_GRAPH");
+    bool want_graph = !(env && env[0] == '0') && !pmcts::ctx_timing(ctx) && budget >= 8;
+    SeqGraph graph;
+    int64_t calls = 0;
+    auto enqueue = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+        pmcts_noise nz{};
+        nz.mode = PMCTS_NOISE_INJECTED;
+        nz.z = (const double *)d;
+        LIB_TRY(pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)(d + o_path),
+                                    (const int32_t *)(d + o_plen), info.max_depth, &nz, nullptr, nullptr,
+                                    (int32_t *)(out + o_steps), (uint8_t *)(out + o_status), (int32_t *)(out + o_bin), nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags));
+        if (copy_down) CUDA_TRY(cudaMemcpyAsync(h + o_steps, d + o_steps, total - o_steps, cudaMemcpyDeviceToHost, st));
+        return PMCTS_OK;
+    };
     const pmcts::SeqRollout rollout = [&](int, const int8_t *path, int len, const double *z, int *bin, int *steps) -> int {
         std::memcpy(h, z, (size_t)n_instants * sizeof(double));
         double *deg = (double *)(h + o_path);
         for (int j = 0; j < len; ++j) deg[j] = 45.0 * (double)path[j];  // ACTIONS[a] (simulatorTLKT.py:29)
         *(int32_t *)(h + o_plen) = len;
-        CUDA_TRY(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
-        pmcts_noise nz{};
-        nz.mode = PMCTS_NOISE_INJECTED;
-        nz.z = (const double *)d;
-        const int rc = pmcts_rollout_batch(ctx, scen_slot, 1, 1, root, dest, tmin, (const double *)(d + o_path),
-                                           (const int32_t *)(d + o_plen), info.max_depth, &nz, nullptr, nullptr,
-                                           (int32_t *)(d + o_steps), (uint8_t *)(d + o_status), (int32_t *)(d + o_bin), nullptr,
-                                           nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, flags);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h + o_steps, d + o_steps, total - o_steps, cudaMemcpyDeviceToHost, st));
+        const int64_t call = calls++;
+        if (graph.exec) {
+            CUDA_TRY(cudaGraphLaunch(graph.exec, st));
+            pmcts::count_launches(ctx, graph.kernels);
+        } else if (want_graph && call == 1) {
+            // (the first iteration ran plainly: every buffer the launch grows on demand has its size)
+            want_graph = false;
+            const int64_t l0 = pmcts_launch_count(ctx);
+            int rc = PMCTS_OK;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                rc = enqueue();
+                cudaGraph_t g = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(st, &g);
+                if (!rc && e == cudaSuccess && g && cudaGraphInstantiate(&graph.exec, g, 0) == cudaSuccess)
+                    graph.kernels = (int)(pmcts_launch_count(ctx) - l0);
+                else
+                    graph.exec = nullptr;
+                if (g) cudaGraphDestroy(g);
+            }
+            cudaGetLastError();  // (a refused capture leaves its error behind; the plain calls below are the answer to it)
+            if (rc < 0 && rc != PMCTS_ERR_CUDA) return rc;
+            if (graph.exec) CUDA_TRY(cudaGraphLaunch(graph.exec, st));
+            else LIB_TRY(enqueue());
+        } else {
+            LIB_TRY(enqueue());
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
-        const uint8_t status = *(uint8_t *)(h + o_status);
+        const uint8_t status = *(volatile uint8_t *)(h + o_status);
         if (status == PMCTS_ST_OUT_OF_GRID || status == PMCTS_ST_PAST_HORIZON || status == PMCTS_ST_DEGENERATE)
             return (int)status;  // what the reference raises on
-        *bin = *(int32_t *)(h + o_bin);
-        *steps = *(int32_t *)(h + o_steps);
+        *bin = *(volatile int32_t *)(h + o_bin);
+        *steps = *(volatile int32_t *)(h + o_steps);
         return 0;
     };
     const int rc = pmcts::forest_sequential(f, local_index, budget, frequency, n_instants, py_state, np_state, rollout, &rep);
