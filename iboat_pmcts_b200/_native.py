@@ -43,7 +43,7 @@ EXPORTS = [
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
     "pmcts_forest_create", "pmcts_forest_destroy", "pmcts_forest_last_error", "pmcts_forest_set_coefficients",
     "pmcts_forest_select", "pmcts_forest_backup", "pmcts_forest_master_apply", "pmcts_forest_tree_size",
-    "pmcts_forest_master_size", "pmcts_forest_export_tree", "pmcts_forest_export_master", "pmcts_python_shuffles",
+    "pmcts_forest_master_size", "pmcts_forest_export_tree", "pmcts_forest_export_master", "pmcts_python_shuffles", "pmcts_python_shuffles_batch",
     "pmcts_forest_master_rows", "pmcts_forest_export_master_rows",
 ]
 
@@ -209,6 +209,7 @@ def lib():
     L.pmcts_forest_master_size.argtypes = [vp]
     L.pmcts_forest_master_size.restype = i64
     L.pmcts_python_shuffles.argtypes = [C.c_uint64, i64, i32, vp]
+    L.pmcts_python_shuffles_batch.argtypes = [vp, i32, i64, i32, vp]
     L.pmcts_forest_export_tree.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.pmcts_forest_export_master.argtypes = [vp, vp, vp, vp]
     L.pmcts_forest_master_rows.argtypes = [vp]

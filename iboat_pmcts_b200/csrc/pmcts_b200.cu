@@ -322,14 +322,23 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
         NoiseStream ns;
         const double *pre = a.prefix ? a.prefix + (size_t)leaf * a.prefix_stride : nullptr;
         const int plen = a.prefix_len ? a.prefix_len[leaf] : 0;
+        // sin / cos of the current position B and of the one before it, A: taken once per position (PosTrig); the
+        // destination's latitude once per rollout
+        PosTrig tb, ta_;
+        trig_lat(blat, tb);
+        ta_ = tb;
+        double sD, cD;
+        sincos(a.dest_lat * kDegToRad, &sD, &cD);
 
         auto step = [&](double action) {
             const double z = ns.draw<false>(nz, n, r, nstep);
             const double la0 = blat, lo0 = blon;
-            st = do_step_literal(sc, bp, k, blat, blon, action, z);
+            st = do_step_literal(sc, bp, k, blat, blon, action, z, &tb);
             if (st == PMCTS_ST_OK) {
                 alat = la0;
                 alon = lo0;
+                ta_ = tb;
+                trig_lat(blat, tb);
                 if (a.traj_lat && nstep < a.traj_stride) a.traj_lat[(size_t)nstep * n + r] = blat;
                 if (a.traj_lon && nstep < a.traj_stride) a.traj_lon[(size_t)nstep * n + r] = blon;
                 ++nstep;
@@ -337,11 +346,14 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
         };
         auto at_dest = [&]() {
             double xa, ya, za, xb, yb, zb;
-            geo_to_cart(alat, alon, xa, ya, za);
-            geo_to_cart(blat, blon, xb, yb, zb);
+            trig_lon(alon, ta_);
+            trig_lon(blon, tb);
+            geo_to_cart(ta_, xa, ya, za);
+            geo_to_cart(tb, xb, yb, zb);
             const int res = at_dest_cart(bp, xa, ya, za, xb, yb, zb, xd, yd, zd, frac);
             if (res < 0) st = PMCTS_ST_DEGENERATE; else at = res;
         };
+        auto bearing = [&]() { return bearing_to(tb, blon, sD, cD, a.dest_lon); };
 
         if (!(a.flags & PMCTS_ROLL_PLAN_EVAL)) {
             // Tree.get_sim_to_estimate_state (worker.py:283-300): the first action always; the rest
@@ -358,16 +370,16 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
         } else {
             // estimate_perfomance_plan (isochrones.py:498-511): whole plan, unchecked.
             for (int j = 0; j < plen && st == PMCTS_ST_OK; ++j) step(pre[j]);
-            if (plen == 0) step(bearing_to(blat, blon, a.dest_lat, a.dest_lon));
+            if (plen == 0) step(bearing());
         }
         // Tree.default_policy (worker.py:264-271)
         if (st == PMCTS_ST_OK) {
-            brg = bearing_to(blat, blon, a.dest_lat, a.dest_lon);
+            brg = bearing();
             at_dest();
             while (st == PMCTS_ST_OK && !at && !is_terminal(sc, k, blat, blon)) {
                 step(brg);
                 if (st != PMCTS_ST_OK) break;
-                brg = bearing_to(blat, blon, a.dest_lat, a.dest_lon);
+                brg = bearing();
                 at_dest();
             }
         }

@@ -78,6 +78,35 @@ __device__ __forceinline__ double py_mod(double a, double m) {
     return r;
 }
 
+// Python's float % 360 on the angles this path takes it of.  In (-360, 720) fmod has nothing to divide: the argument
+// comes back as it is, or less 360 -- a subtraction that loses no bit -- and Python's sign fix is the one rounded add
+// py_mod does.  Same results bit for bit as py_mod(a, 360.0), without the library's long division (three per literal
+// transition); anything else, NaN included, still goes there.
+__device__ __forceinline__ double py_mod360(double a) {
+    if (a > -360.0 && a < 720.0) {
+        if (a < 0.0) return a + 360.0;
+        return a >= 360.0 ? a - 360.0 : a;
+    }
+    return py_mod(a, 360.0);
+}
+
+// sin / cos of a position's latitude and longitude (radians = degrees * kDegToRad, as every formula below forms them).
+// The literal rollout needs them of the same position up to four times -- getDestination, getDistAndBearing and twice
+// fromGeoToCartesian, as B and then as A of the arrival test -- and the same function of the same number is the same
+// number: it takes them once (rollout_batch_kernel).
+struct PosTrig {
+    double sl, cl, so, co;
+    bool lon_valid;
+};
+__device__ __forceinline__ void trig_lat(double lat, PosTrig &t) {
+    sincos(lat * kDegToRad, &t.sl, &t.cl);
+    t.lon_valid = false;
+}
+__device__ __forceinline__ void trig_lon(double lon, PosTrig &t) {
+    if (!t.lon_valid) sincos(lon * kDegToRad, &t.so, &t.co);
+    t.lon_valid = true;
+}
+
 // ---- wind: Simulator.getWind (simulatorTLKT.py:168-179) on the time-blended slab of instant k ----
 // SciPy's linear RegularGridInterpolator semantics (bounds_error=True; cell index clipped to n-2 so
 // the last grid node is reached with weight 1).
@@ -134,12 +163,19 @@ __device__ __forceinline__ double deter_dyn(const BoatParams &bp, double p, doub
 }
 
 // Simulator.getDestination (simulatorTLKT.py:132-166)
+// (lat_trig: sin / cos of lat * kDegToRad when the caller has them)
 __device__ __forceinline__ void get_destination(const BoatParams &bp, double dist, double bearing,
-                                                double lat, double lon, double &olat, double &olon) {
+                                                double lat, double lon, double &olat, double &olon,
+                                                const PosTrig *lat_trig = nullptr) {
     const double latDep = lat * kDegToRad, lonDep = lon * kDegToRad, brg = bearing * kDegToRad;
     const double dr = dist / bp.earth_radius;
     double sl, cl, sd, cd, sb, cb;
-    sincos(latDep, &sl, &cl);
+    if (lat_trig) {
+        sl = lat_trig->sl;
+        cl = lat_trig->cl;
+    } else {
+        sincos(latDep, &sl, &cl);
+    }
     sincos(dr, &sd, &cd);
     sincos(brg, &sb, &cb);
     const double s2 = sl * cd + cl * sd * cb;
@@ -160,7 +196,17 @@ __device__ __forceinline__ double bearing_to(double lat, double lon, double dlat
     sincos(dl, &sL, &cL);
     const double x = cD * sL;
     const double y = cP * sD - sP * cD * cL;
-    return py_mod(atan2(x, y) * 180.0 / kPi + 360.0, 360.0);
+    return py_mod360(atan2(x, y) * 180.0 / kPi + 360.0);
+}
+// The same with sin / cos of both latitudes given (the destination's once per rollout, the position's from its PosTrig).
+__device__ __forceinline__ double bearing_to(const PosTrig &pos, double lon, double sD, double cD, double dlon) {
+    const double sP = pos.sl, cP = pos.cl;
+    const double dl = dlon * kDegToRad - lon * kDegToRad;
+    double sL, cL;
+    sincos(dl, &sL, &cL);
+    const double x = cD * sL;
+    const double y = cP * sD - sP * cD * cL;
+    return py_mod360(atan2(x, y) * 180.0 / kPi + 360.0);
 }
 
 // Haversine distance of Simulator.getDistAndBearing (simulatorTLKT.py:117-122).
@@ -180,6 +226,11 @@ __device__ __forceinline__ void geo_to_cart(double lat, double lon, double &x, d
     x = sl * co;
     y = sl * so;
     z = cl;
+}
+__device__ __forceinline__ void geo_to_cart(const PosTrig &t, double &x, double &y, double &z) {
+    x = t.sl * t.co;
+    y = t.sl * t.so;
+    z = t.cl;
 }
 
 // Tree.is_state_at_dest (worker.py:380-415) on cartesian points.  Returns 1 / 0, -1 = ZeroDivisionError.
@@ -222,19 +273,20 @@ __device__ __forceinline__ double reward_of(double tmax, double tmin, double t_a
 // Simulator.doStep (simulatorTLKT.py:181-216), literal fp64.  z is the standard normal of
 // Boat.addUncertainty (:504-517).
 __device__ __forceinline__ int do_step_literal(const ScenarioView &sc, const BoatParams &bp, int &k,
-                                               double &lat, double &lon, double heading, double z) {
+                                               double &lat, double &lon, double heading, double z,
+                                               const PosTrig *lat_trig = nullptr) {
     if (k < 0 || k >= sc.nT) return PMCTS_ST_PAST_HORIZON;
     double u, v;
     if (!wind_f64(sc, k, lat, lon, u, v)) return PMCTS_ST_OUT_OF_GRID;
     const double mag = sqrt(u * u + v * v);                       // Weather.returnPolarVel
-    const double ang = py_mod(180.0 / kPi * atan2(u, v), 360.0);  // weatherTLKT.py:161-162
-    const double pofsail = fabs(py_mod(ang + 180.0, 360.0) - heading);
+    const double ang = py_mod360(180.0 / kPi * atan2(u, v));  // weatherTLKT.py:161-162
+    const double pofsail = fabs(py_mod360(ang + 180.0) - heading);
     double speed = deter_dyn(bp, pofsail, mag);
     speed = speed + z * (speed * bp.sigma_coeff);
     if (k + 1 >= sc.nT) return PMCTS_ST_PAST_HORIZON;
     const double dl = speed * sc.dt_sec[k];
     double nlat, nlon;
-    get_destination(bp, dl, heading, lat, lon, nlat, nlon);
+    get_destination(bp, dl, heading, lat, lon, nlat, nlon, lat_trig);
     k += 1;
     lat = nlat;
     lon = nlon;

@@ -218,13 +218,15 @@ class Forest:
         # (what Node.__init__ does, worker.py:50-51)
         max_nodes = budget + 2
         perms = np.empty((S_loc, max_nodes, len(ACTIONS)), np.uint8)
-        for ti, t in enumerate(trees):
-            # = rng = random.Random(1000003 * seed + t.id); rng.shuffle(list(range(8))) per node, generated natively
-            # (tests/test_host_forest.py holds the two together)
-            tree_seed = 1000003 * seed + t.id
-            if 0 <= tree_seed < 2 ** 64:
-                N.check_forest(lib.pmcts_python_shuffles(tree_seed, max_nodes, len(ACTIONS), perms[ti].ctypes.data))
-            else:  # (seeds beyond 64 bits: the interpreter's own generator)
+        # = rng = random.Random(1000003 * seed + t.id); rng.shuffle(list(range(8))) per node, generated natively, the
+        # trees' tables side by side (tests/test_host_forest.py holds the two together)
+        tree_seeds = [1000003 * seed + t.id for t in trees]
+        if all(0 <= ts < 2 ** 64 for ts in tree_seeds):
+            seeds64 = np.asarray(tree_seeds, np.uint64)
+            N.check_forest(lib.pmcts_python_shuffles_batch(seeds64.ctypes.data, S_loc, max_nodes, len(ACTIONS),
+                                                           perms.ctypes.data))
+        else:  # (seeds beyond 64 bits: the interpreter's own generator)
+            for ti, tree_seed in enumerate(tree_seeds):
                 rng = rand.Random(tree_seed)
                 for j in range(max_nodes):
                     order = list(range(len(ACTIONS)))

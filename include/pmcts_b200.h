@@ -302,6 +302,9 @@ int64_t pmcts_forest_master_size(pmcts_forest *f);
 /* out[count][n_items] = `count` consecutive random.shuffle(list(range(n_items))) of CPython's
  * random.Random(seed): the action order Node.__init__ draws for every new node (worker.py:50-51), bit for bit. */
 int pmcts_python_shuffles(uint64_t seed, int64_t count, int n_items, uint8_t *out);
+/* The same for n_seeds generators (the worker trees of one search, worker.py:50-51 per tree), filled side by side on
+ * the host runtime's threads: out[n_seeds][count][n_items]. */
+int pmcts_python_shuffles_batch(const uint64_t *seeds, int n_seeds, int64_t count, int n_items, uint8_t *out);
 /* Copies of a worker tree (parent, arm, table[node][8][12] int64, untried actions) and of the master tree
  * (parent, arm, table[node][n_scen][8][12] uint32); any pointer may be NULL. */
 int pmcts_forest_export_tree(pmcts_forest *f, int local_index, int32_t *parent, int8_t *arm, int64_t *table,

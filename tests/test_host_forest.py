@@ -112,6 +112,14 @@ def test_native_shuffles_are_cpythons():
             rng.shuffle(order)
             ref.append(order)
         assert np.array_equal(out, np.array(ref, np.uint8)), seed
+    # the batched form (one generator per worker tree, filled on the runtime's threads) == one call per seed
+    seeds = np.asarray([1000003 * 4 + i for i in range(23)] + [2 ** 40 + 3], np.uint64)
+    batch = np.empty((seeds.size, 322, 8), np.uint8)
+    N.check_forest(L.pmcts_python_shuffles_batch(seeds.ctypes.data, seeds.size, 322, 8, batch.ctypes.data))
+    for i, seed in enumerate(seeds):
+        one = np.empty((322, 8), np.uint8)
+        N.check_forest(L.pmcts_python_shuffles(int(seed), 322, 8, one.ctypes.data))
+        assert np.array_equal(batch[i], one), int(seed)
 
 
 def test_native_generators_are_the_interpreters():
