@@ -438,7 +438,8 @@ def run_api_workload(args):
     fin_ms = eng.kernel_ms(reset=False, kind=N.KERNEL_FINISHER)
     kernel_ms = eng.kernel_ms(reset=True)
     eng.enable_timing(False)
-    dev_ms = sum(x.elapsed_time(y) for x, y in ev)
+    step_each = [x.elapsed_time(y) for x, y in ev]
+    dev_ms = sum(step_each)
     if os.environ.get("PMCTS_BENCH_DEBUG"):
         import gc
         print("rank %d per-step ms: %s | gc %s" % (rank, [round(x.elapsed_time(y), 3) for x, y in ev], gc.get_stats()),
@@ -459,8 +460,11 @@ def run_api_workload(args):
     barrier()
     t0 = time.perf_counter()
     e_tr = e_ro = 0
+    e2e_each = []  # (host clock per call: every call returns host results, so nothing of it is still in flight)
     for i in range(e2e_steps):
+        t_call = time.perf_counter()
         a, b, _ = step(warm + args.steps + 2 + i)
+        e2e_each.append((time.perf_counter() - t_call) * 1e3)
         e_tr += a
         e_ro += b
     eng.synchronize()
@@ -501,9 +505,16 @@ def run_api_workload(args):
                     config=api_config(wl, world),
                     e2e=dict(value=(e_tr if unit_tr else e_ro) / e2e_s, unit="transitions/s" if unit_tr else "rollouts/s",
                              rollouts_per_s=e_ro / e2e_s, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
+                             ms_per_step_median=statistics.median(e2e_each), ms_per_step_min=min(e2e_each),
+                             ms_per_step_max=max(e2e_each), ms_each=[round(x, 3) for x in e2e_each],
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api=dom["api"]),
                     gpu_launches=int(launches), kernel_ms_total=kernel_ms, dominant_kernel_ms=dom_ms,
                     finisher_kernel_ms=fin_ms, wall_s_timed_region=wall, clocks=clocks, roofline=roof,
+                    step_ms=dict(median=statistics.median(step_each), min=min(step_each), max=max(step_each),
+                                 each=[round(x, 3) for x in step_each],
+                                 note="rank 0's timed steps (CUDA events); value and ms_per_step are the mean over all of "
+                                      "them, which single slow steps move (a step of this host-paced workload is hundreds "
+                                      "to thousands of driver calls)"),
                     last_decision=[int(a) for a in decision] if isinstance(decision, list) else decision)
         if wl == "c2":
             line["search_report_last_step"] = {k: (round(v, 4) if isinstance(v, float) else v)

@@ -28,6 +28,7 @@
 #include <functional>
 #include <mutex>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <new>
@@ -72,37 +73,72 @@ class Pool {
     int size() const { return (int)workers_.size() + 1; }
 
     // fn(i) for i in [0, n), on the pool's threads and the caller; returns when all are done.
-    // A search hands the pool three small jobs per wave, a few hundred microseconds apart.  Threads that sleep on a
-    // condition variable between them cost 40-50 us per job to wake and collect -- measured as more than half of the
-    // selection, back-up and master-update time of a 10-scenario search -- so a worker that has finished a job keeps
-    // polling for the next one for kSpinUs and only then goes to sleep, and the caller polls for the last worker.
+    // A search hands the pool three small jobs per wave: the back-up and the master update back to back, the next
+    // selection right behind them, then nothing while the GPU rolls the wave out.  Two things keep such jobs cheap.
+    // (1) A job is finished when its TASKS are, not when every thread has reported: indices are claimed from one
+    // counter that also carries the job's number, the caller claims like everybody else, and a thread that wakes
+    // late finds nothing to claim -- a sleeping or descheduled worker never holds a job up.  (2) A worker that has
+    // run out of tasks polls for the next job for 50 us before it sleeps, which covers the back-to-back jobs of a
+    // wave without keeping the cores busy through the GPU's part (longer polling was measured: faster on a quiet box,
+    // several times slower on a box whose cores were contended).
     void run(int n, const std::function<void(int)> &fn) {
         std::lock_guard<std::mutex> serial(run_mu_);  // one job at a time
-        fn_ = &fn;
-        n_ = n;
-        next_.store(0);
-        running_.store((int)workers_.size());
-        generation_.fetch_add(1);
+        const uint64_t gen = ((ticket_.load() >> 32) + 1) & 0xffffffffu;
+        Job &j = jobs_[gen & 1];
+        j.fn.store(&fn);
+        j.n.store(n);
+        done_.store(0);
+        ticket_.store(gen << 32);  // publishes the job
         if (sleepers_.load() > 0) {
-            // (the lock orders this wake-up after a sleeper's look at the generation: it either saw the new one or is
+            // (the lock orders this wake-up after a sleeper's look at the counter: it either saw the new job or is
             //  waiting by now)
             { std::lock_guard<std::mutex> lk(mu_); }
             cv_.notify_all();
         }
-        work();
-        for (int spins = 0; running_.load() != 0; ++spins) {
+        claim(gen);
+        for (int spins = 0; done_.load() != n; ++spins) {  // tasks other threads are still running
             relax();
-            if ((spins & 1023) == 1023) std::this_thread::yield();
+            if ((spins & 255) == 255) std::this_thread::yield();
         }
-        fn_ = nullptr;
     }
 
   private:
-    static constexpr int kSpinUs = 300;
+    int spin_us_ = 50;  // (PMCTS_POOL_SPIN_US overrides; 0: sleep at once)
+    struct Job {
+        std::atomic<const std::function<void(int)> *> fn{nullptr};
+        std::atomic<int> n{0};
+    };
+
+    // runs unclaimed tasks of job `gen` until there are none, or the pool has moved on to another job.  (Two job
+    // slots alternate: a thread that still holds the number of a finished job may read the slot of the job after
+    // next, but it cannot claim from it -- the counter no longer carries its number.)
+    void claim(uint64_t gen) {
+        Job &j = jobs_[gen & 1];
+        for (;;) {
+            uint64_t t = ticket_.load();
+            if ((t >> 32) != gen) return;
+            if ((int64_t)(t & 0xffffffffu) >= (int64_t)j.n.load()) return;
+            if (!ticket_.compare_exchange_weak(t, t + 1)) continue;
+            (*j.fn.load())((int)(t & 0xffffffffu));
+            done_.fetch_add(1);
+        }
+    }
 
     Pool() : pid_(getpid()) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+        // up to 16 threads, of this process's share of the cores when a launcher runs several ranks on the box
+        // (LOCAL_WORLD_SIZE as torchrun sets it): polling threads must not outnumber the cores.  PMCTS_HOST_THREADS
+        // overrides.
+        unsigned hw = std::thread::hardware_concurrency();
+        if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) {
+            const int ranks = std::atoi(lw);
+            if (ranks > 1 && hw) hw = std::max(1u, hw / (unsigned)ranks);
+        }
+        int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+        if (const char *ht = std::getenv("PMCTS_HOST_THREADS")) {
+            const int want = std::atoi(ht);
+            if (want >= 1) nt = std::min(want, 64);
+        }
+        if (const char *sp = std::getenv("PMCTS_POOL_SPIN_US")) spin_us_ = std::max(0, std::min(std::atoi(sp), 10000));
         for (int t = 1; t < nt; ++t) {
             workers_.emplace_back([this] { loop(); });
             workers_.back().detach();
@@ -115,47 +151,38 @@ class Pool {
         std::this_thread::yield();
 #endif
     }
-    void work() {
-        for (int i = next_.fetch_add(1); i < n_; i = next_.fetch_add(1)) (*fn_)(i);
-    }
     void loop() {
         using clock = std::chrono::steady_clock;
         uint64_t seen = 0;
         for (;;) {
             // poll for the next job, then sleep
-            const clock::time_point until = clock::now() + std::chrono::microseconds(kSpinUs);
+            const clock::time_point until = clock::now() + std::chrono::microseconds(spin_us_);
             bool have = false;
             for (int spins = 0;; ++spins) {
-                if (generation_.load() != seen) {
+                if ((ticket_.load() >> 32) != seen) {
                     have = true;
                     break;
                 }
                 relax();
-                if ((spins & 255) == 255) {
-                    if (clock::now() >= until) break;
-                    std::this_thread::yield();
-                }
+                if ((spins & 63) == 63 && clock::now() >= until) break;
             }
             if (!have) {
                 std::unique_lock<std::mutex> lk(mu_);
                 sleepers_.fetch_add(1);
-                cv_.wait(lk, [&] { return generation_.load() != seen; });
+                cv_.wait(lk, [&] { return (ticket_.load() >> 32) != seen; });
                 sleepers_.fetch_sub(1);
             }
-            // (the caller does not start another job before every worker has checked in: no generation is skipped)
-            seen = generation_.load();
-            work();
-            running_.fetch_sub(1);
+            seen = ticket_.load() >> 32;
+            claim(seen);
         }
     }
     pid_t pid_;
     std::vector<std::thread> workers_;
     std::mutex mu_, run_mu_;
     std::condition_variable cv_;
-    const std::function<void(int)> *fn_ = nullptr;
-    int n_ = 0;
-    std::atomic<int> next_{0}, running_{0}, sleepers_{0};
-    std::atomic<uint64_t> generation_{0};
+    Job jobs_[2];
+    std::atomic<uint64_t> ticket_{0};  // job number << 32 | next unclaimed index
+    std::atomic<int> done_{0}, sleepers_{0};
 };
 
 template <typename F>

@@ -33,7 +33,9 @@ def step(f, i, rec=None):
     mt.get_best_policy(verbose=False)
     t3 = time.perf_counter()
     if rec is not None:
-        rec.append((t1 - t0, t2 - t1, t3 - t2, f.last_search_report["ms_total"] * 1e-3))
+        r = f.last_search_report
+        rec.append((t1 - t0, t2 - t1, t3 - t2, r["ms_total"] * 1e-3, r["ms_select"] * 1e-3, r["ms_wait"] * 1e-3,
+                    r["ms_backup"] * 1e-3, r["ms_master"] * 1e-3))
     return mt
 
 
@@ -43,8 +45,10 @@ rec = []
 for i in range(4, 24):
     step(forests[i], i, rec)
 r = np.median(np.array(rec), 0) * 1e3
-print("medians over 20 steps: launch_search %.3f ms (native driver %.3f), deepcopy + MasterTree %.3f, get_best_policy %.3f"
-      % (r[0], r[3], r[1], r[2]))
+print("medians over 20 steps: launch_search %.3f ms (native driver %.3f: select %.3f, GPU wait %.3f, back-up %.3f, master "
+      "update %.3f), deepcopy + MasterTree %.3f, get_best_policy %.3f; whole step %.3f (min %.3f, max %.3f)"
+      % (r[0], r[3], r[4], r[5], r[6], r[7], r[1], r[2], float(np.median(np.array(rec)[:, :3].sum(1))) * 1e3,
+         float(np.array(rec)[:, :3].sum(1).min()) * 1e3, float(np.array(rec)[:, :3].sum(1).max()) * 1e3))
 print("last native report:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in forests[23].last_search_report.items()})
 pr = cProfile.Profile()
 pr.enable()
