@@ -520,3 +520,12 @@ def test_native_sequential_search_is_the_python_loop(golden_dir, monkeypatch):
     mt = MasterTree(sims, destination, nodes=mn.deepcopy_dict(master))
     mt.get_best_policy(verbose=False)
     assert {str(k): [int(a) for a in v] for k, v in mt.best_policy.items()} == replay["best_policy"]
+    # the iteration replayed from a recorded graph (the default above) and issued call by call (PMCTS_SEQ_GRAPH=0) are
+    # the same launches: same tree, and the replays are counted as the launches they stand for
+    monkeypatch.setenv("PMCTS_SEQ_GRAPH", "0")
+    random.seed(1)
+    np.random.seed(1)
+    plain = ft.Forest(listsimulators=sims, destination=destination, timemin=timemin, budget=replay["budget"])
+    plain.launch_search(STATE0, replay["frequency"], mode="sequential")
+    assert np.array_equal(plain.workers[0].table, tree.table)
+    assert plain.last_search_report["launches"] == forest.last_search_report["launches"] > replay["budget"]
