@@ -331,7 +331,7 @@ constexpr float cos_pmin = 8.191520572e-01f, cos_pmax = -9.396926165e-01f;
 constexpr float sin2_dest_angle = 7.615435393e-09f, inv_radius = 1.569612351e-07f;
 // (near_miss2: a boat that stops within 1/1000 of a step short of the destination.  Round 1 used 1/316; the measured
 //  position error -- 2e-7 relative, 1.6e-5 of a step -- turns into a bearing error of a degree at 1/1000, which moves the
-//  arrival fraction of the next step by less than the histogram's own bin margin.  Over 2^20 rollouts of 8 scenarios the
+//  reward of the step that follows by 5e-6, less than half of the margin the histogram's bin edges carry.  Over 2^20 rollouts of 8 scenarios the
 //  fp32 path decides like the oracle with the margin at 1e-5, 1e-6, 1e-7 and closed; 1e-6 leaves 0.12 % of the rollouts
 //  to the fp64 finisher instead of 0.32 %.)
 constexpr float margin_angle = 2e-4f, margin_along = 2e-5f, near_miss2 = 1e-6f, margin_box = 3e-5f;
