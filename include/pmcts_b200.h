@@ -451,7 +451,10 @@ int pmcts_forest_search(pmcts_ctx *ctx, pmcts_forest *f, const int32_t *scen_slo
  * them, so a seeded script grows the reference's tree.  A rollout is one launch of K2 (PMCTS_PREC_FAST with its fp64
  * re-run: the histogram bin and the number of transitions -- all the tree and the generators depend on -- are exact).
  * Returns 0, a negative error, or the positive PMCTS_ST_* of a rollout the reference would have raised on.
- * Call it for the trees one after the other (forest.py's processes, serialised); report->waves counts master updates. */
+ * Call it for the trees one after the other (forest.py's processes, serialised); report->waves counts master updates.
+ * From the second iteration on the device work of an iteration is replayed from a CUDA graph recorded on the ctx
+ * stream (not while pmcts_enable_timing is on, nor on a stream that cannot be captured, e.g. the legacy default
+ * stream; PMCTS_SEQ_GRAPH=0 in the environment turns it off): the same launches, counted as such in report->launches. */
 int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, int local_index, int scen_slot,
                                    const double root[3], const double dest[2], double tmin, int64_t budget,
                                    int frequency, int roll_flags, pmcts_mt_state *py_state, pmcts_mt_state *np_state,
