@@ -396,13 +396,13 @@ PMCTS_HD float boat_speed(const BoatParams &bp, float u, float v, float sh, floa
     const float cos_pmin = kDefBoat ? defboat::cos_pmin : bp.cos_pmin_f;
     const float cos_pmax = kDefBoat ? defboat::cos_pmax : bp.cos_pmax_f;
     const float m2 = fma_(u, u, v * v);
-    float du = 0.0f, dv = 1.0f, mag = 0.0f;  // atan2(0, 0) = 0: a calm wind "blows north"
-    if (m2 > 0.0f) {
-        const float rm = rsqrt_approx(m2);
-        mag = m2 * rm;
-        du = u * rm;
-        dv = v * rm;
-    }
+    // A wind of exactly zero has no direction (the reference goes by atan2(0, 0) = 0: a calm wind "blows north").
+    // It is not given one here: 0 * rsqrt(0) is not a number, neither is anything computed from it -- the tack /
+    // gybe factor below carries it into the speed whatever minimum and maximum make of the angle -- and the step's
+    // length test (fast_step) hands what is not a number to the literal kernel, which has the reference's rule.  Four
+    // instructions of the step loop (the test, three defaults) for a case interpolated winds do not produce.
+    const float rm = rsqrt_approx(m2);
+    const float mag = m2 * rm, du = u * rm, dv = v * rm;
     const float cosp = -fma_(du, sh, dv * ch);
     const float sinp = fabsf(fma_(du, ch, -dv * sh));
     const float p = atan2_pos(sinp, cosp) * 57.2957795131f;
@@ -490,14 +490,11 @@ PMCTS_HD void bearing_unit(const DestRel &r, float s, float sD, float cD, float 
     const float x = cD * r.sin_dlon;
     const float y = fma_(s * cD, r.h_dlon, r.sin_dlat);
     const float n2 = fma_(x, x, y * y);
-    if (n2 > 0.0f) {
-        const float2 h = pk_mul(pk(x, y), rsqrt_approx(n2));
-        sh = h.x;
-        ch = h.y;
-    } else {  // atan2(0, 0) = 0
-        sh = 0.0f;
-        ch = 1.0f;
-    }
+    // (a boat exactly on the destination -- atan2(0, 0) = 0 in the reference -- gets no heading here: 0 * rsqrt(0) is
+    //  not a number and fast_step's length tests leave the boat to the literal kernel, see boat_speed)
+    const float2 h = pk_mul(pk(x, y), rsqrt_approx(n2));
+    sh = h.x;
+    ch = h.y;
 }
 
 // ---- Tree.is_state_at_dest (worker.py:380-415) -----------------------------------------------------
@@ -604,9 +601,10 @@ PMCTS_HD int fast_step(const ScenarioView &sc, const BoatParams &bp, int &k, dou
     const float dt = kUniformDt ? sc.dt_uniform32 : sc.dt_sec32[k];
 #endif
     const float d = speed * dt * (kDefBoat ? defboat::inv_radius : bp.inv_radius_f);
-    if (!(fabsf(d) <= kMaxStepAngle)) return kStNeedsLiteral;
     m = move_increments(d, sh, ch, s, c);
-    if (!(fabsf(m.sin_dlon) <= kMaxStepAngle)) return kStNeedsLiteral;  // high latitude: dlon = b / cos(lat)
+    // one exit for both limits (a step too long for the short series; at high latitude dlon = b / cos(lat) too large):
+    // what is not a number fails either test -- see boat_speed and bearing_unit
+    if (!(fabsf(d) <= kMaxStepAngle) | !(fabsf(m.sin_dlon) <= kMaxStepAngle)) return kStNeedsLiteral;
     if (kRad) {  // (position in radians)
         lat += (double)m.dlat;
         lon += (double)m.dlon;

@@ -43,9 +43,20 @@ def test_boat_speed_matches_get_deter_dyn():
         want = o.deter_dyn(abs((ang + 180) % 360 - hd), m)
         worst = max(worst, abs(f.boat_speed(u, v, hd) - want))
     assert worst < 1e-6
-    # calm wind: atan2(0, 0) = 0, point of sail |180 - heading|
+    # a wind of exactly zero has no direction; the fp32 path does not give it one (the reference's atan2(0, 0) = 0 is the
+    # literal kernel's business): the speed is not a number, and a transition in such a wind is handed over, not taken
     for hd in (0.0, 45.0, 200.0, 359.0):
-        assert abs(f.boat_speed(0.0, 0.0, hd) - o.deter_dyn(abs(180.0 - hd), 0.0)) < 1e-6
+        assert np.isnan(f.boat_speed(0.0, 0.0, hd))
+    t, la, lo, u, v = synth.wind_fields(0)
+    times, lats, lons = H.sim_axes(la, lo)
+    calm = fastmodel.FastModel(t, la, lo, np.zeros_like(u), np.zeros_like(v), times, lats, lons)
+    n = 8
+    r = calm.step_batch(0, np.full(n, 44.0), np.full(n, 355.0), np.full((1, n), 45.0), nsteps=3, seg_len=3,
+                        z=np.zeros((3, n)))
+    assert r["needs_literal"].all() and (r["k"] == 0).all()
+    got = calm.rollout_batch(2, 4, H.STATE0, DEST, TMIN, prefix=np.array([[0.0], [45.0]]), prefix_len=np.ones(2, np.int32),
+                             z=np.zeros((13, 8)))
+    assert (got["uncertain"] != 0).all()
 
 
 def test_move_and_bearing_building_blocks():

@@ -416,6 +416,61 @@ def test_fast_mode_hands_over_what_it_does_not_cover(eng):
     eng.set_precision(N.PREC_F64)
 
 
+def test_calm_wind_is_left_to_the_literal_kernel(eng):
+    """A wind of exactly zero has no direction: the reference goes by atan2(0, 0) = 0 (weatherTLKT.py:161-162), the
+    mixed-precision kernels give it none -- their speed is then not a number and the step's length test hands the
+    rollout / boat to the fp64 kernel.  A band of dead calm across the route (exact zeros, so the interpolated wind is
+    exactly zero inside it): K2 and K1 in the mixed-precision mode decide and move like the oracle."""
+    from oracle import cport
+    t, la, lo, u, v = synth.wind_fields(3)
+    u, v = u.copy(), v.copy()
+    band = (la >= 44.9) & (la <= 46.1)
+    u[:, band, :] = 0.0
+    v[:, band, :] = 0.0
+    times, lats, lons = H.sim_axes(la, lo)
+    eng.upload_scenario(7, t, la, lo, u, v, times, [lats[0], lats[-1], lons[0], lons[-1]])
+    o = cport.OracleSim(t, la, lo, u, v, times, lats, lons, sigma_coeff=0.2)
+    dest, tmin = [46.77751005, 355.0], 2.0223605
+    n_leaf, rep = 16, 64
+    n = n_leaf * rep
+    rng = np.random.default_rng(5)
+    prefix = 45.0 * rng.integers(0, 8, (n_leaf, 2))
+    plen = rng.integers(1, 3, n_leaf).astype(np.int32)
+    z = rng.standard_normal((13, n))
+    want = o.rollout_batch(n, H.STATE0, dest, tmin, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep), z=z,
+                           nthreads=8)
+    bins = np.zeros((n_leaf, 12), np.uint32)
+    np.add.at(bins, (np.repeat(np.arange(n_leaf), rep), want["bin"]), 1)
+    eng.set_precision(N.PREC_FAST)
+    try:
+        full = eng.rollout_batch_host(7, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen, z=z)
+        redo = eng.last_redo_count()
+        lean = eng.rollout_batch_host(7, n_leaf, rep, H.STATE0, dest, tmin, prefix=prefix, prefix_len=plen, z=z,
+                                      want=("leaf_bins", "stats"))
+        assert eng.last_kernel_variant() == N.VARIANT_TURBO
+        assert redo > 50                                   # (139 of the 1024 reach the band: the wind dies down towards it)
+        for key in ("steps", "status", "bin"):
+            assert np.array_equal(full[key], want[key]), key
+        assert relerr(full["final_lat"], want["final_lat"]) < RTOL and relerr(full["final_lon"], want["final_lon"]) < RTOL
+        assert np.array_equal(full["leaf_bins"], bins) and np.array_equal(lean["leaf_bins"], bins)
+        assert lean["stats"][4] == want["steps"].sum()
+        # K1: boats started inside the band and south of it, raw steps
+        nb, nsteps = 256, 8
+        lat0 = np.where(np.arange(nb) % 2 == 0, 45.5, 44.2) + 1e-3 * np.arange(nb)
+        lon0 = np.full(nb, 355.0) + 2e-3 * np.arange(nb)
+        head = np.tile(45.0 * (np.arange(nb) % 8), (1, 1)).astype(np.float64)
+        zz = rng.standard_normal((nsteps, nb))
+        ref = o.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=nsteps, z=zz)
+        k = np.zeros(nb, np.int32)
+        lat, lon = lat0.copy(), lon0.copy()
+        st = np.zeros(nb, np.uint8)
+        eng.step_batch(7, k, lat, lon, head, nsteps=nsteps, seg_len=nsteps, status=st, z=zz)
+        assert np.array_equal(k, ref["k"]) and np.array_equal(st, ref["status"])
+        assert relerr(lat, ref["lat"]) < RTOL and relerr(lon, ref["lon"]) < RTOL
+    finally:
+        eng.set_precision(N.PREC_F64)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_rollout_forest_equals_per_scenario_launches(eng, mode):
     """One launch over several scenarios (pmcts_rollout_forest) == one pmcts_rollout_batch per scenario, with
