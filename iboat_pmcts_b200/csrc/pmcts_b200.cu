@@ -414,7 +414,7 @@ rollout_batch_kernel(ScenarioView sc0, BoatParams bp, NoiseView nz0, RolloutArgs
 // decisions fell inside the error margins writes nothing: its id goes to a.redo_list and the literal
 // kernel above finishes it (same stream, next launch).  kNoise fixes the noise source at compile time;
 // kLean is the throughput form: per-leaf histograms and statistics only, no per-rollout outputs.
-template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
+template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false, bool kFirstOnly = false>
 // (turbo: a cap of 73 registers lets ptxas keep the pinned constants below; it uses 64, so 8 blocks per SM stay resident)
 __global__ void __launch_bounds__(kBlock, kLean ? (kTurbo ? 7 : 8) : 6)  // lean: 64 registers, 8 blocks per SM
 rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a, ForestSlabs fs) {
@@ -443,7 +443,7 @@ rollout_fast_kernel(ScenarioView sc, BoatParams bp, NoiseView nz, RolloutArgs a,
 #undef PIN_F
     }
     if (live) {
-        fast::rollout_one<kNoise, kLean, kDefBoat, kTurbo>(sc, bp, nz, a, n, r, leaf, o);
+        fast::rollout_one<kNoise, kLean, kDefBoat, kTurbo, kFirstOnly>(sc, bp, nz, a, n, r, leaf, o);
         if (o.why) {
             a.redo_list[atomicAdd(a.redo_count, 1u)] = ((uint32_t)scen << kRedoShift) | (uint32_t)r;
         } else {
@@ -1937,6 +1937,7 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             // turbo: tree mode from a root that can start a step, on a scenario whose terminal box implies every
             // range check of the loop (fast::turbo_ok)
             const bool turbo = defboat && fast::turbo_ok(vw, a);
+            const bool first_only = !(flags & PMCTS_ROLL_REPLAY_FULL_PREFIX);
             ctx->last_variant = !lean ? PMCTS_VARIANT_FULL_OUTPUT : turbo ? PMCTS_VARIANT_TURBO
                                 : defboat ? PMCTS_VARIANT_DEFAULT_BOAT : PMCTS_VARIANT_GENERIC;
             // turbo launches run two rollouts per thread on the packed FP32 pipe (PMCTS_OPT_PACKED_FP32, default on)
@@ -1954,7 +1955,11 @@ static int rollout_impl(pmcts_ctx *ctx, int n_scen, const int32_t *scens, int pr
             else if (packed) PMCTS_LAUNCH_PAIR(PMCTS_NOISE_NONE);
             else
 #undef PMCTS_LAUNCH_PAIR
-            if (lean && turbo && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true);
+            // (turbo, only the first action replayed -- the reference's behaviour: the loop without the prefix test)
+            if (lean && turbo && first_only && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true, true);
+            else if (lean && turbo && first_only && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true, true, true);
+            else if (lean && turbo && first_only) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true, true, true);
+            else if (lean && turbo && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true, true);
             else if (lean && turbo && nz.mode == PMCTS_NOISE_INJECTED) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_INJECTED, true, true, true);
             else if (lean && turbo) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_NONE, true, true, true);
             else if (lean && defboat && nz.mode == PMCTS_NOISE_PHILOX) PMCTS_LAUNCH_ROLL(PMCTS_NOISE_PHILOX, true, true);

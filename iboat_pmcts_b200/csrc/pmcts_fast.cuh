@@ -719,7 +719,10 @@ inline bool turbo_ok(const ScenarioView &sc, const RolloutArgs &a) {
 // kRefreshTrig of them, and a root that can start a step -- every state the loop steps from has passed the
 // terminal test (or is the root), so the step's range checks, the bounds test of the grid position, the load
 // of the step length and the sin / cos refresh are compiled out.
-template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false>
+// kFirstOnly (with kTurbo; the host passes it when PMCTS_ROLL_REPLAY_FULL_PREFIX is not set): at most the FIRST step has
+// a fixed heading -- the reference's own behaviour, quirk Q1 -- so inside the loop the next heading is always the
+// bearing to the destination and the loop carries no test of the step number.
+template <int kNoise, bool kLean, bool kDefBoat = false, bool kTurbo = false, bool kFirstOnly = false>
 PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const NoiseView &nz, const RolloutArgs &a,
                           int64_t n, int64_t r, int64_t leaf, RollOut &o) {
     // kTurbo: the position lives in radians inside the loop -- nothing but the histogram leaves a turbo launch, and
@@ -760,17 +763,21 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
         int trig_left = kRefreshTrig;
         // (not unrolled: two or four steps per pass spare the hand-over moves and the Philox block test, but measured
         //  slower -- 0.947-0.955 ms against 0.903 -- at 64 as at 72 registers)
-        for (;;) {
-            float sh, ch;
-            if (o.nstep < n_fixed) {
-                if (!heading_unit(fixed_heading, sh, ch)) {
-                    o.why |= kWhyStep;
-                    break;
-                }
+        // The heading of the step about to be taken (step o.nstep): a fixed one while the prefix lasts, the bearing to
+        // the destination afterwards.  It is worked out at the END of the step before -- next to the destination's
+        // relative position it starts from -- so that the loop's head has no branch on the step number.
+        float sh = 0.0f, ch = 1.0f;
+        auto heading = [&](bool first) -> bool {
+            if ((!kFirstOnly || first) && o.nstep < n_fixed) {
+                if (!heading_unit(fixed_heading, sh, ch)) return false;
                 if (o.nstep + 1 < n_fixed) fixed_heading = pre[o.nstep + 1];
             } else {
                 bearing_unit(rd, sA, sD, cD, sh, ch);
             }
+            return true;
+        };
+        if (!heading(true)) o.why |= kWhyStep;
+        else for (;;) {
             const float z = ns.draw<kNoise>(nz, n, r, o.nstep);
             Move m;
             o.st = fast_step<false, kDefBoat, kTurbo, kTurbo, kRad>(sc, bp, k, lat, lon, g, sh, ch, sA, cA, z, m);
@@ -800,6 +807,10 @@ PMCTS_HD void rollout_one(const ScenarioView &sc, const BoatParams &bp, const No
             sA = sB;
             cA = cB;
             rd = dest_rel<kRad>(lat, lon, dest_lat, dest_lon);
+            if (!heading(false)) {
+                o.why |= kWhyStep;
+                break;
+            }
         }
     }
     o.ta = NAN;

@@ -136,7 +136,9 @@ void fm_rollout_batch(void *h, int64_t n_leaf, int replicas, const double root[3
     for (int64_t r = 0; r < n; ++r) {
         fast::RollOut o;
         // the same variant selection as rollout_impl (pmcts_b200.cu)
-        if (turbo) fast::rollout_one<-1, false, true, true>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
+        if (turbo && !(flags & PMCTS_ROLL_REPLAY_FULL_PREFIX))
+            fast::rollout_one<-1, false, true, true, true>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
+        else if (turbo) fast::rollout_one<-1, false, true, true>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
         else if (defboat) fast::rollout_one<-1, false, true, false>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
         else fast::rollout_one<-1, false>(m->sc, m->bp, nz, a, n, r, r / replicas, o);
         if (reward) reward[r] = o.rw;
