@@ -1010,7 +1010,7 @@ def setup_c4(eng, torch, dist, dev, rank, world):
                               e2e_note=("every rank times its own host-array calls (no L2 flush); max time over ranks, transitions summed"
                                         if world == 1 else
                                         "exchange and back-up included; host-timed, max over ranks, transitions summed"),
-                              traffic=1797120,  # profiles/r02_k2_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
+                              traffic=1794560,  # profiles/r02_k2_final_full.txt: dram read + write of rollout_fast_kernel<1,1,1,1>
                               traffic_source="profiles/r02_k2_final_full.txt",
                               hbm_bytes_per_launch=N_LEAF * (4 * 8 + 4) + S_local * N_LEAF * 48))
 
