@@ -1176,6 +1176,7 @@ namespace pmcts {
 void set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
 void count_launches(pmcts_ctx *ctx, int n) { ctx->launches += n; }
 bool ctx_timing(const pmcts_ctx *ctx) { return ctx->timing; }
+std::unique_lock<std::recursive_mutex> ctx_lock(pmcts_ctx *ctx) { return std::unique_lock<std::recursive_mutex>(ctx->mu); }
 void **ctx_attachment(pmcts_ctx *ctx, void (*free_fn)(void *), int key) {
     ctx->attachment_free[key] = free_fn;
     return &ctx->attachment[key];

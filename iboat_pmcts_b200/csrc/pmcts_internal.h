@@ -1,6 +1,7 @@
 // pmcts_b200 -- what the translation units of the library share beyond the public C ABI.
 #pragma once
 #include <functional>
+#include <mutex>
 
 #include "../../include/pmcts_b200.h"
 
@@ -19,6 +20,10 @@ void count_launches(pmcts_ctx *ctx, int n);
 // is per-launch timing on (pmcts_enable_timing)?  Its event pairs bracket single launches, so nothing is replayed
 // from a recorded graph while it is.
 bool ctx_timing(const pmcts_ctx *ctx);
+
+// the lock every entry point of a ctx takes (recursive): held by a translation unit across a SEQUENCE of calls that
+// must not interleave with another host thread's -- a stream capture, whose graph would otherwise record them too
+std::unique_lock<std::recursive_mutex> ctx_lock(pmcts_ctx *ctx);
 
 // size of the blocks a peer exchange was created for (pmcts_peer.cu)
 size_t peer_block_bytes(const pmcts_peer *peer);

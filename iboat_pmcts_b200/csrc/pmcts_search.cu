@@ -660,6 +660,8 @@ extern "C" int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, i
             want_graph = false;
             const int64_t l0 = pmcts_launch_count(ctx);
             int rc = PMCTS_OK;
+            // (no other host thread's call on this ctx may land between the two ends of the recording)
+            const std::unique_lock<std::recursive_mutex> recording = pmcts::ctx_lock(ctx);
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
                 rc = enqueue();
                 cudaGraph_t g = nullptr;
