@@ -148,3 +148,39 @@ def test_native_generators_are_the_interpreters():
         assert np.array_equal(got, np.array([np.random.randint(8) for _ in range(count)], np.uint8))
         back, now = ns.to_numpy(like), np.random.get_state()
         assert np.array_equal(back[1], now[1]) and back[2] == now[2]
+
+
+def _master_digest(master):
+    import hashlib
+    h = hashlib.sha256()
+    for k in master:
+        h.update(str(k).encode())
+        h.update(np.ascontiguousarray(master[k]._table).tobytes())
+    return h.hexdigest()
+
+
+def test_search_does_not_depend_on_the_host_threads():
+    """The host runtime's pool (pmcts_forest_host.cpp: tasks claimed from one counter, workers that poll before they
+    sleep) only decides WHO walks a tree or files a scenario's block: one thread, three threads that sleep at once and
+    the default pool return the same master, search after search, with one and with two waves in flight."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import fake_device as fd, test_host_forest as t\n"
+            "for rep in range(2):\n"
+            "    for pipe in (1, 2):\n"
+            "        f, m, _ = fd.run('native', n_scen=10, budget=65, leaves=32, replicas=4, seed=6, pipeline=pipe)\n"
+            "        print(pipe, t._master_digest(m))\n") % (os.path.dirname(here), here)
+    outs = []
+    for env_extra in ({}, {"PMCTS_HOST_THREADS": "1"}, {"PMCTS_HOST_THREADS": "3", "PMCTS_POOL_SPIN_US": "0"},
+                      {"PMCTS_HOST_THREADS": "12", "PMCTS_POOL_SPIN_US": "400"}):
+        env = dict(os.environ, **env_extra)
+        res = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                             text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(res.stdout.split())
+    assert len(outs[0]) == 8 and len(set(outs[0][1::4])) == 1 and len(set(outs[0][3::4])) == 1
+    for other in outs[1:]:
+        assert other == outs[0]
