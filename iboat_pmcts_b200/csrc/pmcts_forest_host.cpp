@@ -458,7 +458,11 @@ struct pmcts_forest {
 
     double master_uct(int32_t m) {
         if (m < 0) return 0.0;
-        if (__atomic_load_n(&master.stamp[m], __ATOMIC_ACQUIRE) == wave) return master.memo[m];
+        if (__atomic_load_n(&master.stamp[m], __ATOMIC_ACQUIRE) == wave) {
+            double memo;
+            __atomic_load(&master.memo[m], &memo, __ATOMIC_RELAXED);
+            return memo;
+        }
         const int32_t p = master.parent[m];
         double acc = 0.0;
         bool any = false;
@@ -475,7 +479,9 @@ struct pmcts_forest {
             }
         }
         const double value = any ? acc : 0.0;
-        master.memo[m] = value;  // (threads that race here store the same value)
+        // (trees that meet at a node nobody has valued this wave race here: they store the same value, as atomic
+        //  accesses, and whoever reads the stamp afterwards finds it)
+        __atomic_store(&master.memo[m], &value, __ATOMIC_RELAXED);
         __atomic_store_n(&master.stamp[m], wave, __ATOMIC_RELEASE);
         return value;
     }
