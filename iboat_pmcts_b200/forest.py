@@ -1,5 +1,5 @@
 """Drop-in mirror of ``code/solver/forest.py`` (reference): ``Forest``, ``create_simulators`` and
-``initialize_simulators``.  (Scenario download / pickle loading / plotting are out of scope.)
+``load_scenarios``, ``initialize_simulators``.  (Scenario download and plotting are out of scope.)
 
 The reference runs one ``multiprocessing.Process`` per scenario around a ``Manager().dict()``
 (forest.py:45-81).  Here the scenarios of this process are rolled out together on its GPU
@@ -542,6 +542,22 @@ def _all_gather_blocks(block, dist, group, world):
 
 
 # ----------------------------------------------------------------------------------------------------
+def load_scenarios(mydate, scenario_ids=range(0, 21), latBound=[-90, 90], lonBound=[0, 360], timeSteps=[0, 64],
+                   directory='../data/'):
+    """The pickled ``Weather`` of every scenario id, cropped (forest.py:118-151): files
+    ``<directory><mydate>_<id, two digits>00z.obj`` as the reference's ``download_scenarios`` names them
+    (id 0 = the ensemble's control run).  ``directory`` is an addition; the default is the reference's fixed path.
+    Files written by the reference unpickle into the mirror ``Weather`` once the module alias of INTEGRATION.md is
+    in place (``Weather.load``)."""
+    from .weatherTLKT import Weather
+    weather_scen = []
+    for ii in scenario_ids:
+        path = '%s%s_%02d00z.obj' % (directory, mydate, ii)
+        weather_scen.append(Weather.load(path, latBound, lonBound, timeSteps))
+        print("Loaded : " + path)
+    return weather_scen
+
+
 def create_simulators(weathers, numberofsim, simtimestep=6, stateinit=(0, 47.5, -3.5 + 360),
                       ndaysim=8, deltalatlon=0.5):
     """One ``Simulator`` per weather scenario (forest.py:154-187).  Shifts each ``weather.time`` to start

@@ -8,6 +8,7 @@ node, every scenario and the probability-weighted global tree -- the two utility
 the best child, and the greedy policies.  The methods of the reference's API read those arrays; node objects
 are only built for what the caller looks at (the nodes along the best policies).
 """
+import math
 import pickle
 
 import numpy as np
@@ -148,6 +149,26 @@ class MasterTree:
                 if g == g:
                     node.guessed_rewards[s] = float(g)
         return float(sol["value"][i, col]), float(sol["explore"][i, col])
+
+    def get_points(self, node, points, probability, coordinate=(0, 0), idscenario=-1, objective="depth"):
+        """Segments of the tree below ``node`` for the reference's tree plots (master.py:187-220), parents before
+        children, children in their order: ``(x0, y0, x, y, depth)`` or, for ``objective="uct"``,
+        ``(x0, y0, x, y, utility, exploitation, exploration)``; a step of unit length in the direction of each arm.
+        Subtrees a scenario never expanded are left out.  (The plots themselves are out of scope.)"""
+        stack = [(child, coordinate[0], coordinate[1]) for child in reversed(node.children)]
+        while stack:  # depth first, children in their order: a child's segment, its whole subtree, then its sibling
+            child, x0, y0 = stack.pop()
+            if idscenario != -1 and not child.is_expanded(idscenario):
+                continue
+            x = x0 + math.sin(child.arm * math.pi / 180)
+            y = y0 + math.cos(child.arm * math.pi / 180)
+            if objective == "uct":
+                value, exploration = self.get_utility(child, idscenario)
+                points.append((x0, y0, x, y, value + exploration, value, exploration))
+            elif objective == "depth":
+                points.append((x0, y0, x, y, child.depth))
+            stack.extend((grandchild, x, y) for grandchild in reversed(child.children))
+        return points
 
     def get_depth(self):
         if isinstance(self.nodes, MasterDict) and self.nodes.arrays() is not None:

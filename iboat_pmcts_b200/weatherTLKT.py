@@ -1,7 +1,8 @@
 """Drop-in mirror of ``code/model/weatherTLKT.py`` (reference) for the rollout path.
 
 ``Weather`` keeps the reference's attributes (``lat, lon, time, u, v``) and methods on the path:
-``Interpolators`` (weatherTLKT.py:369-378), ``returnPolarVel`` (:148-163), ``crop`` (:165-218), ``load`` (:51-78).  The two
+``Interpolators`` (weatherTLKT.py:369-378), ``returnPolarVel`` (:148-163), ``getPolarVel`` (:135-146), ``crop``
+(:165-218), ``load`` (:51-78).  The two
 interpolators are callables with SciPy's ``RegularGridInterpolator`` call convention, evaluated on the GPU
 by ``pmcts_interp_wind`` (same evaluation order as SciPy, bit for bit).  Download and plotting methods of
 the reference are out of scope.
@@ -101,6 +102,15 @@ class Weather:
         self._wslot = None
         self.uInterpolator = _GridInterpolator(self, 0)
         self.vInterpolator = _GridInterpolator(self, 1)
+
+    def getPolarVel(self):
+        """Adds ``wMag`` / ``wAng``: magnitude and direction (degrees, where the wind blows to) of the whole field
+        (weatherTLKT.py:135-146).  Element by element the reference's expressions -- ``math.atan2`` rather than NumPy's
+        vector form, whose last digit may differ."""
+        u, v = np.ma.getdata(self.u), np.ma.getdata(self.v)
+        self.wMag = np.array((u ** 2 + v ** 2) ** 0.5, dtype=np.float64)  # (in the fields' own precision, as there)
+        atan2 = np.frompyfunc(math.atan2, 2, 1)
+        self.wAng = np.mod(180 / math.pi * atan2(u.astype(np.float64), v.astype(np.float64)).astype(np.float64), 360.0)
 
     @staticmethod
     def returnPolarVel(u, v):
