@@ -184,3 +184,29 @@ def test_search_does_not_depend_on_the_host_threads():
     assert len(outs[0]) == 8 and len(set(outs[0][1::4])) == 1 and len(set(outs[0][3::4])) == 1
     for other in outs[1:]:
         assert other == outs[0]
+
+
+@pytest.mark.parametrize("n_scen,budget,leaves,replicas,seed", [
+    (1, 40, 64, 8, 1),       # one tree, the wave larger than the budget: a single short wave
+    (2, 9, 1, 3, 2),         # one leaf per wave: the sequential order, wave by wave
+    (5, 77, 10, 300, 3),     # counts above 255: the 16-bit update block; a ragged last wave
+    (4, 128, 32, 255, 4),    # the largest count one byte holds
+    (12, 33, 11, 2, 5),      # more trees than a typical pool has threads
+])
+def test_native_forest_equals_python_forest_over_shapes(n_scen, budget, leaves, replicas, seed):
+    """The equality of the first test over the corner shapes of a search: same master (keys, order, counters), same
+    worker trees node by node, same launches."""
+    fp, mp, calls_p = run("python", n_scen=n_scen, budget=budget, leaves=leaves, replicas=replicas, seed=seed)
+    fn, mn_, calls_n = run("native", n_scen=n_scen, budget=budget, leaves=leaves, replicas=replicas, seed=seed)
+    assert calls_p == calls_n and len(calls_n) == -(-budget // leaves)
+    assert list(mp) == list(mn_)
+    for k in mp:
+        assert np.array_equal(mp[k]._table, mn_[k]._table), k
+    for i in range(n_scen):
+        tp, tn = fp.workers[i], fn.workers[i]
+        assert len(tp.Nodes) == len(tn.Nodes) == budget + 1
+        for a, b in zip(tp.Nodes, tn.Nodes):
+            assert [int(x) for x in a.origins] == [int(x) for x in b.origins]
+            assert np.array_equal(a._table, b._table)
+        assert int(tn.rootNode.visits()) == budget * replicas
+    assert int(mn_[ft.ROOT_HASH]._table.sum()) == n_scen * budget * replicas
