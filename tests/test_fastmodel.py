@@ -103,7 +103,7 @@ def test_raw_steps_golden_and_seeded():
     assert not r["needs_literal"][2:].any()
 
 
-@pytest.mark.parametrize("scen,flags", [(4, 0), (0, 0), (7, 2)])
+@pytest.mark.parametrize("scen,flags", [(4, 0), (0, 0), (7, 2), (37, 0), (63, 2)])  # (63: the last scenario of config 4)
 def test_rollout_decisions_outside_margins_agree(scen, flags):
     """Every rollout the fp32 path decides itself takes the decisions of the oracle (steps, status,
     histogram bin), its trajectory stays within 2e-7 relative, and few rollouts are left undecided."""
