@@ -9,6 +9,10 @@ count must be zero for the histograms of the search to be the oracle's.  One JSO
 
     python scripts/fastmodel_sweep.py [--scenarios 64] [--leaves 512] [--replicas 256] > profiles/r02_fastmodel_sweep.jsonl
 
+``--k1 BOATS`` does the same for BASELINE config 3 (raw doStep: bench.py's fleet of BOATS boats walking octagons for 500
+steps of 864 s on scenario 0), in chunks of 10^5 boats: boats handed to the literal kernel, status / step count equal to
+the oracle's, worst final position.
+
 TEST INFRASTRUCTURE (loads oracle/ and tests/fastmodel); nothing of the product runs here.
 """
 import argparse
@@ -30,13 +34,49 @@ from iboat_pmcts_b200 import synth  # noqa: E402
 STATE0, DEST, TMIN = (0, 44.0, 355.0), [46.77751005, 355.0], 2.022360548788055  # bench.py
 
 
+def k1(boats, seed):
+    t, la, lo, u, v = synth.wind_fields(0)
+    times = np.linspace(0, 5, 501)
+    f = fastmodel.FastModel(t, la, lo, u, v, times, la, lo)
+    from oracle import cport
+    o = cport.OracleSim(t, la, lo, u, v, times, la, lo)
+    lat0, lon0, h0 = synth.octagon_fleet(boats, seed=7)
+    head = synth.octagon_headings(h0, 500)
+    tot = dict(boats=0, handed_over=0, status_or_steps_differ=0, transitions=0, worst_position_rel=0.0)
+    t0 = time.time()
+    for c0 in range(0, boats, 100000):
+        c1 = min(boats, c0 + 100000)
+        z = np.random.default_rng(seed + c0).standard_normal((500, c1 - c0))
+        hd = np.ascontiguousarray(head[:, c0:c1])
+        got = f.step_batch(0, lat0[c0:c1], lon0[c0:c1], hd, nsteps=500, seg_len=25, z=z)
+        want = o.step_batch(0, lat0[c0:c1], lon0[c0:c1], hd, nsteps=500, seg_len=25, z=z, nthreads=os.cpu_count() or 8)
+        mine = got["needs_literal"] == 0
+        differ = mine & ((got["status"] != want["status"]) | (got["k"] != want["k"]))
+        ok = mine & (want["status"] == 0)
+        rel = max(float(np.max(np.abs(got[k][ok] - want[k][ok]) / np.abs(want[k][ok]))) for k in ("lat", "lon"))
+        line = dict(chunk=[c0, c1], boats=c1 - c0, handed_over=int((~mine).sum()), status_or_steps_differ=int(differ.sum()),
+                    transitions=int(want["k"].sum()), worst_position_rel=rel)
+        for k in ("boats", "handed_over", "status_or_steps_differ", "transitions"):
+            tot[k] += line[k]
+        tot["worst_position_rel"] = max(tot["worst_position_rel"], rel)
+        print(json.dumps(line), flush=True)
+    tot.update(seconds=round(time.time() - t0, 1),
+               note="config 3 on the host build of csrc/pmcts_fast.cuh (K1 arithmetic) against oracle/pmcts_oracle.c, "
+                    "injected normals; positions after 500 fused steps")
+    print(json.dumps(dict(total=tot)), flush=True)
+    return 0 if tot["status_or_steps_differ"] == 0 else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--k1", type=int, default=0)
     ap.add_argument("--scenarios", type=int, default=64)
     ap.add_argument("--leaves", type=int, default=512)
     ap.add_argument("--replicas", type=int, default=256)
     ap.add_argument("--seed", type=int, default=2026)
     a = ap.parse_args()
+    if a.k1:
+        return k1(a.k1, a.seed)
     n_leaf, rep = a.leaves, a.replicas
     n = n_leaf * rep
     tot = dict(rollouts=0, undecided=0, differently=0, transitions=0, arrived=0)
