@@ -637,6 +637,14 @@ int forest_sequential(pmcts_forest *f, int local_index, int64_t budget, int freq
 
 ForestInfo forest_info(const pmcts_forest *f) { return ForestInfo{f->n_scen, f->n_local, f->max_depth}; }
 int forest_local_id(const pmcts_forest *f, int local_index) { return f->trees[local_index].scen; }
+void forest_abandon_pending(pmcts_forest *f) {
+    for (Tree &t : f->trees) {
+        for (const std::vector<int32_t> &wave_leaves : t.waves)
+            for (int32_t leaf : wave_leaves)
+                for (int32_t x = leaf; x >= 0; x = t.parent[x]) t.pending[x] -= 1;
+        t.waves.clear();
+    }
+}
 }  // namespace pmcts
 
 extern "C" {

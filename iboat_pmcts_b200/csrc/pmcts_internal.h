@@ -34,6 +34,10 @@ struct ForestInfo {
 };
 ForestInfo forest_info(const pmcts_forest *f);
 int forest_local_id(const pmcts_forest *f, int local_index);
+// A search that fails between a selection and its back-up leaves waves selected and not filed: their leaves' virtual
+// visits are taken back and the waves dropped, so that the forest can be searched again (the nodes they expanded stay:
+// unvisited leaves, which the next selection treats like any other child without statistics of its own).
+void forest_abandon_pending(pmcts_forest *f);
 
 // Tree.uct_search for one worker tree (pmcts_forest_host.cpp); `rollout(scenario, path, len, z, &bin, &steps)` runs the
 // default policy of a leaf with the normals z[0 .. n_instants) and returns 0 or a negative PMCTS_ERR_* / the positive

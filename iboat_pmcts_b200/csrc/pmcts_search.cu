@@ -534,6 +534,7 @@ struct Driver {
             Wave &w = ring[(index + k) % depth];
             if (w.index >= 0) rc = complete(w);
         }
+        if (rc) pmcts::forest_abandon_pending(f);  // waves selected and never filed: the forest stays searchable
         if (device) {
             if (depth > 1) pmcts_set_stream(ctx, main);
             if (rc) {

@@ -210,3 +210,65 @@ def test_native_forest_equals_python_forest_over_shapes(n_scen, budget, leaves, 
             assert np.array_equal(a._table, b._table)
         assert int(tn.rootNode.visits()) == budget * replicas
     assert int(mn_[ft.ROOT_HASH]._table.sum()) == n_scen * budget * replicas
+
+
+def test_forest_stays_searchable_after_a_failed_search():
+    """A search that fails between a selection and its back-up (here: the rollout stand-in refuses the third wave, with
+    one and with two waves in flight) takes back the virtual visits of the waves it had selected and drops them: the
+    same forest handle is searched again, files every rollout of the completed waves exactly once, and has no
+    selection left waiting for a back-up."""
+    import ctypes as C
+    lib = N.lib()
+    S, B, K, D = 3, 8, 5, 12
+    for pipeline in (1, 2):
+        h = C.c_void_p()
+        ids = np.arange(S, dtype=np.int32)
+        prob = np.full(S, 1.0 / S)
+        max_nodes = 200
+        perms = np.empty((S, max_nodes, 8), np.uint8)
+        seeds = np.arange(1, S + 1, dtype=np.uint64)
+        N.check_forest(lib.pmcts_python_shuffles_batch(seeds.ctypes.data, S, max_nodes, 8, perms.ctypes.data))
+        N.check_forest(lib.pmcts_forest_create(S, S, ids.ctypes.data, D, prob.ctypes.data, 0.1, 0.3, perms.ctypes.data,
+                                               max_nodes, C.byref(h)))
+        try:
+            state = dict(fail_at=2, waves=0)
+
+            def hook(_user, wave, n_local, _ids, b, stride, plen_p, path_p, bins_p):
+                if wave == state["fail_at"]:
+                    return 7
+                bins = np.ctypeslib.as_array(C.cast(bins_p, C.POINTER(C.c_uint32)), shape=(n_local * b, 12))
+                bins[:] = 0
+                bins[:, 3 + wave % 4] = K
+                state["waves"] += 1
+                return 0
+
+            cb = N.ROLLOUT_HOOK_FN(hook)
+            slots = np.zeros(S * 10 * B, np.int8)
+
+            def search(budget):
+                p = N.SearchParams()
+                p.n_leaves, p.replicas, p.budget, p.seed, p.pipeline, p.world, p.rank = B, K, budget, 1, pipeline, 1, 0
+                p.slots_w, p.slots_m, p.rollout_hook = slots.ctypes.data, slots.ctypes.data, cb
+                rep = N.SearchReport()
+                root, dest = np.array([0, 44.0, 355.0]), np.array([46.7, 355.0])
+                return lib.pmcts_forest_search(None, h, None, root.ctypes.data, dest.ctypes.data, 2.0, C.byref(p),
+                                               C.byref(rep)), rep.as_dict()
+
+            rc, rep = search(5 * B)
+            assert rc != 0 and "rollout_hook returned 7" in lib.pmcts_last_error().decode()
+            filed = rep["waves"]
+            assert filed == (2 if pipeline == 1 else 1)   # (two in flight: wave 1 was out when wave 2 was refused)
+            state["fail_at"] = -1
+            rc, rep2 = search(4 * B)
+            assert rc == 0 and rep2["waves"] == 4
+            # every completed wave is in the trees and in the master exactly once; nothing waits for a back-up
+            for i in range(S):
+                n = int(lib.pmcts_forest_tree_size(h, i))
+                table = np.empty((n, 8, 12), np.int64)
+                N.check_forest(lib.pmcts_forest_export_tree(h, i, None, None, table.ctypes.data, None, None))
+                assert int(table[0].sum()) == (filed + 4) * B * K
+            leaf_bins, sl = np.zeros((S * B, 12), np.uint32), np.zeros(S * B, np.int8)
+            assert lib.pmcts_forest_backup(h, B, leaf_bins.ctypes.data, sl.ctypes.data) != 0
+            assert "oldest selection" in lib.pmcts_forest_last_error().decode()
+        finally:
+            lib.pmcts_forest_destroy(h)
