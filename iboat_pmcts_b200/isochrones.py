@@ -9,7 +9,8 @@ from . import _native as N
 from .forest import _raise_unless, _reference_noise
 
 
-def estimate_perfomance_plan(sims, ntra, stateinit, destination, plan=list(), plot=False, verbose=True, seed=None):
+def estimate_perfomance_plan(sims, ntra, stateinit, destination, plan=list(), plot=False, verbose=True, seed=None,
+                             group=None):
     """Mean and variance of the arrival time when every boat first applies the headings of ``plan`` (no
     arrival / terminal test in between) and then sails straight to ``destination``; ``ntra`` noisy runs per
     scenario.  A run that misses the destination counts ``times[-1]``.
@@ -20,13 +21,22 @@ def estimate_perfomance_plan(sims, ntra, stateinit, destination, plan=list(), pl
     ``seed=None``: noise from ``random.gauss`` in the reference's order (one launch per run), so seeded
     scripts reproduce the reference.  ``seed=int``: Philox noise, ONE launch per scenario (K4: the plan-
     evaluation mode of the rollout kernel with its fused sum / sum-of-squares reduction).
+
+    ``group`` (with ``seed``): a ``torch.distributed`` process group whose ranks each hold a share of the scenarios, in
+    rank order (the sharding of ``Forest.launch_search``).  Every rank evaluates its own ``sims``; the per-scenario
+    ``(runs, sum t, sum t^2)`` are all-gathered -- 64 bytes per scenario, the one exchange of this path -- and every
+    rank returns the result over ALL scenarios, which is what one process holding them all returns (the noise stream
+    of a scenario is numbered by its global index).
     """
     if plot:
         raise NotImplementedError("plotting is outside the scope of pmcts_b200")
     k0, lat0, lon0 = int(stateinit[0]), float(stateinit[1]), float(stateinit[2])
     plan = [float(a) for a in plan]
     if seed is not None:
-        return _plan_eval_fused(sims, int(ntra), [k0, lat0, lon0], destination, plan, int(seed), verbose)
+        return _plan_eval_fused(sims, int(ntra), [k0, lat0, lon0], destination, plan, int(seed), verbose, group)
+    if group is not None:
+        raise ValueError("estimate_perfomance_plan: a process group needs seed=int (the reference's own noise order "
+                         "is one generator walked scenario after scenario: it does not shard)")
     mean_arrival_times, var_arrival_times, all_arrival_times = [], [], []
     for si, sim in enumerate(sims):
         eng, scen = sim.scenario()
@@ -65,7 +75,7 @@ def estimate_perfomance_plan(sims, ntra, stateinit, destination, plan=list(), pl
     return [global_mean_time] + mean_arrival_times, [variance_globale] + var_arrival_times
 
 
-def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose):
+def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose, group=None):
     """K4: every scenario's ``ntra`` runs in one launch per group of scenarios, with the count / sum /
     sum of squares of the arrival times reduced in the kernel (no per-run output leaves the GPU)."""
     eng = None
@@ -76,6 +86,11 @@ def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose):
     prefix = np.array(plan, np.float64) if plan else None
     plen = np.array([len(plan)], np.int32) if plan else None
     S = len(sims)
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first = rank * S  # global index of this rank's first scenario: numbers its noise streams
     stats = np.zeros((S, 8))
     prec = eng.precision
     eng.set_precision(N.PREC_FAST)
@@ -85,24 +100,31 @@ def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose):
             try:
                 out = dict(stats=stats[lo:lo + len(chunk)].reshape(-1))
                 eng.rollout_forest(chunk, 1, ntra, root, destination, 0.0, prefix, plen, len(plan), prefix_shared=True,
-                                   seed=seed, stream=lo, out=out, flags=N.ROLL_PLAN_EVAL)
+                                   seed=seed, stream=first + lo, out=out, flags=N.ROLL_PLAN_EVAL)
                 stats[lo:lo + len(chunk)] = out["stats"].reshape(len(chunk), 8)
             except N.PmctsError:  # scenarios with different axes: one launch each
                 for j, scen in enumerate(chunk):
                     out = dict(stats=np.zeros(8))
                     eng.rollout_batch(scen, 1, ntra, root, destination, 0.0, prefix, plen, len(plan), seed=seed,
-                                      stream=lo + j, out=out, flags=N.ROLL_PLAN_EVAL)
+                                      stream=first + lo + j, out=out, flags=N.ROLL_PLAN_EVAL)
                     stats[lo + j] = out["stats"]
     finally:
         eng.set_precision(prec)
-    if (stats[:, 0] != ntra).any():
+    local = stats
+    if world > 1:  # (before anything may raise: every rank takes part in the exchange)
+        stats = _all_gather_stats(local, group, world, getattr(eng, "device", None))
+    if (local[:, 0] != ntra).any():
         # some run ended in an error state (left the weather grid ...): find it and raise what the reference raises
         for si, sim in enumerate(sims):
             e, scen = sim.scenario()
             pre = np.tile(prefix, (ntra, 1)) if prefix is not None else None
-            r = e.rollout_batch_host(scen, ntra, 1, root, destination, 0.0, prefix=pre, seed=seed, stream=si,
+            r = e.rollout_batch_host(scen, ntra, 1, root, destination, 0.0, prefix=pre, seed=seed, stream=first + si,
                                      flags=N.ROLL_PLAN_EVAL, want=("status",))
             _raise_unless(r["status"], (N.ST_ARRIVED, N.ST_HORIZON, N.ST_OUT_OF_BOX))
+    if (stats[:, 0] != ntra).any():
+        raise RuntimeError("estimate_perfomance_plan: runs ended in an error state (scenarios %s%s)"
+                           % (np.flatnonzero(stats[:, 0] != ntra).tolist(), ", other ranks' among them" if world > 1 else ""))
+    S = stats.shape[0]
     estimate_perfomance_plan.last_stats = stats  # per scenario: runs, sum t, sum t^2, arrived, transitions, rollouts
     means = stats[:, 1] / ntra
     variances = np.maximum(stats[:, 2] / ntra - means ** 2, 0.0)
@@ -113,6 +135,18 @@ def _plan_eval_fused(sims, ntra, root, destination, plan, seed, verbose):
             print("arrival time, scenario", nb, "=", means[nb], " variance =", variances[nb])
         print("mean arrival time =", gmean, " global variance =", gvar)
     return [gmean] + means.tolist(), [gvar] + variances.tolist()
+
+
+def _all_gather_stats(stats, group, world, device):
+    """[S_local][8] of every rank -> [world * S_local][8] in rank order (on the device over NCCL, on the host otherwise)."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.from_numpy(np.ascontiguousarray(stats))
+    if dist.get_backend(group) == "nccl":
+        mine = mine.to(torch.device("cuda", device))
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return torch.cat(out).cpu().numpy()
 
 
 # ---- the deterministic isochrone solver (isochrones.py:24-464): a consumer of batched doStep --------------

@@ -156,3 +156,68 @@ def test_native_driver_two_ranks_equal_one_process(pipeline):
         assert report["waves"] == 5 and report["leaves"] == 2 * 70 and report["rollouts"] == 2 * 70 * 24
     root = want[ROOT_HASH][0]
     assert [int(root[s].sum()) for s in range(4)] == [70 * 24] * 4
+
+
+# ---- plan evaluation (estimate_perfomance_plan, seed=int) with the scenarios split over two ranks ----------------
+class _StatsEngine:
+    """Stands in for the engine in the plan evaluation: the fused statistics of a launch are a deterministic function
+    of (scenario slot, noise stream, seed) -- what K4 returns per scenario: runs, sum t, sum t^2, arrived, transitions."""
+    precision = 0
+
+    def set_precision(self, mode):
+        self.precision = mode
+
+    def rollout_forest(self, scens, n_leaf, replicas, root, dest, tmin, prefix, prefix_len, prefix_stride,
+                       prefix_shared=True, z=None, seed=None, stream=0, id0=0, out=None, flags=0):
+        st = out["stats"].reshape(len(scens), 8)
+        for j, slot in enumerate(scens):
+            t = np.random.default_rng([int(seed), int(stream) + j, int(slot)]).uniform(2.0, 3.0, replicas)
+            st[j] = [replicas, t.sum(), (t * t).sum(), replicas - 1, 9 * replicas, replicas, 0, 0]
+
+
+class _StatsSim:
+    times = np.arange(0, 3 + 6 / 24, 6 * (1 / 24))
+
+    def __init__(self, eng, slot):
+        self._eng, self._slot = eng, slot
+
+    def scenario(self):
+        return self._eng, self._slot
+
+
+def _plan_rank_main(rank, world, port, out_dir):
+    from iboat_pmcts_b200.isochrones import estimate_perfomance_plan
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _StatsEngine()
+        sims = [_StatsSim(eng, 100 + s) for s in range(rank * 3, rank * 3 + 3)]  # three scenarios per rank, in rank order
+        res = estimate_perfomance_plan(sims, 40, [0, 44.0, 355.0], [46.7, 355.0], plan=[0, 45], verbose=False, seed=9,
+                                       group=dist.group.WORLD)
+        with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as f:
+            pickle.dump(res, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_plan_evaluation_two_ranks_equal_one_process():
+    """Config 5 sharded like the search: each rank evaluates the plan on its scenarios, the per-scenario (runs, sum t,
+    sum t^2) are all-gathered, and every rank returns the means and variances over all six scenarios that one process
+    holding them all returns -- bit for bit (the noise streams are numbered by global scenario index)."""
+    from iboat_pmcts_b200.isochrones import estimate_perfomance_plan
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_plan_rank_main, args=(world, _free_port(), d), nprocs=world, join=True)
+        got = []
+        for r in range(world):
+            with open(os.path.join(d, "rank%d.pkl" % r), "rb") as f:
+                got.append(pickle.load(f))
+    eng = _StatsEngine()
+    want = estimate_perfomance_plan([_StatsSim(eng, 100 + s) for s in range(6)], 40, [0, 44.0, 355.0], [46.7, 355.0],
+                                    plan=[0, 45], verbose=False, seed=9)
+    assert len(want[0]) == 7 and len(want[1]) == 7
+    assert got[0] == want and got[1] == want
+    with pytest.raises(ValueError):
+        estimate_perfomance_plan([_StatsSim(eng, 100)], 4, [0, 44.0, 355.0], [46.7, 355.0], seed=None, group=object())
