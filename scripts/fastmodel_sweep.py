@@ -74,6 +74,9 @@ def main():
     ap.add_argument("--leaves", type=int, default=512)
     ap.add_argument("--replicas", type=int, default=256)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--philox", action="store_true",
+                    help="noise from Philox counters on both sides (the bench's mode): the model draws its normals with "
+                         "the kernels' fp32 Box-Muller, the oracle with its fp64 one")
     a = ap.parse_args()
     if a.k1:
         return k1(a.k1, a.seed)
@@ -89,11 +92,14 @@ def main():
         rng = np.random.default_rng(a.seed + s)
         prefix = 45.0 * rng.integers(0, 8, (n_leaf, 4))
         plen = rng.integers(1, 5, n_leaf).astype(np.int32)
-        z = rng.standard_normal((times.size, n))
-        got = f.rollout_batch(n_leaf, rep, STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, z=z)
+        if a.philox:
+            noise = dict(seed=a.seed, stream=100 + s)
+        else:
+            noise = dict(z=rng.standard_normal((times.size, n)))
+        got = f.rollout_batch(n_leaf, rep, STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, **noise)
         assert f.last_variant() == 2, "not the turbo variant"
-        want = o.rollout_batch(n, STATE0, DEST, TMIN, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep), z=z,
-                               nthreads=os.cpu_count() or 8)
+        want = o.rollout_batch(n, STATE0, DEST, TMIN, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep),
+                               nthreads=os.cpu_count() or 8, **noise)
         decided = got["uncertain"] == 0
         bad = (got["steps"] != want["steps"]) | (got["status"] != want["status"]) | (got["bin"] != want["bin"])
         rel = max(float(np.max(np.abs(got[k][decided] - want[k][decided]) / np.abs(want[k][decided])))
@@ -105,7 +111,8 @@ def main():
             tot[k] += line[k]
         print(json.dumps(line), flush=True)
     tot.update(scenarios=a.scenarios, undecided_share=tot["undecided"] / tot["rollouts"], seconds=round(time.time() - t0, 1),
-               note="host build of csrc/pmcts_fast.cuh (turbo variant) against oracle/pmcts_oracle.c, injected normals, "
+               noise="philox (fp32 Box-Muller in the model, fp64 in the oracle)" if a.philox else "injected normals",
+               note="host build of csrc/pmcts_fast.cuh (turbo variant) against oracle/pmcts_oracle.c, "
                     "root / destination / Tmin of bench.py; 'differently' counts rollouts the fp32 path decided itself")
     print(json.dumps(dict(total=tot)), flush=True)
     return 0 if tot["differently"] == 0 else 1
