@@ -193,8 +193,11 @@ class MasterTree:
 
     @classmethod
     def load_tree(cls, name, directory="../results/"):
+        """A tree saved by this class, or by the REFERENCE's ``MasterTree.save_tree`` (master.py:390-410): its nodes,
+        histograms, simulators and weather grids come back as this package's classes (``refpickle.load_reference_tree``)."""
+        from .refpickle import load_reference_tree
         with open(directory + name + '.pickle', 'rb') as f:
-            return pickle.load(f)
+            return load_reference_tree(f)
 
 
 def _depth_of(node):

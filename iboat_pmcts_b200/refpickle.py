@@ -7,6 +7,11 @@ holds their ``__dict__``s -- ``MasterNode.rewards`` as an object array of ``Hist
 exactly that from a ``MasterTree`` of this package -- straight from the array-backed master dictionary of a native
 search (``master_node.MasterDict``), node objects of the mirror classes never being built -- so that the reference's
 ``MasterTree.load_tree`` (master.py:400-410) and its plotting methods work on a GPU search's result.
+
+The other way round, ``load_reference_tree`` reads a file the REFERENCE's ``save_tree`` wrote -- the result of a CPU
+search of the reference -- into this package's classes (``MasterTree`` over ``MasterNode`` tables, ``Simulator`` /
+``Weather`` rebuilt from the grids the pickled SciPy interpolators hold), without importing any reference code: its
+decision is then one call of the device reductions.
 """
 import pickle
 import sys
@@ -118,3 +123,65 @@ def dump_reference_tree(tree, file, with_interpolators=True):
                     best_nodes_policy={k: [objs[idx[nd.hash]] for nd in v] for k, v in tree.best_nodes_policy.items()})
         sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))  # (the reference's node graph is recursive)
         pickle.dump(out, file, protocol=4)
+
+
+class _Shell:
+    """What a class of the reference unpickles into here: an object that only carries the pickled ``__dict__``."""
+
+
+class _ShellUnpickler(pickle.Unpickler):
+    def __init__(self, file):
+        super().__init__(file)
+        self._shells = {}
+
+    def find_class(self, module, name):
+        if module in _NAMES and name in _NAMES[module] or (module, name) == ("weatherTLKT", "Weather"):
+            if (module, name) not in self._shells:
+                self._shells[module, name] = type(name, (_Shell,), {"__module__": module})
+            return self._shells[module, name]
+        return super().find_class(module, name)
+
+
+def is_reference_tree(obj):
+    return isinstance(obj, _Shell) and type(obj).__name__ == "MasterTree"
+
+
+def load_reference_tree(file):
+    """A ``master.MasterTree`` of this package from the binary file object ``file`` written by the reference's
+    ``MasterTree.save_tree`` (master.py:390-398); an object pickled by this package's own ``save_tree`` comes back as it
+    is."""
+    from .master import MasterTree
+    from .master_node import MasterNode
+    from .simulatorTLKT import Simulator
+    from .weatherTLKT import Weather
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))
+    src = _ShellUnpickler(file).load()
+    if not is_reference_tree(src):
+        return src
+    sims = []
+    for sim in src.Simulators:
+        u, v = getattr(sim, "uWindAvg", None), getattr(sim, "vWindAvg", None)
+        if u is None or v is None:
+            raise ValueError("the pickled Simulator carries no wind interpolators")
+        t, la, lo = (np.asarray(g, np.float64) for g in u.grid)
+        new = Simulator(np.asarray(sim.times), np.asarray(sim.lats), np.asarray(sim.lons),
+                        Weather(la, lo, t, np.asarray(u.values), np.asarray(v.values)), list(sim.state))
+        new.prevState = list(sim.prevState)
+        sims.append(new)
+    # nodes in the file's dictionary order (the order deepcopy_dict and a reader of tree.nodes see); children in theirs
+    built = {}
+    for key, node in src.nodes.items():
+        new = MasterNode(src.numScenarios, nodehash=node.hash, action=node.arm, rewards=node.rewards)
+        new.depth = node.depth
+        new.guessed_rewards = dict(node.guessed_rewards)
+        built[id(node)] = new
+    nodes = {}
+    for key, node in src.nodes.items():
+        new = built[id(node)]
+        new.parentNode = built[id(node.parentNode)] if node.parentNode is not None else None
+        new.children = [built[id(c)] for c in node.children]
+        nodes[key] = new
+    tree = MasterTree(sims, list(src.destination), nodes=nodes, proba=list(np.asarray(src.probability)))
+    tree.best_policy = {k: list(v) for k, v in src.best_policy.items()}
+    tree.best_nodes_policy = {k: [built[id(nd)] for nd in v] for k, v in src.best_nodes_policy.items()}
+    return tree

@@ -77,3 +77,72 @@ def test_reference_loads_the_tree_and_decides_on_it(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     policy = eval(res.stdout.strip().splitlines()[-1])
     assert set(policy) == {-1, 0, 1, 2, 3} and all(len(v) >= 1 for v in policy.values())
+
+
+def test_tree_saved_by_the_reference_loads_into_this_package(tmp_path):
+    """The other direction: a seeded search of the UNMODIFIED reference (Tree.uct_search on two scenarios into one
+    master dictionary, deepcopy_dict, MasterTree, save_tree) is read by this package's MasterTree.load_tree -- no
+    reference code imported on this side -- into its own classes: same nodes in the same order, same histograms,
+    children wired in the reference's order, simulators whose weather grids are the reference's, the stored policies."""
+    script = textwrap.dedent("""
+        import contextlib, io, json, random, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        from oracle import refshim, gen_golden as G
+        R = refshim.load_reference()
+        wrk, mnode, mstr = R.worker, R.master_node, R.master
+        sims = G.make_sims(R, [0, 1])
+        random.seed(3); np.random.seed(3)
+        master = {hash(()): mnode.MasterNode(2, nodehash=hash(()))}
+        with contextlib.redirect_stdout(io.StringIO()):
+            for w in range(2):
+                tree = wrk.Tree(workerid=w, nscenario=2, budget=60, simulator=sims[w], destination=[46.7, 355.0],
+                                TimeMin=2.0, buffer=[])
+                tree.uct_search([0, 44.0, 355.0], 10, master)
+        class ProxyLike(dict):       # (Manager().dict().items() is a list copy; deepcopy_dict deletes while it iterates)
+            def items(self):
+                return list(dict.items(self))
+        mt = mstr.MasterTree(sims, [46.7, 355.0], nodes=mnode.deepcopy_dict(ProxyLike(master)), proba=[0.25, 0.75])
+        with contextlib.redirect_stdout(io.StringIO()):
+            mt.get_best_policy()
+        mt.save_tree("ref_tree")          # the reference's fixed place: ../results/
+        out = dict(keys=[str(k) for k in mt.nodes],
+                   hist={str(k): [[[int(x) for x in h.h] for h in row] for row in nd.rewards] for k, nd in mt.nodes.items()},
+                   kids={str(k): [str(c.hash) for c in nd.children] for k, nd in mt.nodes.items()},
+                   depth={str(k): nd.depth for k, nd in mt.nodes.items()},
+                   arm={str(k): None if nd.arm is None else int(nd.arm) for k, nd in mt.nodes.items()},
+                   policy={str(k): [int(a) for a in v] for k, v in mt.best_policy.items()},
+                   wind=[float(sims[1].uWindAvg([0.3, 44.2, 355.3])[0]), float(sims[1].vWindAvg([0.3, 44.2, 355.3])[0])],
+                   points=[list(map(float, p)) for p in mt.get_points(mt.nodes[hash(())], [], mt.probability, idscenario=1)])
+        print(json.dumps(out))
+        """) % ROOT
+    (tmp_path / "code").mkdir()
+    (tmp_path / "results").mkdir()
+    res = subprocess.run([sys.executable, "-W", "ignore", "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=600, cwd=str(tmp_path / "code"))
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+    want = json.loads(res.stdout.strip().splitlines()[-1])
+    from iboat_pmcts_b200 import master_node, simulatorTLKT, weatherTLKT
+    mt = MasterTree.load_tree("ref_tree", directory=str(tmp_path / "results") + "/")
+    assert type(mt) is MasterTree and mt.numScenarios == 2 and list(mt.probability) == [0.25, 0.75]
+    assert [str(k) for k in mt.nodes] == want["keys"] and len(mt.nodes) > 60
+    for k, nd in mt.nodes.items():
+        assert type(nd) is master_node.MasterNode and nd.hash == k
+        assert np.array_equal(nd._table, np.array(want["hist"][str(k)]))
+        assert [str(c.hash) for c in nd.children] == want["kids"][str(k)]
+        assert all(c.parentNode is nd for c in nd.children)
+        assert nd.depth == want["depth"][str(k)] and (None if nd.arm is None else int(nd.arm)) == want["arm"][str(k)]
+    assert {str(k): [int(a) for a in v] for k, v in mt.best_policy.items()} == want["policy"]
+    assert all(mt.nodes[nd.hash] is nd for v in mt.best_nodes_policy.values() for nd in v)
+    sim = mt.Simulators[1]
+    assert type(sim) is simulatorTLKT.Simulator and type(sim._weather) is weatherTLKT.Weather and len(sim.times) == 13
+    from iboat_pmcts_b200 import synth
+    t, la, lo, u, v = synth.wind_fields(1)
+    assert np.array_equal(sim._weather.u, u) and np.array_equal(sim._weather.lat, la) and np.array_equal(sim._weather.time, t)
+    got = mt.get_points(mt.nodes[hash(())], [], mt.probability, idscenario=1)
+    assert [list(map(float, p)) for p in got] == want["points"]
+    # and a tree saved by this package in its own format still comes back through the same door
+    mt.save_tree("own", directory=str(tmp_path) + "/")
+    again = MasterTree.load_tree("own", directory=str(tmp_path) + "/")
+    assert type(again) is MasterTree and [str(k) for k in again.nodes] == want["keys"]
