@@ -61,12 +61,19 @@ class Weather:
     @classmethod
     def load(cls, path, latBound=[-90, 90], lonBound=[0, 360], timeSteps=[0, 64]):
         """Loads a pickled ``Weather`` (as saved by the reference's ``Weather.download``,
-        weatherTLKT.py:51-78, 128-133) and crops it.  Pickles written by the reference name the module
-        ``weatherTLKT``: alias it first (``sys.modules['weatherTLKT'] = iboat_pmcts_b200.weatherTLKT``,
-        INTEGRATION.md) so that they unpickle into this class."""
+        weatherTLKT.py:51-78, 128-133) and crops it.  Files written by the reference name the class
+        ``weatherTLKT.Weather``: that name is read as this class, whether or not the module alias of INTEGRATION.md
+        is in place."""
         import pickle
+
+        class _Unpickler(pickle.Unpickler):
+            def find_class(self, module, name):
+                if (module, name) == ("weatherTLKT", "Weather"):
+                    return cls
+                return super().find_class(module, name)
+
         with open(path, 'rb') as f:
-            obj = pickle.load(f)
+            obj = _Unpickler(f).load()
         return obj.crop(latBound, lonBound, timeSteps)
 
     # the device copies are caches, not state: they are dropped on copy / pickle

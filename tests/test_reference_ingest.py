@@ -77,6 +77,10 @@ def test_load_scenarios_and_polar_velocity_like_the_reference(tmp_path):
         got["wMag"], got["wAng"] = w.wMag, w.wAng
     finally:
         del sys.modules["weatherTLKT"]
+    # without the alias too: the reference's class name is read as the mirror class
+    assert "weatherTLKT" not in sys.modules or sys.modules["weatherTLKT"] is not weatherTLKT
+    plain = ft.load_scenarios("20180108", range(1, 2), directory=str(tmp_path / "data") + "/", timeSteps=[0, 16])[0]
+    assert type(plain) is weatherTLKT.Weather and np.array_equal(np.ma.getdata(plain.u), want["time_1_u"])
     assert set(got) == set(want.files)
     for k in want.files:
         assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
