@@ -18,6 +18,7 @@ from . import _native as N
 from . import worker as mt
 from .master_node import MasterNode
 from .simulatorTLKT import A_DICT, ACTIONS, HOURS_TO_DAY, Simulator
+from .utils import out_of_scope
 
 ROOT_HASH = hash(tuple([]))
 
@@ -668,3 +669,7 @@ def _raise_unless(status, allowed):
     for s in np.asarray(status).ravel():
         if int(s) not in allowed and int(s) != N.ST_OK:
             raise_for_status(int(s))
+
+
+download_scenarios = out_of_scope("forest.download_scenarios")
+play_multiple_scenarios = out_of_scope("forest.play_multiple_scenarios")

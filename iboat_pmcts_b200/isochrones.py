@@ -7,6 +7,7 @@ import numpy as np
 
 from . import _native as N
 from .forest import _raise_unless, _reference_noise
+from .utils import out_of_scope
 
 
 def estimate_perfomance_plan(sims, ntra, stateinit, destination, plan=list(), plot=False, verbose=True, seed=None,
@@ -390,3 +391,8 @@ class Isochrone():
 
     def positions_to_states(self):
         return [np.array([i, p[0], p[1]]) for i, p in enumerate(self.liste_positions)]
+
+
+for _name in ("plot_trajectory", "plot_comparision", "plot_comparision_percent", "plot_mean_squared_error",
+              "plot_risk_probability"):
+    globals()[_name] = out_of_scope("isochrones." + _name)

@@ -15,6 +15,7 @@ import numpy as np
 
 from .master_node import MasterDict, MasterNode
 from .simulatorTLKT import ACTIONS
+from .utils import out_of_scope
 from .worker import UCT_COEFF  # bound at import, like the reference (master.py:11; quirk Q4)
 
 ROOT_HASH = hash(tuple([]))
@@ -206,3 +207,7 @@ def _depth_of(node):
         node = node.parentNode
         d += 1
     return d
+
+
+for _name in ("plot_tree", "plot_tree_uct", "plot_best_policy", "plot_hist_best_policy", "draw_points"):
+    setattr(MasterTree, _name, staticmethod(out_of_scope("MasterTree." + _name)))

@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _native as N
 from .engine import Slot, default_engine
+from .utils import out_of_scope
 from .weatherTLKT import Weather  # noqa: F401  (the reference module exposes it too)
 
 #: Headings the boat can follow (degrees), sorted (simulatorTLKT.py:29).
@@ -216,3 +217,7 @@ class Boat:
     def addUncertainty(boatSpeed):
         """Noisy boat speed: one draw from Python's global Mersenne Twister, as in the reference."""
         return rand.gauss(boatSpeed, boatSpeed * Boat.UNCERTAINTY_COEFF)
+
+
+for _name in ("prepareBaseMap", "plotTraj", "animateTraj", "play_scenario"):
+    setattr(Simulator, _name, staticmethod(out_of_scope("Simulator." + _name)))

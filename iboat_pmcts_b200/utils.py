@@ -8,6 +8,19 @@ back-up kernel (``pmcts_backup``) work on such tables, and ``node.Values[i].h`` 
 import numpy as np
 
 
+def out_of_scope(name):
+    """A callable named like one of the reference's plotting / download entry points: calling it says that the
+    feature is outside the scope of this package instead of failing with an AttributeError."""
+    def stub(*args, **kwargs):
+        raise NotImplementedError("%s: the reference's plotting / animation / download code is outside the scope of "
+                                  "pmcts_b200" % name)
+    stub.__name__ = stub.__qualname__ = name
+    return stub
+
+
+Player = out_of_scope("utils.Player")
+
+
 class Hist:
     #: Lower / upper bound of the histogram and number of bins (utils.py:14-20)
     MIN_REWARD = 0

@@ -13,6 +13,7 @@ import numpy as np
 
 from . import _native as N
 from .engine import Slot, default_engine
+from .utils import out_of_scope
 
 
 class _GridInterpolator:
@@ -147,3 +148,7 @@ class Weather:
             out.v = self.v[t0:t1]
             return out
         return self
+
+
+for _name in ("download", "plotQuiver", "plotColorQuiver", "plotMultipleQuiver", "animateQuiver"):
+    setattr(Weather, _name, staticmethod(out_of_scope("Weather." + _name)))
