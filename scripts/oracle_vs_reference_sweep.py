@@ -6,7 +6,9 @@ tests/test_oracle_vs_reference.py on random inputs of scenario 3.  The multi-GPU
 parity rests on the oracle (scripts/fastmodel_sweep.py, the GPU tests), so this script extends the pin: for every
 scenario the reference's own ``Tree.default_policy`` (code/solver/worker.py:255-300) runs ROLLOUTS leaves of mixed depth
 with an injected noise feed, on the destination / Tmin of bench.py, and the oracle is held to its reward, its
-transitions, its arrival flag and fraction, its final state and every position on the way -- all bit for bit.
+transitions, its arrival flag and fraction, its final state and every position on the way -- all bit for bit.  Raw
+``Simulator.doStep`` (simulatorTLKT.py:181-216) is compared the same way on the config-3 axis: 6 boats x 150 steps of
+864 s per scenario, every position of every step.
 
     python scripts/oracle_vs_reference_sweep.py [--scenarios 64] [--rollouts 64] > profiles/r02_oracle_vs_reference_sweep.jsonl
 """
@@ -76,7 +78,31 @@ def one_scenario(args):
     same = dict(reward=np.array_equal(got["reward"], reward), steps=np.array_equal(got["steps"], steps),
                 arrived=np.array_equal(got["status"] == 1, atdest), frac=np.array_equal(got["frac"], frac, equal_nan=True),
                 traj=np.array_equal(got["traj_lat"], tl, equal_nan=True) and np.array_equal(got["traj_lon"], to, equal_nan=True))
-    return dict(scenario=s, rollouts=n, transitions=int(steps.sum()), arrived=int(atdest.sum()),
+    # raw doStep (simulatorTLKT.py:181-216) on the config-3 axis: a few boats of bench.py's fleet, octagon headings
+    from iboat_pmcts_b200 import synth
+    from oracle import cport
+    nb, nsteps = 6, 150
+    t, la, lo, u, v = synth.wind_fields(s)
+    times3 = np.linspace(0, 5, 501)
+    sim3 = simc.Simulator(times3, la, lo, R.weatherTLKT.Weather(la, lo, t, u, v), [0, 44.0, 355.0])
+    lat0, lon0, h0 = synth.octagon_fleet(nb, seed=7 + s)
+    head = synth.octagon_headings(h0, nsteps)
+    z3 = np.random.default_rng(7000 + s).standard_normal((nb, nsteps))
+    feeder3 = G.ZFeeder(z3)
+    simc.rand = feeder3
+    tl3, to3 = np.empty((nsteps, nb)), np.empty((nsteps, nb))
+    for b in range(nb):
+        feeder3.begin(b)
+        sim3.reset([0, lat0[b], lon0[b]])
+        for j in range(nsteps):
+            st = sim3.doStep(float(head[j // 25, b]))
+            tl3[j, b], to3[j, b] = st[1], st[2]
+    o3 = cport.OracleSim(t, la, lo, u, v, times3, la, lo)
+    r3 = o3.step_batch(0, lat0, lon0, head, nsteps=nsteps, seg_len=25, z=np.ascontiguousarray(z3.T), traj=True)
+    same["raw_steps"] = np.array_equal(r3["traj_lat"], tl3) and np.array_equal(r3["traj_lon"], to3)
+    import random
+    simc.rand = random
+    return dict(scenario=s, rollouts=n, transitions=int(steps.sum()), arrived=int(atdest.sum()), raw_steps=nb * nsteps,
                 bit_exact={k: bool(v) for k, v in same.items()}, all_bit_exact=bool(all(same.values())))
 
 
@@ -91,6 +117,7 @@ def main():
         print(json.dumps(line))
     tot = dict(scenarios=len(lines), rollouts=sum(l["rollouts"] for l in lines),
                transitions=sum(l["transitions"] for l in lines), arrived=sum(l["arrived"] for l in lines),
+               raw_steps=sum(l["raw_steps"] for l in lines),
                scenarios_bit_exact=sum(l["all_bit_exact"] for l in lines))
     print(json.dumps(dict(total=tot)))
     return 0 if tot["scenarios_bit_exact"] == len(lines) else 1
