@@ -152,3 +152,29 @@ def test_leaf_batched_selection_spreads_and_backs_up(monkeypatch):
     for node in tree.Nodes[1:]:
         below = sum(1 for n in tree.Nodes if n.origins[:len(node.origins)] == node.origins)
         assert node._table.sum() == below * 32
+
+
+def test_hist_bin_on_and_around_every_threshold():
+    """Hist.add (utils.py:34-47) counts the interior thresholds STRICTLY below the value: on a threshold the value stays
+    in the lower bin, one ulp above it moves up.  The mirror's Hist, the oracle's orc_hist_bin (what the kernels' bins
+    are compared with) and NumPy's own statement of the rule agree on every threshold, its two neighbours, values far
+    outside the range and 10^5 random rewards."""
+    from oracle import cport
+    thresholds = np.asarray(Hist.THRESH[1:-1], np.float64)
+    assert thresholds.size == 11 and np.array_equal(thresholds, 0.125 * np.arange(1, 12))
+    values = [-1e300, -0.1, -0.0, 0.0, 5e-324, 1.5, 1.5000001, 2.0, 1e300]
+    for t in thresholds:
+        values += [float(np.nextafter(t, -np.inf)), float(t), float(np.nextafter(t, np.inf))]
+    values += np.random.default_rng(3).uniform(-0.2, 1.8, 100000).tolist()
+    values = np.asarray(values)
+    want = (values[:, None] > thresholds[None, :]).sum(1)
+    got_oracle = np.array([cport.hist_bin(float(v)) for v in values])
+    assert np.array_equal(got_oracle, want)
+    head = values[:200]
+    assert [Hist.bin_of(float(v)) for v in head] == want[:200].tolist()
+    for k, t in enumerate(thresholds):
+        assert Hist.bin_of(float(t)) == k and Hist.bin_of(float(np.nextafter(t, np.inf))) == k + 1
+    h = Hist()
+    for v in head:
+        h.add(float(v))
+    assert np.array_equal(h.h, np.bincount(want[:200], minlength=12))
