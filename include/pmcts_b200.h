@@ -3,7 +3,7 @@
  * The reference (PBarde/IBoat-PMCTS) is pure Python and has no FFI; the boundary it exposes for
  * this path is its Python object API.  Each entry point below names the reference interface it
  * replaces (file:line in the reference checkout).  The Python mirror of that API
- * (iboat_pmcts_b200/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * (the modules of iboat_pmcts_b200/) binds these symbols with ctypes; INTEGRATION.md shows the stub a
  * maintainer of the reference would add.
  *
  * Conventions
