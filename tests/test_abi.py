@@ -84,3 +84,29 @@ def test_weather_pickle_ingest(tmp_path):
     assert got.lat[0] == 40.5 and got.lat[-1] == 49.5 and got.lon[0] == 345.5 and got.time.size == 24
     assert got.u.dtype == np.float64 and got.u.shape == (24, 19, 29)
     assert np.array_equal(got.u, u[:24, 1:-1, 1:-1])
+
+
+def test_the_boundary_from_plain_c(tmp_path):
+    """tests/c_abi/abi_from_c.c: include/pmcts_b200.h compiled as strict C99 (no warnings), linked against the
+    library, run without Python: no device -> PMCTS_ERR_NO_DEVICE ("no CPU path"); the host runtime of the search driven
+    through the ABI from C."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    from iboat_pmcts_b200 import _native
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "abi_from_c")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-o", exe,
+                          os.path.join(ROOT, "tests", "c_abi", "abi_from_c.c"), "-L", lib_dir,
+                          "-l:" + os.path.basename(_native.LIB_PATH), "-Wl,-rpath," + lib_dir],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    run = subprocess.run([exe] + (["gpu"] if has_gpu else []), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=120)
+    assert run.returncode == 0 and "abi_from_c ok" in run.stdout, run.stdout
