@@ -110,3 +110,34 @@ def test_the_boundary_from_plain_c(tmp_path):
     run = subprocess.run([exe] + (["gpu"] if has_gpu else []), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                          timeout=120)
     assert run.returncode == 0 and "abi_from_c ok" in run.stdout, run.stdout
+
+
+def test_the_ctypes_stub_of_integration_md_binds():
+    """Route B of INTEGRATION.md -- the stub a maintainer of the reference would add -- is executed as written (library
+    path filled in): every symbol it names resolves, its argument lists have the header's lengths, and on a machine
+    without a GPU it stops where it must, at pmcts_create ("no CPU path")."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("```python\nimport ctypes as C, numpy as np")
+    code = text[start + len("```python\n"):text.index("```", start + 10)]
+    code = code.replace('"/path/to/libpmcts_b200.so"', repr(N.LIB_PATH))
+    header = open(os.path.join(ROOT, "include", "pmcts_b200.h")).read()
+
+    def n_params(name):
+        m = re.search(r"\b%s\(([^;]*?)\);" % name, header, re.S)
+        return len([p for p in m.group(1).split(",") if p.strip()])
+
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    scope = {}
+    if has_gpu:
+        exec(code, scope)
+    else:
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            exec(code, scope)
+    L = scope["_L"]
+    for name in ("pmcts_create", "pmcts_scenario_upload", "pmcts_rollout_batch"):
+        assert len(getattr(L, name).argtypes) == n_params(name), name
+    assert scope["PMCTS_MEM_HOST"] == N.MEM_HOST and C.sizeof(scope["Noise"]) == C.sizeof(N.Noise)
