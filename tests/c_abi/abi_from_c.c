@@ -19,6 +19,39 @@
         }                                                             \
     } while (0)
 
+/* The multi-GPU snippets of INTEGRATION.md (route B), kept compiling: never called here (they need GPUs and peers). */
+int integration_md_route_b(pmcts_ctx *ctx, pmcts_forest *forest, const int32_t *scen_slots, const double root[3],
+                           const double dest[2], double tmin, int world, int rank, const int8_t *slots_w,
+                           const int8_t *slots_m, int n_local, int max_depth, uint8_t (*all)[PMCTS_PEER_HANDLE_BYTES],
+                           const uint32_t *d_leaf_bins, int64_t count, void *d_send, void *d_recv, size_t bytes) {
+    uint8_t id[128];
+    if (rank == 0 && pmcts_comm_unique_id(id)) return 1;
+    pmcts_comm *comm;
+    if (pmcts_comm_create(ctx, world, rank, id, &comm)) return 1;
+    pmcts_search_params p;
+    memset(&p, 0, sizeof p);
+    p.n_leaves = 64; p.replicas = 32; p.budget = 320; p.seed = 5; p.pipeline = 1;
+    p.world = world; p.rank = rank; p.comm = comm;
+    p.slots_w = slots_w; p.slots_m = slots_m;
+    pmcts_search_report rep;
+    if (pmcts_forest_search(ctx, forest, scen_slots, root, dest, tmin, &p, &rep)) return 1;
+    if (pmcts_allgather_updates(ctx, comm, d_send, bytes, d_recv)) return 1;
+    uint8_t mine[PMCTS_PEER_HANDLE_BYTES];
+    pmcts_peer *peer;
+    if (pmcts_peer_create(ctx, world, rank, pmcts_search_block_bytes(n_local, p.n_leaves, max_depth, p.replicas), &peer, mine))
+        return 1;
+    if (pmcts_peer_connect(peer, &all[0][0])) return 1;
+    p.comm = NULL;
+    p.peer = peer;
+    const void *gathered;
+    if (pmcts_peer_put_bins(ctx, peer, d_leaf_bins, count, 1) || pmcts_peer_wait(ctx, peer, &gathered)) return 1;
+    int arrived = 0;
+    if (pmcts_peer_poll(ctx, peer, &arrived)) return 1;
+    pmcts_peer_destroy(peer);
+    pmcts_comm_destroy(comm);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     enum { S = 2, B = 8, K = 4, D = 12, MAX_NODES = 64 };
     printf("%s\n", pmcts_version());
