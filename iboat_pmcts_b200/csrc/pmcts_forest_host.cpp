@@ -19,6 +19,7 @@
 //     fp64 whatever the summation order;
 //   * a leaf's wave histogram goes to a random action slot of the leaf (worker.py:62-63,
 //     master_node.py:42-44) and to the slot of the action taken at every ancestor.
+#include <sched.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -129,6 +130,12 @@ class Pool {
         // (LOCAL_WORLD_SIZE as torchrun sets it): polling threads must not outnumber the cores.  PMCTS_HOST_THREADS
         // overrides.
         unsigned hw = std::thread::hardware_concurrency();
+        {   // (the cores this process may run on: a cpuset / taskset narrower than the machine counts)
+            cpu_set_t allowed;
+            CPU_ZERO(&allowed);
+            if (sched_getaffinity(0, sizeof allowed, &allowed) == 0 && CPU_COUNT(&allowed) > 0)
+                hw = hw ? std::min<unsigned>(hw, (unsigned)CPU_COUNT(&allowed)) : (unsigned)CPU_COUNT(&allowed);
+        }
         if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) {
             const int ranks = std::atoi(lw);
             if (ranks > 1 && hw) hw = std::max(1u, hw / (unsigned)ranks);
