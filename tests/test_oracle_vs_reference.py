@@ -71,3 +71,19 @@ def test_arrival_test_and_rollout_bit_exact(world):
         assert got[0] == want[0] and (got[1] is None and want[1] is None or float(got[1]) == want[1])
         hits += bool(got[0])
     assert 5 < hits < 295
+
+
+@pytest.mark.parametrize("scenario", [20, 41, 63])
+def test_rollouts_and_raw_steps_of_other_scenarios_bit_exact(scenario):
+    """A slice of scripts/oracle_vs_reference_sweep.py (which holds the oracle to the reference on ALL 64 scenarios of
+    config 4: profiles/r02_oracle_vs_reference_sweep.jsonl): the reference's own Tree.default_policy on 24 leaves of
+    mixed depth and 6 x 150 raw doStep on the config-3 axis, rewards / arrival fractions / every position equal."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "oracle_vs_reference_sweep.py")
+    spec = importlib.util.spec_from_file_location("oracle_vs_reference_sweep", path)
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    line = sweep.one_scenario((scenario, 24))
+    assert line["all_bit_exact"], line
+    assert line["transitions"] > 24 * 6 and line["raw_steps"] == 900
