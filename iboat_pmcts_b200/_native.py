@@ -37,7 +37,7 @@ EXPORTS = [
     "pmcts_get_stream", "pmcts_get_device", "pmcts_comm_unique_id", "pmcts_comm_create", "pmcts_comm_destroy",
     "pmcts_allgather_updates", "pmcts_peer_create", "pmcts_peer_connect", "pmcts_peer_put_bins", "pmcts_peer_put",
     "pmcts_peer_wait", "pmcts_peer_poll", "pmcts_peer_destroy", "pmcts_search_block_bytes", "pmcts_forest_search", "pmcts_master_policy", "pmcts_pack_bins",
-    "pmcts_forest_search_sequential", "pmcts_python_gauss", "pmcts_numpy_randint8", "pmcts_forest_master_policy",
+    "pmcts_forest_search_sequential", "pmcts_forest_search_sequential_hook", "pmcts_python_gauss", "pmcts_numpy_randint8", "pmcts_forest_master_policy",
     "pmcts_synchronize", "pmcts_join", "pmcts_wait", "pmcts_set_option", "pmcts_set_precision", "pmcts_set_fast_margins", "pmcts_last_redo_count", "pmcts_last_kernel_variant", "pmcts_launch_count", "pmcts_probe_fp32_peak", "pmcts_enable_timing",
     "pmcts_kernel_ms_total", "pmcts_kernel_ms", "pmcts_set_params", "pmcts_scenario_upload", "pmcts_scenario_free",
     "pmcts_get_wind", "pmcts_interp_wind", "pmcts_step_batch", "pmcts_rollout_batch", "pmcts_rollout_forest", "pmcts_backup", "pmcts_hist_stats",
@@ -59,6 +59,12 @@ EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_
 #:          const int32_t *prefix_len, const int8_t *prefix_act, uint32_t *leaf_bins) -- test stand-in for the GPU launch
 ROLLOUT_HOOK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                               C.c_void_p, C.c_void_p)
+
+
+#: int hook(void *user, int64 iteration, int scen_id, const int8_t *path, int len, const double *z, int n_instants,
+#:          int32_t *bin, int32_t *transitions) -- test stand-in for the rollout of the sequential search
+SEQ_ROLLOUT_HOOK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int8), C.c_int,
+                                  C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
 
 
 class SearchParams(C.Structure):
@@ -161,6 +167,8 @@ def lib():
     L.pmcts_master_policy.argtypes = [vp, i64, i32, vp, vp, vp, i64, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp, i32]
     L.pmcts_forest_search_sequential.argtypes = [vp, vp, i32, i32, vp, vp, dbl, i64, i32, i32, C.POINTER(MtState),
                                                  C.POINTER(MtState), C.POINTER(SearchReport)]
+    L.pmcts_forest_search_sequential_hook.argtypes = [vp, i32, i64, i32, C.POINTER(MtState), C.POINTER(MtState),
+                                                      SEQ_ROLLOUT_HOOK_FN, vp, C.POINTER(SearchReport)]
     L.pmcts_python_gauss.argtypes = [C.POINTER(MtState), i64, vp]
     L.pmcts_numpy_randint8.argtypes = [C.POINTER(MtState), i64, vp]
     L.pmcts_forest_master_policy.argtypes = [vp, vp, vp, dbl, i32, vp, vp, vp, vp, vp, vp]

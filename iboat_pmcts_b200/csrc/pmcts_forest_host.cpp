@@ -894,6 +894,29 @@ int pmcts_python_shuffles_batch(const uint64_t *seeds, int n_seeds, int64_t coun
     return fail(PMCTS_ERR_ARG, "out of host memory");
 }
 
+int pmcts_forest_search_sequential_hook(pmcts_forest *f, int local_index, int64_t budget, int frequency,
+                                        pmcts_mt_state *py_state, pmcts_mt_state *np_state,
+                                        pmcts_seq_rollout_hook_fn hook, void *user, pmcts_search_report *report) try {
+    if (!f || !hook) return fail(PMCTS_ERR_ARG, "NULL argument");
+    pmcts_search_report rep{};
+    const int n_instants = f->max_depth + 1;
+    int64_t iteration = 0;
+    const pmcts::SeqRollout rollout = [&](int scen, const int8_t *path, int len, const double *z, int *bin, int *steps) -> int {
+        int32_t b = 0, t = 0;
+        const int rc = hook(user, iteration++, scen, path, len, z, n_instants, &b, &t);
+        if (rc) return fail(rc < 0 ? rc : PMCTS_ERR_ARG, "the rollout hook refused the iteration");
+        if (b < 0 || b >= kB || t < 0 || t > n_instants) return fail(PMCTS_ERR_ARG, "the rollout hook returned a bin / transition count out of range");
+        *bin = b;
+        *steps = t;
+        return 0;
+    };
+    const int rc = pmcts::forest_sequential(f, local_index, budget, frequency, n_instants, py_state, np_state, rollout, &rep);
+    if (report) *report = rep;
+    return rc;
+} catch (const std::bad_alloc &) {
+    return fail(PMCTS_ERR_ARG, "out of host memory");
+}
+
 int pmcts_python_gauss(pmcts_mt_state *state, int64_t count, double *out) {
     if (!state || !out || count < 0) return fail(PMCTS_ERR_ARG, "bad arguments");
     PyRandom py;

@@ -459,6 +459,16 @@ int pmcts_forest_search_sequential(pmcts_ctx *ctx, pmcts_forest *f, int local_in
                                    const double root[3], const double dest[2], double tmin, int64_t budget,
                                    int frequency, int roll_flags, pmcts_mt_state *py_state, pmcts_mt_state *np_state,
                                    pmcts_search_report *report);
+/* The same search with the rollouts handed to a callback instead of the GPU -- TEST INSTRUMENTATION, like
+ * pmcts_search_params.rollout_hook: it lets the host logic of Tree.uct_search (worker.py:147-253, 348-378: tree policy,
+ * node creation shuffles, back-up, master updates, both random streams) be replayed against a recorded run of the
+ * reference without a device.  hook(user, iteration (0-based), scenario id, the leaf's action path, its length, the
+ * normals z[n_instants] its transitions would draw, &bin, &transitions) returns 0 or an error that ends the search. */
+typedef int (*pmcts_seq_rollout_hook_fn)(void *user, int64_t iteration, int scen_id, const int8_t *path, int len,
+                                         const double *z, int n_instants, int32_t *bin, int32_t *transitions);
+int pmcts_forest_search_sequential_hook(pmcts_forest *f, int local_index, int64_t budget, int frequency,
+                                        pmcts_mt_state *py_state, pmcts_mt_state *np_state,
+                                        pmcts_seq_rollout_hook_fn hook, void *user, pmcts_search_report *report);
 /* The two generators above, for checking them against the interpreter: count x random.gauss(0, 1) and count x
  * np.random.randint(8), continuing the given states. */
 int pmcts_python_gauss(pmcts_mt_state *state, int64_t count, double *out);

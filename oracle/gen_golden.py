@@ -257,8 +257,22 @@ def tree_replay(R, destination, timemin, budget=300, frequency=10):
     iters = []
     orig_backup = wrk.Node.back_up
 
+    # (transitions per iteration -- the normals an iteration draws from Python's generator -- for the replay of the
+    #  NATIVE sequential search on the CPU: kept out of the iteration records, see --only-replay-steps)
+    made = {"n": 0}
+    steps_per_iteration = []
+    orig_step = simc.Simulator.doStep
+
+    def counting_step(self, action):
+        made["n"] += 1
+        return orig_step(self, action)
+
+    simc.Simulator.doStep = counting_step
+
     def rec_backup(self, reward):
         iters.append(dict(origins=[int(a) for a in self.origins], reward=float(reward), n_slots_before=len(slots)))
+        steps_per_iteration.append(made["n"])
+        made["n"] = 0
         return orig_backup(self, reward)
 
     wrk.Node.back_up = rec_backup
@@ -267,6 +281,8 @@ def tree_replay(R, destination, timemin, budget=300, frequency=10):
     with contextlib.redirect_stdout(io.StringIO()):
         tree.uct_search([0, 44.0, 355.0], frequency, master)
     wrk.Node.back_up = orig_backup
+    simc.Simulator.doStep = orig_step
+    tree_replay.steps_per_iteration = steps_per_iteration
     np.random.randint = orig_randint
     # slot stream: per iteration one worker slot; every `frequency` iterations `frequency` master slots
     for it in iters:
@@ -394,6 +410,21 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "master_policy_s10.npz"), **fx)
         print("master policy: nodes", fx["parent"].size, "global policy", fx["policy_uniform"][0], "skewed",
               fx["policy_skewed"][0], "guesses", fx["guess_uniform"].shape, "utilities", fx["utility_uniform"].shape)
+        return
+    if "--only-replay-steps" in sys.argv:
+        # the recorded search run once more, counting the transitions of every iteration; written next to the recorded
+        # run only if it IS that run (same leaves, same rewards, same histograms)
+        g = np.load(os.path.join(GOLD, "rollouts_c1.npz"))
+        tr = tree_replay(R, [float(x) for x in g["destination"]], float(g["timemin"]))
+        with open(os.path.join(GOLD, "tree_replay_c1.json")) as f:
+            old = json.load(f)
+        assert tr == old, "the re-run is not the recorded search"
+        steps = tree_replay.steps_per_iteration
+        assert len(steps) == len(old["iterations"]) and min(steps) >= 1
+        with open(os.path.join(GOLD, "tree_replay_c1_steps.json"), "w") as f:
+            json.dump(dict(steps=steps, note="transitions (doStep calls, one normal each) of every iteration of "
+                                             "tree_replay_c1.json"), f)
+        print("replay steps:", len(steps), "iterations,", sum(steps), "transitions")
         return
     if "--only-isochrone" in sys.argv:
         g = np.load(os.path.join(GOLD, "rollouts_c1.npz"))

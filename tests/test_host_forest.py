@@ -272,3 +272,85 @@ def test_forest_stays_searchable_after_a_failed_search():
             assert "oldest selection" in lib.pmcts_forest_last_error().decode()
         finally:
             lib.pmcts_forest_destroy(h)
+
+
+def test_native_sequential_search_replays_the_recorded_reference_run(golden_dir):
+    """pmcts::forest_sequential -- the native Tree.uct_search (worker.py:147-253, 348-378) -- against the run recorded
+    from the UNMODIFIED reference (tests/golden/tree_replay_c1.json: random.seed(1), np.random.seed(1), 300 iterations,
+    master update every 10), on the CPU: the rollouts are handed to a callback that returns what the reference's
+    rollout of that iteration returned (the reward's bin; the transitions made, tree_replay_c1_steps.json), everything
+    else -- tree policy with the master's share, shuffles of the untried actions at node creation and the normals of
+    the transitions from Python's generator, action slots from NumPy's -- runs natively.  Every iteration must pick the
+    reference's leaf; all node histograms and the master's must be the reference's; and the two generators must end
+    where the interpreter's end after the same draws."""
+    import ctypes as C
+    import json
+    import os
+    import random
+    from iboat_pmcts_b200.utils import Hist
+    with open(os.path.join(golden_dir, "tree_replay_c1.json")) as f:
+        rec = json.load(f)
+    with open(os.path.join(golden_dir, "tree_replay_c1_steps.json")) as f:
+        steps = json.load(f)["steps"]
+    its = rec["iterations"]
+    lib = N.lib()
+    h = C.c_void_p()
+    ids, prob = np.zeros(1, np.int32), np.ones(1)
+    N.check_forest(lib.pmcts_forest_create(1, 1, ids.ctypes.data, 12, prob.ctypes.data, rec["uct_coeff"], rec["rho"], None,
+                                           len(its) + 8, C.byref(h)))
+    try:
+        random.seed(1)
+        np.random.seed(1)
+        py, npst = N.MtState.from_python(random.getstate()), N.MtState.from_numpy(np.random.get_state())
+        seen = []
+
+        def hook(_user, iteration, scen, path, length, z, n_instants, bin_p, steps_p):
+            seen.append([45 * int(path[j]) for j in range(length)])
+            if seen[-1] != its[iteration]["origins"] or n_instants != 13 or scen != 0:
+                return 1
+            bin_p[0] = Hist.bin_of(its[iteration]["reward"])
+            steps_p[0] = steps[iteration]
+            return 0
+
+        cb = N.SEQ_ROLLOUT_HOOK_FN(hook)
+        rep = N.SearchReport()
+        rc = lib.pmcts_forest_search_sequential_hook(h, 0, rec["budget"], rec["frequency"], C.byref(py), C.byref(npst), cb,
+                                                     None, C.byref(rep))
+        assert rc == 0, (lib.pmcts_forest_last_error().decode(), len(seen), seen[-1:], its[len(seen) - 1]["origins"])
+        assert seen == [it["origins"] for it in its]
+        assert rep.rollouts == 300 and rep.transitions == sum(steps) and rep.waves == 30
+        # the worker tree: nodes in creation order, their action paths and 8 x 12 histograms
+        n = int(lib.pmcts_forest_tree_size(h, 0))
+        assert n == len(rec["nodes"]) == 301
+        parent, arm, table = np.empty(n, np.int32), np.empty(n, np.int8), np.empty((n, 8, 12), np.int64)
+        N.check_forest(lib.pmcts_forest_export_tree(h, 0, parent.ctypes.data, arm.ctypes.data, table.ctypes.data, None, None))
+        paths = []
+        for i in range(n):
+            paths.append([] if parent[i] < 0 else paths[parent[i]] + [45 * int(arm[i])])
+            assert paths[i] == rec["nodes"][i]["origins"], i
+            assert np.array_equal(table[i], np.array(rec["nodes"][i]["hist"])), i
+        # the master: same nodes (by the hash of their path), same histograms
+        m = int(lib.pmcts_forest_master_size(h))
+        mparent, marm, mtable = np.empty(m, np.int32), np.empty(m, np.int8), np.empty((m, 1, 8, 12), np.uint32)
+        N.check_forest(lib.pmcts_forest_export_master(h, mparent.ctypes.data, marm.ctypes.data, mtable.ctypes.data))
+        assert m == len(rec["master_nodes"])
+        mpaths = []
+        for i in range(m):
+            mpaths.append(() if mparent[i] < 0 else mpaths[mparent[i]] + (45 * int(marm[i]),))
+            assert np.array_equal(mtable[i, 0], np.array(rec["master_nodes"][str(hash(mpaths[i]))])), mpaths[i]
+        # the generators: where the interpreter's are after the same draws (301 shuffles interleaved with the normals of
+        # 3017 transitions; 300 + 300 action slots)
+        slots_drawn = 300 + 300
+        np.random.seed(1)
+        np.random.randint(8, size=slots_drawn)
+        assert npst.to_numpy(np.random.get_state())[2] == np.random.get_state()[2]
+        assert np.array_equal(npst.to_numpy(np.random.get_state())[1], np.random.get_state()[1])
+        random.seed(1)
+        random.shuffle(list(range(8)))             # the root's untried actions (worker.py:51)
+        for k in steps:
+            random.shuffle(list(range(8)))         # the node the iteration expands
+            for _ in range(k):
+                random.gauss(0.0, 1.0)             # one normal per transition (simulatorTLKT.py:515)
+        assert py.to_python() == random.getstate()
+    finally:
+        lib.pmcts_forest_destroy(h)
