@@ -77,6 +77,9 @@ def main():
     ap.add_argument("--philox", action="store_true",
                     help="noise from Philox counters on both sides (the bench's mode): the model draws its normals with "
                          "the kernels' fp32 Box-Muller, the oracle with its fp64 one")
+    ap.add_argument("--mode", choices=("tree", "full-prefix", "plan"), default="tree",
+                    help="tree: the reference's replay of the first action only (quirk Q1); full-prefix: "
+                         "PMCTS_ROLL_REPLAY_FULL_PREFIX; plan: plan evaluation (PMCTS_ROLL_PLAN_EVAL, Tmin 0)")
     a = ap.parse_args()
     if a.k1:
         return k1(a.k1, a.seed)
@@ -96,9 +99,12 @@ def main():
             noise = dict(seed=a.seed, stream=100 + s)
         else:
             noise = dict(z=rng.standard_normal((times.size, n)))
-        got = f.rollout_batch(n_leaf, rep, STATE0, DEST, TMIN, prefix=prefix, prefix_len=plen, **noise)
-        assert f.last_variant() == 2, "not the turbo variant"
-        want = o.rollout_batch(n, STATE0, DEST, TMIN, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep),
+        flags = {"tree": 0, "full-prefix": 2, "plan": 4}[a.mode]
+        tmin = 0.0 if a.mode == "plan" else TMIN
+        got = f.rollout_batch(n_leaf, rep, STATE0, DEST, tmin, prefix=prefix, prefix_len=plen, flags=flags, **noise)
+        assert f.last_variant() == (1 if a.mode == "plan" else 2), "not the variant the product launches"
+        want = o.rollout_batch(n, STATE0, DEST, tmin, prefix=np.repeat(prefix, rep, 0), prefix_len=np.repeat(plen, rep),
+                               replay_full=a.mode == "full-prefix", mode=1 if a.mode == "plan" else 0,
                                nthreads=os.cpu_count() or 8, **noise)
         decided = got["uncertain"] == 0
         bad = (got["steps"] != want["steps"]) | (got["status"] != want["status"]) | (got["bin"] != want["bin"])
@@ -110,9 +116,9 @@ def main():
         for k in tot:
             tot[k] += line[k]
         print(json.dumps(line), flush=True)
-    tot.update(scenarios=a.scenarios, undecided_share=tot["undecided"] / tot["rollouts"], seconds=round(time.time() - t0, 1),
+    tot.update(scenarios=a.scenarios, mode=a.mode, undecided_share=tot["undecided"] / tot["rollouts"], seconds=round(time.time() - t0, 1),
                noise="philox (fp32 Box-Muller in the model, fp64 in the oracle)" if a.philox else "injected normals",
-               note="host build of csrc/pmcts_fast.cuh (turbo variant) against oracle/pmcts_oracle.c, "
+               note="host build of csrc/pmcts_fast.cuh (the variant the product launches in this mode) against oracle/pmcts_oracle.c, "
                     "root / destination / Tmin of bench.py; 'differently' counts rollouts the fp32 path decided itself")
     print(json.dumps(dict(total=tot)), flush=True)
     return 0 if tot["differently"] == 0 else 1
