@@ -141,3 +141,25 @@ def test_the_ctypes_stub_of_integration_md_binds():
     for name in ("pmcts_create", "pmcts_scenario_upload", "pmcts_rollout_batch"):
         assert len(getattr(L, name).argtypes) == n_params(name), name
     assert scope["PMCTS_MEM_HOST"] == N.MEM_HOST and C.sizeof(scope["Noise"]) == C.sizeof(N.Noise)
+
+
+def test_the_module_swap_of_integration_md_works_as_written():
+    """Route A of INTEGRATION.md, executed as written in a fresh interpreter: after the swap the reference's own import
+    lines resolve to the mirror modules, which carry the names a script of the reference uses (no device is touched)."""
+    import subprocess
+    import sys
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    start = text.index("```python\nimport sys, iboat_pmcts_b200")
+    code = text[start + len("```python\n"):text.index("```", start + 10)]
+    check = code + "\n" + "\n".join([
+        "import master, master_node, isochrones, utils",
+        "assert ft.__name__ == 'iboat_pmcts_b200.forest' and mt.__name__ == 'iboat_pmcts_b200.worker'",
+        "assert Weather.__module__ == 'iboat_pmcts_b200.weatherTLKT' and Simulator.__module__ == 'iboat_pmcts_b200.simulatorTLKT'",
+        "assert Boat.UNCERTAINTY_COEFF == 0.2 and mt.RHO == 0.3 and abs(mt.UCT_COEFF - 0.2 * 2 ** -0.5) < 1e-15",
+        "for name in ('Forest', 'create_simulators', 'initialize_simulators', 'load_scenarios'): assert hasattr(ft, name), name",
+        "assert hasattr(master.MasterTree, 'get_best_policy') and hasattr(master_node, 'deepcopy_dict')",
+        "assert hasattr(isochrones, 'Isochrone') and hasattr(isochrones, 'estimate_perfomance_plan') and hasattr(utils, 'Hist')",
+        "print('swap ok')"])
+    res = subprocess.run([sys.executable, "-c", check], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                         cwd=ROOT)
+    assert res.returncode == 0 and "swap ok" in res.stdout, res.stderr[-2000:]
