@@ -11,6 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle_pmcts.so")
+_OVERRIDE = os.environ.get("PMCTS_ORACLE_LIB")  # another build of the checker itself (scripts/sanitize_host.sh)
 
 c_dp = C.POINTER(C.c_double)
 
@@ -51,9 +52,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if not _OVERRIDE and not os.path.exists(LIB_PATH):
             build()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(_OVERRIDE or LIB_PATH)
         L.orc_deter_dyn.restype = C.c_double
         L.orc_deter_dyn.argtypes = [C.POINTER(OrcSim), C.c_double, C.c_double]
         L.orc_reward.restype = C.c_double

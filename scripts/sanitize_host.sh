@@ -1,7 +1,8 @@
 #!/bin/bash
 # Host runtime under the sanitizers: builds libpmcts_b200 twice with instrumented host code (address + undefined,
 # then thread) and runs the CPU suites that drive the native search (thread pool, trees, master, update blocks,
-# generator emulation) against each build.  Device code is compiled as usual and not exercised: no GPU needed.
+# generator emulation) against each build; then the C oracle (the parity checker) the same way against its own suites.
+# Device code is compiled as usual and not exercised: no GPU needed.
 #   scripts/sanitize_host.sh            -> prints the reports that name this library (none expected)
 set -u
 cd "$(dirname "$0")/.."
@@ -25,8 +26,15 @@ build tsan -fsanitize=thread -ltsan
 PMCTS_B200_LIB=$OUT/libpmcts_tsan.so LD_PRELOAD="$GCC_LIB/libtsan.so" PMCTS_HOST_THREADS=8 \
     TSAN_OPTIONS=log_path=$OUT/tsan:halt_on_error=0:report_signal_unsafe=0:exitcode=0 \
     python -m pytest $TESTS -q -m "not gpu" -p no:cacheprovider | tail -1
-echo "reports that name libpmcts (address / undefined / thread):"
-grep -l "libpmcts_" "$OUT"/asan* "$OUT"/ubsan* "$OUT"/tsan* 2>/dev/null | while read -r f; do
-    grep -E "^SUMMARY|runtime error" "$f" | grep "libpmcts_" | sort | uniq -c
+# the checker itself: the C oracle under address + undefined, against its fixtures, the live reference and the host model
+gcc -O1 -g -ffp-contract=off -fno-fast-math -fno-builtin-pow -pthread -fPIC -fsanitize=address,undefined \
+    -fno-omit-frame-pointer -shared -o "$OUT/liboracle_asan.so" oracle/pmcts_oracle.c -lm \
+    || { echo "build of the oracle failed"; exit 1; }
+PMCTS_ORACLE_LIB=$OUT/liboracle_asan.so LD_PRELOAD="$GCC_LIB/libasan.so $GCC_LIB/libubsan.so" \
+    ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:log_path=$OUT/asan_oracle UBSAN_OPTIONS=print_stacktrace=1:log_path=$OUT/ubsan_oracle \
+    python -m pytest tests/test_oracle_golden.py tests/test_oracle_vs_reference.py tests/test_fastmodel.py -q -p no:cacheprovider | tail -1
+echo "reports that name libpmcts / liboracle (address / undefined / thread):"
+grep -lE "libpmcts_|liboracle_|pmcts_oracle" "$OUT"/asan* "$OUT"/ubsan* "$OUT"/tsan* 2>/dev/null | while read -r f; do
+    grep -E "^SUMMARY|runtime error" "$f" | grep -E "libpmcts_|liboracle_|pmcts_oracle" | sort | uniq -c
 done
 echo "(end of reports; logs under $OUT)"
