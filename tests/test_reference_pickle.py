@@ -146,3 +146,116 @@ def test_tree_saved_by_the_reference_loads_into_this_package(tmp_path):
     mt.save_tree("own", directory=str(tmp_path) + "/")
     again = MasterTree.load_tree("own", directory=str(tmp_path) + "/")
     assert type(again) is MasterTree and [str(k) for k in again.nodes] == want["keys"]
+
+
+def test_native_sequential_search_of_three_workers_is_the_references(tmp_path, golden_dir):
+    """Tree.get_master_uct across scenarios (worker.py:302-346: scenarios that never visited a node skipped, the rest
+    weighted by their probability without renormalising) and its share in Tree.best_child (worker.py:224-253), pinned to
+    the reference itself: the UNMODIFIED reference searches three scenarios one after the other into ONE master
+    dictionary (skewed probabilities, the Tutorial's RHO / UCT_COEFF, seeded generators), recording the leaf, reward
+    and transitions of every iteration; the native sequential search then runs the same three searches on the CPU with
+    the rollouts answered from the recording.  It must pick the reference's leaf at every one of the 3 x 120 iterations
+    -- the later trees steer by what the earlier ones left in the master -- and end with the reference's trees, master
+    and generator states."""
+    import ctypes as C
+    import json
+    import random
+    from iboat_pmcts_b200 import _native as N
+    from iboat_pmcts_b200.utils import Hist
+    g = np.load(os.path.join(golden_dir, "rollouts_c1.npz"))
+    dest, tmin = [float(x) for x in g["destination"]], float(g["timemin"])
+    budget, frequency, prob = int(os.environ.get("PMCTS_REPLAY_BUDGET", "120")), 10, [0.5, 0.2, 0.3]
+    script = textwrap.dedent("""
+        import contextlib, io, json, random, sys
+        import numpy as np
+        sys.path.insert(0, %r)
+        from oracle import refshim, gen_golden as G
+        R = refshim.load_reference()
+        simc, wrk, mnode = R.simulatorTLKT, R.worker, R.master_node
+        sims = G.make_sims(R, [0, 1, 2])
+        wrk.RHO, wrk.UCT_COEFF = 0.5, 1 / 2 ** 0.5
+        random.seed(4); np.random.seed(4)
+        made = {"n": 0}
+        orig_step, orig_backup = simc.Simulator.doStep, wrk.Node.back_up
+        def counting_step(self, action):
+            made["n"] += 1
+            return orig_step(self, action)
+        its = []
+        def rec_backup(self, reward):
+            its.append(dict(origins=[int(a) for a in self.origins], reward=float(reward), steps=made["n"]))
+            made["n"] = 0
+            return orig_backup(self, reward)
+        simc.Simulator.doStep, wrk.Node.back_up = counting_step, rec_backup
+        master = {hash(()): mnode.MasterNode(3, nodehash=hash(()))}
+        out = dict(workers=[])
+        with contextlib.redirect_stdout(io.StringIO()):
+            for w in range(3):
+                its = []
+                tree = wrk.Tree(workerid=w, nscenario=3, probability=%r, budget=%d, simulator=sims[w], destination=%r,
+                                TimeMin=%r, buffer=[])
+                tree.uct_search([0, 44.0, 355.0], %d, master)
+                out["workers"].append(dict(iterations=its, nodes=[dict(origins=[int(a) for a in nd.origins],
+                                                                       hist=[[int(x) for x in h.h] for h in nd.Values])
+                                                                  for nd in tree.Nodes]))
+        out["master"] = {str(k): [[[int(x) for x in h.h] for h in row] for row in nd.rewards] for k, nd in master.items()}
+        st = random.getstate()
+        out["py_state"] = [st[0], list(st[1]), st[2]]
+        ns = np.random.get_state()
+        out["np_key"], out["np_pos"] = [int(x) for x in ns[1]], int(ns[2])
+        print(json.dumps(out))
+        """) % (ROOT, prob, budget, dest, tmin, frequency)
+    res = subprocess.run([sys.executable, "-W", "ignore", "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rec = json.loads(res.stdout.strip().splitlines()[-1])
+
+    lib = N.lib()
+    h = C.c_void_p()
+    ids, p = np.arange(3, dtype=np.int32), np.asarray(prob)
+    N.check_forest(lib.pmcts_forest_create(3, 3, ids.ctypes.data, 12, p.ctypes.data, 1 / 2 ** 0.5, 0.5, None, budget + 8,
+                                           C.byref(h)))
+    try:
+        random.seed(4)
+        np.random.seed(4)
+        py, npst = N.MtState.from_python(random.getstate()), N.MtState.from_numpy(np.random.get_state())
+        for w in range(3):
+            its = rec["workers"][w]["iterations"]
+            assert len(its) == budget
+            miss = []
+
+            def hook(_user, iteration, scen, path, length, z, n_instants, bin_p, steps_p, its=its, w=w, miss=miss):
+                got = [45 * int(path[j]) for j in range(length)]
+                if got != its[iteration]["origins"] or scen != w:
+                    miss.append((iteration, got, its[iteration]["origins"]))
+                    return 1
+                bin_p[0] = Hist.bin_of(its[iteration]["reward"])
+                steps_p[0] = its[iteration]["steps"]
+                return 0
+
+            cb = N.SEQ_ROLLOUT_HOOK_FN(hook)
+            rc = lib.pmcts_forest_search_sequential_hook(h, w, budget, frequency, C.byref(py), C.byref(npst), cb, None, None)
+            assert rc == 0 and not miss, (w, miss, lib.pmcts_forest_last_error().decode())
+            n = int(lib.pmcts_forest_tree_size(h, w))
+            nodes = rec["workers"][w]["nodes"]
+            assert n == len(nodes) == budget + 1
+            parent, arm, table = np.empty(n, np.int32), np.empty(n, np.int8), np.empty((n, 8, 12), np.int64)
+            N.check_forest(lib.pmcts_forest_export_tree(h, w, parent.ctypes.data, arm.ctypes.data, table.ctypes.data, None, None))
+            paths = []
+            for i in range(n):
+                paths.append([] if parent[i] < 0 else paths[parent[i]] + [45 * int(arm[i])])
+                assert paths[i] == nodes[i]["origins"] and np.array_equal(table[i], np.array(nodes[i]["hist"])), (w, i)
+        m = int(lib.pmcts_forest_master_size(h))
+        assert m == len(rec["master"])
+        mparent, marm, mtable = np.empty(m, np.int32), np.empty(m, np.int8), np.empty((m, 3, 8, 12), np.uint32)
+        N.check_forest(lib.pmcts_forest_export_master(h, mparent.ctypes.data, marm.ctypes.data, mtable.ctypes.data))
+        mpaths = []
+        for i in range(m):
+            mpaths.append(() if mparent[i] < 0 else mpaths[mparent[i]] + (45 * int(marm[i]),))
+            assert np.array_equal(mtable[i], np.array(rec["master"][str(hash(mpaths[i]))])), mpaths[i]
+        shared = sum(1 for i in range(m) if (mtable[i].reshape(3, -1).sum(1) > 0).sum() >= 2)
+        assert shared > 10   # nodes more than one scenario visited: where the master's value mixes scenarios
+        want_py = (rec["py_state"][0], tuple(rec["py_state"][1]), rec["py_state"][2])
+        assert py.to_python() == want_py
+        assert list(npst.key) == rec["np_key"] and npst.pos == rec["np_pos"]
+    finally:
+        lib.pmcts_forest_destroy(h)
