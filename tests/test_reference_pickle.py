@@ -259,3 +259,49 @@ def test_native_sequential_search_of_three_workers_is_the_references(tmp_path, g
         assert list(npst.key) == rec["np_key"] and npst.pos == rec["np_pos"]
     finally:
         lib.pmcts_forest_destroy(h)
+
+    # The same three searches through the PYTHON classes of the mirror (worker.Tree.uct_search: tree_policy, expand,
+    # best_child, get_master_uct, Node.back_up, integrate_buffer; master_node.MasterNode), the rollout answered from the
+    # recording and drawing the normals its transitions drew: the reference's leaves, trees, master and generator states.
+    from iboat_pmcts_b200 import master_node as mn, synth, worker
+    from iboat_pmcts_b200.forest import create_simulators
+    from iboat_pmcts_b200.weatherTLKT import Weather
+    weathers = [Weather(*[synth.wind_fields(s)[i] for i in (1, 2, 0, 3, 4)]) for s in range(3)]
+    sims = create_simulators(weathers, 3, simtimestep=6, stateinit=(0, 44.0, 355.0), ndaysim=3)
+    saved = (worker.RHO, worker.UCT_COEFF)
+    worker.RHO, worker.UCT_COEFF = 0.5, 1 / 2 ** 0.5
+    try:
+        random.seed(4)
+        np.random.seed(4)
+        master = {hash(()): mn.MasterNode(3, nodehash=hash(()))}
+        for w in range(3):
+            its = rec["workers"][w]["iterations"]
+            tree = worker.Tree(workerid=w, nscenario=3, probability=prob, budget=budget, simulator=sims[w],
+                               destination=dest, TimeMin=tmin, buffer=[])
+
+            def recorded_rollout(leaf, tree=tree, its=its):
+                it = its[tree.ite]
+                assert [int(a) for a in leaf.origins] == it["origins"], (tree.id, tree.ite)
+                for _ in range(it["steps"]):
+                    random.gauss(0.0, 1.0)
+                return it["reward"]
+
+            tree.default_policy = recorded_rollout
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                tree.uct_search([0, 44.0, 355.0], frequency, master)
+            nodes = rec["workers"][w]["nodes"]
+            assert len(tree.Nodes) == len(nodes)
+            for node, want in zip(tree.Nodes, nodes):
+                assert [int(a) for a in node.origins] == want["origins"]
+                assert np.array_equal(np.array([hh.h for hh in node.Values]), np.array(want["hist"]))
+        assert {str(k) for k in master} == set(rec["master"])
+        for k, node in master.items():
+            assert np.array_equal(node._table, np.array(rec["master"][str(k)])), k
+        st = random.getstate()
+        assert (st[0], st[1], st[2]) == want_py
+        ns = np.random.get_state()
+        assert [int(x) for x in ns[1]] == rec["np_key"] and int(ns[2]) == rec["np_pos"]
+    finally:
+        worker.RHO, worker.UCT_COEFF = saved
