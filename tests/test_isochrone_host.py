@@ -10,32 +10,12 @@ import random
 import numpy as np
 
 import pmcts_helpers as H
-from iboat_pmcts_b200 import _native as N
 from iboat_pmcts_b200 import isochrones as iso
 from iboat_pmcts_b200 import simulatorTLKT as SimC
 from iboat_pmcts_b200 import synth
 from iboat_pmcts_b200.forest import create_simulators
 from iboat_pmcts_b200.weatherTLKT import Weather
-
-
-class OracleEngine:
-    """Stands in for engine.Engine.step_batch (host arrays, updated in place) with the oracle's transitions."""
-    precision = N.PREC_F64
-
-    def __init__(self, osim):
-        self.o, self.calls, self.boats = osim, 0, 0
-
-    def set_precision(self, mode):
-        self.precision = mode
-
-    def step_batch(self, scen, k, lat, lon, heading, nsteps=1, seg_len=1, status=None, z=None, **_):
-        assert self.precision == N.PREC_F64 and nsteps == 1
-        r = self.o.step_batch(k, lat, lon, heading, nsteps=1, seg_len=1, z=z)
-        k[:], lat[:], lon[:] = r["k"], r["lat"], r["lon"]
-        if status is not None:
-            status[:] = r["status"]
-        self.calls += 1
-        self.boats += lat.size
+from oracle_engine import on_oracle
 
 
 def test_isochrone_fronts_are_the_references(golden_dir, monkeypatch):
@@ -43,9 +23,8 @@ def test_isochrone_fronts_are_the_references(golden_dir, monkeypatch):
         want = json.load(f)
     t, la, lo, u, v = synth.wind_fields(0)
     sim = create_simulators([Weather(la, lo, t, u, v)], 1, simtimestep=6, stateinit=H.STATE0, ndaysim=3)[0]
-    fake = OracleEngine(H.oracle_sim(0, sigma_coeff=0.0))
-    monkeypatch.setattr(sim, "scenario", lambda: (fake, 0))
     monkeypatch.setattr(SimC.Boat, "UNCERTAINTY_COEFF", 0)   # Tutorial.py:81
+    fake = on_oracle([sim], [H.oracle_sim(0)], monkeypatch)
     random.seed(3)
     solver = iso.Isochrone(sim, H.STATE0, want["destination"], delta_cap=5, increment_cap=9, nb_secteur=300, resolution=100)
     temps, actions, caps_fin, positions = solver.isochrone_methode()
@@ -59,4 +38,4 @@ def test_isochrone_fronts_are_the_references(golden_dir, monkeypatch):
     assert np.array_equal(np.array(positions, dtype=np.float64), np.array(want["liste_positions"], dtype=np.float64))
     # one launch per isochrone for the fronts; only the last leg steps boat by boat
     fronts = len(want["isochrone_stock"])
-    assert fake.boats > 20000 and fake.calls - fronts < 2000
+    assert fronts <= fake.launches < fronts + 2000
