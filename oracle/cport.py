@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle_pmcts.so")
-_OVERRIDE = os.environ.get("PMCTS_ORACLE_LIB")  # another build of the checker itself (scripts/sanitize_host.sh)
+_OVERRIDE = os.environ.get("PMCTS_ORACLE_LIB")  # another build of the checker itself (tests/tools/sanitize_host.sh)
 
 c_dp = C.POINTER(C.c_double)
 

@@ -56,6 +56,21 @@ def test_product_does_not_import_test_infrastructure():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in text and "from oracle" not in text, fn
                 assert "fastmodel" not in text.replace("tests/fastmodel", "") or fn.endswith((".cuh", ".h")), fn
+    # nor do the measurement scripts (what loads the oracle by hand lives under tests/tools/); bench.py does, and only in
+    # its CPU-baseline / reference-arm leg
+    for fn in os.listdir(os.path.join(ROOT, "scripts")):
+        if fn.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "scripts", fn)).read()
+            for word in ("import oracle", "from oracle", "pmcts_helpers", "import fastmodel", "oracle_engine", "liboracle"):
+                assert word not in text, (fn, word)
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in tree.body:   # every import of the oracle sits inside one of the cpu_*_sample functions
+        inside = isinstance(node, ast.FunctionDef) and node.name.startswith("cpu_") and node.name.endswith("_sample")
+        for sub in ast.walk(node):
+            uses = (isinstance(sub, ast.ImportFrom) and (sub.module or "").split(".")[0] == "oracle") or \
+                   (isinstance(sub, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in sub.names))
+            assert not uses or inside, getattr(node, "name", type(node).__name__)
 
 
 def test_weather_pickle_ingest(tmp_path):

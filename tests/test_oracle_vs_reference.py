@@ -75,12 +75,12 @@ def test_arrival_test_and_rollout_bit_exact(world):
 
 @pytest.mark.parametrize("scenario", [20, 41, 63])
 def test_rollouts_and_raw_steps_of_other_scenarios_bit_exact(scenario):
-    """A slice of scripts/oracle_vs_reference_sweep.py (which holds the oracle to the reference on ALL 64 scenarios of
+    """A slice of tests/tools/oracle_vs_reference_sweep.py (which holds the oracle to the reference on ALL 64 scenarios of
     config 4: profiles/r02_oracle_vs_reference_sweep.jsonl): the reference's own Tree.default_policy on 24 leaves of
     mixed depth and 6 x 150 raw doStep on the config-3 axis, rewards / arrival fractions / every position equal."""
     import importlib.util
     import os
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "oracle_vs_reference_sweep.py")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "oracle_vs_reference_sweep.py")
     spec = importlib.util.spec_from_file_location("oracle_vs_reference_sweep", path)
     sweep = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sweep)

@@ -7,7 +7,7 @@ bench.py, same injected normals for both, and counts per scenario: rollouts the 
 (inside a decision margin) and rollouts it decides UNLIKE the oracle (transitions, status or histogram bin) -- the second
 count must be zero for the histograms of the search to be the oracle's.  One JSON line per scenario + a total.
 
-    python scripts/fastmodel_sweep.py [--scenarios 64] [--leaves 512] [--replicas 256] > profiles/r02_fastmodel_sweep.jsonl
+    python tests/tools/fastmodel_sweep.py [--scenarios 64] [--leaves 512] [--replicas 256] > profiles/r02_fastmodel_sweep.jsonl
 
 ``--k1 BOATS`` does the same for BASELINE config 3 (raw doStep: bench.py's fleet of BOATS boats walking octagons for 500
 steps of 864 s on scenario 0), in chunks of 10^5 boats: boats handed to the literal kernel, status / step count equal to
@@ -23,7 +23,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,7 +1,7 @@
 """The fp64 finisher (rollout_batch_kernel on the work list of the mixed-precision launch) and the literal fp64
 rollout kernel on their own: per-launch durations from the library's own event pairs, launches NOT overlapped.
 
-  python scripts/finisher_probe.py            # (PMCTS_B200_LIB=<other build> for A/B comparisons)
+  python tests/tools/finisher_probe.py            # (PMCTS_B200_LIB=<other build> for A/B comparisons)
 
 Three shapes: the c4 shard (8 scenarios x 4096 leaves x 256 replicas), one c2 search wave (10 scenarios x 64 leaves
 x 32 replicas), and a literal-mode launch of 131 072 rollouts.  Also prints a digest of the histograms so that two
@@ -11,8 +11,8 @@ import hashlib
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

@@ -3,14 +3,14 @@
 
 tests/golden/ pins the oracle to the reference bit for bit on scenarios 0-2 (rollouts) and 0 (raw steps), and
 tests/test_oracle_vs_reference.py on random inputs of scenario 3.  The multi-GPU bench rolls out scenarios 0-63, whose
-parity rests on the oracle (scripts/fastmodel_sweep.py, the GPU tests), so this script extends the pin: for every
+parity rests on the oracle (tests/tools/fastmodel_sweep.py, the GPU tests), so this script extends the pin: for every
 scenario the reference's own ``Tree.default_policy`` (code/solver/worker.py:255-300) runs ROLLOUTS leaves of mixed depth
 with an injected noise feed, on the destination / Tmin of bench.py, and the oracle is held to its reward, its
 transitions, its arrival flag and fraction, its final state and every position on the way -- all bit for bit.  Raw
 ``Simulator.doStep`` (simulatorTLKT.py:181-216) is compared the same way on the config-3 axis: 6 boats x 150 steps of
 864 s per scenario, every position of every step.
 
-    python scripts/oracle_vs_reference_sweep.py [--scenarios 64] [--rollouts 64] > profiles/r02_oracle_vs_reference_sweep.jsonl
+    python tests/tools/oracle_vs_reference_sweep.py [--scenarios 64] [--rollouts 64] > profiles/r02_oracle_vs_reference_sweep.jsonl
 """
 import argparse
 import json
@@ -22,7 +22,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -3,9 +3,9 @@
 # then thread) and runs the CPU suites that drive the native search (thread pool, trees, master, update blocks,
 # generator emulation) against each build; then the C oracle (the parity checker) the same way against its own suites.
 # Device code is compiled as usual and not exercised: no GPU needed.
-#   scripts/sanitize_host.sh            -> prints the reports that name this library (none expected)
+#   tests/tools/sanitize_host.sh            -> prints the reports that name this library (none expected)
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 P=iboat_pmcts_b200/csrc
 GCC_LIB=$(dirname "$(gcc -print-file-name=libasan.so)")
 SRC="$P/pmcts_b200.cu $P/pmcts_forest_host.cpp $P/pmcts_search.cu $P/pmcts_master.cu $P/pmcts_peer.cu"
